@@ -1,0 +1,207 @@
+/* b200cfr.h — C ABI of the B200-native vectorized CFR engine.
+ *
+ * Drop-in boundary for the solver hot path of kmurf1999/RustSolver.  The reference has no
+ * FFI of its own (mccfr/cfr are private methods, src/solver/cfr.rs:299,481); these entry
+ * points are what a `cc`/bindgen block in src/solver would bind to replace
+ *   MCCFRTrainer::init   (src/solver/cfr.rs:159-184)  -> rs_create
+ *   MCCFRTrainer::train  (src/solver/cfr.rs:188-297)  -> rs_iterate (+ rs_discount)
+ *   Infoset::get_strategy / get_final_strategy (src/solver/infoset.rs:83-123)
+ *                                                     -> rs_read_infoset / rs_average_strategy
+ *   MCCFRTrainer::calc_br (src/solver/cfr.rs:629-638) -> rs_best_response
+ *   ICardAbstraction::get_cluster / get_size (src/solver/card_abstraction.rs:71-72)
+ *                                                     -> rs_card_table / rs_num_rows
+ * See INTEGRATION.md for the Rust-side stub.
+ *
+ * Conventions: every call returns 0 on success, <0 on error (message via rs_last_error());
+ * nothing panics or aborts across the ABI.  The caller owns every input array; the engine
+ * copies during rs_create and never retains host pointers.  Outputs go to caller buffers
+ * with explicit capacities.  One host thread per handle (thread-compatible).  There is no
+ * CPU fallback: rs_create fails if no sm_100-class CUDA device is usable.
+ */
+#ifndef B200CFR_H
+#define B200CFR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* error codes */
+#define RS_OK 0
+#define RS_ERR_INVALID -1    /* bad argument / malformed tree (reference: panic!) */
+#define RS_ERR_CUDA -2       /* CUDA runtime error or no device */
+#define RS_ERR_NCCL -3       /* NCCL error */
+#define RS_ERR_CAPACITY -4   /* output buffer too small */
+#define RS_ERR_UNSUPPORTED -5
+
+/* node types (src/solver/nodes.rs:47-52) */
+#define RS_NODE_ACTION 0
+#define RS_NODE_TERMINAL 1
+#define RS_NODE_PUBLIC_CHANCE 2
+#define RS_NODE_PRIVATE_CHANCE 3
+/* terminal types (src/solver/nodes.rs:17-21) */
+#define RS_TERM_ALLIN 0
+#define RS_TERM_SHOWDOWN 1
+#define RS_TERM_UNCONTESTED 2
+/* betting rounds (src/solver/state.rs:7-22) */
+#define RS_ROUND_FLOP 0
+#define RS_ROUND_TURN 1
+#define RS_ROUND_RIVER 2
+
+/* Tree<GameTreeNode> (src/solver/tree.rs:12-24) flattened: node id = arena index. */
+typedef struct rs_tree {
+    uint32_t n_nodes;
+    const uint8_t* type;          /* [n_nodes] RS_NODE_* */
+    const int32_t* parent;        /* [n_nodes] -1 for the root */
+    const uint32_t* child_offset; /* [n_nodes+1] CSR into children, action order */
+    const uint32_t* children;     /* [child_offset[n_nodes]] */
+    const uint8_t* player;        /* ActionNode.player      (nodes.rs:8) */
+    const uint32_t* an_index;     /* ActionNode.index       (nodes.rs:7) */
+    const uint8_t* round_idx;     /* ActionNode.round_idx   (nodes.rs:9) */
+    const uint32_t* value;        /* TerminalNode.value     (nodes.rs:35) */
+    const uint8_t* ttype;         /* TerminalNode.ttype     (nodes.rs:36) */
+    const uint8_t* last_to_act;   /* TerminalNode.last_to_act (nodes.rs:37) */
+} rs_tree;
+
+/* hand_ranges after remove_invalid_combos (src/solver/cfr.rs:161-163): (c0,c1) pairs,
+ * card = 4*rank + suit.  Unweighted like the reference (HoleCards has no weight). */
+typedef struct rs_ranges {
+    uint32_t n_hands[2];
+    const uint8_t* hands[2]; /* [n_hands[p]][2] */
+} rs_ranges;
+
+/* card abstraction per round_idx (src/solver/card_abstraction.rs:62-66) */
+#define RS_ABS_NONE 0        /* one row per live hand (lossless, no suit merging) */
+#define RS_ABS_ISOMORPHIC 1  /* ISOMORPHIC: canonical suit-isomorphic index (card_abstraction.rs:186-214) */
+#define RS_ABS_CLUSTER_ARR 2 /* EMD / OCHS: cluster_arr[canonical index] (card_abstraction.rs:216-298) */
+#define RS_ABS_BUCKET_TABLE 3 /* caller-supplied bucket key per (board, hand) */
+typedef struct rs_round_abstraction {
+    uint32_t kind;
+    const uint32_t* cluster_arr; /* RS_ABS_CLUSTER_ARR: contents of round_N_{emd,ochs}.dat (LE u32) */
+    uint64_t cluster_arr_len;
+    const uint32_t* bucket_table[2]; /* RS_ABS_BUCKET_TABLE: [n_boards(round)][n_hands[p]] keys */
+} rs_round_abstraction;
+typedef struct rs_abstraction {
+    uint32_t n_rounds; /* = number of betting rounds in the tree (card_abs.len(), cfr.rs:167-172) */
+    rs_round_abstraction rounds[3];
+} rs_abstraction;
+
+#define RS_NCCL_ID_BYTES 128
+typedef struct rs_config {
+    uint64_t board_mask;       /* Options.board_mask (options.rs:17) */
+    int32_t device;            /* CUDA device ordinal */
+    /* board sharding over one process per GPU: rank r owns a contiguous slice of
+     * the first dealt-card level; world_size 1 = single GPU */
+    int32_t rank;
+    int32_t world_size;
+    uint8_t nccl_id[RS_NCCL_ID_BYTES]; /* from rs_nccl_unique_id on rank 0, broadcast by the host */
+    /* shard the boards of the ROOT round's children by subgame instead (config 5 style) is done
+     * by creating one engine per subgame batch: see rs_create_batch */
+    uint32_t flags;            /* RS_FLAG_* */
+    uint32_t threads_per_block; /* 0 = default */
+    /* train() discount schedule (cfr.rs:190-194,248-262); 0 interval = off */
+    uint64_t discount_interval;
+    uint64_t discount_cap;
+} rs_config;
+#define RS_FLAG_NO_GRAPH 1u     /* launch kernels directly instead of replaying a CUDA graph */
+#define RS_FLAG_OWN_REACH_AVG 2u /* weight strategy_sum by the player's own reach instead of the
+                                    reference's counterfactual reach (cfr.rs:618-619) */
+
+typedef struct rs_engine rs_engine;
+
+typedef struct rs_stats {
+    uint64_t iterations;            /* completed iterations (both players traversed, cfr.rs:216-226) */
+    uint64_t updates_per_iteration; /* infoset-action cells updated per iteration on THIS rank */
+    uint64_t updates_per_iteration_global;
+    double device_ms;               /* CUDA-event time spent inside rs_iterate */
+    uint64_t kernel_launches;       /* kernels launched (or graph-replayed) by rs_iterate */
+    uint64_t table_bytes;           /* regret + strategy_sum bytes resident on this rank */
+    uint32_t n_rounds;
+    uint32_t n_boards[3];           /* global boards per round_idx */
+    uint32_t n_boards_local[3];
+    uint32_t n_hands[2];
+    uint64_t n_combos;              /* generate_all_hole_card_combos().len() (cfr.rs:73-98) */
+} rs_stats;
+
+const char* rs_last_error(void);
+int rs_version(void);
+/* number of usable CUDA devices, 0 when none (never fails) */
+int rs_device_count(void);
+/* fills RS_NCCL_ID_BYTES bytes; call on rank 0 and broadcast */
+int rs_nccl_unique_id(uint8_t* out);
+
+int rs_create(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs,
+              const rs_config* cfg, rs_engine** out);
+/* Batch of independent subgames sharing one tree shape and abstraction kind but with their own
+ * boards (BASELINE config 5): board_masks[n_subgames]; ranges are given unfiltered and each
+ * subgame drops the combos hitting its own board.  Subgames behave as extra boards of round 0. */
+int rs_create_batch(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs,
+                    const rs_config* cfg, const uint64_t* board_masks, uint32_t n_subgames,
+                    rs_engine** out);
+void rs_destroy(rs_engine* e);
+
+/* train(): run n_iters synchronous full-tree CFR iterations; returns after the device is idle */
+int rs_iterate(rs_engine* e, uint64_t n_iters);
+/* discount sweep of train()'s monitor thread (cfr.rs:248-261): every table *= d */
+int rs_discount(rs_engine* e, float d);
+int rs_reset(rs_engine* e);
+
+/* infoset_table[round,player][board][action node] -> [row][n_actions] (README.md:45-47).
+ * an_index is ActionNode.index; board_id indexes the round's board table (rs_board_id).
+ * Either output may be NULL.  *n_rows_out / *n_actions_out report the slab shape. */
+int rs_read_infoset(rs_engine* e, uint32_t an_index, uint32_t board_id, float* regrets,
+                    float* strategy_sum, size_t cap_floats, uint32_t* n_rows_out,
+                    uint32_t* n_actions_out);
+int rs_write_infoset(rs_engine* e, uint32_t an_index, uint32_t board_id, const float* regrets,
+                     const float* strategy_sum, size_t n_floats);
+/* Infoset::get_final_strategy (infoset.rs:104-123) for every row of the slab */
+int rs_average_strategy(rs_engine* e, uint32_t an_index, uint32_t board_id, float* out,
+                        size_t cap_floats, uint32_t* n_rows_out, uint32_t* n_actions_out);
+/* Infoset::get_strategy (infoset.rs:83-102) for every row of the slab */
+int rs_current_strategy(rs_engine* e, uint32_t an_index, uint32_t board_id, float* out,
+                        size_t cap_floats, uint32_t* n_rows_out, uint32_t* n_actions_out);
+
+/* board table (README.md:41-43): dealt cards beyond the root board, in deal order -> board id */
+int rs_board_id(rs_engine* e, uint32_t round_idx, const uint8_t* dealt, uint32_t n_dealt,
+                uint32_t* board_id_out);
+/* card table (README.md:36-39): hand slot -> row (0xFFFF = hand hits the board) */
+int rs_card_table(rs_engine* e, uint32_t round_idx, uint32_t player, uint32_t board_id,
+                  uint16_t* rows_out, size_t cap, uint32_t* n_rows_out);
+
+/* out[p] = value of player p's best response against the other player's average strategy,
+ * in the reference's payoff convention (+-pot, cfr.rs:525-556), per deal.
+ * exploitability = (out[0] + out[1]) / 2. */
+int rs_best_response(rs_engine* e, double out[2]);
+/* out[p] = expected value for player p when both play their average strategies */
+int rs_average_value(rs_engine* e, double out[2]);
+/* counterfactual values at the root for the last traversal of `player` in rs_iterate */
+int rs_root_values(rs_engine* e, uint32_t player, float* out, size_t cap);
+
+int rs_stats_get(rs_engine* e, rs_stats* out);
+
+/* ---- host-only plan introspection (no GPU needed): integer parity surface ---- */
+typedef struct rs_plan rs_plan;
+int rs_plan_create(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs,
+                   const rs_config* cfg, const uint64_t* board_masks, uint32_t n_subgames,
+                   rs_plan** out);
+void rs_plan_destroy(rs_plan* p);
+int rs_plan_stats(const rs_plan* p, rs_stats* out);
+int rs_plan_board_id(const rs_plan* p, uint32_t round_idx, const uint8_t* dealt, uint32_t n_dealt,
+                     uint32_t* board_id_out);
+int rs_plan_card_table(const rs_plan* p, uint32_t round_idx, uint32_t player, uint32_t board_id,
+                       uint16_t* rows_out, size_t cap, uint32_t* n_rows_out);
+/* element offset of slab (an_index, board_id) inside its (round,player) table, and its shape */
+int rs_plan_infoset_offset(const rs_plan* p, uint32_t an_index, uint32_t board_id,
+                           uint64_t* offset_out, uint32_t* n_rows_out, uint32_t* n_actions_out);
+/* showdown ordering of `player`'s live hands on a final-round board: hand slots, weakest first,
+ * and for each slot its strength-class id (equal id = tie) */
+int rs_plan_showdown_order(const rs_plan* p, uint32_t player, uint32_t board_id,
+                           uint16_t* order_out, uint32_t* class_out, size_t cap,
+                           uint32_t* n_live_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CFR_H */

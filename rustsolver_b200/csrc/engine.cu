@@ -1,0 +1,834 @@
+// Host engine behind the C ABI (include/b200cfr.h): owns device memory, the per-round launch
+// descriptors, the CUDA graph of one iteration and (when board-sharded) the NCCL communicator.
+//
+// Replaces MCCFRTrainer::{init, train} (src/solver/cfr.rs:159-297) and the InfosetTable
+// (src/solver/infoset.rs:6-49).  No CPU fallback: without a CUDA device rs_create fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/b200cfr.h"
+#include "kernels.cuh"
+#include "plan.h"
+
+namespace rs {
+
+thread_local std::string g_last_error;
+
+static int set_err(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+// ---- NCCL through dlopen: the library loads on CPU-only hosts and single-GPU runs never touch it ----
+namespace nccl {
+typedef struct {
+    char internal[128];
+} UniqueId;
+typedef void* Comm;
+typedef int (*GetUniqueId_t)(UniqueId*);
+typedef int (*CommInitRank_t)(Comm*, int, UniqueId, int);
+typedef int (*AllReduce_t)(const void*, void*, size_t, int, int, Comm, cudaStream_t);
+typedef int (*CommDestroy_t)(Comm);
+typedef const char* (*GetErrorString_t)(int);
+struct Api {
+    void* lib = nullptr;
+    GetUniqueId_t GetUniqueId = nullptr;
+    CommInitRank_t CommInitRank = nullptr;
+    AllReduce_t AllReduce = nullptr;
+    CommDestroy_t CommDestroy = nullptr;
+    GetErrorString_t GetErrorString = nullptr;
+};
+static Api g_api;
+constexpr int kFloat32 = 7;  // ncclFloat32
+constexpr int kSum = 0;      // ncclSum
+
+static bool load(std::string* err) {
+    if (g_api.lib) return true;
+    const char* env = getenv("RS_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) {
+        if (!n || !*n) continue;
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) {
+        *err = "cannot dlopen libnccl.so.2 (set RS_NCCL_LIB to its path)";
+        return false;
+    }
+    g_api.lib = lib;
+    g_api.GetUniqueId = (GetUniqueId_t)dlsym(lib, "ncclGetUniqueId");
+    g_api.CommInitRank = (CommInitRank_t)dlsym(lib, "ncclCommInitRank");
+    g_api.AllReduce = (AllReduce_t)dlsym(lib, "ncclAllReduce");
+    g_api.CommDestroy = (CommDestroy_t)dlsym(lib, "ncclCommDestroy");
+    g_api.GetErrorString = (GetErrorString_t)dlsym(lib, "ncclGetErrorString");
+    if (!g_api.GetUniqueId || !g_api.CommInitRank || !g_api.AllReduce || !g_api.CommDestroy) {
+        *err = "libnccl is missing expected symbols";
+        g_api = Api();
+        return false;
+    }
+    return true;
+}
+}  // namespace nccl
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return set_err(RS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));      \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t count) {
+        n = count;
+        if (count == 0) count = 1;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    cudaError_t upload(const T* src, size_t count) {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    cudaError_t upload(const std::vector<T>& v) { return upload(v.data(), v.size()); }
+    cudaError_t zero() { return cudaMemset(p, 0, (n ? n : 1) * sizeof(T)); }
+};
+
+struct RoundDev {
+    // per player q
+    DevBuf<uint16_t> row_of_hand[2], row_start[2], row_hands[2];
+    DevBuf<uint32_t> n_rows[2];
+    DevBuf<uint64_t> board_off[2];
+    DevBuf<float> regrets[2], ssum[2];
+    DevBuf<float> chance_scale;
+    DevBuf<int32_t> parent_board;
+    // programs, per traverser: [0] up, [1] down
+    DevBuf<Op> ops[2][2];
+    DevBuf<uint32_t> prog_start[2][2];
+    int n_r[2][2] = {{0, 0}, {0, 0}}, n_v[2][2] = {{0, 0}, {0, 0}};
+    bool has_down = false;
+    // transients
+    DevBuf<float> leaf_reach, root_cfv, gathered;
+    uint32_t n_segs = 0, n_leaves = 0, n_boards = 0;
+};
+
+struct Engine {
+    Plan plan;
+    int device = 0;
+    int threads = 512;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool use_graph = true;
+    nccl::Comm comm = nullptr;
+
+    DevBuf<uint8_t> cards[2];
+    DevBuf<uint16_t> same[2], card_hands[2];
+    RoundDev rd[3];
+    // showdown tables (final round), per player
+    DevBuf<uint16_t> sd_sorted[2], sd_lohi[2];
+    DevBuf<uint32_t> sd_nlive[2];
+    DevBuf<uint8_t> sd_cj[2], sd_ncard[2], sd_cpos[2];
+    DevBuf<float> scratch;  // strategy read-outs
+
+    uint64_t iterations = 0;
+    double device_ms = 0;
+    uint64_t launches = 0;
+    uint64_t launches_per_iter = 0;
+    uint64_t table_bytes = 0;
+    uint64_t updates_global = 0;
+    uint64_t discount_interval = 0, discount_cap = 0;
+    size_t max_smem = 0;
+
+    ~Engine() {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        if (graph) cudaGraphDestroy(graph);
+        if (comm && nccl::g_api.CommDestroy) nccl::g_api.CommDestroy(comm);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    int init(const rs_config* cfg);
+    int fill_launch(SegLaunch* a, uint32_t k, int trav, int down) const;
+    int enqueue_traversal(int trav, int mode, uint64_t* count);
+    int enqueue_iteration(uint64_t* count);
+    int iterate(uint64_t n);
+    int root_sum(int player, double* out);
+};
+
+template <class T>
+static std::vector<T> slice(const std::vector<T>& v, size_t lo, size_t hi, size_t stride) {
+    if (v.empty()) return {};
+    return std::vector<T>(v.begin() + lo * stride, v.begin() + hi * stride);
+}
+
+int Engine::init(const rs_config* cfg) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(RS_ERR_CUDA, std::string("no CUDA device available (the engine has no CPU fallback): ") +
+                                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    device = cfg->device;
+    if (device < 0 || device >= ndev) return set_err(RS_ERR_INVALID, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return set_err(RS_ERR_UNSUPPORTED, "kernels are built for sm_100a only; found an older device");
+    threads = cfg->threads_per_block ? int(cfg->threads_per_block) : 512;
+    if (threads < 64 || threads > 512 || (threads & 31)) return set_err(RS_ERR_INVALID, "threads_per_block must be a multiple of 32 in 64..512");
+    use_graph = !(cfg->flags & RS_FLAG_NO_GRAPH);
+    discount_interval = cfg->discount_interval;
+    discount_cap = cfg->discount_cap;
+    CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ev0));
+    CU(cudaEventCreate(&ev1));
+
+    const Plan& P = plan;
+    for (int q = 0; q < 2; ++q) {
+        CU(cards[q].upload(P.hand_cards[q]));
+        CU(same[q].upload(P.same[q]));
+        CU(card_hands[q].upload(P.card_hands[q]));
+    }
+    size_t smem_need = 0;
+    const int HP[2] = {int((P.H[0] + 3) & ~3u), int((P.H[1] + 3) & ~3u)};
+    for (uint32_t k = 0; k < P.n_rounds; ++k) {
+        RoundDev& R = rd[k];
+        const uint32_t lo = P.local_lo[k], hi = P.local_hi[k], nb = hi - lo;
+        R.n_boards = nb;
+        R.n_segs = uint32_t(P.segs[k].size());
+        R.n_leaves = (k + 1 < P.n_rounds) ? uint32_t(P.segs[k + 1].size()) : 0;
+        for (int q = 0; q < 2; ++q) {
+            const RoundPlayerTables& T = P.tabs[k][q];
+            const uint32_t H = P.H[q];
+            CU(R.row_of_hand[q].upload(slice(T.row_of_hand, lo, hi, H)));
+            CU(R.row_start[q].upload(slice(T.row_start, lo, hi, H + 1)));
+            CU(R.row_hands[q].upload(slice(T.row_hands, lo, hi, H)));
+            CU(R.n_rows[q].upload(slice(T.n_rows, lo, hi, 1)));
+            CU(R.board_off[q].upload(slice(T.board_off, lo, hi, 1)));
+            const size_t cells = size_t(T.board_off[P.n_boards[k]]);
+            CU(R.regrets[q].alloc(cells));
+            CU(R.ssum[q].alloc(cells));
+            CU(R.regrets[q].zero());
+            CU(R.ssum[q].zero());
+            table_bytes += 2 * cells * sizeof(float);
+        }
+        CU(R.chance_scale.upload(slice(P.chance_scale[k], lo, hi, 1)));
+        std::vector<int32_t> pb(nb, -1);
+        if (k > 0)
+            for (uint32_t b = 0; b < nb; ++b) {
+                int32_t g = P.board_parent[k][lo + b];
+                // the replicated root board of a sharded single subgame has local id 0
+                pb[b] = g - int32_t(P.local_lo[k - 1]);
+            }
+        CU(R.parent_board.upload(pb));
+        for (int p = 0; p < 2; ++p)
+            for (int down = 0; down < 2; ++down) {
+                std::vector<Op> all;
+                std::vector<uint32_t> start;
+                int nr = 1, nv = 1;
+                for (const Segment& sg : P.segs[k]) {
+                    const Program& pr = down ? sg.down[p] : sg.up[p];
+                    start.push_back(uint32_t(all.size()));
+                    if (pr.ops.empty()) {
+                        Op end{};
+                        end.type = OP_END;
+                        all.push_back(end);
+                    } else {
+                        all.insert(all.end(), pr.ops.begin(), pr.ops.end());
+                        if (down) R.has_down = true;
+                    }
+                    nr = std::max(nr, int(pr.n_r));
+                    nv = std::max(nv, int(pr.n_v));
+                }
+                CU(R.ops[p][down].upload(all));
+                CU(R.prog_start[p][down].upload(start));
+                R.n_r[p][down] = nr;
+                R.n_v[p][down] = down ? 0 : nv;
+                smem_need = std::max(smem_need, seg_kernel_smem_bytes(nr, down ? 0 : nv, HP[p], HP[1 - p]));
+            }
+        const size_t maxH = std::max(P.H[0], P.H[1]);
+        CU(R.leaf_reach.alloc(size_t(R.n_leaves) * nb * maxH));
+        CU(R.root_cfv.alloc(size_t(R.n_segs) * nb * maxH));
+        CU(R.gathered.alloc(size_t(R.n_leaves) * nb * maxH));
+        CU(R.gathered.zero());
+    }
+    // showdown tables live on the final round's local boards
+    {
+        const uint32_t k = P.n_rounds - 1;
+        const uint32_t lo = P.local_lo[k], hi = P.local_hi[k];
+        for (int q = 0; q < 2; ++q) {
+            const ShowdownTables& S = P.sd[q];
+            const uint32_t H = P.H[q];
+            CU(sd_sorted[q].upload(slice(S.sorted, lo, hi, H)));
+            CU(sd_nlive[q].upload(slice(S.n_live, lo, hi, 1)));
+            CU(sd_cj[q].upload(slice(S.cj, lo, hi, size_t(H) * 2)));
+            CU(sd_ncard[q].upload(slice(S.n_card, lo, hi, 52)));
+            CU(sd_lohi[q].upload(slice(S.lohi, lo, hi, size_t(H) * 2)));
+            CU(sd_cpos[q].upload(slice(S.cpos, lo, hi, size_t(H) * 4)));
+        }
+    }
+    int max_optin = 0;
+    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (smem_need > size_t(max_optin))
+        return set_err(RS_ERR_UNSUPPORTED, "betting tree too deep/wide for one CTA's shared memory: need " +
+                                               std::to_string(smem_need) + " B, device allows " + std::to_string(max_optin));
+    max_smem = smem_need;
+    CU(configure_segment_kernels(smem_need));
+    CU(scratch.alloc(size_t(1326) * MAX_ACTIONS));
+
+    updates_global = P.updates_per_iter_local;
+    if (P.world > 1) {
+        std::string err;
+        if (!nccl::load(&err)) return set_err(RS_ERR_NCCL, err);
+        nccl::UniqueId id;
+        static_assert(sizeof(id) == RS_NCCL_ID_BYTES, "nccl id size");
+        memcpy(&id, cfg->nccl_id, sizeof(id));
+        int rc = nccl::g_api.CommInitRank(&comm, P.world, id, P.rank);
+        if (rc != 0)
+            return set_err(RS_ERR_NCCL, std::string("ncclCommInitRank: ") +
+                                            (nccl::g_api.GetErrorString ? nccl::g_api.GetErrorString(rc) : "error"));
+        // global update count: all-reduce the local count once (as two floats of 24 bits each is lossy; use double via 2 x u32 halves)
+        DevBuf<float> tmp;
+        CU(tmp.alloc(4));
+        uint64_t u = P.updates_per_iter_local;
+        // replicated (unsharded) rounds are counted once: subtract on ranks > 0
+        if (P.rank > 0)
+            for (uint32_t k = 0; k < P.shard_round; ++k)
+                for (int q = 0; q < 2; ++q) u -= P.tabs[k][q].board_off[P.n_boards[k]];
+        float parts[4] = {float(u & 0xFFFFF), float((u >> 20) & 0xFFFFF), float((u >> 40) & 0xFFFFF), 0.f};
+        CU(cudaMemcpy(tmp.p, parts, sizeof(parts), cudaMemcpyHostToDevice));
+        rc = nccl::g_api.AllReduce(tmp.p, tmp.p, 4, nccl::kFloat32, nccl::kSum, comm, stream);
+        if (rc != 0) return set_err(RS_ERR_NCCL, "ncclAllReduce failed");
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaMemcpy(parts, tmp.p, sizeof(parts), cudaMemcpyDeviceToHost));
+        updates_global = uint64_t(parts[0]) + (uint64_t(parts[1]) << 20) + (uint64_t(parts[2]) << 40);
+    }
+    CU(cudaDeviceSynchronize());
+    return RS_OK;
+}
+
+int Engine::fill_launch(SegLaunch* a, uint32_t k, int trav, int down) const {
+    const Plan& P = plan;
+    const RoundDev& R = rd[k];
+    memset(a, 0, sizeof(*a));
+    for (int q = 0; q < 2; ++q) {
+        a->pl[q].cards = cards[q].p;
+        a->pl[q].same = same[q].p;
+        a->pl[q].card_hands = card_hands[q].p;
+        a->pl[q].H = int(P.H[q]);
+        a->pl[q].Hpad = int((P.H[q] + 3) & ~3u);
+        a->rp[q].row_of_hand = R.row_of_hand[q].p;
+        a->rp[q].row_start = R.row_start[q].p;
+        a->rp[q].row_hands = R.row_hands[q].p;
+        a->rp[q].n_rows = R.n_rows[q].p;
+        a->rp[q].board_off = R.board_off[q].p;
+        a->rp[q].regrets = R.regrets[q].p;
+        a->rp[q].ssum = R.ssum[q].p;
+        if (k == P.n_rounds - 1) {
+            a->sd[q].sorted = sd_sorted[q].p;
+            a->sd[q].n_live = sd_nlive[q].p;
+            a->sd[q].cj = sd_cj[q].p;
+            a->sd[q].n_card = sd_ncard[q].p;
+            a->sd[q].lohi = sd_lohi[q].p;
+            a->sd[q].cpos = sd_cpos[q].p;
+        }
+    }
+    a->ops = R.ops[trav][down].p;
+    a->prog_start = R.prog_start[trav][down].p;
+    a->chance_scale = R.chance_scale.p;
+    a->parent_board = R.parent_board.p;
+    a->parent_reach = k > 0 ? rd[k - 1].leaf_reach.p : nullptr;
+    a->leaf_reach = R.leaf_reach.p;
+    a->root_cfv = R.root_cfv.p;
+    a->gathered = R.gathered.p;
+    a->n_boards = int(R.n_boards);
+    a->n_boards_parent = k > 0 ? int(rd[k - 1].n_boards) : 0;
+    a->n_segs = int(R.n_segs);
+    a->trav = trav;
+    a->n_r = R.n_r[trav][down];
+    a->n_v = R.n_v[trav][down];
+    return RS_OK;
+}
+
+int Engine::enqueue_traversal(int trav, int mode, uint64_t* count) {
+    const Plan& P = plan;
+    const int HP[2] = {int((P.H[0] + 3) & ~3u), int((P.H[1] + 3) & ~3u)};
+    SegLaunch a;
+    // down pass: reach at every chance leaf, street by street (cfr.rs:502-522 scatter)
+    for (uint32_t k = 0; k + 1 < P.n_rounds; ++k) {
+        if (!rd[k].has_down) continue;
+        fill_launch(&a, k, trav, 1);
+        size_t smem = seg_kernel_smem_bytes(a.n_r, a.n_v, HP[trav], HP[1 - trav]);
+        CU(launch_segment_kernel(a, mode, threads, smem, stream));
+        ++*count;
+    }
+    // up pass: deepest street first, then gather over dealt cards into the parent street
+    for (int k = int(P.n_rounds) - 1; k >= 0; --k) {
+        fill_launch(&a, uint32_t(k), trav, 0);
+        size_t smem = seg_kernel_smem_bytes(a.n_r, a.n_v, HP[trav], HP[1 - trav]);
+        CU(launch_segment_kernel(a, mode, threads, smem, stream));
+        ++*count;
+        if (k > 0) {
+            const RoundDev& C = rd[k];
+            RoundDev& Par = rd[k - 1];
+            const bool sharded_here = (P.world > 1 && uint32_t(k) == P.shard_round);
+            const int per_parent = sharded_here ? 0 : int(P.deal_count[k]);
+            CU(launch_gather(C.root_cfv.p, Par.gathered.p, int(Par.n_leaves), int(Par.n_boards), int(C.n_boards),
+                             per_parent, int(P.H[trav]), stream));
+            ++*count;
+            if (sharded_here) {
+                // the one exchange step of the path: counterfactual values at the shared chance nodes
+                int rc = nccl::g_api.AllReduce(Par.gathered.p, Par.gathered.p, size_t(Par.n_leaves) * Par.n_boards * P.H[trav],
+                                               nccl::kFloat32, nccl::kSum, comm, stream);
+                if (rc != 0) return set_err(RS_ERR_NCCL, "ncclAllReduce failed");
+                ++*count;
+            }
+        }
+    }
+    return RS_OK;
+}
+
+int Engine::enqueue_iteration(uint64_t* count) {
+    // players alternate, player 0 first; player 1 sees player 0's fresh regrets (cfr.rs:216-224)
+    for (int p = 0; p < 2; ++p) {
+        int rc = enqueue_traversal(p, KM_CFR, count);
+        if (rc != RS_OK) return rc;
+    }
+    return RS_OK;
+}
+
+int Engine::iterate(uint64_t n) {
+    CU(cudaSetDevice(device));
+    if (n == 0) return RS_OK;
+    if (use_graph && !graph_exec) {
+        uint64_t cnt = 0;
+        CU(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_iteration(&cnt);
+        cudaError_t e = cudaStreamEndCapture(stream, &graph);
+        if (rc != RS_OK) return rc;
+        if (e != cudaSuccess) return set_err(RS_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        CU(cudaGraphInstantiate(&graph_exec, graph, 0));
+        launches_per_iter = cnt;
+    }
+    CU(cudaEventRecord(ev0, stream));
+    for (uint64_t i = 0; i < n; ++i) {
+        if (use_graph) {
+            CU(cudaGraphLaunch(graph_exec, stream));
+            launches += launches_per_iter;
+        } else {
+            uint64_t cnt = 0;
+            int rc = enqueue_iteration(&cnt);
+            if (rc != RS_OK) return rc;
+            launches += cnt;
+            launches_per_iter = cnt;
+        }
+        ++iterations;
+        if (discount_interval && iterations % discount_interval == 0 && (!discount_cap || iterations <= discount_cap)) {
+            // monitor thread of train(): d = p/(p+1), p = t / DISCOUNT_INTERVAL (cfr.rs:248-261)
+            const float pf = float(iterations / discount_interval);
+            const float d = pf / (pf + 1.0f);
+            for (uint32_t k = 0; k < plan.n_rounds; ++k)
+                for (int q = 0; q < 2; ++q) {
+                    CU(launch_scale(rd[k].regrets[q].p, rd[k].regrets[q].n, d, stream));
+                    CU(launch_scale(rd[k].ssum[q].p, rd[k].ssum[q].n, d, stream));
+                    launches += 2;
+                }
+        }
+    }
+    CU(cudaEventRecord(ev1, stream));
+    CU(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ev0, ev1));
+    device_ms += ms;
+    return RS_OK;
+}
+
+int Engine::root_sum(int player, double* out) {
+    const Plan& P = plan;
+    const RoundDev& R = rd[0];
+    std::vector<float> v(size_t(R.n_boards) * P.H[player]);
+    CU(cudaMemcpy(v.data(), R.root_cfv.p, v.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    double s = 0;
+    for (float x : v) s += x;
+    *out = s;
+    return RS_OK;
+}
+
+}  // namespace rs
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace rs;
+
+struct rs_engine {
+    Engine e;
+};
+struct rs_plan {
+    Plan p;
+};
+
+extern "C" {
+
+const char* rs_last_error(void) { return g_last_error.c_str(); }
+int rs_version(void) { return 100; }
+
+int rs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rs_nccl_unique_id(uint8_t* out) {
+    if (!out) return set_err(RS_ERR_INVALID, "null output");
+    std::string err;
+    if (!nccl::load(&err)) return set_err(RS_ERR_NCCL, err);
+    nccl::UniqueId id;
+    int rc = nccl::g_api.GetUniqueId(&id);
+    if (rc != 0) return set_err(RS_ERR_NCCL, "ncclGetUniqueId failed");
+    memcpy(out, &id, RS_NCCL_ID_BYTES);
+    return RS_OK;
+}
+
+int rs_plan_create(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs, const rs_config* cfg,
+                   const uint64_t* board_masks, uint32_t n_subgames, rs_plan** out) {
+    if (!out) return set_err(RS_ERR_INVALID, "null output");
+    *out = nullptr;
+    if (!cfg) return set_err(RS_ERR_INVALID, "null config");
+    std::unique_ptr<rs_plan> h(new (std::nothrow) rs_plan());
+    if (!h) return set_err(RS_ERR_INVALID, "out of memory");
+    std::string err;
+    uint64_t one = cfg->board_mask;
+    try {
+        if (!compile_plan(tree, ranges, abs, cfg, board_masks ? board_masks : &one, board_masks ? n_subgames : 1, &h->p, &err))
+            return set_err(RS_ERR_INVALID, err);
+    } catch (const std::exception& ex) {
+        return set_err(RS_ERR_INVALID, std::string("plan compile failed: ") + ex.what());
+    }
+    *out = h.release();
+    return RS_OK;
+}
+
+void rs_plan_destroy(rs_plan* p) { delete p; }
+
+static int create_impl(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs, const rs_config* cfg,
+                       const uint64_t* board_masks, uint32_t n_sub, rs_engine** out) {
+    if (!out) return set_err(RS_ERR_INVALID, "null output");
+    *out = nullptr;
+    if (!cfg) return set_err(RS_ERR_INVALID, "null config");
+    std::unique_ptr<rs_engine> h(new (std::nothrow) rs_engine());
+    if (!h) return set_err(RS_ERR_INVALID, "out of memory");
+    std::string err;
+    try {
+        if (!compile_plan(tree, ranges, abs, cfg, board_masks, n_sub, &h->e.plan, &err)) return set_err(RS_ERR_INVALID, err);
+        int rc = h->e.init(cfg);
+        if (rc != RS_OK) return rc;
+    } catch (const std::exception& ex) {
+        return set_err(RS_ERR_INVALID, std::string("engine creation failed: ") + ex.what());
+    }
+    *out = h.release();
+    return RS_OK;
+}
+
+int rs_create(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs, const rs_config* cfg,
+              rs_engine** out) {
+    if (!cfg) return set_err(RS_ERR_INVALID, "null config");
+    uint64_t one = cfg->board_mask;
+    return create_impl(tree, ranges, abs, cfg, &one, 1, out);
+}
+
+int rs_create_batch(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs, const rs_config* cfg,
+                    const uint64_t* board_masks, uint32_t n_subgames, rs_engine** out) {
+    if (!board_masks || n_subgames == 0) return set_err(RS_ERR_INVALID, "need at least one subgame board");
+    return create_impl(tree, ranges, abs, cfg, board_masks, n_subgames, out);
+}
+
+void rs_destroy(rs_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->e.device);
+    delete e;
+}
+
+int rs_iterate(rs_engine* e, uint64_t n_iters) {
+    if (!e) return set_err(RS_ERR_INVALID, "null engine");
+    return e->e.iterate(n_iters);
+}
+
+int rs_discount(rs_engine* e, float d) {
+    if (!e) return set_err(RS_ERR_INVALID, "null engine");
+    Engine& E = e->e;
+    CU(cudaSetDevice(E.device));
+    for (uint32_t k = 0; k < E.plan.n_rounds; ++k)
+        for (int q = 0; q < 2; ++q) {
+            CU(launch_scale(E.rd[k].regrets[q].p, E.rd[k].regrets[q].n, d, E.stream));
+            CU(launch_scale(E.rd[k].ssum[q].p, E.rd[k].ssum[q].n, d, E.stream));
+        }
+    CU(cudaStreamSynchronize(E.stream));
+    return RS_OK;
+}
+
+int rs_reset(rs_engine* e) {
+    if (!e) return set_err(RS_ERR_INVALID, "null engine");
+    Engine& E = e->e;
+    CU(cudaSetDevice(E.device));
+    for (uint32_t k = 0; k < E.plan.n_rounds; ++k)
+        for (int q = 0; q < 2; ++q) {
+            CU(E.rd[k].regrets[q].zero());
+            CU(E.rd[k].ssum[q].zero());
+        }
+    E.iterations = 0;
+    E.device_ms = 0;
+    E.launches = 0;
+    return RS_OK;
+}
+
+// locate slab (an_index, board_id): returns table pointers + shape
+static int locate(const Plan& P, uint32_t an_index, uint32_t board_id, uint32_t* k_out, int* q_out, uint64_t* off,
+                  uint32_t* n_rows, uint32_t* n_act) {
+    if (an_index >= P.an_to_pnode.size() || P.an_to_pnode[an_index] < 0) return set_err(RS_ERR_INVALID, "unknown ActionNode.index");
+    const PNode& n = P.nodes[P.an_to_pnode[an_index]];
+    const uint32_t k = n.round_k;
+    const int q = n.player;
+    if (board_id >= P.n_boards[k]) return set_err(RS_ERR_INVALID, "board_id out of range for the node's round");
+    if (board_id < P.local_lo[k] || board_id >= P.local_hi[k]) return set_err(RS_ERR_INVALID, "board is owned by another rank");
+    const RoundPlayerTables& T = P.tabs[k][q];
+    *k_out = k;
+    *q_out = q;
+    *n_rows = T.n_rows[board_id];
+    *n_act = uint32_t(n.children.size());
+    *off = T.board_off[board_id] + uint64_t(T.n_rows[board_id]) * n.cum_a;
+    return RS_OK;
+}
+
+int rs_plan_infoset_offset(const rs_plan* p, uint32_t an_index, uint32_t board_id, uint64_t* offset_out,
+                           uint32_t* n_rows_out, uint32_t* n_actions_out) {
+    if (!p) return set_err(RS_ERR_INVALID, "null plan");
+    uint32_t k, nr, na;
+    int q;
+    uint64_t off;
+    int rc = locate(p->p, an_index, board_id, &k, &q, &off, &nr, &na);
+    if (rc != RS_OK) return rc;
+    if (offset_out) *offset_out = off;
+    if (n_rows_out) *n_rows_out = nr;
+    if (n_actions_out) *n_actions_out = na;
+    return RS_OK;
+}
+
+int rs_read_infoset(rs_engine* e, uint32_t an_index, uint32_t board_id, float* regrets, float* strategy_sum,
+                    size_t cap_floats, uint32_t* n_rows_out, uint32_t* n_actions_out) {
+    if (!e) return set_err(RS_ERR_INVALID, "null engine");
+    Engine& E = e->e;
+    uint32_t k, nr, na;
+    int q;
+    uint64_t off;
+    int rc = locate(E.plan, an_index, board_id, &k, &q, &off, &nr, &na);
+    if (rc != RS_OK) return rc;
+    if (n_rows_out) *n_rows_out = nr;
+    if (n_actions_out) *n_actions_out = na;
+    const size_t n = size_t(nr) * na;
+    if ((regrets || strategy_sum) && cap_floats < n) return set_err(RS_ERR_CAPACITY, "output buffer too small");
+    CU(cudaSetDevice(E.device));
+    if (regrets) CU(cudaMemcpy(regrets, E.rd[k].regrets[q].p + off, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (strategy_sum) CU(cudaMemcpy(strategy_sum, E.rd[k].ssum[q].p + off, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return RS_OK;
+}
+
+int rs_write_infoset(rs_engine* e, uint32_t an_index, uint32_t board_id, const float* regrets, const float* strategy_sum,
+                     size_t n_floats) {
+    if (!e) return set_err(RS_ERR_INVALID, "null engine");
+    Engine& E = e->e;
+    uint32_t k, nr, na;
+    int q;
+    uint64_t off;
+    int rc = locate(E.plan, an_index, board_id, &k, &q, &off, &nr, &na);
+    if (rc != RS_OK) return rc;
+    const size_t n = size_t(nr) * na;
+    if (n_floats != n) return set_err(RS_ERR_INVALID, "slab size mismatch");
+    CU(cudaSetDevice(E.device));
+    if (regrets) CU(cudaMemcpy(E.rd[k].regrets[q].p + off, regrets, n * sizeof(float), cudaMemcpyHostToDevice));
+    if (strategy_sum) CU(cudaMemcpy(E.rd[k].ssum[q].p + off, strategy_sum, n * sizeof(float), cudaMemcpyHostToDevice));
+    return RS_OK;
+}
+
+static int strategy_impl(rs_engine* e, uint32_t an_index, uint32_t board_id, float* out, size_t cap, uint32_t* n_rows_out,
+                         uint32_t* n_actions_out, bool average) {
+    if (!e) return set_err(RS_ERR_INVALID, "null engine");
+    Engine& E = e->e;
+    uint32_t k, nr, na;
+    int q;
+    uint64_t off;
+    int rc = locate(E.plan, an_index, board_id, &k, &q, &off, &nr, &na);
+    if (rc != RS_OK) return rc;
+    if (n_rows_out) *n_rows_out = nr;
+    if (n_actions_out) *n_actions_out = na;
+    const size_t n = size_t(nr) * na;
+    if (!out) return RS_OK;
+    if (cap < n) return set_err(RS_ERR_CAPACITY, "output buffer too small");
+    CU(cudaSetDevice(E.device));
+    const float* src = (average ? E.rd[k].ssum[q].p : E.rd[k].regrets[q].p) + off;
+    CU(launch_normalize(src, E.scratch.p, nr, na, E.stream));
+    CU(cudaStreamSynchronize(E.stream));
+    CU(cudaMemcpy(out, E.scratch.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return RS_OK;
+}
+
+int rs_average_strategy(rs_engine* e, uint32_t an_index, uint32_t board_id, float* out, size_t cap_floats,
+                        uint32_t* n_rows_out, uint32_t* n_actions_out) {
+    return strategy_impl(e, an_index, board_id, out, cap_floats, n_rows_out, n_actions_out, true);
+}
+int rs_current_strategy(rs_engine* e, uint32_t an_index, uint32_t board_id, float* out, size_t cap_floats,
+                        uint32_t* n_rows_out, uint32_t* n_actions_out) {
+    return strategy_impl(e, an_index, board_id, out, cap_floats, n_rows_out, n_actions_out, false);
+}
+
+static int board_id_impl(const Plan& P, uint32_t round_idx, const uint8_t* dealt, uint32_t n_dealt, uint32_t* out) {
+    if (round_idx >= P.n_rounds) return set_err(RS_ERR_INVALID, "round_idx out of range");
+    if (n_dealt != round_idx) return set_err(RS_ERR_INVALID, "need exactly round_idx dealt cards");
+    if (P.n_sub != 1) return set_err(RS_ERR_UNSUPPORTED, "board lookup by dealt cards needs a single root board; batch boards are their own ids");
+    uint32_t id = 0;
+    uint64_t mask = P.board_mask[0][0];
+    for (uint32_t k = 1; k <= round_idx; ++k) {
+        const int c = dealt[k - 1];
+        if (c >= 52 || (mask & (1ull << c))) return set_err(RS_ERR_INVALID, "dealt card already on the board");
+        const uint32_t idx = uint32_t(__builtin_popcountll(~mask & ((1ull << c) - 1)));
+        id = id * P.deal_count[k] + idx;
+        mask |= 1ull << c;
+    }
+    *out = id;
+    return RS_OK;
+}
+
+int rs_plan_board_id(const rs_plan* p, uint32_t round_idx, const uint8_t* dealt, uint32_t n_dealt, uint32_t* board_id_out) {
+    if (!p || !board_id_out) return set_err(RS_ERR_INVALID, "null argument");
+    return board_id_impl(p->p, round_idx, dealt, n_dealt, board_id_out);
+}
+int rs_board_id(rs_engine* e, uint32_t round_idx, const uint8_t* dealt, uint32_t n_dealt, uint32_t* board_id_out) {
+    if (!e || !board_id_out) return set_err(RS_ERR_INVALID, "null argument");
+    return board_id_impl(e->e.plan, round_idx, dealt, n_dealt, board_id_out);
+}
+
+static int card_table_impl(const Plan& P, uint32_t round_idx, uint32_t player, uint32_t board_id, uint16_t* rows_out,
+                           size_t cap, uint32_t* n_rows_out) {
+    if (round_idx >= P.n_rounds || player > 1) return set_err(RS_ERR_INVALID, "round/player out of range");
+    if (board_id >= P.n_boards[round_idx]) return set_err(RS_ERR_INVALID, "board_id out of range");
+    if (board_id < P.local_lo[round_idx] || board_id >= P.local_hi[round_idx])
+        return set_err(RS_ERR_INVALID, "board is owned by another rank");
+    const RoundPlayerTables& T = P.tabs[round_idx][player];
+    const uint32_t H = P.H[player];
+    if (n_rows_out) *n_rows_out = T.n_rows[board_id];
+    if (rows_out) {
+        if (cap < H) return set_err(RS_ERR_CAPACITY, "output buffer too small");
+        memcpy(rows_out, &T.row_of_hand[size_t(board_id) * H], H * sizeof(uint16_t));
+    }
+    return RS_OK;
+}
+int rs_plan_card_table(const rs_plan* p, uint32_t round_idx, uint32_t player, uint32_t board_id, uint16_t* rows_out,
+                       size_t cap, uint32_t* n_rows_out) {
+    if (!p) return set_err(RS_ERR_INVALID, "null plan");
+    return card_table_impl(p->p, round_idx, player, board_id, rows_out, cap, n_rows_out);
+}
+int rs_card_table(rs_engine* e, uint32_t round_idx, uint32_t player, uint32_t board_id, uint16_t* rows_out, size_t cap,
+                  uint32_t* n_rows_out) {
+    if (!e) return set_err(RS_ERR_INVALID, "null engine");
+    return card_table_impl(e->e.plan, round_idx, player, board_id, rows_out, cap, n_rows_out);
+}
+
+int rs_plan_showdown_order(const rs_plan* p, uint32_t player, uint32_t board_id, uint16_t* order_out, uint32_t* class_out,
+                           size_t cap, uint32_t* n_live_out) {
+    if (!p || player > 1) return set_err(RS_ERR_INVALID, "bad argument");
+    const Plan& P = p->p;
+    const uint32_t k = P.n_rounds - 1;
+    const ShowdownTables& S = P.sd[player];
+    if (S.n_live.empty()) return set_err(RS_ERR_INVALID, "tree has no showdown terminals");
+    if (board_id >= P.n_boards[k]) return set_err(RS_ERR_INVALID, "board_id out of range");
+    const uint32_t H = P.H[player];
+    const uint32_t nl = S.n_live[board_id];
+    if (n_live_out) *n_live_out = nl;
+    if (cap < nl) return set_err(RS_ERR_CAPACITY, "output buffer too small");
+    for (uint32_t i = 0; i < nl; ++i) {
+        if (order_out) order_out[i] = S.sorted[size_t(board_id) * H + i];
+        if (class_out) class_out[i] = S.cls[size_t(board_id) * H + i];
+    }
+    return RS_OK;
+}
+
+static int score_impl(rs_engine* e, int mode, double out[2]) {
+    if (!e || !out) return set_err(RS_ERR_INVALID, "null argument");
+    Engine& E = e->e;
+    CU(cudaSetDevice(E.device));
+    for (int p = 0; p < 2; ++p) {
+        uint64_t cnt = 0;
+        int rc = E.enqueue_traversal(p, mode, &cnt);
+        if (rc != RS_OK) return rc;
+        CU(cudaStreamSynchronize(E.stream));
+        double s = 0;
+        rc = E.root_sum(p, &s);
+        if (rc != RS_OK) return rc;
+        // with subgame batches every rank owns different root boards: the caller sums over ranks
+        out[p] = s;
+    }
+    return RS_OK;
+}
+
+int rs_best_response(rs_engine* e, double out[2]) { return score_impl(e, KM_BR, out); }
+int rs_average_value(rs_engine* e, double out[2]) { return score_impl(e, KM_EVAL, out); }
+
+int rs_root_values(rs_engine* e, uint32_t player, float* out, size_t cap) {
+    if (!e || !out || player > 1) return set_err(RS_ERR_INVALID, "bad argument");
+    Engine& E = e->e;
+    const size_t n = size_t(E.rd[0].n_boards) * E.plan.H[player];
+    if (cap < n) return set_err(RS_ERR_CAPACITY, "output buffer too small");
+    CU(cudaSetDevice(E.device));
+    CU(cudaMemcpy(out, E.rd[0].root_cfv.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return RS_OK;
+}
+
+static void fill_stats(const Plan& P, rs_stats* s) {
+    memset(s, 0, sizeof(*s));
+    s->updates_per_iteration = P.updates_per_iter_local;
+    s->updates_per_iteration_global = P.updates_per_iter_global;
+    s->n_rounds = P.n_rounds;
+    for (uint32_t k = 0; k < P.n_rounds; ++k) {
+        s->n_boards[k] = P.n_boards[k];
+        s->n_boards_local[k] = P.local_hi[k] - P.local_lo[k];
+    }
+    s->n_hands[0] = P.H[0];
+    s->n_hands[1] = P.H[1];
+    s->n_combos = P.n_combos.empty() ? 0 : P.n_combos[0];
+}
+
+int rs_plan_stats(const rs_plan* p, rs_stats* out) {
+    if (!p || !out) return set_err(RS_ERR_INVALID, "null argument");
+    fill_stats(p->p, out);
+    return RS_OK;
+}
+
+int rs_stats_get(rs_engine* e, rs_stats* out) {
+    if (!e || !out) return set_err(RS_ERR_INVALID, "null argument");
+    fill_stats(e->e.plan, out);
+    out->iterations = e->e.iterations;
+    out->device_ms = e->e.device_ms;
+    out->kernel_launches = e->e.launches;
+    out->table_bytes = e->e.table_bytes;
+    out->updates_per_iteration_global = e->e.updates_global;
+    return RS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,708 @@
+#include "plan.h"
+
+#include <algorithm>
+#include <functional>
+#include <numeric>
+#include <unordered_map>
+
+#include "hand_indexer.h"
+#include "poker.h"
+
+namespace rs {
+
+namespace {
+
+struct Builder {
+    const rs_tree* t;
+    Plan* P;
+    std::string err;
+    uint32_t max_round = 0;
+
+    bool fail(const std::string& m) {
+        if (err.empty()) err = m;
+        return false;
+    }
+
+    // DFS copy of the reference tree into PNodes. Returns PNode id or -1.
+    int32_t copy_node(uint32_t id, uint32_t round_k, int depth) {
+        if (id >= t->n_nodes) return fail("child id out of range"), -1;
+        if (depth > 4096) return fail("tree too deep / cyclic"), -1;
+        uint32_t c0 = t->child_offset[id], c1 = t->child_offset[id + 1];
+        max_round = std::max(max_round, round_k);
+        switch (t->type[id]) {
+            case RS_NODE_ACTION: {
+                if (c1 <= c0) return fail("action node without children"), -1;
+                if (t->player[id] > 1) return fail("player must be 0 or 1"), -1;
+                if (t->round_idx[id] != round_k) return fail("ActionNode.round_idx does not match chance depth"), -1;
+                int32_t me = int32_t(P->nodes.size());
+                P->nodes.emplace_back();
+                {
+                    PNode& n = P->nodes[me];
+                    n.kind = PK_ACTION;
+                    n.player = t->player[id];
+                    n.round_k = uint8_t(round_k);
+                    n.an_index = t->an_index[id];
+                    n.src_node = int32_t(id);
+                }
+                std::vector<int32_t> ch;
+                for (uint32_t i = c0; i < c1; ++i) {
+                    int32_t c = copy_node(t->children[i], round_k, depth + 1);
+                    if (c < 0) return -1;
+                    ch.push_back(c);
+                }
+                P->nodes[me].children = ch;
+                return me;
+            }
+            case RS_NODE_TERMINAL: {
+                int32_t me = int32_t(P->nodes.size());
+                P->nodes.emplace_back();
+                PNode n;
+                n.round_k = uint8_t(round_k);
+                n.value = t->value[id];
+                n.last_to_act = t->last_to_act[id];
+                n.src_node = int32_t(id);
+                uint32_t abs_round = P->first_round + round_k;
+                if (t->ttype[id] == RS_TERM_UNCONTESTED) {
+                    n.kind = PK_FOLD;
+                    P->nodes[me] = n;
+                } else if (abs_round >= RS_ROUND_RIVER) {
+                    n.kind = PK_SHOWDOWN;
+                    P->nodes[me] = n;
+                } else {
+                    // ALLIN (or showdown) before the river: expected showdown over run-outs.
+                    // The reference's cfr() evaluates these with undealt cards (cfr.rs:544-556,
+                    // a latent bug); mccfr() is right in expectation because the whole board is
+                    // pre-sampled (cfr.rs:114-122).  We insert the run-out chance nodes.
+                    n.kind = PK_CHANCE;
+                    P->nodes[me] = n;
+                    int32_t cur = me;
+                    uint32_t rk = round_k;
+                    while (P->first_round + rk + 1 < RS_ROUND_RIVER) {
+                        int32_t nx = int32_t(P->nodes.size());
+                        P->nodes.emplace_back();
+                        PNode c;
+                        c.kind = PK_CHANCE;
+                        c.round_k = uint8_t(rk + 1);
+                        c.value = n.value;
+                        P->nodes[nx] = c;
+                        P->nodes[cur].children = {nx};
+                        cur = nx;
+                        rk++;
+                    }
+                    int32_t sdn = int32_t(P->nodes.size());
+                    P->nodes.emplace_back();
+                    PNode s;
+                    s.kind = PK_SHOWDOWN;
+                    s.round_k = uint8_t(rk + 1);
+                    s.value = n.value;
+                    s.last_to_act = n.last_to_act;
+                    P->nodes[sdn] = s;
+                    P->nodes[cur].children = {sdn};
+                    max_round = std::max(max_round, rk + 1);
+                }
+                return me;
+            }
+            case RS_NODE_PUBLIC_CHANCE: {
+                if (c1 != c0 + 1) return fail("public chance node needs exactly one child"), -1;
+                if (P->first_round + round_k >= RS_ROUND_RIVER) return fail("chance node after the river"), -1;
+                int32_t me = int32_t(P->nodes.size());
+                P->nodes.emplace_back();
+                P->nodes[me].kind = PK_CHANCE;
+                P->nodes[me].round_k = uint8_t(round_k);
+                P->nodes[me].src_node = int32_t(id);
+                int32_t c = copy_node(t->children[c0], round_k + 1, depth + 1);
+                if (c < 0) return -1;
+                P->nodes[me].children = {c};
+                return me;
+            }
+            default:
+                return fail("unexpected node type below the root"), -1;
+        }
+    }
+
+    // carve the PNode tree into per-round segments
+    void make_segment(uint32_t k, int32_t root) {
+        uint32_t sid = uint32_t(P->segs[k].size());
+        P->segs[k].emplace_back();
+        P->segs[k][sid].root = root;
+        std::vector<int32_t> leaves;
+        std::function<void(int32_t)> walk = [&](int32_t id) {
+            PNode& n = P->nodes[id];
+            if (n.kind == PK_CHANCE) {
+                leaves.push_back(id);
+                return;
+            }
+            for (int32_t c : n.children) walk(c);
+        };
+        walk(root);
+        P->segs[k][sid].leaves = leaves;
+        for (int32_t leaf : leaves) {
+            P->nodes[leaf].leaf_id = int32_t(P->segs[k + 1].size());
+            make_segment(k + 1, P->nodes[leaf].children[0]);
+        }
+    }
+};
+
+// ---- program generation -------------------------------------------------------------------
+
+struct ProgGen {
+    const Plan* P;
+    int trav;
+    bool down_only;
+    Program prog;
+    uint32_t r_top = 0, v_top = 0;
+
+    uint16_t alloc_r() {
+        uint16_t s = uint16_t(r_top++);
+        prog.n_r = std::max(prog.n_r, r_top);
+        return s;
+    }
+    uint16_t alloc_v(uint32_t n) {
+        uint16_t s = uint16_t(v_top);
+        v_top += n;
+        prog.n_v = std::max(prog.n_v, v_top);
+        return s;
+    }
+
+    bool reaches_leaf(int32_t id) const {
+        const PNode& n = P->nodes[id];
+        if (n.kind == PK_CHANCE) return true;
+        for (int32_t c : n.children)
+            if (reaches_leaf(c)) return true;
+        return false;
+    }
+    bool needs_m(int32_t id) const {  // does node `id` consume M of its incoming reach?
+        const PNode& n = P->nodes[id];
+        if (n.kind == PK_FOLD) return true;
+        if (n.kind == PK_ACTION && n.player == trav) {
+            // traverser node: strategy_sum weight, and children share the same reach
+            return true;
+        }
+        return false;
+    }
+    // any descendant reachable without an opponent action that needs M of this reach
+    bool subtree_needs_m(int32_t id) const {
+        const PNode& n = P->nodes[id];
+        if (needs_m(id)) return true;
+        if (n.kind == PK_ACTION && n.player == trav) {
+            for (int32_t c : n.children)
+                if (subtree_needs_m(c)) return true;
+        }
+        return false;
+    }
+
+    void emit(const Op& op) { prog.ops.push_back(op); }
+
+    void gen(int32_t id, uint16_t r, uint16_t out, bool acc) {
+        const PNode& n = P->nodes[id];
+        Op op{};
+        op.flags = acc ? OPF_ACC : 0;
+        switch (n.kind) {
+            case PK_FOLD: {
+                if (down_only) return;
+                op.type = OP_FOLD;
+                op.r_src = r;
+                op.v_out = out;
+                // cfr.rs:525-531: -value if player == last_to_act else +value
+                op.coef = (trav == n.last_to_act) ? -float(n.value) : float(n.value);
+                emit(op);
+                return;
+            }
+            case PK_SHOWDOWN: {
+                if (down_only) return;
+                op.type = OP_SHOWDOWN;
+                op.r_src = r;
+                op.v_out = out;
+                op.coef = float(n.value);  // cfr.rs:532-543
+                emit(op);
+                prog.has_showdown = true;
+                return;
+            }
+            case PK_CHANCE: {
+                op.leaf = uint32_t(n.leaf_id);
+                if (down_only) {
+                    op.type = OP_LEAF_DOWN;
+                    op.r_src = r;
+                } else {
+                    op.type = OP_LEAF_UP;
+                    op.v_out = out;
+                }
+                emit(op);
+                return;
+            }
+            default: break;
+        }
+        // action node
+        uint8_t A = uint8_t(n.children.size());
+        if (n.player != trav) {
+            for (uint8_t a = 0; a < A; ++a) {
+                int32_t c = n.children[a];
+                if (down_only && !reaches_leaf(c)) continue;
+                uint16_t r2 = alloc_r();
+                Op o{};
+                o.type = OP_OPP_REACH;
+                o.a = a;
+                o.n_act = A;
+                o.r_src = r;
+                o.r_dst = r2;
+                o.cum_a = n.cum_a;
+                o.an_index = n.an_index;
+                emit(o);
+                if (!down_only && subtree_needs_m(c)) {
+                    Op m{};
+                    m.type = OP_CALC_M;
+                    m.r_dst = r2;
+                    emit(m);
+                }
+                gen(c, r2, out, acc || a > 0);
+                r_top--;
+            }
+        } else {
+            if (down_only) {
+                for (uint8_t a = 0; a < A; ++a)
+                    if (reaches_leaf(n.children[a])) gen(n.children[a], r, 0, false);
+                return;
+            }
+            uint16_t vb = alloc_v(A);
+            for (uint8_t a = 0; a < A; ++a) gen(n.children[a], r, uint16_t(vb + a), false);
+            Op o{};
+            o.type = OP_TRAV;
+            o.flags = acc ? OPF_ACC : 0;
+            o.n_act = A;
+            o.r_src = r;
+            o.v_base = vb;
+            o.v_out = out;
+            o.cum_a = n.cum_a;
+            o.an_index = n.an_index;
+            emit(o);
+            v_top -= A;
+        }
+    }
+
+    Program run(uint32_t seg_id, int32_t root) {
+        uint16_t r0 = alloc_r();
+        Op l{};
+        l.type = OP_LOAD_ROOT;
+        l.r_dst = r0;
+        l.leaf = seg_id;
+        emit(l);
+        if (!down_only && subtree_needs_m(root)) {
+            Op m{};
+            m.type = OP_CALC_M;
+            m.r_dst = r0;
+            emit(m);
+        }
+        uint16_t v0 = 0;
+        if (!down_only) v0 = alloc_v(1);
+        gen(root, r0, v0, false);
+        if (!down_only) {
+            Op o{};
+            o.type = OP_ROOT_OUT;
+            o.v_out = v0;
+            o.leaf = seg_id;
+            emit(o);
+        }
+        Op e{};
+        e.type = OP_END;
+        emit(e);
+        return prog;
+    }
+};
+
+}  // namespace
+
+bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs,
+                  const rs_config* cfg, const uint64_t* board_masks, uint32_t n_sub, Plan* P,
+                  std::string* err) {
+    auto fail = [&](const std::string& m) {
+        if (err) *err = m;
+        return false;
+    };
+    if (!tree || !ranges || !cfg || !P) return fail("null argument");
+    if (!tree->type || !tree->parent || !tree->child_offset || !tree->children || !tree->player ||
+        !tree->an_index || !tree->round_idx || !tree->value || !tree->ttype || !tree->last_to_act)
+        return fail("rs_tree has a null array");
+    if (tree->n_nodes < 2) return fail("tree needs at least a root and one child");
+    if (n_sub == 0 || !board_masks) return fail("need at least one board");
+    int nb0 = __builtin_popcountll(board_masks[0]);
+    if (nb0 < 3 || nb0 > 5) return fail("invalid board mask");  // state.rs:63
+    for (uint32_t i = 0; i < n_sub; ++i) {
+        if (__builtin_popcountll(board_masks[i]) != nb0) return fail("all subgame boards must have the same number of cards");
+        if (board_masks[i] >> 52) return fail("board mask has bits above card 51");
+    }
+    *P = Plan();
+    P->first_round = uint32_t(nb0 - 3);
+    P->n_sub = n_sub;
+    P->flags = cfg->flags;
+    P->rank = cfg->world_size > 1 ? cfg->rank : 0;
+    P->world = cfg->world_size > 1 ? cfg->world_size : 1;
+    if (P->rank < 0 || P->rank >= P->world) return fail("rank out of range");
+
+    // ---- tree ----
+    if (tree->type[0] != RS_NODE_PRIVATE_CHANCE) return fail("root must be the private chance node (tree_builder.rs:60-66)");
+    if (tree->child_offset[1] - tree->child_offset[0] != 1) return fail("private chance root needs exactly one child");
+    Builder B{tree, P};
+    int32_t root = B.copy_node(tree->children[tree->child_offset[0]], 0, 0);
+    if (root < 0) return fail(B.err);
+    P->n_rounds = B.max_round + 1;
+    if (P->first_round + P->n_rounds > 3) return fail("tree has more betting rounds than the board allows");
+    B.make_segment(0, root);
+
+    // action-node numbering per (round, player), in ActionNode.index order
+    {
+        uint32_t max_an = 0;
+        for (auto& n : P->nodes)
+            if (n.kind == PK_ACTION) max_an = std::max(max_an, n.an_index + 1);
+        P->an_to_pnode.assign(max_an, -1);
+        for (size_t i = 0; i < P->nodes.size(); ++i)
+            if (P->nodes[i].kind == PK_ACTION) {
+                if (P->an_to_pnode[P->nodes[i].an_index] != -1) return fail("duplicate ActionNode.index");
+                P->an_to_pnode[P->nodes[i].an_index] = int32_t(i);
+            }
+        for (uint32_t an = 0; an < max_an; ++an) {
+            int32_t id = P->an_to_pnode[an];
+            if (id < 0) continue;
+            PNode& n = P->nodes[id];
+            if (n.children.size() > 8) return fail("more than 8 actions at a node is not supported");
+            RoundPlayerTables& T = P->tabs[n.round_k][n.player];
+            n.tab_j = int32_t(T.n_nodes++);
+            n.cum_a = T.sum_a;
+            T.sum_a += uint32_t(n.children.size());
+            T.node_an_index.push_back(an);
+            T.node_n_act.push_back(uint32_t(n.children.size()));
+        }
+    }
+
+    // ---- hands ----
+    for (int q = 0; q < 2; ++q) {
+        uint32_t H = ranges->n_hands[q];
+        if (H == 0 || H > 1326) return fail("range size must be in 1..1326");
+        if (!ranges->hands[q]) return fail("null range");
+        P->H[q] = H;
+        P->hand_cards[q].assign(ranges->hands[q], ranges->hands[q] + 2 * size_t(H));
+        std::vector<uint8_t> seen(52 * 52, 0);
+        for (uint32_t h = 0; h < H; ++h) {
+            uint8_t a = P->hand_cards[q][2 * h], b = P->hand_cards[q][2 * h + 1];
+            if (a >= 52 || b >= 52 || a == b) return fail("bad hole cards in range");
+            int hi = std::max(a, b), lo = std::min(a, b);
+            if (seen[hi * 52 + lo]) return fail("duplicate combo in range");
+            seen[hi * 52 + lo] = 1;
+        }
+    }
+    for (int q = 0; q < 2; ++q) {
+        std::vector<int32_t> slot(52 * 52, -1);
+        const auto& oc = P->hand_cards[1 - q];
+        for (uint32_t h = 0; h < P->H[1 - q]; ++h) {
+            int a = oc[2 * h], b = oc[2 * h + 1];
+            slot[std::max(a, b) * 52 + std::min(a, b)] = int32_t(h);
+        }
+        P->same[q].assign(P->H[q], 0xFFFF);
+        P->card_hands[q].assign(52 * 52, 0xFFFF);
+        uint32_t cnt[52] = {0};
+        for (uint32_t h = 0; h < P->H[q]; ++h) {
+            int a = P->hand_cards[q][2 * h], b = P->hand_cards[q][2 * h + 1];
+            int32_t s = slot[std::max(a, b) * 52 + std::min(a, b)];
+            if (s >= 0) P->same[q][h] = uint16_t(s);
+            P->card_hands[q][a * 52 + cnt[a]++] = uint16_t(h);
+            P->card_hands[q][b * 52 + cnt[b]++] = uint16_t(h);
+        }
+    }
+
+    // ---- boards (board_table, README.md:41-43) ----
+    P->n_boards[0] = n_sub;
+    P->board_mask[0].assign(board_masks, board_masks + n_sub);
+    P->board_parent[0].assign(n_sub, -1);
+    P->board_card[0].assign(n_sub, 0xFF);
+    for (uint32_t k = 1; k < P->n_rounds; ++k) {
+        uint32_t per = uint32_t(52 - (nb0 + int(k) - 1));
+        P->deal_count[k] = per;
+        P->n_boards[k] = P->n_boards[k - 1] * per;
+        P->board_mask[k].reserve(P->n_boards[k]);
+        for (uint32_t pb = 0; pb < P->n_boards[k - 1]; ++pb) {
+            uint64_t pm = P->board_mask[k - 1][pb];
+            for (int c = 0; c < 52; ++c) {  // ascending card order (cfr.rs:63-68)
+                if (pm & (1ull << c)) continue;
+                P->board_mask[k].push_back(pm | (1ull << c));
+                P->board_parent[k].push_back(int32_t(pb));
+                P->board_card[k].push_back(uint8_t(c));
+            }
+        }
+    }
+    // sharding
+    for (uint32_t k = 0; k < P->n_rounds; ++k) {
+        P->local_lo[k] = 0;
+        P->local_hi[k] = P->n_boards[k];
+    }
+    if (P->world > 1) {
+        if (n_sub > 1) {
+            P->shard_round = 0;
+        } else {
+            if (P->n_rounds < 2) return fail("a single-board river subgame has nothing to shard across GPUs");
+            P->shard_round = 1;
+        }
+        uint32_t sr = P->shard_round;
+        uint64_t n = P->n_boards[sr];
+        if (n < uint64_t(P->world)) return fail("fewer boards than ranks at the sharded level");
+        P->local_lo[sr] = uint32_t(n * uint64_t(P->rank) / uint64_t(P->world));
+        P->local_hi[sr] = uint32_t(n * uint64_t(P->rank + 1) / uint64_t(P->world));
+        for (uint32_t k = sr + 1; k < P->n_rounds; ++k) {
+            P->local_lo[k] = P->local_lo[k - 1] * P->deal_count[k];
+            P->local_hi[k] = P->local_hi[k - 1] * P->deal_count[k];
+        }
+    }
+
+    // ---- chance weights (cfr.rs:491, 510) ----
+    P->n_combos.assign(n_sub, 0);
+    P->chance_scale[0].assign(n_sub, 0.f);
+    for (uint32_t s = 0; s < n_sub; ++s) {
+        uint64_t bm = board_masks[s];
+        // generate_all_hole_card_combos (cfr.rs:73-98): non-overlapping (h0,h1) pairs.
+        // count = live0*live1 - sum_c n0[c]*n1[c] + shared identical combos
+        uint64_t live[2] = {0, 0};
+        uint64_t nc[2][52] = {{0}};
+        for (int q = 0; q < 2; ++q)
+            for (uint32_t h = 0; h < P->H[q]; ++h) {
+                int a = P->hand_cards[q][2 * h], b = P->hand_cards[q][2 * h + 1];
+                if (bm & ((1ull << a) | (1ull << b))) continue;
+                live[q]++;
+                nc[q][a]++;
+                nc[q][b]++;
+            }
+        uint64_t overlap = 0;
+        for (int c = 0; c < 52; ++c) overlap += nc[0][c] * nc[1][c];
+        uint64_t ident = 0;
+        for (uint32_t h = 0; h < P->H[0]; ++h) {
+            int a = P->hand_cards[0][2 * h], b = P->hand_cards[0][2 * h + 1];
+            if (bm & ((1ull << a) | (1ull << b))) continue;
+            if (P->same[0][h] != 0xFFFF) ident++;
+        }
+        uint64_t n = live[0] * live[1] - overlap + ident;
+        if (n == 0) return fail("no compatible hole-card combos for a subgame");
+        P->n_combos[s] = n;
+        P->chance_scale[0][s] = float(1.0 / double(n));
+    }
+    for (uint32_t k = 1; k < P->n_rounds; ++k) {
+        P->chance_scale[k].resize(P->n_boards[k]);
+        double len = double(52 - (nb0 + int(k) - 1) - 4);  // cfr.rs:49-70: 52 - board - both hands
+        for (uint32_t b = 0; b < P->n_boards[k]; ++b)
+            P->chance_scale[k][b] = float(double(P->chance_scale[k - 1][P->board_parent[k][b]]) / len);
+    }
+    // NOTE: chance_scale[k] for k>=1 is derived in double from the fp32 parent to stay
+    // identical on every rank; the oracle uses the same fp32 constants.
+
+    // ---- card tables (README.md:36-39; card_abstraction.rs:75-184, 204-209) ----
+    for (uint32_t k = 0; k < P->n_rounds; ++k) {
+        uint32_t kind = RS_ABS_NONE;
+        const rs_round_abstraction* ra = nullptr;
+        if (abs && k < abs->n_rounds) {
+            ra = &abs->rounds[k];
+            kind = ra->kind;
+        }
+        if (kind > RS_ABS_BUCKET_TABLE) return fail("unknown abstraction kind");
+        HandIndexer indexer;
+        int nbc = nb0 + int(k);
+        if (kind == RS_ABS_ISOMORPHIC || kind == RS_ABS_CLUSTER_ARR) {
+            // hand_indexer_s::init(2, [2, 3|4|5]) (card_abstraction.rs:88-90)
+            if (!indexer.init(2, {2, uint8_t(nbc)})) return fail("hand indexer init failed");
+            if (kind == RS_ABS_CLUSTER_ARR) {
+                if (!ra->cluster_arr) return fail("cluster_arr is null");
+                if (ra->cluster_arr_len < indexer.size(1)) return fail("cluster_arr shorter than the round's canonical-hand count");
+            }
+        }
+        for (int q = 0; q < 2; ++q) {
+            RoundPlayerTables& T = P->tabs[k][q];
+            uint32_t H = P->H[q];
+            uint32_t nB = P->n_boards[k];
+            if (kind == RS_ABS_BUCKET_TABLE && !ra->bucket_table[q]) return fail("bucket_table is null");
+            T.row_of_hand.assign(size_t(nB) * H, 0xFFFF);
+            T.row_start.assign(size_t(nB) * (H + 1), 0);
+            T.row_hands.assign(size_t(nB) * H, 0xFFFF);
+            T.n_rows.assign(nB, 0);
+            T.board_off.assign(size_t(nB) + 1, 0);
+            std::unordered_map<uint64_t, uint32_t> dense;
+            std::vector<uint32_t> row_count;
+            for (uint32_t b = P->local_lo[k]; b < P->local_hi[k]; ++b) {
+                uint64_t bm = P->board_mask[k][b];
+                uint8_t cards[7];
+                {
+                    int i = 2;
+                    uint64_t m = bm;
+                    while (m) {  // ascending-card order via trailing_zeros (cfr.rs:78-82)
+                        cards[i++] = uint8_t(__builtin_ctzll(m));
+                        m &= m - 1;
+                    }
+                }
+                dense.clear();
+                row_count.clear();
+                uint16_t* roh = &T.row_of_hand[size_t(b) * H];
+                for (uint32_t h = 0; h < H; ++h) {
+                    uint8_t a = P->hand_cards[q][2 * h], c = P->hand_cards[q][2 * h + 1];
+                    if (bm & ((1ull << a) | (1ull << c))) continue;
+                    uint64_t key;
+                    if (kind == RS_ABS_NONE) {
+                        key = h;
+                    } else if (kind == RS_ABS_BUCKET_TABLE) {
+                        key = ra->bucket_table[q][size_t(b) * H + h];
+                    } else {
+                        cards[0] = a;
+                        cards[1] = c;
+                        key = indexer.get_index(cards);
+                        if (kind == RS_ABS_CLUSTER_ARR) key = ra->cluster_arr[key];  // index_to_cluster, card_abstraction.rs:20-29
+                    }
+                    auto it = dense.find(key);
+                    uint32_t row;
+                    if (it == dense.end()) {  // first-seen order (deterministic here; channel order in the reference)
+                        row = uint32_t(dense.size());
+                        dense.emplace(key, row);
+                        row_count.push_back(0);
+                    } else {
+                        row = it->second;
+                    }
+                    roh[h] = uint16_t(row);
+                    row_count[row]++;
+                }
+                uint32_t nr = uint32_t(row_count.size());
+                T.n_rows[b] = nr;
+                uint16_t* rs_ = &T.row_start[size_t(b) * (H + 1)];
+                uint32_t acc = 0;
+                for (uint32_t r = 0; r < nr; ++r) {
+                    rs_[r] = uint16_t(acc);
+                    acc += row_count[r];
+                }
+                for (uint32_t r = nr; r <= H; ++r) rs_[r] = uint16_t(acc);
+                std::vector<uint32_t> fill(nr, 0);
+                uint16_t* rh = &T.row_hands[size_t(b) * H];
+                for (uint32_t h = 0; h < H; ++h) {
+                    uint16_t r = roh[h];
+                    if (r == 0xFFFF) continue;
+                    rh[rs_[r] + fill[r]++] = uint16_t(h);
+                }
+            }
+            // local slab offsets: board b holds n_rows[b] * sum_a floats, [node][row][A]
+            uint64_t off = 0;
+            for (uint32_t b = 0; b < nB; ++b) {
+                T.board_off[b] = off;
+                if (b >= P->local_lo[k] && b < P->local_hi[k]) off += uint64_t(T.n_rows[b]) * T.sum_a;
+            }
+            T.board_off[nB] = off;
+        }
+    }
+
+    // ---- showdown permutations (final round must be the river) ----
+    bool any_showdown = false;
+    for (auto& n : P->nodes)
+        if (n.kind == PK_SHOWDOWN) {
+            any_showdown = true;
+            if (P->first_round + n.round_k != RS_ROUND_RIVER) return fail("showdown before the river");
+        }
+    if (any_showdown) {
+        uint32_t k = P->n_rounds - 1;
+        uint32_t nB = P->n_boards[k];
+        std::vector<uint32_t> str[2];
+        for (int q = 0; q < 2; ++q) {
+            uint32_t H = P->H[q];
+            ShowdownTables& S = P->sd[q];
+            S.sorted.assign(size_t(nB) * H, 0xFFFF);
+            S.n_live.assign(nB, 0);
+            S.cls.assign(size_t(nB) * H, 0);
+            S.cj.assign(size_t(nB) * H * 2, 0);
+            S.n_card.assign(size_t(nB) * 52, 0);
+            S.lohi.assign(size_t(nB) * H * 2, 0);
+            S.cpos.assign(size_t(nB) * H * 4, 0);
+            str[q].resize(H);
+        }
+        std::vector<uint16_t> order[2];
+        for (uint32_t b = P->local_lo[k]; b < P->local_hi[k]; ++b) {
+            uint64_t bm = P->board_mask[k][b];
+            for (int q = 0; q < 2; ++q) {
+                uint32_t H = P->H[q];
+                ShowdownTables& S = P->sd[q];
+                order[q].clear();
+                for (uint32_t h = 0; h < H; ++h) {
+                    uint64_t hm = (1ull << P->hand_cards[q][2 * h]) | (1ull << P->hand_cards[q][2 * h + 1]);
+                    if (hm & bm) {
+                        str[q][h] = 0;
+                        continue;
+                    }
+                    str[q][h] = evaluate_mask(bm | hm) + 1;  // TrainHand::get_hand + evaluate (cfr.rs:38-46, 534)
+                    order[q].push_back(uint16_t(h));
+                }
+                std::stable_sort(order[q].begin(), order[q].end(),
+                                 [&](uint16_t x, uint16_t y) { return str[q][x] < str[q][y]; });
+                uint32_t nl = uint32_t(order[q].size());
+                S.n_live[b] = nl;
+                uint32_t cls = 0;
+                uint32_t ccount[52] = {0};
+                for (uint32_t i = 0; i < nl; ++i) {
+                    uint16_t h = order[q][i];
+                    if (i > 0 && str[q][h] != str[q][order[q][i - 1]]) cls++;
+                    S.sorted[size_t(b) * H + i] = h;
+                    S.cls[size_t(b) * H + i] = cls;
+                    uint8_t c0 = P->hand_cards[q][2 * h], c1 = P->hand_cards[q][2 * h + 1];
+                    S.cj[(size_t(b) * H + h) * 2 + 0] = uint8_t(ccount[c0]++);
+                    S.cj[(size_t(b) * H + h) * 2 + 1] = uint8_t(ccount[c1]++);
+                }
+                for (int c = 0; c < 52; ++c) S.n_card[size_t(b) * 52 + c] = uint8_t(ccount[c]);
+            }
+            // traverser-role positions against the other player's sorted lists
+            for (int q = 0; q < 2; ++q) {
+                int o = 1 - q;
+                uint32_t H = P->H[q], Ho = P->H[o];
+                ShowdownTables& S = P->sd[q];
+                const std::vector<uint16_t>& oo = order[o];
+                // strengths of opp in sorted order
+                std::vector<uint32_t> os(oo.size());
+                for (size_t i = 0; i < oo.size(); ++i) os[i] = str[o][oo[i]];
+                // per-card sorted strength lists of the opponent
+                std::vector<uint32_t> cl[52];
+                for (size_t i = 0; i < oo.size(); ++i) {
+                    uint16_t h = oo[i];
+                    cl[P->hand_cards[o][2 * h]].push_back(os[i]);
+                    cl[P->hand_cards[o][2 * h + 1]].push_back(os[i]);
+                }
+                (void)Ho;
+                for (uint32_t h = 0; h < H; ++h) {
+                    uint32_t s = str[q][h];
+                    if (s == 0) continue;
+                    uint32_t lo = uint32_t(std::lower_bound(os.begin(), os.end(), s) - os.begin());
+                    uint32_t hi = uint32_t(std::upper_bound(os.begin(), os.end(), s) - os.begin());
+                    S.lohi[(size_t(b) * H + h) * 2 + 0] = uint16_t(lo);
+                    S.lohi[(size_t(b) * H + h) * 2 + 1] = uint16_t(hi);
+                    for (int w = 0; w < 2; ++w) {
+                        const auto& L = cl[P->hand_cards[q][2 * h + w]];
+                        uint32_t clo = uint32_t(std::lower_bound(L.begin(), L.end(), s) - L.begin());
+                        uint32_t chi = uint32_t(std::upper_bound(L.begin(), L.end(), s) - L.begin());
+                        S.cpos[(size_t(b) * H + h) * 4 + 2 * w + 0] = uint8_t(clo);
+                        S.cpos[(size_t(b) * H + h) * 4 + 2 * w + 1] = uint8_t(chi);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- programs ----
+    for (uint32_t k = 0; k < P->n_rounds; ++k)
+        for (uint32_t s = 0; s < P->segs[k].size(); ++s) {
+            Segment& sg = P->segs[k][s];
+            for (int p = 0; p < 2; ++p) {
+                ProgGen up{P, p, false};
+                sg.up[p] = up.run(s, sg.root);
+                if (!sg.leaves.empty()) {
+                    ProgGen dn{P, p, true};
+                    sg.down[p] = dn.run(s, sg.root);
+                }
+            }
+        }
+
+    // ---- update counts (one update = one (node, board, row, action) cell) ----
+    for (uint32_t k = 0; k < P->n_rounds; ++k)
+        for (int q = 0; q < 2; ++q) {
+            const RoundPlayerTables& T = P->tabs[k][q];
+            for (uint32_t b = P->local_lo[k]; b < P->local_hi[k]; ++b)
+                P->updates_per_iter_local += uint64_t(T.n_rows[b]) * T.sum_a;
+        }
+    P->updates_per_iter_global = P->updates_per_iter_local;  // engine all-reduces this when sharded
+    return true;
+}
+
+}  // namespace rs

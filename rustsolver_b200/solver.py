@@ -1,0 +1,526 @@
+"""Python face of the host-side mirror: the names a user of RustSolver's `src/solver` knows.
+
+    Options / ActionAbstraction / default_flop()        options.rs, action_abstraction.rs
+    build_game_tree(options) -> (n_actions, GameTree)   tree_builder.rs:9-14
+    MCCFRTrainer.init(options) / .train(iterations)     cfr.rs:159-297
+    trainer.get_strategy / get_final_strategy           infoset.rs:83-123
+    trainer.calc_br()                                   cfr.rs:629-638
+
+Everything heavy happens behind the C ABI of libb200cfr.so (include/b200cfr.h); numpy arrays are
+the host buffers.  There is no Python or CPU fallback: without the built library `load()` raises,
+and without a B200-class device `MCCFRTrainer.init` raises EngineError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import (EngineError, check, f32p, f64p, i32p, rs_abstraction, rs_config, rs_ranges,
+                   rs_round_abstraction, rs_stats, rs_tree, u8p, u16p, u32p, u64p)
+
+RS_ABS_NONE, RS_ABS_ISOMORPHIC, RS_ABS_CLUSTER_ARR, RS_ABS_BUCKET_TABLE = 0, 1, 2, 3
+RS_FLAG_NO_GRAPH = 1
+NODE_ACTION, NODE_TERMINAL, NODE_PUBLIC_CHANCE, NODE_PRIVATE_CHANCE = 0, 1, 2, 3
+TERM_ALLIN, TERM_SHOWDOWN, TERM_UNCONTESTED = 0, 1, 2
+ACTION_NAMES = {0: "Bet", 1: "Raise", 2: "Check", 3: "Call", 4: "Fold"}
+
+
+def _ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(t)
+
+
+def get_card_mask(s: str) -> int:
+    """rust_poker::hand_range::get_card_mask (options.rs:57)."""
+    m = C.c_uint64()
+    check(_lib.load().rsh_get_card_mask(s.encode(), C.byref(m)))
+    return m.value
+
+
+def range_from_string(s: str, board_mask: int = 0) -> np.ndarray:
+    """HandRange::from_string + remove_invalid_combos -> uint8 [n, 2]."""
+    lib = _lib.load()
+    out = np.zeros((1326, 2), dtype=np.uint8)
+    n = lib.rsh_range_from_string(s.encode(), board_mask, _ptr(out, u8p), 1326)
+    if n < 0:
+        check(n)
+    return out[:n].copy()
+
+
+def evaluate(cards: Sequence[int]) -> int:
+    a = np.asarray(cards, dtype=np.uint8)
+    return int(_lib.load().rsh_evaluate(_ptr(a, u8p), len(a)))
+
+
+@dataclass
+class ActionAbstraction:
+    bet_sizes: List[List[float]] = field(default_factory=list)
+    raise_sizes: List[List[float]] = field(default_factory=list)
+
+
+@dataclass
+class Options:
+    """options.rs:10-28, field for field (hand_ranges as range strings or uint8 [n,2] arrays)."""
+    n_players: int = 2
+    hand_ranges: List = field(default_factory=lambda: ["random", "random"])
+    stack_sizes: List[int] = field(default_factory=lambda: [500, 500])
+    board_mask: int = 0
+    starting_pot: int = 0
+    all_in_threshold: float = 0.67  # declared, never read by the rules (state.rs uses constants.rs)
+    action_abstraction: ActionAbstraction = field(default_factory=ActionAbstraction)
+    max_raises: int = 2  # declared, never read
+
+    def _handle(self):
+        lib = _lib.load()
+        h = lib.rsh_options_new(self.board_mask, self.starting_pot, self.stack_sizes[0], self.stack_sizes[1])
+        aa = self.action_abstraction
+        nb = np.asarray([len(x) for x in aa.bet_sizes], dtype=np.uint32)
+        nr = np.asarray([len(x) for x in aa.raise_sizes], dtype=np.uint32)
+        if len(nb) != len(nr):
+            lib.rsh_options_free(h)
+            raise ValueError("bet_sizes and raise_sizes need one entry per round")
+        bets = np.asarray([v for x in aa.bet_sizes for v in x] + [0.0], dtype=np.float64)
+        raises = np.asarray([v for x in aa.raise_sizes for v in x] + [0.0], dtype=np.float64)
+        check(lib.rsh_options_set_sizes(h, len(nb), _ptr(nb, u32p), _ptr(bets, f64p), _ptr(nr, u32p), _ptr(raises, f64p)))
+        try:
+            for p in range(2):
+                r = self.hand_ranges[p]
+                if isinstance(r, str):
+                    check(lib.rsh_options_set_range(h, p, r.encode()))
+                else:
+                    a = np.ascontiguousarray(r, dtype=np.uint8)
+                    check(lib.rsh_options_set_range_hands(h, p, _ptr(a, u8p), len(a)))
+        except Exception:
+            lib.rsh_options_free(h)
+            raise
+        return h
+
+    def ranges(self) -> List[np.ndarray]:
+        """hand_ranges after remove_invalid_combos (cfr.rs:161-163)."""
+        lib = _lib.load()
+        h = self._handle()
+        try:
+            out = []
+            for p in range(2):
+                buf = np.zeros((1326, 2), dtype=np.uint8)
+                n = lib.rsh_options_range(h, p, _ptr(buf, u8p), 1326)
+                if n < 0:
+                    check(n)
+                out.append(buf[:n].copy())
+            return out
+        finally:
+            lib.rsh_options_free(h)
+
+
+def default_flop() -> Options:
+    """options::default_flop() (options.rs:52-81) — a river spot despite its name."""
+    return Options(n_players=2, stack_sizes=[500, 500], board_mask=get_card_mask("4d5dAs3cKs"), starting_pot=35,
+                   all_in_threshold=0.67, max_raises=2, hand_ranges=["random", "random"],
+                   action_abstraction=ActionAbstraction(bet_sizes=[[0.5, 1.0]], raise_sizes=[[3.0]]))
+
+
+class GameTree:
+    """Tree<GameTreeNode> (tree.rs:12-24) flattened into numpy arrays; node id = arena index."""
+
+    def __init__(self, type, parent, child_offset, children, player, an_index, round_idx, value, ttype,
+                 last_to_act, round=None, action_kind=None, action_amount=None):
+        self.type = np.ascontiguousarray(type, dtype=np.uint8)
+        self.parent = np.ascontiguousarray(parent, dtype=np.int32)
+        self.child_offset = np.ascontiguousarray(child_offset, dtype=np.uint32)
+        self.children = np.ascontiguousarray(children, dtype=np.uint32)
+        self.player = np.ascontiguousarray(player, dtype=np.uint8)
+        self.an_index = np.ascontiguousarray(an_index, dtype=np.uint32)
+        self.round_idx = np.ascontiguousarray(round_idx, dtype=np.uint8)
+        self.value = np.ascontiguousarray(value, dtype=np.uint32)
+        self.ttype = np.ascontiguousarray(ttype, dtype=np.uint8)
+        self.last_to_act = np.ascontiguousarray(last_to_act, dtype=np.uint8)
+        self.round = None if round is None else np.ascontiguousarray(round, dtype=np.uint8)
+        self.action_kind = None if action_kind is None else np.ascontiguousarray(action_kind, dtype=np.uint8)
+        self.action_amount = None if action_amount is None else np.ascontiguousarray(action_amount, dtype=np.float64)
+
+    @property
+    def n_nodes(self) -> int:
+        return len(self.type)
+
+    @property
+    def n_actions(self) -> int:
+        return int((self.type == NODE_ACTION).sum())
+
+    def children_of(self, i: int) -> np.ndarray:
+        return self.children[self.child_offset[i]:self.child_offset[i + 1]]
+
+    def view(self) -> rs_tree:
+        t = rs_tree()
+        t.n_nodes = self.n_nodes
+        t.type = _ptr(self.type, u8p)
+        t.parent = _ptr(self.parent, i32p)
+        t.child_offset = _ptr(self.child_offset, u32p)
+        t.children = _ptr(self.children, u32p)
+        t.player = _ptr(self.player, u8p)
+        t.an_index = _ptr(self.an_index, u32p)
+        t.round_idx = _ptr(self.round_idx, u8p)
+        t.value = _ptr(self.value, u32p)
+        t.ttype = _ptr(self.ttype, u8p)
+        t.last_to_act = _ptr(self.last_to_act, u8p)
+        return t
+
+    def dump(self) -> List[str]:
+        """One line per node in the notation of SURVEY.md Appendix A."""
+        out = []
+        for i in range(self.n_nodes):
+            ch = [int(c) for c in self.children_of(i)]
+            t = self.type[i]
+            if t == NODE_PRIVATE_CHANCE:
+                out.append(f"{i} P ->{ch}")
+            elif t == NODE_PUBLIC_CHANCE:
+                out.append(f"{i} C ->{ch}")
+            elif t == NODE_TERMINAL:
+                k = {TERM_ALLIN: "L", TERM_SHOWDOWN: "S", TERM_UNCONTESTED: "U"}[int(self.ttype[i])]
+                out.append(f"{i} {k} {int(self.value[i])}/{int(self.last_to_act[i])}")
+            else:
+                acts = []
+                for e in range(self.child_offset[i], self.child_offset[i + 1]):
+                    kind = int(self.action_kind[e])
+                    amt = float(self.action_amount[e])
+                    acts.append({2: "X", 3: "C", 4: "F"}.get(kind) or (("B" if kind == 0 else "R") + f"{amt:g}"))
+                out.append(f"{i} A {int(self.an_index[i])}/P{int(self.player[i])} [{','.join(acts)}] ->{ch}")
+        return out
+
+
+def build_game_tree(options: Options):
+    """tree_builder.rs:9-14 -> (n_actions, GameTree).  Raises EngineError where the reference panics."""
+    lib = _lib.load()
+    h = options._handle()
+    th = C.c_void_p()
+    try:
+        check(lib.rsh_build_game_tree(h, C.byref(th)))
+    finally:
+        lib.rsh_options_free(h)
+    try:
+        v = rs_tree()
+        check(lib.rsh_tree_view(th, C.byref(v)))
+        n = v.n_nodes
+        ne = lib.rsh_tree_n_edges(th)
+
+        def arr(p, count, dt):
+            return np.ctypeslib.as_array(p, shape=(count,)).astype(dt, copy=True) if count else np.zeros(0, dt)
+
+        tree = GameTree(arr(v.type, n, np.uint8), arr(v.parent, n, np.int32), arr(v.child_offset, n + 1, np.uint32),
+                        arr(v.children, ne, np.uint32), arr(v.player, n, np.uint8), arr(v.an_index, n, np.uint32),
+                        arr(v.round_idx, n, np.uint8), arr(v.value, n, np.uint32), arr(v.ttype, n, np.uint8),
+                        arr(v.last_to_act, n, np.uint8), arr(lib.rsh_tree_round(th), n, np.uint8),
+                        arr(lib.rsh_tree_action_kind(th), ne, np.uint8), arr(lib.rsh_tree_action_amount(th), ne, np.float64))
+        return int(lib.rsh_tree_n_actions(th)), tree
+    finally:
+        lib.rsh_tree_free(th)
+
+
+class HandIndexer:
+    """rust_poker::hand_indexer_s (card_abstraction.rs:88-90)."""
+
+    def __init__(self, cards_per_round: Sequence[int]):
+        self._lib = _lib.load()
+        cpr = np.asarray(cards_per_round, dtype=np.uint8)
+        self.cards_per_round = [int(x) for x in cpr]
+        self._h = self._lib.rsh_indexer_new(len(cpr), _ptr(cpr, u8p))
+        if not self._h:
+            raise EngineError(-1, self._lib.rs_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.rsh_indexer_free(self._h)
+            self._h = None
+
+    def size(self, round: int) -> int:
+        return int(self._lib.rsh_indexer_size(self._h, round))
+
+    def get_index(self, cards: Sequence[int]) -> int:
+        a = np.asarray(cards, dtype=np.uint8)
+        return int(self._lib.rsh_indexer_index(self._h, _ptr(a, u8p)))
+
+    def index_many(self, cards: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(cards, dtype=np.uint8)
+        assert a.ndim == 2 and a.shape[1] == sum(self.cards_per_round)
+        out = np.zeros(len(a), dtype=np.uint64)
+        self._lib.rsh_indexer_index_many(self._h, _ptr(a, u8p), len(a), _ptr(out, u64p))
+        return out
+
+    def get_hand(self, round: int, index: int) -> List[int]:
+        n = sum(self.cards_per_round[:round + 1])
+        out = np.zeros(n, dtype=np.uint8)
+        check(self._lib.rsh_indexer_get_hand(self._h, round, index, _ptr(out, u8p)))
+        return [int(x) for x in out]
+
+
+@dataclass
+class CardAbstraction:
+    """One entry of MCCFRTrainer.card_abs (cfr.rs:167-172; card_abstraction.rs:62-66)."""
+    kind: int = RS_ABS_NONE
+    cluster_arr: Optional[np.ndarray] = None        # EMD / OCHS: contents of round_N_{emd,ochs}.dat
+    bucket_table: Optional[List[np.ndarray]] = None  # explicit keys [n_boards, n_hands] per player
+
+    @staticmethod
+    def ISOMORPHIC():
+        return CardAbstraction(RS_ABS_ISOMORPHIC)
+
+    @staticmethod
+    def NONE():
+        return CardAbstraction(RS_ABS_NONE)
+
+    @staticmethod
+    def from_file(path: str):
+        """EMD::init / OCHS::init: headerless little-endian u32 per canonical index (card_abstraction.rs:227-229)."""
+        return CardAbstraction(RS_ABS_CLUSTER_ARR, cluster_arr=np.fromfile(path, dtype="<u4"))
+
+
+def _abstraction_struct(card_abs: Sequence[CardAbstraction], keep: list) -> rs_abstraction:
+    ab = rs_abstraction()
+    ab.n_rounds = len(card_abs)
+    for k, ca in enumerate(card_abs):
+        ra = ab.rounds[k]
+        ra.kind = ca.kind
+        if ca.kind == RS_ABS_CLUSTER_ARR:
+            arr = np.ascontiguousarray(ca.cluster_arr, dtype=np.uint32)
+            keep.append(arr)
+            ra.cluster_arr = _ptr(arr, u32p)
+            ra.cluster_arr_len = len(arr)
+        if ca.kind == RS_ABS_BUCKET_TABLE:
+            for p in range(2):
+                arr = np.ascontiguousarray(ca.bucket_table[p], dtype=np.uint32)
+                keep.append(arr)
+                ra.bucket_table[p] = _ptr(arr, u32p)
+    return ab
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * _lib.RS_NCCL_ID_BYTES)()
+    check(_lib.load().rs_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+class _PlanOrEngine:
+    """Shared accessors of rs_plan (host only) and rs_engine."""
+    _prefix = "rs_"
+
+    def _fn(self, name):
+        return getattr(self._lib, self._prefix + name)
+
+    def board_id(self, round_idx: int, dealt: Sequence[int]) -> int:
+        a = np.asarray(list(dealt) + [0], dtype=np.uint8)
+        out = C.c_uint32()
+        check(self._fn("board_id")(self._h, round_idx, _ptr(a, u8p), len(dealt), C.byref(out)))
+        return out.value
+
+    def card_table(self, round_idx: int, player: int, board_id: int) -> np.ndarray:
+        """card table (README.md:36-39): hand slot -> row, 0xFFFF where the hand hits the board."""
+        out = np.zeros(self.n_hands[player], dtype=np.uint16)
+        nr = C.c_uint32()
+        check(self._fn("card_table")(self._h, round_idx, player, board_id, _ptr(out, u16p), len(out), C.byref(nr)))
+        return out
+
+    def num_rows(self, round_idx: int, player: int, board_id: int) -> int:
+        nr = C.c_uint32()
+        check(self._fn("card_table")(self._h, round_idx, player, board_id, None, 0, C.byref(nr)))
+        return nr.value
+
+
+class Plan(_PlanOrEngine):
+    """Host-only compile of the engine's integer tables (no GPU): board/card tables, slab offsets."""
+    _prefix = "rs_plan_"
+
+    def __init__(self, tree: GameTree, ranges: Sequence[np.ndarray], board_mask: int,
+                 card_abs: Sequence[CardAbstraction] = (), board_masks: Optional[Sequence[int]] = None,
+                 rank: int = 0, world_size: int = 1):
+        self._lib = _lib.load()
+        self._keep = []
+        tv = tree.view()
+        rr = rs_ranges()
+        hs = [np.ascontiguousarray(r, dtype=np.uint8) for r in ranges]
+        for p in range(2):
+            rr.n_hands[p] = len(hs[p])
+            rr.hands[p] = _ptr(hs[p], u8p)
+        ab = _abstraction_struct(card_abs, self._keep)
+        cfg = rs_config()
+        cfg.board_mask = board_mask
+        cfg.rank, cfg.world_size = rank, world_size
+        h = C.c_void_p()
+        if board_masks is not None:
+            bm = np.asarray(board_masks, dtype=np.uint64)
+            check(self._lib.rs_plan_create(C.byref(tv), C.byref(rr), C.byref(ab), C.byref(cfg), _ptr(bm, u64p), len(bm), C.byref(h)))
+        else:
+            check(self._lib.rs_plan_create(C.byref(tv), C.byref(rr), C.byref(ab), C.byref(cfg), None, 0, C.byref(h)))
+        self._h = h
+        self.n_hands = [len(hs[0]), len(hs[1])]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.rs_plan_destroy(self._h)
+            self._h = None
+
+    def stats(self) -> rs_stats:
+        s = rs_stats()
+        check(self._lib.rs_plan_stats(self._h, C.byref(s)))
+        return s
+
+    def infoset_offset(self, an_index: int, board_id: int):
+        off, nr, na = C.c_uint64(), C.c_uint32(), C.c_uint32()
+        check(self._lib.rs_plan_infoset_offset(self._h, an_index, board_id, C.byref(off), C.byref(nr), C.byref(na)))
+        return off.value, nr.value, na.value
+
+    def showdown_order(self, player: int, board_id: int):
+        order = np.zeros(self.n_hands[player], dtype=np.uint16)
+        cls = np.zeros(self.n_hands[player], dtype=np.uint32)
+        nl = C.c_uint32()
+        check(self._lib.rs_plan_showdown_order(self._h, player, board_id, _ptr(order, u16p), _ptr(cls, u32p), len(order), C.byref(nl)))
+        return order[:nl.value].copy(), cls[:nl.value].copy()
+
+
+class Engine(_PlanOrEngine):
+    """rs_engine handle: the device-resident infoset tables plus the iteration graph."""
+
+    def __init__(self, tree: GameTree, ranges: Sequence[np.ndarray], board_mask: int,
+                 card_abs: Sequence[CardAbstraction] = (), board_masks: Optional[Sequence[int]] = None,
+                 device: int = 0, rank: int = 0, world_size: int = 1, nccl_id: Optional[bytes] = None,
+                 flags: int = 0, threads_per_block: int = 0, discount_interval: int = 0, discount_cap: int = 0):
+        self._lib = _lib.load()
+        self._keep = []
+        self.tree = tree
+        tv = tree.view()
+        rr = rs_ranges()
+        hs = [np.ascontiguousarray(r, dtype=np.uint8) for r in ranges]
+        for p in range(2):
+            rr.n_hands[p] = len(hs[p])
+            rr.hands[p] = _ptr(hs[p], u8p)
+        ab = _abstraction_struct(card_abs, self._keep)
+        cfg = rs_config()
+        cfg.board_mask = board_mask
+        cfg.device, cfg.rank, cfg.world_size = device, rank, world_size
+        if nccl_id is not None:
+            C.memmove(cfg.nccl_id, nccl_id, _lib.RS_NCCL_ID_BYTES)
+        cfg.flags = flags
+        cfg.threads_per_block = threads_per_block
+        cfg.discount_interval, cfg.discount_cap = discount_interval, discount_cap
+        h = C.c_void_p()
+        if board_masks is not None:
+            bm = np.asarray(board_masks, dtype=np.uint64)
+            check(self._lib.rs_create_batch(C.byref(tv), C.byref(rr), C.byref(ab), C.byref(cfg), _ptr(bm, u64p), len(bm), C.byref(h)))
+        else:
+            check(self._lib.rs_create(C.byref(tv), C.byref(rr), C.byref(ab), C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.n_hands = [len(hs[0]), len(hs[1])]
+        self.ranges = hs
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rs_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def iterate(self, n: int = 1):
+        check(self._lib.rs_iterate(self._h, n))
+
+    def discount(self, d: float):
+        check(self._lib.rs_discount(self._h, d))
+
+    def reset(self):
+        check(self._lib.rs_reset(self._h))
+
+    def stats(self) -> rs_stats:
+        s = rs_stats()
+        check(self._lib.rs_stats_get(self._h, C.byref(s)))
+        return s
+
+    def _shape(self, an_index: int, board_id: int):
+        nr, na = C.c_uint32(), C.c_uint32()
+        check(self._lib.rs_read_infoset(self._h, an_index, board_id, None, None, 0, C.byref(nr), C.byref(na)))
+        return nr.value, na.value
+
+    def read_infoset(self, an_index: int, board_id: int = 0):
+        """-> (regrets, strategy_sum), each float32 [rows, n_actions] (README.md:45-47)."""
+        nr, na = self._shape(an_index, board_id)
+        r = np.zeros((nr, na), dtype=np.float32)
+        s = np.zeros((nr, na), dtype=np.float32)
+        check(self._lib.rs_read_infoset(self._h, an_index, board_id, _ptr(r, f32p), _ptr(s, f32p), r.size, None, None))
+        return r, s
+
+    def write_infoset(self, an_index: int, board_id: int, regrets: np.ndarray, strategy_sum: np.ndarray):
+        r = np.ascontiguousarray(regrets, dtype=np.float32)
+        s = np.ascontiguousarray(strategy_sum, dtype=np.float32)
+        check(self._lib.rs_write_infoset(self._h, an_index, board_id, _ptr(r, f32p), _ptr(s, f32p), r.size))
+
+    def average_strategy(self, an_index: int, board_id: int = 0) -> np.ndarray:
+        nr, na = self._shape(an_index, board_id)
+        out = np.zeros((nr, na), dtype=np.float32)
+        check(self._lib.rs_average_strategy(self._h, an_index, board_id, _ptr(out, f32p), out.size, None, None))
+        return out
+
+    def current_strategy(self, an_index: int, board_id: int = 0) -> np.ndarray:
+        nr, na = self._shape(an_index, board_id)
+        out = np.zeros((nr, na), dtype=np.float32)
+        check(self._lib.rs_current_strategy(self._h, an_index, board_id, _ptr(out, f32p), out.size, None, None))
+        return out
+
+    def best_response(self):
+        out = (C.c_double * 2)()
+        check(self._lib.rs_best_response(self._h, out))
+        return [out[0], out[1]]
+
+    def average_value(self):
+        out = (C.c_double * 2)()
+        check(self._lib.rs_average_value(self._h, out))
+        return [out[0], out[1]]
+
+    def root_values(self, player: int) -> np.ndarray:
+        st = self.stats()
+        out = np.zeros(st.n_boards_local[0] * self.n_hands[player], dtype=np.float32)
+        check(self._lib.rs_root_values(self._h, player, _ptr(out, f32p), out.size))
+        return out.reshape(st.n_boards_local[0], self.n_hands[player])
+
+
+class MCCFRTrainer:
+    """MCCFRTrainer of src/solver/cfr.rs:150-297 with its hot path on the GPU."""
+
+    def __init__(self):
+        self.engine: Optional[Engine] = None
+        self.game_tree: Optional[GameTree] = None
+        self.hand_ranges: List[np.ndarray] = []
+        self.initial_board_mask = 0
+        self.card_abs: List[CardAbstraction] = []
+
+    @staticmethod
+    def init(options: Options, card_abs: Optional[Sequence[CardAbstraction]] = None, **engine_kwargs) -> "MCCFRTrainer":
+        """cfr.rs:159-184: remove_invalid_combos, build_game_tree, card abstraction, create_infosets."""
+        t = MCCFRTrainer()
+        t.hand_ranges = options.ranges()
+        n_actions, t.game_tree = build_game_tree(options)
+        t.initial_board_mask = options.board_mask
+        n_rounds = int(t.game_tree.round_idx.max()) + 1
+        # the reference instantiates ISOMORPHIC for its single round (cfr.rs:171)
+        t.card_abs = list(card_abs) if card_abs is not None else [CardAbstraction.ISOMORPHIC() for _ in range(n_rounds)]
+        t.engine = Engine(t.game_tree, t.hand_ranges, options.board_mask, t.card_abs, **engine_kwargs)
+        return t
+
+    def train(self, iterations: int):
+        """cfr.rs:188-297: each iteration traverses and updates player 0 then player 1 (cfr.rs:216-226)."""
+        self.engine.iterate(iterations)
+
+    def get_strategy(self, an_index: int, cluster_idx: int, board_id: int = 0) -> np.ndarray:
+        """Infoset::get_strategy (infoset.rs:83-102) of infosets[an_index][cluster_idx]."""
+        return self.engine.current_strategy(an_index, board_id)[cluster_idx]
+
+    def get_final_strategy(self, an_index: int, cluster_idx: int, board_id: int = 0) -> np.ndarray:
+        """Infoset::get_final_strategy (infoset.rs:104-123)."""
+        return self.engine.average_strategy(an_index, board_id)[cluster_idx]
+
+    def calc_br(self) -> List[float]:
+        """cfr.rs:629-638 (a stub in the reference; a true best response here)."""
+        return self.engine.best_response()
+
+    def exploitability(self, bb: float = 1.0) -> dict:
+        br = self.engine.best_response()
+        chips = 0.5 * (br[0] + br[1])
+        return {"chips": chips, "mbb_per_game": 1000.0 * chips / bb, "br": br}
