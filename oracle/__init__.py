@@ -1,0 +1,225 @@
+"""CPU oracle for the CFR hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may
+import this package.  rustsolver_b200 never does.  PARITY UNPINNED for CFR outputs (the reference
+cannot be built here and ships no CFR fixtures) — see the header of cfr_oracle.c.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "liborc.so"
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+i32p = C.POINTER(C.c_int32)
+f64p = C.POINTER(C.c_double)
+VP = C.c_void_p
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(f"{LIB_PATH} missing: run `python -m rustsolver_b200.build` (builds oracle/liborc.so with gcc)")
+    lib = C.CDLL(str(LIB_PATH))
+    lib.orc_evaluate.restype = C.c_uint32
+    lib.orc_evaluate.argtypes = [u8p, C.c_int]
+    lib.orc_create.restype = VP
+    lib.orc_create.argtypes = [C.c_int, u8p, u32p, u32p, u8p, u32p, u8p, u32p, u8p, u8p, C.c_int, u8p, C.c_int, u8p,
+                               C.c_uint64, C.POINTER(u32p)]
+    lib.orc_destroy.argtypes = [VP]
+    lib.orc_set_options.argtypes = [VP, C.c_int, C.c_int, C.c_int]
+    lib.orc_iterate.argtypes = [VP, C.c_int]
+    lib.orc_traverse_player.argtypes = [VP, C.c_int]
+    lib.orc_best_response.argtypes = [VP, f64p]
+    lib.orc_average_value.argtypes = [VP, f64p]
+    lib.orc_root_cfv.argtypes = [VP, C.c_int, f64p]
+    lib.orc_discount.argtypes = [VP, C.c_double]
+    lib.orc_n_rounds.restype = C.c_int
+    lib.orc_n_rounds.argtypes = [VP]
+    lib.orc_n_boards.restype = C.c_int
+    lib.orc_n_boards.argtypes = [VP, C.c_int]
+    lib.orc_board_mask.restype = C.c_uint64
+    lib.orc_board_mask.argtypes = [VP, C.c_int, C.c_int]
+    lib.orc_n_combos.restype = C.c_double
+    lib.orc_n_combos.argtypes = [VP]
+    lib.orc_n_rows.restype = C.c_int
+    lib.orc_n_rows.argtypes = [VP, C.c_int, C.c_int, C.c_int]
+    lib.orc_rows.argtypes = [VP, C.c_int, C.c_int, C.c_int, i32p]
+    lib.orc_updates_per_iter.restype = C.c_uint64
+    lib.orc_updates_per_iter.argtypes = [VP]
+    lib.orc_get_slab.restype = C.c_int
+    lib.orc_get_slab.argtypes = [VP, C.c_int, C.c_int, C.c_int, f64p]
+    lib.orc_set_slab.restype = C.c_int
+    lib.orc_set_slab.argtypes = [VP, C.c_int, C.c_int, C.c_int, f64p]
+    lib.orc_get_islab.restype = C.c_int
+    lib.orc_get_islab.argtypes = [VP, C.c_int, C.c_int, C.c_int, i32p]
+    lib.orc_strengths.argtypes = [VP, C.c_int, C.c_int, u32p]
+    lib.orc_literal_cfr.restype = C.c_long
+    lib.orc_literal_cfr.argtypes = [VP, C.c_int, C.c_int, C.c_int, f64p]
+    lib.orc_literal_mccfr.restype = C.c_long
+    lib.orc_literal_mccfr.argtypes = [VP, C.c_long, C.c_int, C.c_uint64, C.c_long, C.c_long, C.c_long]
+    lib.orc_literal_to_double.argtypes = [VP, C.c_double]
+    lib.orc_num_threads.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def evaluate(cards: Sequence[int]) -> int:
+    a = np.asarray(cards, dtype=np.uint8)
+    return int(load().orc_evaluate(a.ctypes.data_as(u8p), len(a)))
+
+
+class OracleGame:
+    """Wraps orc_game.  `tree` is any object with the rs_tree arrays as attributes (numpy or lists)."""
+
+    def __init__(self, tree, ranges: Sequence[np.ndarray], board_mask: int,
+                 keys: Optional[List[List[Optional[np.ndarray]]]] = None, fast_terminals: bool = True,
+                 chance_sum: bool = False):
+        self.lib = load()
+        g = lambda name, dt: np.ascontiguousarray(getattr(tree, name) if not isinstance(tree, dict) else tree[name], dtype=dt)
+        self.type = g("type", np.uint8)
+        self.child_offset = g("child_offset", np.uint32)
+        self.children = g("children", np.uint32)
+        self.player = g("player", np.uint8)
+        self.an_index = g("an_index", np.uint32)
+        self.round_idx = g("round_idx", np.uint8)
+        self.value = g("value", np.uint32)
+        self.ttype = g("ttype", np.uint8)
+        self.last_to_act = g("last_to_act", np.uint8)
+        self.ranges = [np.ascontiguousarray(r, dtype=np.uint8) for r in ranges]
+        self._keys_keep = []
+        karr = (u32p * 6)()
+        if keys is not None:
+            for k, per_round in enumerate(keys):
+                if per_round is None:
+                    continue
+                for q in range(2):
+                    if per_round[q] is None:
+                        continue
+                    a = np.ascontiguousarray(per_round[q], dtype=np.uint32)
+                    self._keys_keep.append(a)
+                    karr[k * 2 + q] = a.ctypes.data_as(u32p)
+        p = lambda a, t: a.ctypes.data_as(t)
+        self.h = self.lib.orc_create(len(self.type), p(self.type, u8p), p(self.child_offset, u32p), p(self.children, u32p),
+                                     p(self.player, u8p), p(self.an_index, u32p), p(self.round_idx, u8p), p(self.value, u32p),
+                                     p(self.ttype, u8p), p(self.last_to_act, u8p), len(self.ranges[0]), p(self.ranges[0], u8p),
+                                     len(self.ranges[1]), p(self.ranges[1], u8p), board_mask, karr)
+        self.lib.orc_set_options(self.h, int(chance_sum), 0, int(fast_terminals))
+        self.n_hands = [len(self.ranges[0]), len(self.ranges[1])]
+        self.action_nodes = {int(self.an_index[i]): i for i in range(len(self.type)) if self.type[i] == 0}
+
+    def set_options(self, chance_sum=False, fast_terminals=True):
+        self.lib.orc_set_options(self.h, int(chance_sum), 0, int(fast_terminals))
+
+    # --- vector-form fp64 CFR ---
+    def iterate(self, n: int = 1):
+        self.lib.orc_iterate(self.h, n)
+
+    def traverse_player(self, p: int):
+        self.lib.orc_traverse_player(self.h, p)
+
+    def best_response(self):
+        out = (C.c_double * 2)()
+        self.lib.orc_best_response(self.h, out)
+        return [out[0], out[1]]
+
+    def average_value(self):
+        out = (C.c_double * 2)()
+        self.lib.orc_average_value(self.h, out)
+        return [out[0], out[1]]
+
+    def root_cfv(self, p: int) -> np.ndarray:
+        out = np.zeros(self.n_hands[p], dtype=np.float64)
+        self.lib.orc_root_cfv(self.h, p, out.ctypes.data_as(f64p))
+        return out
+
+    def discount(self, d: float):
+        self.lib.orc_discount(self.h, d)
+
+    # --- shapes ---
+    @property
+    def n_rounds(self) -> int:
+        return self.lib.orc_n_rounds(self.h)
+
+    def n_boards(self, k: int) -> int:
+        return self.lib.orc_n_boards(self.h, k)
+
+    def board_mask(self, k: int, b: int) -> int:
+        return int(self.lib.orc_board_mask(self.h, k, b))
+
+    @property
+    def n_combos(self) -> float:
+        return self.lib.orc_n_combos(self.h)
+
+    def n_rows(self, k: int, q: int, b: int) -> int:
+        return self.lib.orc_n_rows(self.h, k, q, b)
+
+    def rows(self, k: int, q: int, b: int) -> np.ndarray:
+        out = np.zeros(self.n_hands[q], dtype=np.int32)
+        self.lib.orc_rows(self.h, k, q, b, out.ctypes.data_as(i32p))
+        return out
+
+    @property
+    def updates_per_iter(self) -> int:
+        return int(self.lib.orc_updates_per_iter(self.h))
+
+    def _slab_shape(self, an: int, b: int):
+        node = self.action_nodes[an]
+        k, q = int(self.round_idx[node]), int(self.player[node])
+        A = int(self.child_offset[node + 1] - self.child_offset[node])
+        return self.n_rows(k, q, b), A
+
+    def get_slab(self, an: int, b: int = 0):
+        """-> (regrets, strategy_sum) float64 [rows, A]."""
+        nr, A = self._slab_shape(an, b)
+        r = np.zeros((nr, A), dtype=np.float64)
+        s = np.zeros((nr, A), dtype=np.float64)
+        self.lib.orc_get_slab(self.h, an, b, 0, r.ctypes.data_as(f64p))
+        self.lib.orc_get_slab(self.h, an, b, 1, s.ctypes.data_as(f64p))
+        return r, s
+
+    def set_slab(self, an: int, b: int, regrets: np.ndarray, ssum: np.ndarray):
+        r = np.ascontiguousarray(regrets, dtype=np.float64)
+        s = np.ascontiguousarray(ssum, dtype=np.float64)
+        self.lib.orc_set_slab(self.h, an, b, 0, r.ctypes.data_as(f64p))
+        self.lib.orc_set_slab(self.h, an, b, 1, s.ctypes.data_as(f64p))
+
+    def get_islab(self, an: int, b: int = 0):
+        nr, A = self._slab_shape(an, b)
+        r = np.zeros((nr, A), dtype=np.int32)
+        s = np.zeros((nr, A), dtype=np.int32)
+        self.lib.orc_get_islab(self.h, an, b, 0, r.ctypes.data_as(i32p))
+        self.lib.orc_get_islab(self.h, an, b, 1, s.ctypes.data_as(i32p))
+        return r, s
+
+    def strengths(self, q: int, b: int) -> np.ndarray:
+        out = np.zeros(self.n_hands[q], dtype=np.uint32)
+        self.lib.orc_strengths(self.h, q, b, out.ctypes.data_as(u32p))
+        return out
+
+    # --- literal scalar restatements ---
+    def literal_cfr(self, iterations: int = 1, stride: int = 1, offset: int = 0):
+        util = (C.c_double * 2)()
+        n = self.lib.orc_literal_cfr(self.h, iterations, stride, offset, util)
+        return int(n), [util[0], util[1]]
+
+    def literal_mccfr(self, iterations: int, n_threads: int = 8, seed: int = 1, discount_interval: int = 0,
+                      discount_cap: int = 0, prune_after: int = -1) -> int:
+        return int(self.lib.orc_literal_mccfr(self.h, iterations, n_threads, seed, discount_interval, discount_cap, prune_after))
+
+    def literal_to_double(self, scale: float):
+        self.lib.orc_literal_to_double(self.h, scale)
+
+    @property
+    def num_threads(self) -> int:
+        return self.lib.orc_num_threads()

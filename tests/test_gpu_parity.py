@@ -1,0 +1,139 @@
+"""GPU parity: the CUDA path through the C ABI against the fp64 oracle, per iteration.
+
+Tolerance (north_star: "within a stated relative tolerance, e.g. 1e-4 in fp32"): norm-wise per
+action node, |gpu - oracle|_inf <= TOL * |oracle|_inf(node) + 1e-6 * |oracle|_inf(table), TOL = 1e-4
+(tests/util.py:compare_tables), checked after EVERY iteration: the first iterations of a free run
+from zero tables, then lock-step iterations restarted from the oracle's state (util.lockstep).
+"""
+import numpy as np
+import pytest
+
+import rustsolver_b200 as rb
+from oracle import OracleGame
+from rustsolver_b200 import configs
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _pair(options, card_abs=None, keys=None, **kw):
+    n, tree = rb.build_game_tree(options)
+    ranges = options.ranges()
+    eng = rb.Engine(tree, ranges, options.board_mask, card_abs or [], **kw)
+    orc = OracleGame(tree, ranges, options.board_mask, keys=keys)
+    return tree, eng, orc
+
+
+def test_river_small_ranges_per_iteration():
+    o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]], [[3.0]])
+    tree, eng, orc = _pair(o)
+    for it in range(5):
+        eng.iterate(1)
+        orc.iterate(1)
+        util.compare_tables(eng, orc, tree, TOL)
+    br_g, br_o = eng.best_response(), orc.best_response()
+    ev_g, ev_o = eng.average_value(), orc.average_value()
+    assert np.allclose(br_g, br_o, rtol=1e-4, atol=1e-4), (br_g, br_o)
+    assert np.allclose(ev_g, ev_o, rtol=1e-4, atol=1e-4), (ev_g, ev_o)
+
+
+def test_river_default_flop_full_ranges():
+    o = rb.default_flop()
+    tree, eng, orc = _pair(o, [rb.CardAbstraction.ISOMORPHIC()])
+    for it in range(3):
+        eng.iterate(1)
+        orc.iterate(1)
+        util.compare_tables(eng, orc, tree, TOL)
+    assert eng.stats().updates_per_iteration == 41078
+
+
+def test_no_graph_matches_graph():
+    o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]], [[3.0]])
+    n, tree = rb.build_game_tree(o)
+    r = o.ranges()
+    e1 = rb.Engine(tree, r, o.board_mask)
+    e2 = rb.Engine(tree, r, o.board_mask, flags=rb.RS_FLAG_NO_GRAPH)
+    e1.iterate(7)
+    e2.iterate(7)
+    for an in range(tree.n_actions):
+        a, b = e1.read_infoset(an), e2.read_infoset(an)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])  # bit-reproducible
+
+
+def test_turn_river_small_ranges():
+    o = util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]] * 2, [[3.0]] * 2)
+    tree, eng, orc = _pair(o)
+    util.lockstep(eng, orc, tree, n_free=2, n_locked=3, tol=TOL)
+    br_g, br_o = eng.best_response(), orc.best_response()
+    assert np.allclose(br_g, br_o, rtol=1e-4, atol=1e-4), (br_g, br_o)
+
+
+def test_flop_rooted_small_ranges_with_allin_runouts():
+    # short stacks force ALLIN terminals on the flop and turn -> run-out chance nodes
+    o = util.small_options("4d5dAs", ["AA,KK,AKs,76s,54s", "QQ,JJ,AQs,65s,32s"], [[1.0]] * 3, [[3.0]] * 3, pot=40, stacks=(60, 60))
+    tree, eng, orc = _pair(o)
+    assert (tree.ttype[tree.type == 1] == 0).any(), "expected ALLIN terminals"
+    util.lockstep(eng, orc, tree, n_free=1, n_locked=2, tol=TOL)
+
+
+def test_bucketed_rows_many_to_one():
+    o = util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]] * 2, [[3.0]] * 2)
+    n, tree = rb.build_game_tree(o)
+    r = o.ranges()
+    k0 = util.bucket_keys_for(None, r, 1, 7, seed=3)
+    k1 = util.bucket_keys_for(None, r, 48, 11, seed=4)
+    abs_ = [rb.CardAbstraction(rb.RS_ABS_BUCKET_TABLE, bucket_table=k0), rb.CardAbstraction(rb.RS_ABS_BUCKET_TABLE, bucket_table=k1)]
+    eng = rb.Engine(tree, r, o.board_mask, abs_)
+    orc = OracleGame(tree, r, o.board_mask, keys=[k0, k1])
+    util.lockstep(eng, orc, tree, n_free=2, n_locked=3, tol=TOL)
+
+
+def test_single_iteration_from_oracle_state():
+    """Restart the GPU from the oracle's state every iteration: isolates one-step error from drift."""
+    o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]], [[3.0]])
+    tree, eng, orc = _pair(o)
+    orc.iterate(20)
+    util.lockstep(eng, orc, tree, n_free=0, n_locked=3, tol=2e-5)
+
+
+def test_discount_sweep():
+    o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]], [[3.0]])
+    tree, eng, orc = _pair(o)
+    eng.iterate(2)
+    orc.iterate(2)
+    eng.discount(0.5)
+    orc.discount(0.5)
+    util.compare_tables(eng, orc, tree, TOL)
+
+
+def test_exploitability_curve_matches_oracle():
+    o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]], [[3.0]])
+    tree, eng, orc = _pair(o)
+    done = 0
+    for target in (10, 50, 200):
+        eng.iterate(target - done)
+        orc.iterate(target - done)
+        done = target
+        eg = sum(eng.best_response()) / 2
+        eo = sum(orc.best_response()) / 2
+        # stated bound: exploitability agrees to 2% relative or 0.02 chips (mbb/g at bb=1: 20)
+        assert abs(eg - eo) <= max(0.02 * abs(eo), 0.02), (target, eg, eo)
+    assert eg < 3.0
+
+
+def test_batch_of_river_subgames():
+    w = configs.config5(n_subgames=6)
+    n, tree = rb.build_game_tree(w.options)
+    ranges = configs.workload_ranges(w)
+    eng = rb.Engine(tree, ranges, 0, w.card_abs, board_masks=w.board_masks)
+    eng.iterate(2)
+    for s, bm in enumerate(w.board_masks):
+        o = OracleGame(tree, ranges, bm)
+        o.iterate(2)
+        for an in range(tree.n_actions):
+            gr, gs = eng.read_infoset(an, s)
+            orr, os_ = o.get_slab(an, 0)
+            assert gr.shape == orr.shape
+            assert np.abs(gr - orr).max() <= TOL * max(np.abs(orr).max(), 1e-12)
+            assert np.abs(gs - os_).max() <= TOL * max(np.abs(os_).max(), 1e-12)
