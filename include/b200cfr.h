@@ -181,6 +181,29 @@ int rs_root_values(rs_engine* e, uint32_t player, float* out, size_t cap);
 
 int rs_stats_get(rs_engine* e, rs_stats* out);
 
+/* Per-hand reach weights of `player`'s range at the root (n = n_hands[player]; default 1.0 = the
+ * reference's unweighted HandRange, cfr.rs:124).  Copied host->device on the engine's stream; the
+ * next rs_iterate sees them.  This is the per-step host input of a re-solve loop. */
+int rs_set_range_weights(rs_engine* e, uint32_t player, const float* weights, size_t n);
+
+/* Kernel-level profile of ONE iteration launched kernel by kernel (no graph) with a CUDA event pair
+ * around every launch on the engine's stream.  The iteration is a real one (tables are updated). */
+#define RS_KERNEL_SEGMENT_DOWN 0
+#define RS_KERNEL_SEGMENT_UP 1
+#define RS_KERNEL_GATHER 2
+#define RS_KERNEL_ALLREDUCE 3
+typedef struct rs_kernel_time {
+    uint32_t kind;      /* RS_KERNEL_* */
+    uint32_t round_idx;
+    uint32_t traverser;
+    uint32_t grid;      /* CTAs launched */
+    float ms;           /* CUDA-event duration */
+    uint64_t table_bytes; /* algorithmic infoset-table bytes of this launch: 16 B per traverser cell
+                             (regret + strategy_sum read+write) + 4 B per opponent cell (regret read) */
+    uint64_t vector_bytes; /* reach / value vectors read or written in HBM by this launch */
+} rs_kernel_time;
+int rs_profile_iteration(rs_engine* e, rs_kernel_time* out, size_t cap, uint32_t* n_out);
+
 /* ---- host-only plan introspection (no GPU needed): integer parity surface ---- */
 typedef struct rs_plan rs_plan;
 int rs_plan_create(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs,

@@ -53,6 +53,11 @@ class rs_stats(C.Structure):
                 ("n_hands", C.c_uint32 * 2), ("n_combos", C.c_uint64)]
 
 
+class rs_kernel_time(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("round_idx", C.c_uint32), ("traverser", C.c_uint32), ("grid", C.c_uint32),
+                ("ms", C.c_float), ("table_bytes", C.c_uint64), ("vector_bytes", C.c_uint64)]
+
+
 # every symbol the two headers declare: name -> (restype, argtypes)
 VP = C.c_void_p
 ENGINE_API = {
@@ -78,6 +83,8 @@ ENGINE_API = {
     "rs_average_value": (C.c_int, [VP, f64p]),
     "rs_root_values": (C.c_int, [VP, C.c_uint32, f32p, C.c_size_t]),
     "rs_stats_get": (C.c_int, [VP, C.POINTER(rs_stats)]),
+    "rs_set_range_weights": (C.c_int, [VP, C.c_uint32, f32p, C.c_size_t]),
+    "rs_profile_iteration": (C.c_int, [VP, C.POINTER(rs_kernel_time), C.c_size_t, u32p]),
     "rs_plan_create": (C.c_int, [C.POINTER(rs_tree), C.POINTER(rs_ranges), C.POINTER(rs_abstraction),
                                  C.POINTER(rs_config), u64p, C.c_uint32, C.POINTER(VP)]),
     "rs_plan_destroy": (None, [VP]),

@@ -143,6 +143,10 @@ struct Engine {
     DevBuf<uint32_t> sd_nlive[2];
     DevBuf<uint8_t> sd_cj[2], sd_ncard[2], sd_cpos[2];
     DevBuf<float> scratch;  // strategy read-outs
+    DevBuf<float> root_weights[2];
+    // profiling: when non-null, enqueue_traversal brackets every launch with an event pair
+    std::vector<rs_kernel_time>* prof = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 
     uint64_t iterations = 0;
     double device_ms = 0;
@@ -168,6 +172,9 @@ struct Engine {
     int enqueue_iteration(uint64_t* count);
     int iterate(uint64_t n);
     int root_sum(int player, double* out);
+    int prof_begin();
+    int prof_end(uint32_t kind, uint32_t k, int trav, uint32_t grid, uint64_t table_bytes, uint64_t vector_bytes);
+    uint64_t table_bytes_of(uint32_t k, int trav) const;
 };
 
 template <class T>
@@ -199,6 +206,8 @@ int Engine::init(const rs_config* cfg) {
 
     const Plan& P = plan;
     for (int q = 0; q < 2; ++q) {
+        std::vector<float> ones(P.H[q], 1.0f);
+        CU(root_weights[q].upload(ones));
         CU(cards[q].upload(P.hand_cards[q]));
         CU(same[q].upload(P.same[q]));
         CU(card_hands[q].upload(P.card_hands[q]));
@@ -352,6 +361,8 @@ int Engine::fill_launch(SegLaunch* a, uint32_t k, int trav, int down) const {
     a->chance_scale = R.chance_scale.p;
     a->parent_board = R.parent_board.p;
     a->parent_reach = k > 0 ? rd[k - 1].leaf_reach.p : nullptr;
+    a->root_weights[0] = root_weights[0].p;
+    a->root_weights[1] = root_weights[1].p;
     a->leaf_reach = R.leaf_reach.p;
     a->root_cfv = R.root_cfv.p;
     a->gathered = R.gathered.p;
@@ -364,37 +375,91 @@ int Engine::fill_launch(SegLaunch* a, uint32_t k, int trav, int down) const {
     return RS_OK;
 }
 
+int Engine::prof_begin() {
+    if (!prof) return RS_OK;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    prof_events.emplace_back(a, b);
+    CU(cudaEventRecord(a, stream));
+    return RS_OK;
+}
+
+int Engine::prof_end(uint32_t kind, uint32_t k, int trav, uint32_t grid, uint64_t tb, uint64_t vb) {
+    if (!prof) return RS_OK;
+    CU(cudaEventRecord(prof_events.back().second, stream));
+    rs_kernel_time t;
+    memset(&t, 0, sizeof(t));
+    t.kind = kind;
+    t.round_idx = k;
+    t.traverser = uint32_t(trav);
+    t.grid = grid;
+    t.table_bytes = tb;
+    t.vector_bytes = vb;
+    prof->push_back(t);
+    return RS_OK;
+}
+
+// algorithmic infoset-table bytes of one up-pass launch on round k for traverser `trav`:
+// traverser cells: regret R+W, strategy_sum R+W = 16 B; opponent cells: regret read = 4 B
+uint64_t Engine::table_bytes_of(uint32_t k, int trav) const {
+    const Plan& P = plan;
+    const uint64_t own = P.tabs[k][trav].board_off[P.n_boards[k]];
+    const uint64_t opp = P.tabs[k][1 - trav].board_off[P.n_boards[k]];
+    return own * 16 + opp * 4;
+}
+
 int Engine::enqueue_traversal(int trav, int mode, uint64_t* count) {
     const Plan& P = plan;
     const int HP[2] = {int((P.H[0] + 3) & ~3u), int((P.H[1] + 3) & ~3u)};
     SegLaunch a;
+    int rc;
     // down pass: reach at every chance leaf, street by street (cfr.rs:502-522 scatter)
     for (uint32_t k = 0; k + 1 < P.n_rounds; ++k) {
         if (!rd[k].has_down) continue;
         fill_launch(&a, k, trav, 1);
         size_t smem = seg_kernel_smem_bytes(a.n_r, a.n_v, HP[trav], HP[1 - trav]);
+        if ((rc = prof_begin()) != RS_OK) return rc;
         CU(launch_segment_kernel(a, mode, threads, smem, stream));
+        const uint64_t opp_cells = P.tabs[k][1 - trav].board_off[P.n_boards[k]];
+        if ((rc = prof_end(RS_KERNEL_SEGMENT_DOWN, k, trav, uint32_t(a.n_boards) * uint32_t(a.n_segs), opp_cells * 4,
+                           uint64_t(rd[k].n_leaves) * rd[k].n_boards * P.H[1 - trav] * 4)) != RS_OK)
+            return rc;
         ++*count;
     }
     // up pass: deepest street first, then gather over dealt cards into the parent street
     for (int k = int(P.n_rounds) - 1; k >= 0; --k) {
         fill_launch(&a, uint32_t(k), trav, 0);
         size_t smem = seg_kernel_smem_bytes(a.n_r, a.n_v, HP[trav], HP[1 - trav]);
+        if ((rc = prof_begin()) != RS_OK) return rc;
         CU(launch_segment_kernel(a, mode, threads, smem, stream));
+        const uint64_t vec = uint64_t(rd[k].n_segs) * rd[k].n_boards * (P.H[trav] + (k > 0 ? P.H[1 - trav] : 0)) * 4 +
+                             uint64_t(rd[k].n_leaves) * rd[k].n_boards * P.H[trav] * 4;
+        if ((rc = prof_end(RS_KERNEL_SEGMENT_UP, uint32_t(k), trav, uint32_t(a.n_boards) * uint32_t(a.n_segs),
+                           table_bytes_of(uint32_t(k), trav), vec)) != RS_OK)
+            return rc;
         ++*count;
         if (k > 0) {
             const RoundDev& C = rd[k];
             RoundDev& Par = rd[k - 1];
             const bool sharded_here = (P.world > 1 && uint32_t(k) == P.shard_round);
             const int per_parent = sharded_here ? 0 : int(P.deal_count[k]);
+            if ((rc = prof_begin()) != RS_OK) return rc;
             CU(launch_gather(C.root_cfv.p, Par.gathered.p, int(Par.n_leaves), int(Par.n_boards), int(C.n_boards),
                              per_parent, int(P.H[trav]), stream));
+            if ((rc = prof_end(RS_KERNEL_GATHER, uint32_t(k), trav, 0, 0,
+                               (uint64_t(C.n_segs) * C.n_boards + uint64_t(Par.n_leaves) * Par.n_boards) * P.H[trav] * 4)) != RS_OK)
+                return rc;
             ++*count;
             if (sharded_here) {
                 // the one exchange step of the path: counterfactual values at the shared chance nodes
-                int rc = nccl::g_api.AllReduce(Par.gathered.p, Par.gathered.p, size_t(Par.n_leaves) * Par.n_boards * P.H[trav],
-                                               nccl::kFloat32, nccl::kSum, comm, stream);
-                if (rc != 0) return set_err(RS_ERR_NCCL, "ncclAllReduce failed");
+                if ((rc = prof_begin()) != RS_OK) return rc;
+                int nrc = nccl::g_api.AllReduce(Par.gathered.p, Par.gathered.p, size_t(Par.n_leaves) * Par.n_boards * P.H[trav],
+                                                nccl::kFloat32, nccl::kSum, comm, stream);
+                if (nrc != 0) return set_err(RS_ERR_NCCL, "ncclAllReduce failed");
+                if ((rc = prof_end(RS_KERNEL_ALLREDUCE, uint32_t(k), trav, 0, 0,
+                                   uint64_t(Par.n_leaves) * Par.n_boards * P.H[trav] * 4)) != RS_OK)
+                    return rc;
                 ++*count;
             }
         }
@@ -797,6 +862,44 @@ int rs_root_values(rs_engine* e, uint32_t player, float* out, size_t cap) {
     if (cap < n) return set_err(RS_ERR_CAPACITY, "output buffer too small");
     CU(cudaSetDevice(E.device));
     CU(cudaMemcpy(out, E.rd[0].root_cfv.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return RS_OK;
+}
+
+int rs_set_range_weights(rs_engine* e, uint32_t player, const float* weights, size_t n) {
+    if (!e || !weights || player > 1) return set_err(RS_ERR_INVALID, "bad argument");
+    Engine& E = e->e;
+    if (n != E.plan.H[player]) return set_err(RS_ERR_INVALID, "weights length must equal the range size");
+    CU(cudaSetDevice(E.device));
+    CU(cudaMemcpyAsync(E.root_weights[player].p, weights, n * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+    return RS_OK;
+}
+
+int rs_profile_iteration(rs_engine* e, rs_kernel_time* out, size_t cap, uint32_t* n_out) {
+    if (!e || !n_out) return set_err(RS_ERR_INVALID, "null argument");
+    Engine& E = e->e;
+    CU(cudaSetDevice(E.device));
+    std::vector<rs_kernel_time> rec;
+    E.prof = &rec;
+    uint64_t cnt = 0;
+    int rc = E.enqueue_iteration(&cnt);
+    E.prof = nullptr;
+    cudaError_t se = cudaStreamSynchronize(E.stream);
+    for (size_t i = 0; i < E.prof_events.size(); ++i) {
+        if (rc == RS_OK && se == cudaSuccess && i < rec.size())
+            cudaEventElapsedTime(&rec[i].ms, E.prof_events[i].first, E.prof_events[i].second);
+        cudaEventDestroy(E.prof_events[i].first);
+        cudaEventDestroy(E.prof_events[i].second);
+    }
+    E.prof_events.clear();
+    if (rc != RS_OK) return rc;
+    if (se != cudaSuccess) return set_err(RS_ERR_CUDA, cudaGetErrorString(se));
+    E.iterations += 1;
+    E.launches += cnt;
+    *n_out = uint32_t(rec.size());
+    if (out) {
+        if (cap < rec.size()) return set_err(RS_ERR_CAPACITY, "output buffer too small");
+        memcpy(out, rec.data(), rec.size() * sizeof(rs_kernel_time));
+    }
     return RS_OK;
 }
 

@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(512) segment_kernel(const __grid_constant__ Se
             case OP_LOAD_ROOT: {
                 float* dst = S.R + r_dst * HoP;
                 if (A.parent_reach == nullptr) {
-                    for (int h = tid; h < Ho; h += T) dst[h] = (row_o[h] != 0xFFFF) ? 1.0f : 0.0f;
+                    const float* __restrict__ w = A.root_weights[o];
+                    for (int h = tid; h < Ho; h += T) dst[h] = (row_o[h] != 0xFFFF) ? w[h] : 0.0f;
                 } else {
                     const float* src = A.parent_reach + (size_t(s) * A.n_boards_parent + A.parent_board[b]) * Ho;
                     for (int h = tid; h < Ho; h += T) dst[h] = (row_o[h] != 0xFFFF) ? src[h] : 0.0f;  // dealt card removes hands

@@ -60,6 +60,7 @@ struct SegLaunch {
     const float* chance_scale;    // [n_boards]
     const int32_t* parent_board;  // [n_boards] local id in the parent round
     const float* parent_reach;    // [n_segs][n_boards_parent][H_opp] or null at the root round
+    const float* root_weights[2]; // [H] per player: range weights at the root round
     float* leaf_reach;            // [n_leaves][n_boards][H_opp]
     float* root_cfv;              // [n_segs][n_boards][H_trav]
     const float* gathered;        // [n_leaves][n_boards][H_trav]

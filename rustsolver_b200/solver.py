@@ -464,6 +464,21 @@ class Engine(_PlanOrEngine):
         check(self._lib.rs_current_strategy(self._h, an_index, board_id, _ptr(out, f32p), out.size, None, None))
         return out
 
+    def set_range_weights(self, player: int, weights: np.ndarray):
+        """Per-hand reach weights of `player`'s range (host buffer -> device, async on the engine stream)."""
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        check(self._lib.rs_set_range_weights(self._h, player, _ptr(w, f32p), w.size))
+
+    def profile_iteration(self):
+        """One real iteration launched kernel by kernel with CUDA events -> list of dicts."""
+        cap = 64
+        buf = (_lib.rs_kernel_time * cap)()
+        n = C.c_uint32()
+        check(self._lib.rs_profile_iteration(self._h, buf, cap, C.byref(n)))
+        kinds = {0: "segment_down", 1: "segment_up", 2: "gather", 3: "allreduce"}
+        return [dict(kind=kinds[buf[i].kind], round_idx=buf[i].round_idx, traverser=buf[i].traverser, grid=buf[i].grid,
+                     ms=buf[i].ms, table_bytes=buf[i].table_bytes, vector_bytes=buf[i].vector_bytes) for i in range(n.value)]
+
     def best_response(self):
         out = (C.c_double * 2)()
         check(self._lib.rs_best_response(self._h, out))
