@@ -191,7 +191,7 @@ def run_ours(args):
     w, tree, ranges = build_workload(args.workload)
     t0 = time.perf_counter()
     eng = rb.Engine(tree, ranges, w.options.board_mask, w.card_abs, board_masks=w.board_masks, device=local_rank,
-                    rank=rank, world_size=world, nccl_id=nccl_id, threads_per_block=args.threads)
+                    rank=rank, world_size=world, nccl_id=nccl_id)
     create_s = time.perf_counter() - t0
     st = eng.stats()
     upd_global = int(st.updates_per_iteration_global)
@@ -276,15 +276,15 @@ def run_ours(args):
     for _ in range(3):
         flush_l2()
         prof_runs.append(eng.profile_iteration())
-    last_round = st.n_rounds - 1
-    dom = [[k for k in run if k["kind"] == "segment_up" and k["round_idx"] == last_round] for run in prof_runs]
+    dom = [[k for k in run if k["kind"] == "traversal" and k["phase"] == 0] for run in prof_runs]
     dom_ms = float(np.mean([k["ms"] for run in dom for k in run]))
     dom_bytes = float(np.mean([k["table_bytes"] for run in dom for k in run]))
+    dom_vec = float(np.mean([k["vector_bytes"] for run in dom for k in run]))
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     total_ms = float(np.mean([sum(k["ms"] for k in run) for run in prof_runs]))
     shares = {}
     for k in prof_runs[-1]:
-        key = f'{k["kind"]}_r{k["round_idx"]}'
+        key = f'{k["kind"]}_p{k["traverser"]}_phase{k["phase"]}'
         shares[key] = shares.get(key, 0.0) + k["ms"]
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
@@ -295,9 +295,10 @@ def run_ours(args):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": f"segment_kernel<CFR> up pass, round_idx {last_round} (mean of both traversers)",
+                "kernel": "task_kernel<CFR>: persistent dataflow kernel, one launch = one player's traversal of the whole tree (mean of both players)",
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
-                "kernel_share_of_iteration": (2 * dom_ms) / total_ms if total_ms > 0 else None,
+                "l2_vector_bytes_per_launch": dom_vec,
+                "kernel_share_of_iteration": sum(k["ms"] for k in dom[-1]) / sum(k["ms"] for k in prof_runs[-1]),
                 "per_kernel_ms": {k: round(v, 5) for k, v in shares.items()},
                 "whole_iteration_frac": (upd_global * BYTES_PER_UPDATE / world) / (ms_per_step * 1e-3) / 1e9 / peak}
 
@@ -318,7 +319,7 @@ def run_ours(args):
                        "table_bytes_per_gpu": int(st.table_bytes),
                        "parallelism": "single GPU" if world == 1 else f"river boards sharded over {world} GPUs + NCCL all-reduce at the chance nodes",
                        "l2": "flushed between timed steps (256 MiB device write); each step timed by CUDA events on the launch stream",
-                       "threads_per_block": args.threads or 512},
+                       "threads_per_block": 256},
             "updates_per_sec": value * upd_global,
             "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -188,13 +188,11 @@ int rs_set_range_weights(rs_engine* e, uint32_t player, const float* weights, si
 
 /* Kernel-level profile of ONE iteration launched kernel by kernel (no graph) with a CUDA event pair
  * around every launch on the engine's stream.  The iteration is a real one (tables are updated). */
-#define RS_KERNEL_SEGMENT_DOWN 0
-#define RS_KERNEL_SEGMENT_UP 1
-#define RS_KERNEL_GATHER 2
+#define RS_KERNEL_TRAVERSAL 0 /* persistent task kernel: one traversal (or one phase of it when sharded) */
 #define RS_KERNEL_ALLREDUCE 3
 typedef struct rs_kernel_time {
     uint32_t kind;      /* RS_KERNEL_* */
-    uint32_t round_idx;
+    uint32_t phase;     /* 0, or 1 for the part of a sharded traversal after the all-reduce */
     uint32_t traverser;
     uint32_t grid;      /* CTAs launched */
     float ms;           /* CUDA-event duration */

@@ -6,7 +6,7 @@ import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libb200cfr.so"
+LIB_PATH = Path(os.environ.get("RS_ENGINE_LIB", str(_HERE / "libb200cfr.so")))
 
 u8p = C.POINTER(C.c_uint8)
 u16p = C.POINTER(C.c_uint16)
@@ -54,7 +54,7 @@ class rs_stats(C.Structure):
 
 
 class rs_kernel_time(C.Structure):
-    _fields_ = [("kind", C.c_uint32), ("round_idx", C.c_uint32), ("traverser", C.c_uint32), ("grid", C.c_uint32),
+    _fields_ = [("kind", C.c_uint32), ("phase", C.c_uint32), ("traverser", C.c_uint32), ("grid", C.c_uint32),
                 ("ms", C.c_float), ("table_bytes", C.c_uint64), ("vector_bytes", C.c_uint64)]
 
 

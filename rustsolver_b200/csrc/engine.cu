@@ -114,14 +114,9 @@ struct RoundDev {
     DevBuf<float> regrets[2], ssum[2];
     DevBuf<float> chance_scale;
     DevBuf<int32_t> parent_board;
-    // programs, per traverser: [0] up, [1] down
-    DevBuf<Op> ops[2][2];
-    DevBuf<uint32_t> prog_start[2][2];
-    int n_r[2][2] = {{0, 0}, {0, 0}}, n_v[2][2] = {{0, 0}, {0, 0}};
-    bool has_down = false;
-    // transients
-    DevBuf<float> leaf_reach, root_cfv, gathered;
-    uint32_t n_segs = 0, n_leaves = 0, n_boards = 0;
+    // transients of one traversal (shared by both traversers, sized for the larger)
+    DevBuf<float> rbuf, cbuf, gathered;
+    uint32_t n_leaves = 0, n_boards = 0;
 };
 
 struct Engine {
@@ -144,6 +139,12 @@ struct Engine {
     DevBuf<uint8_t> sd_cj[2], sd_ncard[2], sd_cpos[2];
     DevBuf<float> scratch;  // strategy read-outs
     DevBuf<float> root_weights[2];
+    DevBuf<NodeTask> tasks[2];
+    DevBuf<uint32_t> flags;
+    DevBuf<TaskCtl> ctl;
+    int slots = 1;
+    size_t smem_bytes = 0;
+    int blocks_per_sm = 1, n_sms = 148;
     // profiling: when non-null, enqueue_traversal brackets every launch with an event pair
     std::vector<rs_kernel_time>* prof = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -155,7 +156,6 @@ struct Engine {
     uint64_t table_bytes = 0;
     uint64_t updates_global = 0;
     uint64_t discount_interval = 0, discount_cap = 0;
-    size_t max_smem = 0;
 
     ~Engine() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -167,14 +167,14 @@ struct Engine {
     }
 
     int init(const rs_config* cfg);
-    int fill_launch(SegLaunch* a, uint32_t k, int trav, int down) const;
+    void fill_args(TaskArgs* a, int trav) const;
     int enqueue_traversal(int trav, int mode, uint64_t* count);
     int enqueue_iteration(uint64_t* count);
     int iterate(uint64_t n);
     int root_sum(int player, double* out);
     int prof_begin();
     int prof_end(uint32_t kind, uint32_t k, int trav, uint32_t grid, uint64_t table_bytes, uint64_t vector_bytes);
-    uint64_t table_bytes_of(uint32_t k, int trav) const;
+    uint64_t table_bytes_of(int trav, int phase) const;
 };
 
 template <class T>
@@ -195,8 +195,9 @@ int Engine::init(const rs_config* cfg) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return set_err(RS_ERR_UNSUPPORTED, "kernels are built for sm_100a only; found an older device");
-    threads = cfg->threads_per_block ? int(cfg->threads_per_block) : 512;
-    if (threads < 64 || threads > 512 || (threads & 31)) return set_err(RS_ERR_INVALID, "threads_per_block must be a multiple of 32 in 64..512");
+    threads = TASK_THREADS;
+    if (cfg->threads_per_block && cfg->threads_per_block != uint32_t(TASK_THREADS))
+        return set_err(RS_ERR_INVALID, "threads_per_block: this build runs " + std::to_string(TASK_THREADS) + " threads per CTA");
     use_graph = !(cfg->flags & RS_FLAG_NO_GRAPH);
     discount_interval = cfg->discount_interval;
     discount_cap = cfg->discount_cap;
@@ -212,13 +213,12 @@ int Engine::init(const rs_config* cfg) {
         CU(same[q].upload(P.same[q]));
         CU(card_hands[q].upload(P.card_hands[q]));
     }
-    size_t smem_need = 0;
     const int HP[2] = {int((P.H[0] + 3) & ~3u), int((P.H[1] + 3) & ~3u)};
+    const size_t maxH = std::max(P.H[0], P.H[1]);
     for (uint32_t k = 0; k < P.n_rounds; ++k) {
         RoundDev& R = rd[k];
         const uint32_t lo = P.local_lo[k], hi = P.local_hi[k], nb = hi - lo;
         R.n_boards = nb;
-        R.n_segs = uint32_t(P.segs[k].size());
         R.n_leaves = (k + 1 < P.n_rounds) ? uint32_t(P.segs[k + 1].size()) : 0;
         for (int q = 0; q < 2; ++q) {
             const RoundPlayerTables& T = P.tabs[k][q];
@@ -238,43 +238,31 @@ int Engine::init(const rs_config* cfg) {
         CU(R.chance_scale.upload(slice(P.chance_scale[k], lo, hi, 1)));
         std::vector<int32_t> pb(nb, -1);
         if (k > 0)
-            for (uint32_t b = 0; b < nb; ++b) {
-                int32_t g = P.board_parent[k][lo + b];
-                // the replicated root board of a sharded single subgame has local id 0
-                pb[b] = g - int32_t(P.local_lo[k - 1]);
-            }
+            for (uint32_t b = 0; b < nb; ++b) pb[b] = P.board_parent[k][lo + b] - int32_t(P.local_lo[k - 1]);
         CU(R.parent_board.upload(pb));
-        for (int p = 0; p < 2; ++p)
-            for (int down = 0; down < 2; ++down) {
-                std::vector<Op> all;
-                std::vector<uint32_t> start;
-                int nr = 1, nv = 1;
-                for (const Segment& sg : P.segs[k]) {
-                    const Program& pr = down ? sg.down[p] : sg.up[p];
-                    start.push_back(uint32_t(all.size()));
-                    if (pr.ops.empty()) {
-                        Op end{};
-                        end.type = OP_END;
-                        all.push_back(end);
-                    } else {
-                        all.insert(all.end(), pr.ops.begin(), pr.ops.end());
-                        if (down) R.has_down = true;
-                    }
-                    nr = std::max(nr, int(pr.n_r));
-                    nv = std::max(nv, int(pr.n_v));
-                }
-                CU(R.ops[p][down].upload(all));
-                CU(R.prog_start[p][down].upload(start));
-                R.n_r[p][down] = nr;
-                R.n_v[p][down] = down ? 0 : nv;
-                smem_need = std::max(smem_need, seg_kernel_smem_bytes(nr, down ? 0 : nv, HP[p], HP[1 - p]));
-            }
-        const size_t maxH = std::max(P.H[0], P.H[1]);
-        CU(R.leaf_reach.alloc(size_t(R.n_leaves) * nb * maxH));
-        CU(R.root_cfv.alloc(size_t(R.n_segs) * nb * maxH));
+        const size_t n_r = std::max(P.tl[0].n_rbuf[k], P.tl[1].n_rbuf[k]);
+        const size_t n_c = std::max(P.tl[0].n_cbuf[k], P.tl[1].n_cbuf[k]);
+        CU(R.rbuf.alloc(n_r * nb * maxH));
+        CU(R.cbuf.alloc(n_c * nb * maxH));
         CU(R.gathered.alloc(size_t(R.n_leaves) * nb * maxH));
         CU(R.gathered.zero());
     }
+    uint32_t max_tickets = 0;
+    for (int p = 0; p < 2; ++p) {
+        CU(tasks[p].upload(P.tl[p].tasks));
+        max_tickets = std::max(max_tickets, P.tl[p].n_tickets);
+        slots = std::max(slots, int(std::max(P.tl[p].max_terminal, 1 + P.tl[p].max_children)));
+    }
+    CU(flags.alloc(max_tickets));
+    CU(flags.zero());
+    {
+        TaskCtl c0;
+        c0.ticket = 0;
+        c0.exited = 0;
+        c0.epoch = 1;  // flags start at 0 = "never completed"
+        CU(ctl.upload(&c0, 1));
+    }
+    size_t smem_need = std::max(task_kernel_smem_bytes(slots, HP[0], HP[1]), task_kernel_smem_bytes(slots, HP[1], HP[0]));
     // showdown tables live on the final round's local boards
     {
         const uint32_t k = P.n_rounds - 1;
@@ -293,10 +281,12 @@ int Engine::init(const rs_config* cfg) {
     int max_optin = 0;
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (smem_need > size_t(max_optin))
-        return set_err(RS_ERR_UNSUPPORTED, "betting tree too deep/wide for one CTA's shared memory: need " +
+        return set_err(RS_ERR_UNSUPPORTED, "node too wide for one CTA's shared memory: need " +
                                                std::to_string(smem_need) + " B, device allows " + std::to_string(max_optin));
-    max_smem = smem_need;
-    CU(configure_segment_kernels(smem_need));
+    smem_bytes = smem_need;
+    CU(configure_task_kernels(smem_need, &blocks_per_sm));
+    if (blocks_per_sm < 1) return set_err(RS_ERR_UNSUPPORTED, "task kernel does not fit on an SM");
+    n_sms = prop.multiProcessorCount;
     CU(scratch.alloc(size_t(1326) * MAX_ACTIONS));
 
     updates_global = P.updates_per_iter_local;
@@ -330,9 +320,8 @@ int Engine::init(const rs_config* cfg) {
     return RS_OK;
 }
 
-int Engine::fill_launch(SegLaunch* a, uint32_t k, int trav, int down) const {
+void Engine::fill_args(TaskArgs* a, int trav) const {
     const Plan& P = plan;
-    const RoundDev& R = rd[k];
     memset(a, 0, sizeof(*a));
     for (int q = 0; q < 2; ++q) {
         a->pl[q].cards = cards[q].p;
@@ -340,39 +329,44 @@ int Engine::fill_launch(SegLaunch* a, uint32_t k, int trav, int down) const {
         a->pl[q].card_hands = card_hands[q].p;
         a->pl[q].H = int(P.H[q]);
         a->pl[q].Hpad = int((P.H[q] + 3) & ~3u);
-        a->rp[q].row_of_hand = R.row_of_hand[q].p;
-        a->rp[q].row_start = R.row_start[q].p;
-        a->rp[q].row_hands = R.row_hands[q].p;
-        a->rp[q].n_rows = R.n_rows[q].p;
-        a->rp[q].board_off = R.board_off[q].p;
-        a->rp[q].regrets = R.regrets[q].p;
-        a->rp[q].ssum = R.ssum[q].p;
-        if (k == P.n_rounds - 1) {
-            a->sd[q].sorted = sd_sorted[q].p;
-            a->sd[q].n_live = sd_nlive[q].p;
-            a->sd[q].cj = sd_cj[q].p;
-            a->sd[q].n_card = sd_ncard[q].p;
-            a->sd[q].lohi = sd_lohi[q].p;
-            a->sd[q].cpos = sd_cpos[q].p;
+        a->sd[q].sorted = sd_sorted[q].p;
+        a->sd[q].n_live = sd_nlive[q].p;
+        a->sd[q].cj = sd_cj[q].p;
+        a->sd[q].n_card = sd_ncard[q].p;
+        a->sd[q].lohi = sd_lohi[q].p;
+        a->sd[q].cpos = sd_cpos[q].p;
+        a->root_weights[q] = root_weights[q].p;
+    }
+    for (uint32_t k = 0; k < P.n_rounds; ++k) {
+        const RoundDev& R = rd[k];
+        RoundArgs& ra = a->rounds[k];
+        for (int q = 0; q < 2; ++q) {
+            ra.rp[q].row_of_hand = R.row_of_hand[q].p;
+            ra.rp[q].row_start = R.row_start[q].p;
+            ra.rp[q].row_hands = R.row_hands[q].p;
+            ra.rp[q].n_rows = R.n_rows[q].p;
+            ra.rp[q].board_off = R.board_off[q].p;
+            ra.rp[q].regrets = R.regrets[q].p;
+            ra.rp[q].ssum = R.ssum[q].p;
+        }
+        ra.chance_scale = R.chance_scale.p;
+        ra.parent_board = R.parent_board.p;
+        ra.rbuf = R.rbuf.p;
+        ra.cbuf = R.cbuf.p;
+        ra.gathered = R.gathered.p;
+        ra.n_boards = int(R.n_boards);
+        if (k + 1 < P.n_rounds) {
+            const bool sharded_next = (P.world > 1 && k + 1 == P.shard_round);
+            ra.per_parent = sharded_next ? 0 : int(P.deal_count[k + 1]);
+            ra.n_boards_next = int(rd[k + 1].n_boards);
         }
     }
-    a->ops = R.ops[trav][down].p;
-    a->prog_start = R.prog_start[trav][down].p;
-    a->chance_scale = R.chance_scale.p;
-    a->parent_board = R.parent_board.p;
-    a->parent_reach = k > 0 ? rd[k - 1].leaf_reach.p : nullptr;
-    a->root_weights[0] = root_weights[0].p;
-    a->root_weights[1] = root_weights[1].p;
-    a->leaf_reach = R.leaf_reach.p;
-    a->root_cfv = R.root_cfv.p;
-    a->gathered = R.gathered.p;
-    a->n_boards = int(R.n_boards);
-    a->n_boards_parent = k > 0 ? int(rd[k - 1].n_boards) : 0;
-    a->n_segs = int(R.n_segs);
+    a->tasks = tasks[trav].p;
+    a->n_tasks = uint32_t(P.tl[trav].tasks.size());
+    a->flags = flags.p;
+    a->ctl = ctl.p;
     a->trav = trav;
-    a->n_r = R.n_r[trav][down];
-    a->n_v = R.n_v[trav][down];
-    return RS_OK;
+    a->slots = slots;
 }
 
 int Engine::prof_begin() {
@@ -385,13 +379,13 @@ int Engine::prof_begin() {
     return RS_OK;
 }
 
-int Engine::prof_end(uint32_t kind, uint32_t k, int trav, uint32_t grid, uint64_t tb, uint64_t vb) {
+int Engine::prof_end(uint32_t kind, uint32_t phase, int trav, uint32_t grid, uint64_t tb, uint64_t vb) {
     if (!prof) return RS_OK;
     CU(cudaEventRecord(prof_events.back().second, stream));
     rs_kernel_time t;
     memset(&t, 0, sizeof(t));
     t.kind = kind;
-    t.round_idx = k;
+    t.phase = phase;
     t.traverser = uint32_t(trav);
     t.grid = grid;
     t.table_bytes = tb;
@@ -400,68 +394,52 @@ int Engine::prof_end(uint32_t kind, uint32_t k, int trav, uint32_t grid, uint64_
     return RS_OK;
 }
 
-// algorithmic infoset-table bytes of one up-pass launch on round k for traverser `trav`:
-// traverser cells: regret R+W, strategy_sum R+W = 16 B; opponent cells: regret read = 4 B
-uint64_t Engine::table_bytes_of(uint32_t k, int trav) const {
+// algorithmic infoset-table bytes of one traversal launch: traverser cells regret R+W and strategy_sum
+// R+W = 16 B, opponent cells regret read = 4 B.  Phase 1 of a sharded traversal only updates the
+// traverser's tables of the replicated rounds above the shard level.
+uint64_t Engine::table_bytes_of(int trav, int phase) const {
     const Plan& P = plan;
-    const uint64_t own = P.tabs[k][trav].board_off[P.n_boards[k]];
-    const uint64_t opp = P.tabs[k][1 - trav].board_off[P.n_boards[k]];
-    return own * 16 + opp * 4;
+    uint64_t bytes = 0;
+    const bool split = P.tl[trav].phase_cut < P.tl[trav].n_tickets;
+    for (uint32_t k = 0; k < P.n_rounds; ++k) {
+        const uint64_t own = P.tabs[k][trav].board_off[P.n_boards[k]];
+        const uint64_t opp = P.tabs[k][1 - trav].board_off[P.n_boards[k]];
+        const bool above = split && k < P.shard_round;
+        if (phase == 0) bytes += opp * 4 + (above ? 0 : own * 16);
+        else bytes += above ? own * 16 : 0;
+    }
+    return bytes;
 }
 
 int Engine::enqueue_traversal(int trav, int mode, uint64_t* count) {
     const Plan& P = plan;
-    const int HP[2] = {int((P.H[0] + 3) & ~3u), int((P.H[1] + 3) & ~3u)};
-    SegLaunch a;
+    const TaskList& tl = P.tl[trav];
+    TaskArgs a;
+    fill_args(&a, trav);
     int rc;
-    // down pass: reach at every chance leaf, street by street (cfr.rs:502-522 scatter)
-    for (uint32_t k = 0; k + 1 < P.n_rounds; ++k) {
-        if (!rd[k].has_down) continue;
-        fill_launch(&a, k, trav, 1);
-        size_t smem = seg_kernel_smem_bytes(a.n_r, a.n_v, HP[trav], HP[1 - trav]);
+    const uint32_t cuts[3] = {0, tl.phase_cut, tl.n_tickets};
+    for (int phase = 0; phase < 2; ++phase) {
+        a.t0 = cuts[phase];
+        a.t1 = cuts[phase + 1];
+        if (a.t1 <= a.t0) continue;
+        const int grid = int(std::min<uint64_t>(uint64_t(a.t1 - a.t0), uint64_t(n_sms) * blocks_per_sm));
         if ((rc = prof_begin()) != RS_OK) return rc;
-        CU(launch_segment_kernel(a, mode, threads, smem, stream));
-        const uint64_t opp_cells = P.tabs[k][1 - trav].board_off[P.n_boards[k]];
-        if ((rc = prof_end(RS_KERNEL_SEGMENT_DOWN, k, trav, uint32_t(a.n_boards) * uint32_t(a.n_segs), opp_cells * 4,
-                           uint64_t(rd[k].n_leaves) * rd[k].n_boards * P.H[1 - trav] * 4)) != RS_OK)
+        CU(launch_task_kernel(a, mode, grid, smem_bytes, stream));
+        uint64_t vec = 0;
+        for (uint32_t k = 0; k < P.n_rounds; ++k)
+            vec += (uint64_t(tl.n_rbuf[k]) * P.H[1 - trav] + uint64_t(tl.n_cbuf[k]) * P.H[trav]) * rd[k].n_boards * 8;
+        if ((rc = prof_end(RS_KERNEL_TRAVERSAL, uint32_t(phase), trav, uint32_t(grid), table_bytes_of(trav, phase), vec)) != RS_OK)
             return rc;
         ++*count;
-    }
-    // up pass: deepest street first, then gather over dealt cards into the parent street
-    for (int k = int(P.n_rounds) - 1; k >= 0; --k) {
-        fill_launch(&a, uint32_t(k), trav, 0);
-        size_t smem = seg_kernel_smem_bytes(a.n_r, a.n_v, HP[trav], HP[1 - trav]);
-        if ((rc = prof_begin()) != RS_OK) return rc;
-        CU(launch_segment_kernel(a, mode, threads, smem, stream));
-        const uint64_t vec = uint64_t(rd[k].n_segs) * rd[k].n_boards * (P.H[trav] + (k > 0 ? P.H[1 - trav] : 0)) * 4 +
-                             uint64_t(rd[k].n_leaves) * rd[k].n_boards * P.H[trav] * 4;
-        if ((rc = prof_end(RS_KERNEL_SEGMENT_UP, uint32_t(k), trav, uint32_t(a.n_boards) * uint32_t(a.n_segs),
-                           table_bytes_of(uint32_t(k), trav), vec)) != RS_OK)
-            return rc;
-        ++*count;
-        if (k > 0) {
-            const RoundDev& C = rd[k];
-            RoundDev& Par = rd[k - 1];
-            const bool sharded_here = (P.world > 1 && uint32_t(k) == P.shard_round);
-            const int per_parent = sharded_here ? 0 : int(P.deal_count[k]);
+        if (phase == 0 && tl.phase_cut < tl.n_tickets) {
+            // the one exchange step of the path: counterfactual values at the shared chance nodes
+            RoundDev& Par = rd[P.shard_round - 1];
             if ((rc = prof_begin()) != RS_OK) return rc;
-            CU(launch_gather(C.root_cfv.p, Par.gathered.p, int(Par.n_leaves), int(Par.n_boards), int(C.n_boards),
-                             per_parent, int(P.H[trav]), stream));
-            if ((rc = prof_end(RS_KERNEL_GATHER, uint32_t(k), trav, 0, 0,
-                               (uint64_t(C.n_segs) * C.n_boards + uint64_t(Par.n_leaves) * Par.n_boards) * P.H[trav] * 4)) != RS_OK)
-                return rc;
+            const size_t n = size_t(Par.n_leaves) * Par.n_boards * P.H[trav];
+            int nrc = nccl::g_api.AllReduce(Par.gathered.p, Par.gathered.p, n, nccl::kFloat32, nccl::kSum, comm, stream);
+            if (nrc != 0) return set_err(RS_ERR_NCCL, "ncclAllReduce failed");
+            if ((rc = prof_end(RS_KERNEL_ALLREDUCE, 0, trav, 0, 0, n * 4)) != RS_OK) return rc;
             ++*count;
-            if (sharded_here) {
-                // the one exchange step of the path: counterfactual values at the shared chance nodes
-                if ((rc = prof_begin()) != RS_OK) return rc;
-                int nrc = nccl::g_api.AllReduce(Par.gathered.p, Par.gathered.p, size_t(Par.n_leaves) * Par.n_boards * P.H[trav],
-                                                nccl::kFloat32, nccl::kSum, comm, stream);
-                if (nrc != 0) return set_err(RS_ERR_NCCL, "ncclAllReduce failed");
-                if ((rc = prof_end(RS_KERNEL_ALLREDUCE, uint32_t(k), trav, 0, 0,
-                                   uint64_t(Par.n_leaves) * Par.n_boards * P.H[trav] * 4)) != RS_OK)
-                    return rc;
-                ++*count;
-            }
         }
     }
     return RS_OK;
@@ -526,7 +504,8 @@ int Engine::root_sum(int player, double* out) {
     const Plan& P = plan;
     const RoundDev& R = rd[0];
     std::vector<float> v(size_t(R.n_boards) * P.H[player]);
-    CU(cudaMemcpy(v.data(), R.root_cfv.p, v.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(v.data(), R.cbuf.p + size_t(P.tl[player].root_cbuf) * R.n_boards * P.H[player], v.size() * sizeof(float),
+                  cudaMemcpyDeviceToHost));
     double s = 0;
     for (float x : v) s += x;
     *out = s;
@@ -861,7 +840,9 @@ int rs_root_values(rs_engine* e, uint32_t player, float* out, size_t cap) {
     const size_t n = size_t(E.rd[0].n_boards) * E.plan.H[player];
     if (cap < n) return set_err(RS_ERR_CAPACITY, "output buffer too small");
     CU(cudaSetDevice(E.device));
-    CU(cudaMemcpy(out, E.rd[0].root_cfv.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaStreamSynchronize(E.stream));
+    CU(cudaMemcpy(out, E.rd[0].cbuf.p + size_t(E.plan.tl[player].root_cbuf) * E.rd[0].n_boards * E.plan.H[player],
+                  n * sizeof(float), cudaMemcpyDeviceToHost));
     return RS_OK;
 }
 

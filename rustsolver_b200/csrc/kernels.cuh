@@ -1,9 +1,10 @@
-// Device side of the B200 CFR engine (sm_100a).
+// Device side of the B200 CFR engine (sm_100a): a persistent dataflow kernel over the task graph
+// of one traversal (tasks.h).  One CTA executes one (node-task, board) instance at a time with
+// its working vectors in shared memory; instances exchange opponent-reach and counterfactual-
+// value vectors through L2-resident global buffers and order themselves with release/acquire
+// flags, so every SM stays busy on independent boards/nodes and a whole traversal is ONE launch.
 //
-// One CTA = one (street segment, board): it interprets the segment's DFS program with every
-// transient vector (opponent reach, counterfactual-reach mass, counterfactual values) resident
-// in shared memory, so HBM traffic is the infoset tables themselves plus one reach vector in and
-// one value vector out per CTA.  Restates, in vector form:
+// Restates, in vector form:
 //   regret matching                Infoset::get_strategy          src/solver/infoset.rs:83-102
 //   average strategy               Infoset::get_final_strategy    src/solver/infoset.rs:104-123
 //   opponent reach propagation     cfr.rs:582-586
@@ -15,12 +16,16 @@
 #include <stdint.h>
 
 #include "plan.h"
+#include "tasks.h"
 
 namespace rs {
 
-constexpr int MAX_ACTIONS = 8;
-constexpr int CM_STRIDE = 53;  // per-card prefix row: entry 0 = 0, entries 1..n_c inclusive sums
-constexpr int MAX_SCAN_ITEMS = 8;
+constexpr int MAX_ACTIONS = MAX_TASK_CHILDREN;
+constexpr int CM_STRIDE = 53;   // per-card prefix row: entry 0 = 0, entries 1..n_c inclusive sums
+constexpr int TASK_THREADS = 256;
+constexpr int MAX_HPT = 6;      // hands per thread: ceil(1326 / 256)
+constexpr int HAND_CHUNK = 3;   // hands / rows whose loads are batched in registers
+constexpr int FAST_ACTIONS = 4; // nodes up to this many actions keep their table rows in registers
 
 enum KernelMode { KM_CFR = 0, KM_BR = 1, KM_EVAL = 2 };
 
@@ -51,35 +56,37 @@ struct DevShowdown {
     const uint8_t* cpos;     // [nb][H][4]
 };
 
-struct SegLaunch {
-    DevPlayer pl[2];
+struct RoundArgs {
     DevRoundPlayer rp[2];
-    DevShowdown sd[2];
-    const Op* ops;
-    const uint32_t* prog_start;   // [n_segs]
-    const float* chance_scale;    // [n_boards]
-    const int32_t* parent_board;  // [n_boards] local id in the parent round
-    const float* parent_reach;    // [n_segs][n_boards_parent][H_opp] or null at the root round
-    const float* root_weights[2]; // [H] per player: range weights at the root round
-    float* leaf_reach;            // [n_leaves][n_boards][H_opp]
-    float* root_cfv;              // [n_segs][n_boards][H_trav]
-    const float* gathered;        // [n_leaves][n_boards][H_trav]
+    const float* chance_scale;    // [nb]
+    const int32_t* parent_board;  // [nb] local id in the parent round
+    float* rbuf;                  // [n_rbuf][nb][H_opp]   opponent reach per buffer id
+    float* cbuf;                  // [n_cbuf][nb][H_trav]  counterfactual values per buffer id
+    float* gathered;              // [n_leaves][nb][H_trav]
     int n_boards;
-    int n_boards_parent;
-    int n_segs;
-    int trav;
-    int n_r;  // R/M slots provisioned in shared memory
-    int n_v;  // V slots
+    int per_parent;  // boards of the NEXT round per board of this one (0: every local next-round board hangs off board 0)
+    int n_boards_next;
+    int pad;
 };
 
-size_t seg_kernel_smem_bytes(int n_r, int n_v, int Hp_pad, int Ho_pad);
+struct TaskArgs {
+    DevPlayer pl[2];
+    DevShowdown sd[2];  // final round
+    RoundArgs rounds[3];
+    const NodeTask* tasks;
+    uint32_t n_tasks;
+    uint32_t* flags;  // [n_tickets] epoch of completion
+    TaskCtl* ctl;
+    const float* root_weights[2];
+    int trav;
+    uint32_t t0, t1;  // ticket range of this launch
+    int slots;        // H-sized scratch vectors provisioned in shared memory
+};
 
-cudaError_t launch_segment_kernel(const SegLaunch& a, int mode, int threads, size_t smem, cudaStream_t st);
-cudaError_t configure_segment_kernels(size_t max_smem);
+size_t task_kernel_smem_bytes(int slots, int Hp_pad, int Ho_pad);
+cudaError_t configure_task_kernels(size_t smem, int* blocks_per_sm);
+cudaError_t launch_task_kernel(const TaskArgs& a, int mode, int grid, size_t smem, cudaStream_t st);
 
-// gathered[l][pb][h] = sum over child boards cb in [start(pb), start(pb)+count) of root_cfv[l][cb][h]
-cudaError_t launch_gather(const float* root_cfv, float* gathered, int n_leaves, int n_parent, int n_child,
-                          int per_parent /* 0: every child board belongs to parent 0 */, int H, cudaStream_t st);
 cudaError_t launch_scale(float* data, size_t n, float d, cudaStream_t st);
 // out[row][a] = regret-matched strategy of in[row][0..A)
 cudaError_t launch_normalize(const float* in, float* out, uint32_t n_rows, uint32_t A, cudaStream_t st);

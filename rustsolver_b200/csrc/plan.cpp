@@ -1,6 +1,7 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <cstring>
 #include <functional>
 #include <numeric>
 #include <unordered_map>
@@ -126,15 +127,19 @@ struct Builder {
         P->segs[k].emplace_back();
         P->segs[k][sid].root = root;
         std::vector<int32_t> leaves;
-        std::function<void(int32_t)> walk = [&](int32_t id) {
+        std::function<void(int32_t, int)> walk = [&](int32_t id, int depth) {
             PNode& n = P->nodes[id];
+            n.depth = depth;
             if (n.kind == PK_CHANCE) {
                 leaves.push_back(id);
                 return;
             }
-            for (int32_t c : n.children) walk(c);
+            for (int32_t c : n.children) {
+                P->nodes[c].parent = id;
+                walk(c, depth + 1);
+            }
         };
-        walk(root);
+        walk(root, 0);
         P->segs[k][sid].leaves = leaves;
         for (int32_t leaf : leaves) {
             P->nodes[leaf].leaf_id = int32_t(P->segs[k + 1].size());
@@ -143,169 +148,302 @@ struct Builder {
     }
 };
 
-// ---- program generation -------------------------------------------------------------------
+// ---- task-graph generation (tasks.h) -----------------------------------------------------------
 
-struct ProgGen {
-    const Plan* P;
+struct TaskGen {
+    Plan* P;
     int trav;
-    bool down_only;
-    Program prog;
-    uint32_t r_top = 0, v_top = 0;
+    TaskList tl;
+    std::string err;
 
-    uint16_t alloc_r() {
-        uint16_t s = uint16_t(r_top++);
-        prog.n_r = std::max(prog.n_r, r_top);
-        return s;
-    }
-    uint16_t alloc_v(uint32_t n) {
-        uint16_t s = uint16_t(v_top);
-        v_top += n;
-        prog.n_v = std::max(prog.n_v, v_top);
-        return s;
-    }
+    struct RSrc {
+        int32_t buf = RIN_INITIAL;
+        uint8_t parent_round = 0;
+    };
+    std::vector<RSrc> rsrc;                 // per PNode: where its incoming opponent reach lives
+    std::vector<int32_t> cbuf, tbuf;        // per PNode: value buffer / terminal-partial buffer
+    std::vector<int32_t> down_task, up_task;  // per PNode: node-task index
+    std::vector<int32_t> rbuf_producer[3];  // reach buffer id -> node-task index writing it
+    std::vector<int32_t> leaf_rbuf[3];      // leaf id -> reach buffer (of the leaf's round) the child street reads
+    std::vector<int32_t> leaf_gather[3];    // leaf id -> node-task index of its gather
+    std::vector<int32_t> segroot_cbuf[3], segroot_task[3];
 
-    bool reaches_leaf(int32_t id) const {
-        const PNode& n = P->nodes[id];
-        if (n.kind == PK_CHANCE) return true;
-        for (int32_t c : n.children)
-            if (reaches_leaf(c)) return true;
-        return false;
+    struct Pending {
+        NodeTask t;
+        int32_t pnode;
+        int depth;
+    };
+
+    int32_t new_rbuf(uint32_t k) {
+        rbuf_producer[k].push_back(-1);
+        return int32_t(tl.n_rbuf[k]++);
     }
-    bool needs_m(int32_t id) const {  // does node `id` consume M of its incoming reach?
-        const PNode& n = P->nodes[id];
-        if (n.kind == PK_FOLD) return true;
-        if (n.kind == PK_ACTION && n.player == trav) {
-            // traverser node: strategy_sum weight, and children share the same reach
-            return true;
+    int32_t new_cbuf(uint32_t k) { return int32_t(tl.n_cbuf[k]++); }
+
+    static NodeTask blank(uint8_t kind, uint32_t k) {
+        NodeTask t;
+        std::memset(&t, 0, sizeof(t));
+        t.kind = kind;
+        t.round_k = uint8_t(k);
+        t.r_in = RIN_INITIAL;
+        t.out = -1;
+        t.aux = -1;
+        for (int i = 0; i < MAX_TASK_DEPS; ++i) t.dep[i] = -1;
+        return t;
+    }
+    bool add_dep(NodeTask& t, int32_t task, uint8_t kind) {
+        if (task < 0) return true;
+        if (t.n_dep >= MAX_TASK_DEPS) {
+            err = "too many dependencies for one task";
+            return false;
         }
-        return false;
+        t.dep[t.n_dep] = task;
+        t.dep_kind[t.n_dep] = kind;
+        t.n_dep++;
+        return true;
     }
-    // any descendant reachable without an opponent action that needs M of this reach
-    bool subtree_needs_m(int32_t id) const {
-        const PNode& n = P->nodes[id];
-        if (needs_m(id)) return true;
-        if (n.kind == PK_ACTION && n.player == trav) {
-            for (int32_t c : n.children)
-                if (subtree_needs_m(c)) return true;
+    bool add_rin_dep(NodeTask& t, const RSrc& r, uint32_t k) {
+        t.r_in = r.buf;
+        t.rin_parent_round = r.parent_round;
+        if (r.buf == RIN_INITIAL) return true;
+        if (r.parent_round) return add_dep(t, rbuf_producer[k - 1][r.buf], DK_PARENT_BOARD);
+        return add_dep(t, rbuf_producer[k][r.buf], DK_SAME_BOARD);
+    }
+    uint32_t emit(NodeTask t) {
+        t.first = tl.n_tickets;
+        t.count = P->boards_local(t.round_k);
+        tl.n_tickets += t.count;
+        tl.tasks.push_back(t);
+        return uint32_t(tl.tasks.size() - 1);
+    }
+
+    // assign reach sources + value buffers for one street segment (DFS), collect its nodes
+    void assign(uint32_t k, int32_t id, const RSrc& r, std::vector<int32_t>& order) {
+        PNode& n = P->nodes[id];
+        rsrc[id] = r;
+        order.push_back(id);
+        if (n.kind != PK_ACTION) return;
+        cbuf[id] = new_cbuf(k);
+        const bool opp = (n.player != trav);
+        bool has_term = false;
+        for (int32_t c : n.children) {
+            const PNode& cn = P->nodes[c];
+            if (cn.kind == PK_FOLD || cn.kind == PK_SHOWDOWN) {
+                has_term = true;
+                rsrc[c] = r;  // unused for opp parents (staged in shared memory)
+                continue;
+            }
+            RSrc cr = r;
+            if (opp) {
+                cr.buf = new_rbuf(k);
+                cr.parent_round = 0;
+            }
+            assign(k, c, cr, order);
         }
-        return false;
+        if (opp && has_term) tbuf[id] = new_cbuf(k);
     }
 
-    void emit(const Op& op) { prog.ops.push_back(op); }
-
-    void gen(int32_t id, uint16_t r, uint16_t out, bool acc) {
-        const PNode& n = P->nodes[id];
-        Op op{};
-        op.flags = acc ? OPF_ACC : 0;
-        switch (n.kind) {
-            case PK_FOLD: {
-                if (down_only) return;
-                op.type = OP_FOLD;
-                op.r_src = r;
-                op.v_out = out;
-                // cfr.rs:525-531: -value if player == last_to_act else +value
-                op.coef = (trav == n.last_to_act) ? -float(n.value) : float(n.value);
-                emit(op);
-                return;
+    bool run() {
+        const size_t N = P->nodes.size();
+        rsrc.assign(N, RSrc());
+        cbuf.assign(N, -1);
+        tbuf.assign(N, -1);
+        down_task.assign(N, -1);
+        up_task.assign(N, -1);
+        const uint32_t R = P->n_rounds;
+        std::vector<std::vector<int32_t>> seg_nodes[3];
+        for (uint32_t k = 0; k < R; ++k) {
+            leaf_rbuf[k].assign(k + 1 < R ? P->segs[k + 1].size() : 0, -1);
+            leaf_gather[k].assign(leaf_rbuf[k].size(), -1);
+            segroot_cbuf[k].assign(P->segs[k].size(), -1);
+            segroot_task[k].assign(P->segs[k].size(), -1);
+        }
+        // ---------------- down tasks, street by street ----------------
+        for (uint32_t k = 0; k < R; ++k) {
+            std::vector<Pending> pend;
+            seg_nodes[k].resize(P->segs[k].size());
+            for (uint32_t s = 0; s < P->segs[k].size(); ++s) {
+                RSrc root;
+                if (k > 0) {
+                    root.buf = leaf_rbuf[k - 1][s];
+                    root.parent_round = 1;
+                    if (root.buf < 0) {
+                        err = "internal: chance leaf without a reach buffer";
+                        return false;
+                    }
+                }
+                const int32_t rootid = P->segs[k][s].root;
+                assign(k, rootid, root, seg_nodes[k][s]);
+                if (P->nodes[rootid].kind != PK_ACTION) cbuf[rootid] = new_cbuf(k);
+                segroot_cbuf[k][s] = cbuf[rootid];
             }
-            case PK_SHOWDOWN: {
-                if (down_only) return;
-                op.type = OP_SHOWDOWN;
-                op.r_src = r;
-                op.v_out = out;
-                op.coef = float(n.value);  // cfr.rs:532-543
-                emit(op);
-                prog.has_showdown = true;
-                return;
-            }
-            case PK_CHANCE: {
-                op.leaf = uint32_t(n.leaf_id);
-                if (down_only) {
-                    op.type = OP_LEAF_DOWN;
-                    op.r_src = r;
+            // chance leaves whose inherited source is not a buffer of this round get a copy task
+            for (uint32_t s = 0; s < P->segs[k].size(); ++s)
+                for (int32_t id : seg_nodes[k][s]) {
+                    PNode& n = P->nodes[id];
+                    if (n.kind == PK_CHANCE) {
+                        RSrc r = rsrc[id];
+                        if (r.parent_round || r.buf == RIN_INITIAL) {
+                            NodeTask t = blank(TK_CHANCE_DOWN, k);
+                            RSrc keep = r;
+                            const int32_t nb = new_rbuf(k);
+                            t.aux = nb;
+                            // dependency is added at emission (producer index known by then for parent rounds)
+                            pend.push_back({t, id, n.depth});
+                            rsrc[id].buf = nb;
+                            rsrc[id].parent_round = 0;
+                            // stash the original source in the task
+                            pend.back().t.r_in = keep.buf;
+                            pend.back().t.rin_parent_round = keep.parent_round;
+                        }
+                        leaf_rbuf[k][n.leaf_id] = rsrc[id].buf;
+                    } else if (n.kind == PK_ACTION && n.player != trav) {
+                        NodeTask t = blank(TK_DOWN, k);
+                        t.n_act = uint8_t(n.children.size());
+                        t.cum_a = n.cum_a;
+                        t.an_index = n.an_index;
+                        t.out = tbuf[id];
+                        uint32_t nterm = 0;
+                        for (size_t a = 0; a < n.children.size(); ++a) {
+                            const int32_t c = n.children[a];
+                            const PNode& cn = P->nodes[c];
+                            TaskChild& tc = t.child[a];
+                            tc.buf = -1;
+                            if (cn.kind == PK_FOLD) {
+                                tc.kind = CK_FOLD;
+                                tc.coef = (trav == cn.last_to_act) ? -float(cn.value) : float(cn.value);  // cfr.rs:525-531
+                                nterm++;
+                            } else if (cn.kind == PK_SHOWDOWN) {
+                                tc.kind = CK_SHOWDOWN;
+                                tc.coef = float(cn.value);  // cfr.rs:532-543
+                                nterm++;
+                            } else {
+                                tc.kind = cn.kind == PK_CHANCE ? CK_CHANCE : CK_ACTION;
+                                tc.buf = rsrc[c].buf;
+                            }
+                        }
+                        tl.max_terminal = std::max(tl.max_terminal, nterm);
+                        pend.push_back({t, id, n.depth});
+                    }
+                }
+            std::stable_sort(pend.begin(), pend.end(), [](const Pending& a, const Pending& b) { return a.depth < b.depth; });
+            for (Pending& pe : pend) {
+                NodeTask t = pe.t;
+                if (t.kind == TK_CHANCE_DOWN) {
+                    RSrc src;
+                    src.buf = t.r_in;
+                    src.parent_round = t.rin_parent_round;
+                    if (!add_rin_dep(t, src, k)) return false;
+                    const uint32_t ti = emit(t);
+                    rbuf_producer[k][t.aux] = int32_t(ti);
+                    down_task[pe.pnode] = int32_t(ti);
                 } else {
-                    op.type = OP_LEAF_UP;
-                    op.v_out = out;
+                    if (!add_rin_dep(t, rsrc[pe.pnode], k)) return false;
+                    const uint32_t ti = emit(t);
+                    down_task[pe.pnode] = int32_t(ti);
+                    for (int a = 0; a < t.n_act; ++a)
+                        if (t.child[a].buf >= 0) rbuf_producer[k][t.child[a].buf] = int32_t(ti);
                 }
-                emit(op);
-                return;
             }
-            default: break;
         }
-        // action node
-        uint8_t A = uint8_t(n.children.size());
-        if (n.player != trav) {
-            for (uint8_t a = 0; a < A; ++a) {
-                int32_t c = n.children[a];
-                if (down_only && !reaches_leaf(c)) continue;
-                uint16_t r2 = alloc_r();
-                Op o{};
-                o.type = OP_OPP_REACH;
-                o.a = a;
-                o.n_act = A;
-                o.r_src = r;
-                o.r_dst = r2;
-                o.cum_a = n.cum_a;
-                o.an_index = n.an_index;
-                emit(o);
-                if (!down_only && subtree_needs_m(c)) {
-                    Op m{};
-                    m.type = OP_CALC_M;
-                    m.r_dst = r2;
-                    emit(m);
+        // ---------------- up tasks, deepest street first ----------------
+        tl.phase_cut = 0;
+        for (int k = int(R) - 1; k >= 0; --k) {
+            std::vector<Pending> pend;
+            for (uint32_t s = 0; s < P->segs[k].size(); ++s)
+                for (int32_t id : seg_nodes[k][s]) {
+                    PNode& n = P->nodes[id];
+                    const bool is_root = (id == P->segs[k][s].root);
+                    if (n.kind == PK_SHOWDOWN && is_root) {
+                        NodeTask t = blank(TK_ROOT_SHOWDOWN, uint32_t(k));
+                        t.out = cbuf[id];
+                        t.child[0].kind = CK_SHOWDOWN;
+                        t.child[0].coef = float(n.value);
+                        pend.push_back({t, id, n.depth});
+                    } else if (n.kind == PK_CHANCE && is_root) {
+                        NodeTask t = blank(TK_CHANCE_UP, uint32_t(k));
+                        t.out = cbuf[id];
+                        t.aux = n.leaf_id;
+                        pend.push_back({t, id, n.depth});
+                    } else if (n.kind == PK_ACTION) {
+                        const bool opp = (n.player != trav);
+                        NodeTask t = blank(opp ? TK_UP_OPP : TK_UP_TRAV, uint32_t(k));
+                        t.n_act = uint8_t(n.children.size());
+                        t.cum_a = n.cum_a;
+                        t.an_index = n.an_index;
+                        t.out = cbuf[id];
+                        t.aux = opp ? tbuf[id] : -1;
+                        for (size_t a = 0; a < n.children.size(); ++a) {
+                            const int32_t c = n.children[a];
+                            const PNode& cn = P->nodes[c];
+                            TaskChild& tc = t.child[a];
+                            tc.buf = -1;
+                            if (cn.kind == PK_FOLD) {
+                                tc.kind = CK_FOLD;
+                                tc.coef = (trav == cn.last_to_act) ? -float(cn.value) : float(cn.value);
+                            } else if (cn.kind == PK_SHOWDOWN) {
+                                tc.kind = CK_SHOWDOWN;
+                                tc.coef = float(cn.value);
+                            } else if (cn.kind == PK_CHANCE) {
+                                tc.kind = CK_CHANCE;
+                                tc.buf = cn.leaf_id;
+                            } else {
+                                tc.kind = CK_ACTION;
+                                tc.buf = cbuf[c];
+                            }
+                        }
+                        if (!opp) tl.max_children = std::max<uint32_t>(tl.max_children, t.n_act);
+                        pend.push_back({t, id, n.depth});
+                    }
                 }
-                gen(c, r2, out, acc || a > 0);
-                r_top--;
+            std::stable_sort(pend.begin(), pend.end(), [](const Pending& a, const Pending& b) { return a.depth > b.depth; });
+            for (Pending& pe : pend) {
+                NodeTask t = pe.t;
+                const PNode& n = P->nodes[pe.pnode];
+                if (t.kind == TK_ROOT_SHOWDOWN) {
+                    if (!add_rin_dep(t, rsrc[pe.pnode], uint32_t(k))) return false;
+                } else if (t.kind == TK_CHANCE_UP) {
+                    if (!add_dep(t, leaf_gather[k][n.leaf_id], DK_SAME_BOARD)) return false;
+                } else {
+                    if (t.kind == TK_UP_TRAV) {
+                        if (!add_rin_dep(t, rsrc[pe.pnode], uint32_t(k))) return false;
+                    } else {
+                        t.r_in = RIN_INITIAL;
+                        if (!add_dep(t, down_task[pe.pnode], DK_SAME_BOARD)) return false;
+                    }
+                    for (size_t a = 0; a < n.children.size(); ++a) {
+                        const PNode& cn = P->nodes[n.children[a]];
+                        if (cn.kind == PK_ACTION) {
+                            if (!add_dep(t, up_task[n.children[a]], DK_SAME_BOARD)) return false;
+                        } else if (cn.kind == PK_CHANCE) {
+                            if (!add_dep(t, leaf_gather[k][cn.leaf_id], DK_SAME_BOARD)) return false;
+                        }
+                    }
+                }
+                const uint32_t ti = emit(t);
+                up_task[pe.pnode] = int32_t(ti);
+                for (uint32_t s = 0; s < P->segs[k].size(); ++s)
+                    if (P->segs[k][s].root == pe.pnode) segroot_task[k][s] = int32_t(ti);
             }
-        } else {
-            if (down_only) {
-                for (uint8_t a = 0; a < A; ++a)
-                    if (reaches_leaf(n.children[a])) gen(n.children[a], r, 0, false);
-                return;
+            if (k > 0) {
+                // gather the roots of street k into the chance leaves of street k-1 (cfr.rs:502-522)
+                for (uint32_t l = 0; l < P->segs[k].size(); ++l) {
+                    NodeTask t = blank(TK_GATHER, uint32_t(k - 1));
+                    t.out = int32_t(l);
+                    t.aux = segroot_cbuf[k][l];
+                    if (!add_dep(t, segroot_task[k][l], DK_CHILD_BOARDS)) return false;
+                    leaf_gather[k - 1][l] = int32_t(emit(t));
+                }
+                if (P->world > 1 && uint32_t(k) == P->shard_round) tl.phase_cut = tl.n_tickets;
             }
-            uint16_t vb = alloc_v(A);
-            for (uint8_t a = 0; a < A; ++a) gen(n.children[a], r, uint16_t(vb + a), false);
-            Op o{};
-            o.type = OP_TRAV;
-            o.flags = acc ? OPF_ACC : 0;
-            o.n_act = A;
-            o.r_src = r;
-            o.v_base = vb;
-            o.v_out = out;
-            o.cum_a = n.cum_a;
-            o.an_index = n.an_index;
-            emit(o);
-            v_top -= A;
         }
-    }
-
-    Program run(uint32_t seg_id, int32_t root) {
-        uint16_t r0 = alloc_r();
-        Op l{};
-        l.type = OP_LOAD_ROOT;
-        l.r_dst = r0;
-        l.leaf = seg_id;
-        emit(l);
-        if (!down_only && subtree_needs_m(root)) {
-            Op m{};
-            m.type = OP_CALC_M;
-            m.r_dst = r0;
-            emit(m);
+        if (!(P->world > 1 && P->shard_round >= 1)) tl.phase_cut = tl.n_tickets;
+        tl.root_cbuf = segroot_cbuf[0][0];
+        if (tl.max_terminal > MAX_TERMINAL_CHILDREN) {
+            err = "more than 3 terminal children under one action node";
+            return false;
         }
-        uint16_t v0 = 0;
-        if (!down_only) v0 = alloc_v(1);
-        gen(root, r0, v0, false);
-        if (!down_only) {
-            Op o{};
-            o.type = OP_ROOT_OUT;
-            o.v_out = v0;
-            o.leaf = seg_id;
-            emit(o);
-        }
-        Op e{};
-        e.type = OP_END;
-        emit(e);
-        return prog;
+        return true;
     }
 };
 
@@ -680,19 +818,12 @@ bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstrac
         }
     }
 
-    // ---- programs ----
-    for (uint32_t k = 0; k < P->n_rounds; ++k)
-        for (uint32_t s = 0; s < P->segs[k].size(); ++s) {
-            Segment& sg = P->segs[k][s];
-            for (int p = 0; p < 2; ++p) {
-                ProgGen up{P, p, false};
-                sg.up[p] = up.run(s, sg.root);
-                if (!sg.leaves.empty()) {
-                    ProgGen dn{P, p, true};
-                    sg.down[p] = dn.run(s, sg.root);
-                }
-            }
-        }
+    // ---- task graphs, one per traverser ----
+    for (int p = 0; p < 2; ++p) {
+        TaskGen g{P, p};
+        if (!g.run()) return fail(g.err);
+        P->tl[p] = std::move(g.tl);
+    }
 
     // ---- update counts (one update = one (node, board, row, action) cell) ----
     for (uint32_t k = 0; k < P->n_rounds; ++k)

@@ -13,46 +13,19 @@
 #include <vector>
 
 #include "../../include/b200cfr.h"
+#include "tasks.h"
 
 namespace rs {
 
-enum OpType : uint8_t {
-    OP_LOAD_ROOT = 0,  // R[dst] <- root reach of this segment on this board
-    OP_OPP_REACH = 1,  // R[dst] <- R[src] * sigma_opp(node, action a)
-    OP_CALC_M = 2,     // M[dst] <- per traverser hand: sum of compatible opponent reach in R[dst]
-    OP_FOLD = 3,       // V[out] (+)= coef * M[src]
-    OP_SHOWDOWN = 4,   // V[out] (+)= coef * (win - lose) from R[src]
-    OP_TRAV = 5,       // traverser node: combine children V[base..base+A), update tables, V[out] (+)= value
-    OP_LEAF_DOWN = 6,  // write R[src] to leaf_reach[leaf][board]
-    OP_LEAF_UP = 7,    // V[out] (+)= gathered[leaf][board]
-    OP_ROOT_OUT = 8,   // write V[out] to root_cfv[seg][board]
-    OP_END = 9
-};
-
-constexpr uint8_t OPF_ACC = 1;  // accumulate into V[out] instead of overwriting
-
-struct Op {  // 32 bytes, read uniformly by every thread of the CTA
-    uint8_t type;
-    uint8_t flags;
-    uint8_t a;      // action index (OP_OPP_REACH)
-    uint8_t n_act;  // actions of the node (OP_OPP_REACH / OP_TRAV)
-    uint16_t r_src;
-    uint16_t r_dst;
-    uint16_t v_base;
-    uint16_t v_out;
-    uint32_t cum_a;  // sum of n_actions of earlier action nodes of the same (round, player): slab offset = n_rows * cum_a
-    uint32_t leaf;   // chance-leaf id within the round (OP_LEAF_*), segment id (OP_ROOT_OUT / OP_LOAD_ROOT)
-    float coef;      // +-pot for terminals (cfr.rs:525-556); chance weight is applied per board
-    uint32_t an_index;
-    uint32_t pad;
-};
-static_assert(sizeof(Op) == 32, "Op must stay 32 bytes");
-
-struct Program {
-    std::vector<Op> ops;
-    uint32_t n_r = 0;  // R (and M) slots
-    uint32_t n_v = 0;  // V slots
-    bool has_showdown = false;
+struct TaskList {  // one traversal (one traverser) of the whole tree, in ticket order
+    std::vector<NodeTask> tasks;
+    uint32_t n_tickets = 0;
+    uint32_t phase_cut = 0;     // tickets [0, phase_cut) precede the cross-GPU all-reduce, [phase_cut, n) follow it
+    uint32_t n_rbuf[3] = {0, 0, 0};  // reach buffers per round
+    uint32_t n_cbuf[3] = {0, 0, 0};  // value buffers per round
+    uint32_t max_children = 1;       // widest traverser node (value slots in shared memory)
+    uint32_t max_terminal = 0;       // most terminal children under one opponent node
+    int32_t root_cbuf = -1;          // value buffer (round 0) holding the root counterfactual values
 };
 
 struct PNode {  // tree node after ALLIN run-out expansion
@@ -66,6 +39,8 @@ struct PNode {  // tree node after ALLIN run-out expansion
     int32_t tab_j = -1;   // index among action nodes of (round_k, player)
     uint32_t cum_a = 0;
     int32_t leaf_id = -1;  // chance: id within round_k == child segment id in round_k+1
+    int32_t parent = -1;
+    int32_t depth = 0;     // depth inside the street segment (segment root = 0)
     std::vector<int32_t> children;
 };
 enum { PK_ACTION = 0, PK_FOLD = 1, PK_SHOWDOWN = 2, PK_CHANCE = 3 };
@@ -73,8 +48,6 @@ enum { PK_ACTION = 0, PK_FOLD = 1, PK_SHOWDOWN = 2, PK_CHANCE = 3 };
 struct Segment {
     int32_t root = -1;        // PNode id
     std::vector<int32_t> leaves;  // chance-leaf PNode ids in DFS order
-    Program up[2];            // per traverser
-    Program down[2];          // per traverser (empty when the segment has no leaves)
 };
 
 struct RoundPlayerTables {  // per (round k, player q), boards are GLOBAL ids
@@ -127,6 +100,7 @@ struct Plan {
     RoundPlayerTables tabs[3][2];
     ShowdownTables sd[2];
     std::vector<int32_t> an_to_pnode;  // ActionNode.index -> PNode id
+    TaskList tl[2];                    // per traverser
 
     uint64_t updates_per_iter_local = 0, updates_per_iter_global = 0;
     uint32_t flags = 0;

@@ -475,8 +475,8 @@ class Engine(_PlanOrEngine):
         buf = (_lib.rs_kernel_time * cap)()
         n = C.c_uint32()
         check(self._lib.rs_profile_iteration(self._h, buf, cap, C.byref(n)))
-        kinds = {0: "segment_down", 1: "segment_up", 2: "gather", 3: "allreduce"}
-        return [dict(kind=kinds[buf[i].kind], round_idx=buf[i].round_idx, traverser=buf[i].traverser, grid=buf[i].grid,
+        kinds = {0: "traversal", 3: "allreduce"}
+        return [dict(kind=kinds[buf[i].kind], phase=buf[i].phase, traverser=buf[i].traverser, grid=buf[i].grid,
                      ms=buf[i].ms, table_bytes=buf[i].table_bytes, vector_bytes=buf[i].vector_bytes) for i in range(n.value)]
 
     def best_response(self):

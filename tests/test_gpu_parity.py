@@ -64,7 +64,7 @@ def test_no_graph_matches_graph():
 def test_turn_river_small_ranges():
     o = util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]] * 2, [[3.0]] * 2)
     tree, eng, orc = _pair(o)
-    util.lockstep(eng, orc, tree, n_free=2, n_locked=3, tol=TOL)
+    util.lockstep(eng, orc, tree, n_free=1, n_locked=4, tol=TOL)
     br_g, br_o = eng.best_response(), orc.best_response()
     assert np.allclose(br_g, br_o, rtol=1e-4, atol=1e-4), (br_g, br_o)
 
@@ -86,7 +86,7 @@ def test_bucketed_rows_many_to_one():
     abs_ = [rb.CardAbstraction(rb.RS_ABS_BUCKET_TABLE, bucket_table=k0), rb.CardAbstraction(rb.RS_ABS_BUCKET_TABLE, bucket_table=k1)]
     eng = rb.Engine(tree, r, o.board_mask, abs_)
     orc = OracleGame(tree, r, o.board_mask, keys=[k0, k1])
-    util.lockstep(eng, orc, tree, n_free=2, n_locked=3, tol=TOL)
+    util.lockstep(eng, orc, tree, n_free=1, n_locked=4, tol=TOL)
 
 
 def test_single_iteration_from_oracle_state():
