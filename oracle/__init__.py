@@ -70,6 +70,8 @@ def load():
     lib.orc_literal_mccfr.argtypes = [VP, C.c_long, C.c_int, C.c_uint64, C.c_long, C.c_long, C.c_long]
     lib.orc_literal_to_double.argtypes = [VP, C.c_double]
     lib.orc_num_threads.restype = C.c_int
+    lib.orc_chance_partials.restype = C.c_int
+    lib.orc_chance_partials.argtypes = [VP, C.c_int, C.c_int, C.c_int, f64p, C.c_int]
     _lib = lib
     return lib
 
@@ -142,6 +144,12 @@ class OracleGame:
         out = np.zeros(self.n_hands[p], dtype=np.float64)
         self.lib.orc_root_cfv(self.h, p, out.ctypes.data_as(f64p))
         return out
+
+    def chance_partials(self, p: int, lo: int, hi: int, cap_nodes: int = 64) -> np.ndarray:
+        """Partial values of the round-0 chance nodes over dealt boards [lo, hi) -> [n_chance, H[p]]."""
+        out = np.zeros((cap_nodes, self.n_hands[p]), dtype=np.float64)
+        n = self.lib.orc_chance_partials(self.h, p, lo, hi, out.ctypes.data_as(f64p), cap_nodes)
+        return out[:n].copy()
 
     def discount(self, d: float):
         self.lib.orc_discount(self.h, d)

@@ -158,6 +158,11 @@ typedef struct orc_game {
     int strength_ready;
     int* order[2];      /* [river board * H + i] live hand slots, weakest first */
     int* n_live[2];     /* [river board] */
+    /* board sharding emulation: chance nodes of round 0 only deal boards in [shard_lo, shard_hi)
+     * and record their (partial) values, in DFS order, into rec */
+    int shard_lo, shard_hi;
+    double* rec;
+    int rec_n, rec_cap;
 } orc_game;
 
 static void* xcalloc(size_t n, size_t sz) {
@@ -586,6 +591,7 @@ static void walk(walk_ctx* c, int node, int k, int b, const double* reach, doubl
             int per = g->deal_count[k + 1];
             for (int i = 0; i < per; ++i) {
                 int cb = b * per + i;
+                if (k == 0 && g->shard_hi > 0 && (cb < g->shard_lo || cb >= g->shard_hi)) continue; /* another rank's board */
                 for (int j = 0; j < Ho; ++j) r2[j] = (g->hmask[o][j] & g->bmask[k + 1][cb]) ? 0.0 : reach[j];
                 walk(c, g->children[g->child_off[node]], k + 1, cb, r2, pi / len, tmp);
                 for (int h = 0; h < Hp; ++h)
@@ -593,6 +599,10 @@ static void walk(walk_ctx* c, int node, int k, int b, const double* reach, doubl
             }
             free(r2);
             free(tmp);
+            if (k == 0 && g->rec && g->rec_n < g->rec_cap) {
+                memcpy(g->rec + (size_t)g->rec_n * Hp, out, 8 * (size_t)Hp);
+                g->rec_n++;
+            }
             return;
         }
         case NODE_TERMINAL: {
@@ -722,6 +732,22 @@ void orc_average_value(orc_game* g, double out[2]) {
         traverse(g, p, MODE_EVAL);
         out[p] = g->root_value[p];
     }
+}
+
+/* Values of the round-0 chance nodes for traverser p under the AVERAGE strategies (no table update), summed
+ * over the dealt boards in [lo, hi) only: the partial sums a board-sharded rank contributes before the
+ * all-reduce.  Returns the number of chance nodes written (DFS order), each H[p] doubles. */
+int orc_chance_partials(orc_game* g, int p, int lo, int hi, double* out, int cap_nodes) {
+    g->shard_lo = lo;
+    g->shard_hi = hi;
+    g->rec = out;
+    g->rec_n = 0;
+    g->rec_cap = cap_nodes;
+    traverse(g, p, MODE_EVAL);
+    int n = g->rec_n;
+    g->rec = NULL;
+    g->shard_lo = g->shard_hi = 0;
+    return n;
 }
 
 void orc_root_cfv(orc_game* g, int p, double* out) { memcpy(out, g->root_cfv[p], 8 * (size_t)g->H[p]); }

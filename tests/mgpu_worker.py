@@ -1,0 +1,133 @@
+"""torchrun worker: board-sharded engine (one rank per GPU) vs the fp64 oracle.
+
+    torchrun --nproc-per-node N tests/mgpu_worker.py [turn|flop|batch]
+
+Every rank builds the same game, owns a slice of the first dealt-card level (or of the subgame batch),
+iterates in lock-step, and checks ITS OWN slabs against the oracle; replicated root-street slabs are
+checked on every rank.  Exit code 0 = parity on all ranks.
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import rustsolver_b200 as rb  # noqa: E402
+from oracle import OracleGame  # noqa: E402
+from rustsolver_b200 import configs  # noqa: E402
+from tests import util  # noqa: E402
+
+TOL = 1e-4
+
+
+def main():
+    case = sys.argv[1] if len(sys.argv) > 1 else "turn"
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt = torch.tensor(list(rb.nccl_unique_id()), dtype=torch.uint8, device=dev)
+    dist.broadcast(idt, 0)
+    nccl_id = bytes(idt.cpu().tolist())
+
+    board_masks = None
+    if case == "turn":
+        o = util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]] * 2, [[3.0]] * 2)
+    elif case == "flop":
+        o = util.small_options("4d5dAs", ["AA,KK,AKs,76s,54s", "QQ,JJ,AQs,65s,32s"], [[1.0]] * 3, [[3.0]] * 3, pot=40, stacks=(60, 60))
+    else:
+        w = configs.config5(n_subgames=8)
+        o = w.options
+        board_masks = w.board_masks
+    n, tree = rb.build_game_tree(o)
+    ranges = configs.workload_ranges(w) if case == "batch" else o.ranges()
+    eng = rb.Engine(tree, ranges, o.board_mask, [], board_masks=board_masks, device=local, rank=rank, world_size=world,
+                    nccl_id=nccl_id)
+    st = eng.stats()
+    n_iters = 3
+    ok = True
+    msg = ""
+    try:
+        if case == "batch":
+            n_iters = 2  # free run from zero tables; see tests/util.py:lockstep for why not more
+            eng.iterate(n_iters)
+            lo = rank * len(board_masks) // world
+            hi = (rank + 1) * len(board_masks) // world
+            for s in range(lo, hi):
+                og = OracleGame(tree, ranges, board_masks[s])
+                og.iterate(n_iters)
+                for an in range(tree.n_actions):
+                    gr, gs = eng.read_infoset(an, s)
+                    orr, os_ = og.get_slab(an, 0)
+                    assert np.abs(gr - orr).max() <= TOL * max(np.abs(orr).max(), 1e-12), (s, an)
+                    assert np.abs(gs - os_).max() <= TOL * max(np.abs(os_).max(), 1e-12), (s, an)
+        else:
+            og = OracleGame(tree, ranges, o.board_mask)
+            nb = [st.n_boards[k] for k in range(st.n_rounds)]
+            lo1 = rank * nb[1] // world
+            hi1 = (rank + 1) * nb[1] // world
+            per2 = nb[2] // nb[1] if st.n_rounds > 2 else 0
+
+            def mine(k, b):
+                if k == 0:
+                    return True
+                if k == 1:
+                    return lo1 <= b < hi1
+                return lo1 * per2 <= b < hi1 * per2
+
+            for it in range(n_iters):
+                if it > 0:  # lock-step: restart from the oracle's state (see tests/util.py)
+                    for an, b in util.all_slabs(tree, nb):
+                        k = int(tree.round_idx[np.nonzero((tree.type == 0) & (tree.an_index == an))[0][0]])
+                        if mine(k, b):
+                            r, s = og.get_slab(an, b)
+                            eng.write_infoset(an, b, r.astype(np.float32), s.astype(np.float32))
+                eng.iterate(1)
+                og.iterate(1)
+                scales, diffs, table = {}, {}, {"R": 0.0, "S": 0.0}
+                for an, b in util.all_slabs(tree, nb):
+                    orr, os_ = og.get_slab(an, b)
+                    for oarr, nm in ((orr, "R"), (os_, "S")):
+                        if oarr.size:
+                            m = float(np.abs(oarr).max())
+                            scales[(an, nm)] = max(scales.get((an, nm), 0.0), m)
+                            table[nm] = max(table[nm], m)
+                    k = int(tree.round_idx[np.nonzero((tree.type == 0) & (tree.an_index == an))[0][0]])
+                    if not mine(k, b):
+                        continue
+                    gr, gs = eng.read_infoset(an, b)
+                    for g, oarr, nm in ((gr, orr, "R"), (gs, os_, "S")):
+                        if oarr.size:
+                            diffs[(an, b, nm)] = float(np.abs(g - oarr).max())
+                for (an, b, nm), d in diffs.items():
+                    bound = TOL * scales[(an, nm)] + util.ABS_FLOOR * table[nm]
+                    assert d <= bound, (it, an, b, nm, d, bound)
+            # best response goes through the same all-reduce
+            br, obr = eng.best_response(), og.best_response()
+            assert np.allclose(br, obr, rtol=1e-4, atol=1e-4), (br, obr)
+    except AssertionError as e:
+        ok = False
+        msg = repr(e)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if not ok:
+        print(f"[rank {rank}] FAILED {msg}", flush=True)
+    if rank == 0:
+        print(f"mgpu_worker {case} world={world}: {'OK' if flag.item() == 1 else 'FAILED'} "
+              f"(boards local {[st.n_boards_local[k] for k in range(st.n_rounds)]})", flush=True)
+    eng.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

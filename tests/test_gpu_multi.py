@@ -1,0 +1,30 @@
+"""Board-sharded engine on >= 2 GPUs (one process per GPU under torchrun, NCCL) against the oracle."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("case", ["turn", "flop", "batch"])
+def test_sharded_engine_matches_oracle(case):
+    n = _n_gpus()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29641", str(ROOT / "tests" / "mgpu_worker.py"), case]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert f"mgpu_worker {case} world={world}: OK" in r.stdout

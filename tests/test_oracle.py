@@ -1,0 +1,96 @@
+"""The oracle against its own committed goldens and against itself (naive vs fast terminals, literal vs vector)."""
+import json
+from pathlib import Path
+
+import numpy as np
+
+import rustsolver_b200 as rb
+from oracle import OracleGame
+from tests import util
+
+GOLDEN = Path(__file__).parent / "golden"
+
+
+def _small():
+    o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]], [[3.0]])
+    _, tree = rb.build_game_tree(o)
+    return o, tree
+
+
+def test_oracle_reproduces_golden_trajectory():
+    g = json.loads((GOLDEN / "cfr_small_river.json").read_text())
+    o, tree = _small()
+    og = OracleGame(tree, o.ranges(), o.board_mask, fast_terminals=True)  # golden was written with the naive terminals
+    done = 0
+    for it in (1, 2, 5):
+        og.iterate(it - done)
+        done = it
+        for an, (r, s) in g[str(it)].items():
+            gr, gs = og.get_slab(int(an), 0)
+            assert np.allclose(gr, np.array(r), rtol=1e-10, atol=1e-13)
+            assert np.allclose(gs, np.array(s), rtol=1e-10, atol=1e-16)
+    assert np.allclose(og.best_response(), g["br_after_5"], rtol=1e-9)
+    assert np.allclose(og.average_value(), g["ev_after_5"], rtol=1e-9)
+
+
+def test_naive_and_fast_terminals_agree_on_two_streets():
+    o = util.small_options("4d5dAs3c", ["AA,KK,AKs,76s,54s,T9s", "QQ,JJ,AQs,65s,32s,KQo"], [[0.5, 1.0]] * 2, [[3.0]] * 2)
+    _, tree = rb.build_game_tree(o)
+    a = OracleGame(tree, o.ranges(), o.board_mask, fast_terminals=False)
+    b = OracleGame(tree, o.ranges(), o.board_mask, fast_terminals=True)
+    a.iterate(2)
+    b.iterate(2)
+    for an in a.action_nodes:
+        k = int(tree.round_idx[a.action_nodes[an]])
+        for bd in range(a.n_boards(k)):
+            ra, sa = a.get_slab(an, bd)
+            rb_, sb = b.get_slab(an, bd)
+            assert np.allclose(ra, rb_, rtol=1e-9, atol=1e-15) and np.allclose(sa, sb, rtol=1e-9, atol=1e-18)
+
+
+def test_average_strategies_are_zero_sum_and_exploitability_falls():
+    o, tree = _small()
+    og = OracleGame(tree, o.ranges(), o.board_mask)
+    og.iterate(1)
+    e1 = sum(og.best_response()) / 2
+    og.iterate(199)
+    ev = og.average_value()
+    assert abs(ev[0] + ev[1]) < 1e-9            # +-pot payoffs are zero-sum (cfr.rs:525-556)
+    e200 = sum(og.best_response()) / 2
+    assert 0 <= e200 < 0.1 * e1
+
+
+def test_literal_scalar_cfr_converges_to_the_same_region():
+    """(a) literal i32 x10000 in-place cfr() vs (b) vector fp64: agreement at convergence level."""
+    o, tree = _small()
+    vec = OracleGame(tree, o.ranges(), o.board_mask)
+    lit = OracleGame(tree, o.ranges(), o.board_mask)
+    vec.iterate(150)
+    visited, _ = lit.literal_cfr(150)
+    assert visited == int(lit.n_combos)
+    lit.literal_to_double(10000.0)
+    ev, el = sum(vec.best_response()) / 2, sum(lit.best_response()) / 2
+    assert el < 4.0 and ev < 4.0
+    assert abs(vec.average_value()[0] - lit.average_value()[0]) < 0.5
+
+
+def test_literal_mccfr_reduces_exploitability():
+    o, tree = _small()
+    g = OracleGame(tree, o.ranges(), o.board_mask)
+    g.literal_to_double(100.0)
+    e0 = sum(g.best_response()) / 2
+    g.literal_mccfr(200000, n_threads=2, seed=3)
+    g.literal_to_double(100.0)
+    e1 = sum(g.best_response()) / 2
+    assert e1 < 0.5 * e0
+
+
+def test_chance_sum_switch_documents_the_reference_quirk():
+    """cfr.rs:511-521 returns the SUM over deals while passing reach/len down; the oracle's default is the mean."""
+    o = util.small_options("4d5dAs3c", ["AA,KK", "QQ,JJ"], [[1.0]] * 2, [[3.0]] * 2)
+    _, tree = rb.build_game_tree(o)
+    a = OracleGame(tree, o.ranges(), o.board_mask, chance_sum=False)
+    b = OracleGame(tree, o.ranges(), o.board_mask, chance_sum=True)
+    _, ua = a.literal_cfr(1)
+    _, ub = b.literal_cfr(1)
+    assert ua != ub
