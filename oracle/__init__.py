@@ -76,6 +76,23 @@ def load():
     return lib
 
 
+def row_alignment(engine_rows_of_slot: np.ndarray, oracle_rows_of_slot: np.ndarray, n_rows: int) -> np.ndarray:
+    """The engine numbers the rows of a lossless table by its board-local hand order, the oracle by hand slot.
+    Both expose hand slot -> row (card table); this returns idx with engine_row = idx[oracle_row]."""
+    idx = np.full(n_rows, -1, dtype=np.int64)
+    g = np.asarray(engine_rows_of_slot, dtype=np.int64)
+    o = np.asarray(oracle_rows_of_slot, dtype=np.int64)
+    live = o >= 0
+    assert np.array_equal(live, g != 0xFFFF), "engine and oracle disagree on which hands the board removes"
+    idx[o[live]] = g[live]
+    assert (idx >= 0).all()
+    # same partition of the hands into rows on both sides
+    back = np.full(n_rows, -1, dtype=np.int64)
+    back[g[live]] = o[live]
+    assert np.array_equal(back[idx], np.arange(n_rows)), "engine and oracle rows are not the same partition"
+    return idx
+
+
 def evaluate(cards: Sequence[int]) -> int:
     a = np.asarray(cards, dtype=np.uint8)
     return int(load().orc_evaluate(a.ctypes.data_as(u8p), len(a)))

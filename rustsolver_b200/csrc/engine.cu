@@ -107,9 +107,10 @@ struct DevBuf {
 };
 
 struct RoundDev {
-    // per player q
-    DevBuf<uint16_t> row_of_hand[2], row_start[2], row_hands[2];
-    DevBuf<uint32_t> n_rows[2];
+    // per player q, board-local hand order (plan.h: LocalTables)
+    DevBuf<uint16_t> row_of_pos[2], row_start[2], row_pos[2], cl_pos[2], parent_pos[2], child_pos[2], slot_of_pos[2];
+    DevBuf<HandRec> hrec[2];
+    DevBuf<uint32_t> n_rows[2], n_rows_pad[2], n_live[2];
     DevBuf<uint64_t> board_off[2];
     DevBuf<float> regrets[2], ssum[2];
     DevBuf<float> chance_scale;
@@ -130,16 +131,11 @@ struct Engine {
     bool use_graph = true;
     nccl::Comm comm = nullptr;
 
-    DevBuf<uint8_t> cards[2];
-    DevBuf<uint16_t> same[2], card_hands[2];
     RoundDev rd[3];
-    // showdown tables (final round), per player
-    DevBuf<uint16_t> sd_sorted[2], sd_lohi[2];
-    DevBuf<uint32_t> sd_nlive[2];
-    DevBuf<uint8_t> sd_cj[2], sd_ncard[2], sd_cpos[2];
     DevBuf<float> scratch;  // strategy read-outs
     DevBuf<float> root_weights[2];
     DevBuf<NodeTask> tasks[2];
+    DevBuf<TaskSrc> srcs[2];
     DevBuf<uint32_t> flags;
     DevBuf<TaskCtl> ctl;
     int slots = 1;
@@ -172,6 +168,7 @@ struct Engine {
     int enqueue_iteration(uint64_t* count);
     int iterate(uint64_t n);
     int root_sum(int player, double* out);
+    int root_values(int player, std::vector<float>* out);
     int prof_begin();
     int prof_end(uint32_t kind, uint32_t k, int trav, uint32_t grid, uint64_t table_bytes, uint64_t vector_bytes);
     uint64_t table_bytes_of(int trav, int phase) const;
@@ -195,9 +192,8 @@ int Engine::init(const rs_config* cfg) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return set_err(RS_ERR_UNSUPPORTED, "kernels are built for sm_100a only; found an older device");
-    threads = TASK_THREADS;
-    if (cfg->threads_per_block && cfg->threads_per_block != uint32_t(TASK_THREADS))
-        return set_err(RS_ERR_INVALID, "threads_per_block: this build runs " + std::to_string(TASK_THREADS) + " threads per CTA");
+    if (cfg->threads_per_block)
+        return set_err(RS_ERR_INVALID, "threads_per_block is derived from the range size (4 hands per thread) and cannot be set");
     use_graph = !(cfg->flags & RS_FLAG_NO_GRAPH);
     discount_interval = cfg->discount_interval;
     discount_cap = cfg->discount_cap;
@@ -209,12 +205,11 @@ int Engine::init(const rs_config* cfg) {
     for (int q = 0; q < 2; ++q) {
         std::vector<float> ones(P.H[q], 1.0f);
         CU(root_weights[q].upload(ones));
-        CU(cards[q].upload(P.hand_cards[q]));
-        CU(same[q].upload(P.same[q]));
-        CU(card_hands[q].upload(P.card_hands[q]));
     }
     const int HP[2] = {int((P.H[0] + 3) & ~3u), int((P.H[1] + 3) & ~3u)};
-    const size_t maxH = std::max(P.H[0], P.H[1]);
+    const size_t maxHP = size_t(std::max(HP[0], HP[1]));
+    threads = int(((maxHP / 4) + 31) / 32 * 32);
+    if (threads > MAX_TASK_THREADS) return set_err(RS_ERR_UNSUPPORTED, "range larger than 1326 hands");
     for (uint32_t k = 0; k < P.n_rounds; ++k) {
         RoundDev& R = rd[k];
         const uint32_t lo = P.local_lo[k], hi = P.local_hi[k], nb = hi - lo;
@@ -222,11 +217,21 @@ int Engine::init(const rs_config* cfg) {
         R.n_leaves = (k + 1 < P.n_rounds) ? uint32_t(P.segs[k + 1].size()) : 0;
         for (int q = 0; q < 2; ++q) {
             const RoundPlayerTables& T = P.tabs[k][q];
-            const uint32_t H = P.H[q];
-            CU(R.row_of_hand[q].upload(slice(T.row_of_hand, lo, hi, H)));
-            CU(R.row_start[q].upload(slice(T.row_start, lo, hi, H + 1)));
-            CU(R.row_hands[q].upload(slice(T.row_hands, lo, hi, H)));
+            const LocalTables& L = P.loc[k][q];
+            const size_t hp = L.Hpad;
+            CU(R.row_of_pos[q].upload(slice(L.row_of_pos, lo, hi, hp)));
+            CU(R.row_start[q].upload(slice(L.row_start, lo, hi, hp + 4)));
+            CU(R.row_pos[q].upload(slice(L.row_pos, lo, hi, hp)));
+            CU(R.cl_pos[q].upload(slice(L.cl_pos, lo, hi, 2 * hp)));
+            CU(R.slot_of_pos[q].upload(slice(L.slot_of_pos, lo, hi, hp)));
+            CU(R.hrec[q].upload(slice(L.hrec, lo, hi, hp)));
+            if (k > 0) {
+                CU(R.parent_pos[q].upload(slice(L.parent_pos, lo, hi, hp)));
+                CU(R.child_pos[q].upload(slice(L.child_pos, lo, hi, size_t(P.loc[k - 1][q].Hpad))));
+            }
             CU(R.n_rows[q].upload(slice(T.n_rows, lo, hi, 1)));
+            CU(R.n_rows_pad[q].upload(slice(L.n_rows_pad, lo, hi, 1)));
+            CU(R.n_live[q].upload(slice(L.n_live, lo, hi, 1)));
             CU(R.board_off[q].upload(slice(T.board_off, lo, hi, 1)));
             const size_t cells = size_t(T.board_off[P.n_boards[k]]);
             CU(R.regrets[q].alloc(cells));
@@ -242,14 +247,17 @@ int Engine::init(const rs_config* cfg) {
         CU(R.parent_board.upload(pb));
         const size_t n_r = std::max(P.tl[0].n_rbuf[k], P.tl[1].n_rbuf[k]);
         const size_t n_c = std::max(P.tl[0].n_cbuf[k], P.tl[1].n_cbuf[k]);
-        CU(R.rbuf.alloc(n_r * nb * maxH));
-        CU(R.cbuf.alloc(n_c * nb * maxH));
-        CU(R.gathered.alloc(size_t(R.n_leaves) * nb * maxH));
+        CU(R.rbuf.alloc(n_r * nb * maxHP));
+        CU(R.cbuf.alloc(n_c * nb * maxHP));
+        CU(R.gathered.alloc(size_t(R.n_leaves) * nb * maxHP));
+        CU(R.rbuf.zero());
+        CU(R.cbuf.zero());
         CU(R.gathered.zero());
     }
     uint32_t max_tickets = 0;
     for (int p = 0; p < 2; ++p) {
         CU(tasks[p].upload(P.tl[p].tasks));
+        CU(srcs[p].upload(P.tl[p].srcs));
         max_tickets = std::max(max_tickets, P.tl[p].n_tickets);
         slots = std::max(slots, int(std::max(P.tl[p].max_terminal, 1 + P.tl[p].max_children)));
     }
@@ -263,28 +271,13 @@ int Engine::init(const rs_config* cfg) {
         CU(ctl.upload(&c0, 1));
     }
     size_t smem_need = std::max(task_kernel_smem_bytes(slots, HP[0], HP[1]), task_kernel_smem_bytes(slots, HP[1], HP[0]));
-    // showdown tables live on the final round's local boards
-    {
-        const uint32_t k = P.n_rounds - 1;
-        const uint32_t lo = P.local_lo[k], hi = P.local_hi[k];
-        for (int q = 0; q < 2; ++q) {
-            const ShowdownTables& S = P.sd[q];
-            const uint32_t H = P.H[q];
-            CU(sd_sorted[q].upload(slice(S.sorted, lo, hi, H)));
-            CU(sd_nlive[q].upload(slice(S.n_live, lo, hi, 1)));
-            CU(sd_cj[q].upload(slice(S.cj, lo, hi, size_t(H) * 2)));
-            CU(sd_ncard[q].upload(slice(S.n_card, lo, hi, 52)));
-            CU(sd_lohi[q].upload(slice(S.lohi, lo, hi, size_t(H) * 2)));
-            CU(sd_cpos[q].upload(slice(S.cpos, lo, hi, size_t(H) * 4)));
-        }
-    }
     int max_optin = 0;
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (smem_need > size_t(max_optin))
         return set_err(RS_ERR_UNSUPPORTED, "node too wide for one CTA's shared memory: need " +
                                                std::to_string(smem_need) + " B, device allows " + std::to_string(max_optin));
     smem_bytes = smem_need;
-    CU(configure_task_kernels(smem_need, &blocks_per_sm));
+    CU(configure_task_kernels(smem_need, threads, &blocks_per_sm));
     if (blocks_per_sm < 1) return set_err(RS_ERR_UNSUPPORTED, "task kernel does not fit on an SM");
     n_sms = prop.multiProcessorCount;
     CU(scratch.alloc(size_t(1326) * MAX_ACTIONS));
@@ -324,30 +317,30 @@ void Engine::fill_args(TaskArgs* a, int trav) const {
     const Plan& P = plan;
     memset(a, 0, sizeof(*a));
     for (int q = 0; q < 2; ++q) {
-        a->pl[q].cards = cards[q].p;
-        a->pl[q].same = same[q].p;
-        a->pl[q].card_hands = card_hands[q].p;
-        a->pl[q].H = int(P.H[q]);
-        a->pl[q].Hpad = int((P.H[q] + 3) & ~3u);
-        a->sd[q].sorted = sd_sorted[q].p;
-        a->sd[q].n_live = sd_nlive[q].p;
-        a->sd[q].cj = sd_cj[q].p;
-        a->sd[q].n_card = sd_ncard[q].p;
-        a->sd[q].lohi = sd_lohi[q].p;
-        a->sd[q].cpos = sd_cpos[q].p;
+        a->H[q] = int(P.H[q]);
+        a->Hpad[q] = int((P.H[q] + 3) & ~3u);
         a->root_weights[q] = root_weights[q].p;
     }
     for (uint32_t k = 0; k < P.n_rounds; ++k) {
         const RoundDev& R = rd[k];
         RoundArgs& ra = a->rounds[k];
         for (int q = 0; q < 2; ++q) {
-            ra.rp[q].row_of_hand = R.row_of_hand[q].p;
-            ra.rp[q].row_start = R.row_start[q].p;
-            ra.rp[q].row_hands = R.row_hands[q].p;
-            ra.rp[q].n_rows = R.n_rows[q].p;
-            ra.rp[q].board_off = R.board_off[q].p;
-            ra.rp[q].regrets = R.regrets[q].p;
-            ra.rp[q].ssum = R.ssum[q].p;
+            DevRoundPlayer& d = ra.rp[q];
+            d.row_of_pos = R.row_of_pos[q].p;
+            d.row_start = R.row_start[q].p;
+            d.row_pos = R.row_pos[q].p;
+            d.cl_pos = R.cl_pos[q].p;
+            d.parent_pos = R.parent_pos[q].p;
+            d.child_pos = R.child_pos[q].p;
+            d.slot_of_pos = R.slot_of_pos[q].p;
+            d.hrec = R.hrec[q].p;
+            d.n_rows = R.n_rows[q].p;
+            d.n_rows_pad = R.n_rows_pad[q].p;
+            d.n_live = R.n_live[q].p;
+            d.board_off = R.board_off[q].p;
+            d.regrets = R.regrets[q].p;
+            d.ssum = R.ssum[q].p;
+            d.identity = P.loc[k][q].identity ? 1 : 0;
         }
         ra.chance_scale = R.chance_scale.p;
         ra.parent_board = R.parent_board.p;
@@ -362,6 +355,7 @@ void Engine::fill_args(TaskArgs* a, int trav) const {
         }
     }
     a->tasks = tasks[trav].p;
+    a->srcs = srcs[trav].p;
     a->n_tasks = uint32_t(P.tl[trav].tasks.size());
     a->flags = flags.p;
     a->ctl = ctl.p;
@@ -424,10 +418,10 @@ int Engine::enqueue_traversal(int trav, int mode, uint64_t* count) {
         if (a.t1 <= a.t0) continue;
         const int grid = int(std::min<uint64_t>(uint64_t(a.t1 - a.t0), uint64_t(n_sms) * blocks_per_sm));
         if ((rc = prof_begin()) != RS_OK) return rc;
-        CU(launch_task_kernel(a, mode, grid, smem_bytes, stream));
+        CU(launch_task_kernel(a, mode, grid, threads, smem_bytes, stream));
         uint64_t vec = 0;
         for (uint32_t k = 0; k < P.n_rounds; ++k)
-            vec += (uint64_t(tl.n_rbuf[k]) * P.H[1 - trav] + uint64_t(tl.n_cbuf[k]) * P.H[trav]) * rd[k].n_boards * 8;
+            vec += (uint64_t(tl.n_rbuf[k]) * P.H[1 - trav] + uint64_t(tl.n_cbuf[k]) * P.H[trav]) * rd[k].n_boards * 8;  // written once, read once
         if ((rc = prof_end(RS_KERNEL_TRAVERSAL, uint32_t(phase), trav, uint32_t(grid), table_bytes_of(trav, phase), vec)) != RS_OK)
             return rc;
         ++*count;
@@ -435,7 +429,7 @@ int Engine::enqueue_traversal(int trav, int mode, uint64_t* count) {
             // the one exchange step of the path: counterfactual values at the shared chance nodes
             RoundDev& Par = rd[P.shard_round - 1];
             if ((rc = prof_begin()) != RS_OK) return rc;
-            const size_t n = size_t(Par.n_leaves) * Par.n_boards * P.H[trav];
+            const size_t n = size_t(Par.n_leaves) * Par.n_boards * ((P.H[trav] + 3) & ~3u);
             int nrc = nccl::g_api.AllReduce(Par.gathered.p, Par.gathered.p, n, nccl::kFloat32, nccl::kSum, comm, stream);
             if (nrc != 0) return set_err(RS_ERR_NCCL, "ncclAllReduce failed");
             if ((rc = prof_end(RS_KERNEL_ALLREDUCE, 0, trav, 0, 0, n * 4)) != RS_OK) return rc;
@@ -500,12 +494,29 @@ int Engine::iterate(uint64_t n) {
     return RS_OK;
 }
 
-int Engine::root_sum(int player, double* out) {
+// root counterfactual values of `player` by hand slot, [root boards][H]
+int Engine::root_values(int player, std::vector<float>* out) {
     const Plan& P = plan;
     const RoundDev& R = rd[0];
-    std::vector<float> v(size_t(R.n_boards) * P.H[player]);
-    CU(cudaMemcpy(v.data(), R.cbuf.p + size_t(P.tl[player].root_cbuf) * R.n_boards * P.H[player], v.size() * sizeof(float),
+    const size_t hp = (P.H[player] + 3) & ~3u;
+    std::vector<float> v(size_t(R.n_boards) * hp);
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaMemcpy(v.data(), R.cbuf.p + size_t(P.tl[player].root_cbuf) * R.n_boards * hp, v.size() * sizeof(float),
                   cudaMemcpyDeviceToHost));
+    out->assign(size_t(R.n_boards) * P.H[player], 0.f);
+    const LocalTables& L = P.loc[0][player];
+    for (uint32_t b = 0; b < R.n_boards; ++b) {
+        const uint32_t gb = P.local_lo[0] + b;
+        for (uint32_t i = 0; i < L.n_live[gb]; ++i)
+            (*out)[size_t(b) * P.H[player] + L.slot_of_pos[size_t(gb) * L.Hpad + i]] = v[size_t(b) * hp + i];
+    }
+    return RS_OK;
+}
+
+int Engine::root_sum(int player, double* out) {
+    std::vector<float> v;
+    int rc = root_values(player, &v);
+    if (rc != RS_OK) return rc;
     double s = 0;
     for (float x : v) s += x;
     *out = s;
@@ -657,7 +668,7 @@ static int locate(const Plan& P, uint32_t an_index, uint32_t board_id, uint32_t*
     *q_out = q;
     *n_rows = T.n_rows[board_id];
     *n_act = uint32_t(n.children.size());
-    *off = T.board_off[board_id] + uint64_t(T.n_rows[board_id]) * n.cum_a;
+    *off = T.board_off[board_id] + uint64_t(P.loc[k][q].n_rows_pad[board_id]) * n.cum_a;
     return RS_OK;
 }
 
@@ -840,9 +851,10 @@ int rs_root_values(rs_engine* e, uint32_t player, float* out, size_t cap) {
     const size_t n = size_t(E.rd[0].n_boards) * E.plan.H[player];
     if (cap < n) return set_err(RS_ERR_CAPACITY, "output buffer too small");
     CU(cudaSetDevice(E.device));
-    CU(cudaStreamSynchronize(E.stream));
-    CU(cudaMemcpy(out, E.rd[0].cbuf.p + size_t(E.plan.tl[player].root_cbuf) * E.rd[0].n_boards * E.plan.H[player],
-                  n * sizeof(float), cudaMemcpyDeviceToHost));
+    std::vector<float> v;
+    int rc = E.root_values(int(player), &v);
+    if (rc != RS_OK) return rc;
+    memcpy(out, v.data(), n * sizeof(float));
     return RS_OK;
 }
 

@@ -1,28 +1,16 @@
 #include "kernels.cuh"
 
 #ifndef RS_MIN_BLOCKS
-#define RS_MIN_BLOCKS 4  // resident CTAs per SM the register allocator must allow
+#define RS_MIN_BLOCKS 2  // resident CTAs per SM the register allocator must allow (at MAX_TASK_THREADS threads)
 #endif
 
 namespace rs {
 
 namespace {
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
-}
-
-__device__ __forceinline__ float warp_incl_scan(float v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        float t = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += t;
-    }
-    return v;
-}
-
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -31,163 +19,604 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-
-struct Ctx {
-    int tid, lane, warp, nwarps, T;
-    int p, o, Hp, Ho, HpP, HoP;
-    int hpt_p, hpt_o;  // hands per thread actually needed
-    float* Rin;  // [HoP]
-    float* X;    // [slots][Hmax]
-    int Hx;      // stride of X
-    float* P;    // [HoP + 4]
-    float* CM;   // [52][CM_STRIDE]
-    float* CS;   // [64]
-    float* WS;   // [32]
-    const uint8_t* __restrict__ cards_p;
-    const uint8_t* __restrict__ cards_o;
-    const uint16_t* __restrict__ same_p;
-    const uint16_t* __restrict__ card_hands_o;
-};
-
-// Sum of `r` (opponent reach, shared memory) per card: CS[c]; returns the total over all hands.
-// One warp per card, fixed reduction order => run-to-run reproducible.
-__device__ __forceinline__ float card_sums(const Ctx& c, const float* r) {
-    __syncthreads();  // previous readers of CS are done; r is visible
-    for (int card = c.warp; card < 52; card += c.nwarps) {
-        float a = 0.f;
-        const uint16_t i0 = c.card_hands_o[card * 52 + c.lane];
-        if (i0 != 0xFFFF) a += r[i0];
-        if (c.lane + 32 < 52) {
-            const uint16_t i1 = c.card_hands_o[card * 52 + c.lane + 32];
-            if (i1 != 0xFFFF) a += r[i1];
-        }
-        a = warp_sum(a);
-        if (c.lane == 0) c.CS[card] = a;
-    }
-    __syncthreads();
-    const float t = c.CS[c.lane] + (c.lane + 32 < 52 ? c.CS[c.lane + 32] : 0.f);
-    return 0.5f * warp_sum(t);  // every hand holds two cards
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stcg4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float f4get(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void f4set(float4& v, int i, float x) {
+    if (i == 0) v.x = x;
+    else if (i == 1) v.y = x;
+    else if (i == 2) v.z = x;
+    else v.w = x;
+}
+__device__ __forceinline__ void unpack4(uint2 u, uint32_t (&o)[4]) {
+    o[0] = u.x & 0xffffu;
+    o[1] = u.x >> 16;
+    o[2] = u.y & 0xffffu;
+    o[3] = u.y >> 16;
 }
 
-// mass of opponent reach compatible with traverser hand h (inclusion-exclusion over its two cards)
-__device__ __forceinline__ float compat_mass(const Ctx& c, const float* r, float total, int h) {
-    const int c0 = c.cards_p[2 * h], c1 = c.cards_p[2 * h + 1];
-    const uint16_t sm = c.same_p[h];
-    float v = total - c.CS[c0] - c.CS[c1];
-    if (sm != 0xFFFF) v += r[sm];
+struct Ctx {
+    int tid, lane, warp, nwarps;
+    int pos4;  // first of the four hands this thread owns
+    int p, o, Hp, Ho, HpP, HoP, Hx;
+    float* Rs;   // [HoP]        opponent reach being scanned
+    float* X;    // [slots][Hx]
+    float* P;    // [HoP + 4]    exclusive prefix of reach by position (strength order on the river)
+    float* GB;   // [2*HoP + 8]  exclusive prefix of reach over the opponent's per-card lists
+    float* WSA;  // [32]
+    float* WSB;  // [32]
+};
+
+// Exclusive prefix sums of opponent reach r (shared memory, HoP floats, zero past the live hands):
+//   P[i]  = reach of the i weakest hands           (position order)
+//   GB[e] = reach of the first e entries of the opponent's concatenated per-card lists
+// One pass: every thread scans its 4 positions and its 8 list entries; warp shuffles + one cross-warp step.
+// Returns the total reach (all threads).
+__device__ __forceinline__ float scan_reach(const Ctx& c, const float* r, const uint16_t* __restrict__ cl_pos_b) {
+    __syncthreads();  // r is complete; previous readers of P / GB are done
+    float4 x = f4zero();
+    if (c.pos4 < c.HoP) x = *reinterpret_cast<const float4*>(r + c.pos4);
+    float y[8];
+    {
+        uint4 u = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (8 * c.tid < 2 * c.HoP) u = __ldg(reinterpret_cast<const uint4*>(cl_pos_b) + c.tid);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t a = w[i] & 0xffffu, b = w[i] >> 16;
+            y[2 * i] = a != 0xffffu ? r[a] : 0.f;
+            y[2 * i + 1] = b != 0xffffu ? r[b] : 0.f;
+        }
+    }
+    const float la = (x.x + x.y) + (x.z + x.w);
+    float lb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) lb += y[i];
+    float ia = la, ib = lb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float ta = __shfl_up_sync(0xffffffffu, ia, d);
+        const float tb = __shfl_up_sync(0xffffffffu, ib, d);
+        if (c.lane >= d) {
+            ia += ta;
+            ib += tb;
+        }
+    }
+    if (c.lane == 31) {
+        c.WSA[c.warp] = ia;
+        c.WSB[c.warp] = ib;
+    }
+    __syncthreads();
+    // every warp scans the (<= 11) warp totals itself
+    float wa = c.lane < c.nwarps ? c.WSA[c.lane] : 0.f;
+    float wb = c.lane < c.nwarps ? c.WSB[c.lane] : 0.f;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+        const float ta = __shfl_up_sync(0xffffffffu, wa, d);
+        const float tb = __shfl_up_sync(0xffffffffu, wb, d);
+        if (c.lane >= d) {
+            wa += ta;
+            wb += tb;
+        }
+    }
+    const float total = __shfl_sync(0xffffffffu, wa, c.nwarps - 1);
+    const float total_b = __shfl_sync(0xffffffffu, wb, c.nwarps - 1);
+    const float base_a = c.warp > 0 ? __shfl_sync(0xffffffffu, wa, c.warp - 1) : 0.f;
+    const float base_b = c.warp > 0 ? __shfl_sync(0xffffffffu, wb, c.warp - 1) : 0.f;
+    float ea = base_a + ia - la, eb = base_b + ib - lb;
+    if (c.pos4 < c.HoP) {
+        float4 o;
+        o.x = ea;
+        o.y = ea + x.x;
+        o.z = o.y + x.y;
+        o.w = o.z + x.z;
+        *reinterpret_cast<float4*>(c.P + c.pos4) = o;
+    }
+    if (8 * c.tid < 2 * c.HoP) {
+        float4 o0, o1;
+        o0.x = eb;
+        o0.y = o0.x + y[0];
+        o0.z = o0.y + y[1];
+        o0.w = o0.z + y[2];
+        o1.x = o0.w + y[3];
+        o1.y = o1.x + y[4];
+        o1.z = o1.y + y[5];
+        o1.w = o1.z + y[6];
+        *reinterpret_cast<float4*>(c.GB + 8 * c.tid) = o0;
+        *reinterpret_cast<float4*>(c.GB + 8 * c.tid + 4) = o1;
+    }
+    if (c.tid == 0) {
+        c.P[c.HoP] = total;
+        c.GB[2 * c.HoP] = total_b;
+    }
+    __syncthreads();
+    return total;
+}
+
+// After scan_reach: for the traverser's hand record `rec`
+//   mass = opponent reach compatible with the hand (total - both cards' sums + the identical combo)
+//   sd   = weaker minus stronger compatible opponent reach (showdown, cfr.rs:532-556)
+__device__ __forceinline__ void hand_terms(const Ctx& c, const float* r, float total, const uint4& rec, float& mass, float& sd) {
+    const uint32_t lo = rec.x & 0xffffu, hi = rec.x >> 16;
+    const uint32_t s0 = rec.y & 0xffffu, dlo0 = (rec.y >> 16) & 0xffu, dhi0 = rec.y >> 24;
+    const uint32_t s1 = rec.z & 0xffffu, dlo1 = (rec.z >> 16) & 0xffu, dhi1 = rec.z >> 24;
+    const uint32_t n0 = rec.w & 0xffu, n1 = (rec.w >> 8) & 0xffu, same = rec.w >> 16;
+    const float g0s = c.GB[s0], g0e = c.GB[s0 + n0], g1s = c.GB[s1], g1e = c.GB[s1 + n1];
+    mass = total - (g0e - g0s) - (g1e - g1s) + (same != 0xffffu ? r[same] : 0.f);
+    sd = c.P[lo] + c.P[hi] - total - c.GB[s0 + dlo0] - c.GB[s0 + dhi0] + g0s + g0e - c.GB[s1 + dlo1] - c.GB[s1 + dhi1] + g1s + g1e;
+}
+__device__ __forceinline__ float hand_mass(const Ctx& c, const float* r, float total, const uint4& rec) {
+    const uint32_t s0 = rec.y & 0xffffu, s1 = rec.z & 0xffffu;
+    const uint32_t n0 = rec.w & 0xffu, n1 = (rec.w >> 8) & 0xffu, same = rec.w >> 16;
+    return total - (c.GB[s0 + n0] - c.GB[s0]) - (c.GB[s1 + n1] - c.GB[s1]) + (same != 0xffffu ? r[same] : 0.f);
+}
+
+// Opponent reach of the thread's four positions for this task (masked by what the board removes).
+__device__ __forceinline__ float4 load_reach4(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b) {
+    float4 r = f4zero();
+    if (c.pos4 >= c.HoP) return r;
+    if (nt.r_in == RIN_INITIAL) {
+        const uint32_t nl = Rk.rp[c.o].n_live[b];
+        uint32_t s[4];
+        unpack4(__ldg(reinterpret_cast<const uint2*>(Rk.rp[c.o].slot_of_pos + size_t(b) * c.HoP + c.pos4)), s);
+        const float* __restrict__ w = A.root_weights[c.o];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f4set(r, i, uint32_t(c.pos4 + i) < nl ? __ldg(w + s[i]) : 0.f);
+    } else if (nt.rin_parent_round) {
+        const RoundArgs& Rp = A.rounds[k - 1];
+        const float* src = Rp.rbuf + (size_t(nt.r_in) * Rp.n_boards + Rk.parent_board[b]) * c.HoP;
+        uint32_t pp[4];
+        unpack4(__ldg(reinterpret_cast<const uint2*>(Rk.rp[c.o].parent_pos + size_t(b) * c.HoP + c.pos4)), pp);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f4set(r, i, pp[i] != 0xffffu ? __ldcg(src + pp[i]) : 0.f);  // the dealt card removes hands
+    } else {
+        r = ldcg4(Rk.rbuf + (size_t(nt.r_in) * Rk.n_boards + b) * c.HoP + c.pos4);
+    }
+    return r;
+}
+
+// Sum of the value vectors feeding one child (thread's four positions).
+__device__ __forceinline__ float4 child_value4(const TaskArgs& A, const Ctx& c, const RoundArgs& Rk, const TaskChild& ch, int b) {
+    float4 v = f4zero();
+    if (c.pos4 >= c.HpP) return v;
+    for (int s = 0; s < ch.n_src; ++s) {
+        const TaskSrc sr = A.srcs[ch.src_first + s];
+        const float* base = (sr.kind == SK_CBUF ? Rk.cbuf : Rk.gathered) + (size_t(sr.buf) * Rk.n_boards + b) * c.HpP;
+        v = f4add(v, ldcg4(base + c.pos4));
+    }
     return v;
 }
 
-// Showdown values on river board b: acc[i] += cf * (weaker - stronger compatible opponent reach) for the
-// thread's hands h = tid + i*T (cfr.rs:532-556).  r = opponent reach in shared memory.
-__device__ __forceinline__ void showdown_eval(const Ctx& c, const DevShowdown& so, const DevShowdown& sp, int b,
-                                              const uint16_t* __restrict__ row_o, const uint16_t* __restrict__ row_p,
-                                              const float* r, float cf, float* acc) {
-    __syncthreads();  // previous users of CM / P / WS are done; r is visible
-    const int nl = int(so.n_live[b]);
-    const uint16_t* __restrict__ sorted = so.sorted + size_t(b) * c.Ho;
-    const uint8_t* __restrict__ cj = so.cj + size_t(b) * c.Ho * 2;
-    // (1) scatter reach into the per-card lists (strength order inside each list)
-    for (int h = c.tid; h < c.Ho; h += c.T) {
-        if (row_o[h] == 0xFFFF) continue;
-        const float v = r[h];
-        c.CM[c.cards_o[2 * h] * CM_STRIDE + 1 + cj[2 * h]] = v;
-        c.CM[c.cards_o[2 * h + 1] * CM_STRIDE + 1 + cj[2 * h + 1]] = v;
-    }
-    // (2) blocked gather of reach in strength order + local sums
-    const int items = (nl + c.T - 1) / c.T;
-    float x[MAX_HPT];
-    float local = 0.f;
+// Regret matching of one row held in registers (infoset.rs:83-123).
+template <int NA>
+__device__ __forceinline__ void sigma_row(const float (&g)[4 * NA], int i, float (&sg)[NA]) {
+    float norm = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAX_HPT; ++j) {
-        x[j] = 0.f;
-        const int i = c.tid * items + j;
-        if (j < items && i < nl) x[j] = r[sorted[i]];
-        local += x[j];
+    for (int a = 0; a < NA; ++a) {
+        sg[a] = fmaxf(g[i * NA + a], 0.f);
+        norm += sg[a];
     }
-    const float incl = warp_incl_scan(local, c.lane);
-    if (c.lane == 31) c.WS[c.warp] = incl;
-    __syncthreads();
-    // (3) per-card exclusive scans, one warp per card (<= 51 entries, two per lane)
-    const uint8_t* __restrict__ ncard = so.n_card + size_t(b) * 52;
-    for (int card = c.warp; card < 52; card += c.nwarps) {
-        const int nc = ncard[card];
-        float* row = c.CM + card * CM_STRIDE;
-        const int e0 = 2 * c.lane, e1 = e0 + 1;
-        const float v0 = e0 < nc ? row[1 + e0] : 0.f;
-        const float v1 = e1 < nc ? row[1 + e1] : 0.f;
-        const float in2 = warp_incl_scan(v0 + v1, c.lane);
-        const float ex = in2 - (v0 + v1);
-        if (e0 < nc) row[1 + e0] = ex + v0;
-        if (e1 < nc) row[1 + e1] = ex + v0 + v1;
-        if (c.lane == 0) row[0] = 0.f;
-    }
-    // (4) finish the block scan: P[i] = reach of the i weakest hands
-    float base = incl - local;
-    for (int w = 0; w < c.warp; ++w) base += c.WS[w];
+    const float inv = norm > 0.f ? 1.0f / norm : 0.f;
 #pragma unroll
-    for (int j = 0; j < MAX_HPT; ++j) {
-        const int i = c.tid * items + j;
-        if (j < items && i < nl) {
-            base += x[j];
-            c.P[i + 1] = base;
+    for (int a = 0; a < NA; ++a) sg[a] = norm > 0.f ? sg[a] * inv : 1.0f / float(NA);
+}
+
+// Four table rows x NA actions into registers.  identity: rows are the thread's four positions (contiguous 4*NA
+// floats, NA 128-bit loads); otherwise rows come from row_of_pos and are loaded one by one.
+template <int NA>
+__device__ __forceinline__ void load_rows(const float* __restrict__ slab, bool identity, int pos4, uint32_t n_rows_pad,
+                                          const uint32_t (&rows)[4], float (&g)[4 * NA]) {
+    if (identity) {
+        if (uint32_t(pos4) < n_rows_pad) {
+#pragma unroll
+            for (int v = 0; v < NA; ++v) {
+                const float4 t = *reinterpret_cast<const float4*>(slab + size_t(pos4) * NA + 4 * v);
+                g[4 * v] = t.x;
+                g[4 * v + 1] = t.y;
+                g[4 * v + 2] = t.z;
+                g[4 * v + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4 * NA; ++e) g[e] = 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int a = 0; a < NA; ++a) g[i * NA + a] = rows[i] != 0xffffu ? slab[size_t(rows[i]) * NA + a] : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TK_DOWN: opponent node (cfr.rs:582-586) + its terminal children (cfr.rs:523-558)
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int NA>
+__device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b) {
+    const DevRoundPlayer& O = Rk.rp[c.o];
+    const uint32_t nrp = O.n_rows_pad[b];
+    const float* __restrict__ slab = (MODE == KM_CFR ? O.regrets : O.ssum) + O.board_off[b] + size_t(nrp) * nt.cum_a;
+    const float4 r4 = load_reach4(A, c, nt, Rk, k, b);
+    uint32_t rows[4] = {0xffffu, 0xffffu, 0xffffu, 0xffffu};
+    if (!O.identity && c.pos4 < c.HoP) unpack4(__ldg(reinterpret_cast<const uint2*>(O.row_of_pos + size_t(b) * c.HoP + c.pos4)), rows);
+    float g[4 * NA];
+    load_rows<NA>(slab, O.identity != 0, c.pos4, nrp, rows, g);
+    float4 v[NA];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float sg[NA];
+        sigma_row<NA>(g, i, sg);
+        const float r = f4get(r4, i);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) f4set(v[a], i, r * sg[a]);
+    }
+    int slot = 0;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+        const int ck = nt.child[a].kind;
+        if (c.pos4 < c.HoP) {
+            if (ck == CK_FOLD || ck == CK_SHOWDOWN) *reinterpret_cast<float4*>(c.X + slot * c.Hx + c.pos4) = v[a];
+            else stcg4(Rk.rbuf + (size_t(nt.child[a].buf) * Rk.n_boards + b) * c.HoP + c.pos4, v[a]);
+        }
+        if (ck == CK_FOLD || ck == CK_SHOWDOWN) ++slot;
+    }
+    if (nt.out < 0) return;
+    // terminal children: their values only depend on the child reach staged in shared memory
+    const DevRoundPlayer& Pp = Rk.rp[c.p];
+    const uint32_t nl_p = Pp.n_live[b];
+    const float scale = Rk.chance_scale[b];
+    const uint16_t* __restrict__ cl = O.cl_pos + size_t(b) * 2 * c.HoP;
+    float4 acc = f4zero();
+    uint4 rec[4];
+    if (c.pos4 < c.HpP) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rec[i] = __ldg(reinterpret_cast<const uint4*>(Pp.hrec + size_t(b) * c.HpP + c.pos4 + i));
+    }
+    slot = 0;
+    for (int a = 0; a < NA; ++a) {
+        const int ck = nt.child[a].kind;
+        if (ck != CK_FOLD && ck != CK_SHOWDOWN) continue;
+        const float* r = c.X + slot * c.Hx;
+        ++slot;
+        const float cf = nt.child[a].coef * scale;
+        const float total = scan_reach(c, r, cl);
+        if (c.pos4 < c.HpP) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (uint32_t(c.pos4 + i) < nl_p) {
+                    float m, sd;
+                    if (ck == CK_FOLD) {
+                        m = hand_mass(c, r, total, rec[i]);
+                        f4set(acc, i, f4get(acc, i) + cf * m);
+                    } else {
+                        hand_terms(c, r, total, rec[i], m, sd);
+                        f4set(acc, i, f4get(acc, i) + cf * sd);
+                    }
+                }
+            }
         }
     }
-    if (c.tid == 0) c.P[0] = 0.f;
-    __syncthreads();
-    // (5) combine: weaker minus stronger, minus the hands sharing a card with h
-    const uint16_t* __restrict__ lohi = sp.lohi + size_t(b) * c.Hp * 2;
-    const uchar4* __restrict__ cpos = reinterpret_cast<const uchar4*>(sp.cpos) + size_t(b) * c.Hp;
-    const float ptot = c.P[nl];
+    if (c.pos4 < c.HpP) stcg4(Rk.cbuf + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4, acc);
+}
+
+// any number of actions, any row mapping: scalar loads, two passes over the actions
+template <int MODE>
+__device__ __forceinline__ void task_down_generic(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b) {
+    const DevRoundPlayer& O = Rk.rp[c.o];
+    const uint32_t nrp = O.n_rows_pad[b];
+    const float* __restrict__ slab = (MODE == KM_CFR ? O.regrets : O.ssum) + O.board_off[b] + size_t(nrp) * nt.cum_a;
+    const float4 r4 = load_reach4(A, c, nt, Rk, k, b);
+    const int n_act = nt.n_act;
+    const uint32_t nl_o = O.n_live[b];
+    uint32_t rows[4] = {0xffffu, 0xffffu, 0xffffu, 0xffffu};
+    if (c.pos4 < c.HoP) unpack4(__ldg(reinterpret_cast<const uint2*>(O.row_of_pos + size_t(b) * c.HoP + c.pos4)), rows);
+    if (c.pos4 < c.HoP) {
+        for (int i = 0; i < 4; ++i) {
+            const bool live = uint32_t(c.pos4 + i) < nl_o && rows[i] != 0xffffu;
+            const float r = live ? f4get(r4, i) : 0.f;
+            float norm = 0.f;
+            if (live)
+                for (int a = 0; a < n_act; ++a) norm += fmaxf(slab[size_t(rows[i]) * n_act + a], 0.f);
+            int slot = 0;
+            for (int a = 0; a < n_act; ++a) {
+                float v = 0.f;
+                if (live) v = norm > 0.f ? r * fmaxf(slab[size_t(rows[i]) * n_act + a], 0.f) / norm : r / float(n_act);
+                const int ck = nt.child[a].kind;
+                if (ck == CK_FOLD || ck == CK_SHOWDOWN) c.X[(slot++) * c.Hx + c.pos4 + i] = v;
+                else __stcg(Rk.rbuf + (size_t(nt.child[a].buf) * Rk.n_boards + b) * c.HoP + c.pos4 + i, v);
+            }
+        }
+    }
+    if (nt.out < 0) return;
+    const DevRoundPlayer& Pp = Rk.rp[c.p];
+    const uint32_t nl_p = Pp.n_live[b];
+    const float scale = Rk.chance_scale[b];
+    const uint16_t* __restrict__ cl = O.cl_pos + size_t(b) * 2 * c.HoP;
+    float4 acc = f4zero();
+    int slot = 0;
+    for (int a = 0; a < n_act; ++a) {
+        const int ck = nt.child[a].kind;
+        if (ck != CK_FOLD && ck != CK_SHOWDOWN) continue;
+        const float* r = c.X + slot * c.Hx;
+        ++slot;
+        const float cf = nt.child[a].coef * scale;
+        const float total = scan_reach(c, r, cl);
+        if (c.pos4 < c.HpP) {
+            for (int i = 0; i < 4; ++i) {
+                if (uint32_t(c.pos4 + i) < nl_p) {
+                    const uint4 rec = __ldg(reinterpret_cast<const uint4*>(Pp.hrec + size_t(b) * c.HpP + c.pos4 + i));
+                    float m, sd;
+                    hand_terms(c, r, total, rec, m, sd);
+                    f4set(acc, i, f4get(acc, i) + cf * (ck == CK_FOLD ? m : sd));
+                }
+            }
+        }
+    }
+    if (c.pos4 < c.HpP) stcg4(Rk.cbuf + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TK_UP_TRAV: traverser node (cfr.rs:588, 612-621)
+// ------------------------------------------------------------------------------------------------
+// common front part: stage the reach, run the scan, produce per-hand mass and showdown term
+__device__ __forceinline__ void trav_terms(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b,
+                                           bool need_sd, float4& mass, float4& sd) {
+    const float4 r4 = load_reach4(A, c, nt, Rk, k, b);
+    if (c.pos4 < c.HoP) *reinterpret_cast<float4*>(c.Rs + c.pos4) = r4;
+    const float total = scan_reach(c, c.Rs, Rk.rp[c.o].cl_pos + size_t(b) * 2 * c.HoP);
+    mass = f4zero();
+    sd = f4zero();
+    const DevRoundPlayer& Pp = Rk.rp[c.p];
+    const uint32_t nl_p = Pp.n_live[b];
+    if (c.pos4 < c.HpP) {
 #pragma unroll
-    for (int i = 0; i < MAX_HPT; ++i) {
-        const int h = c.tid + i * c.T;
-        if (h < c.Hp && row_p[h] != 0xFFFF) {
-            const int c0 = c.cards_p[2 * h], c1 = c.cards_p[2 * h + 1];
-            const int lo = lohi[2 * h], hi = lohi[2 * h + 1];
-            const uchar4 cp = cpos[h];
-            const float* r0 = c.CM + c0 * CM_STRIDE;
-            const float* r1 = c.CM + c1 * CM_STRIDE;
-            const float win = c.P[lo] - r0[cp.x] - r1[cp.z];
-            const float lose = (ptot - c.P[hi]) - (r0[ncard[c0]] - r0[cp.y]) - (r1[ncard[c1]] - r1[cp.w]);
-            acc[i] += cf * (win - lose);
+        for (int i = 0; i < 4; ++i) {
+            if (uint32_t(c.pos4 + i) < nl_p) {
+                const uint4 rec = __ldg(reinterpret_cast<const uint4*>(Pp.hrec + size_t(b) * c.HpP + c.pos4 + i));
+                float m, s = 0.f;
+                if (need_sd) hand_terms(c, c.Rs, total, rec, m, s);
+                else m = hand_mass(c, c.Rs, total, rec);
+                f4set(mass, i, m);
+                f4set(sd, i, s);
+            }
         }
     }
 }
 
+template <int MODE, int NA>
+__device__ __forceinline__ void task_trav(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b) {
+    const DevRoundPlayer& Pp = Rk.rp[c.p];
+    const float scale = Rk.chance_scale[b];
+    // child values that come from other tasks: issue the loads first
+    float4 v[NA];
+    bool need_sd = false;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+        v[a] = f4zero();
+        const int ck = nt.child[a].kind;
+        if (ck == CK_VALUE) v[a] = child_value4(A, c, Rk, nt.child[a], b);
+        need_sd |= (ck == CK_SHOWDOWN);
+    }
+    float4 mass, sd;
+    trav_terms(A, c, nt, Rk, k, b, need_sd, mass, sd);
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+        const int ck = nt.child[a].kind;
+        const float cf = nt.child[a].coef * scale;
+        if (ck == CK_FOLD) v[a] = make_float4(cf * mass.x, cf * mass.y, cf * mass.z, cf * mass.w);
+        else if (ck == CK_SHOWDOWN) v[a] = make_float4(cf * sd.x, cf * sd.y, cf * sd.z, cf * sd.w);
+    }
+    const uint32_t nrp = Pp.n_rows_pad[b];
+    const uint32_t nl_p = Pp.n_live[b];
+    float* out = Rk.cbuf + (size_t(nt.out) * Rk.n_boards + b) * c.HpP;
+    float* tabR = Pp.regrets + Pp.board_off[b] + size_t(nrp) * nt.cum_a;
+    float* tabS = Pp.ssum + Pp.board_off[b] + size_t(nrp) * nt.cum_a;
+    if (Pp.identity) {
+        // rows are the thread's own four positions: everything stays in registers
+        if (uint32_t(c.pos4) >= nrp) {
+            if (c.pos4 < c.HpP) stcg4(out + c.pos4, f4zero());
+            return;
+        }
+        const uint32_t none[4] = {0, 0, 0, 0};
+        float g[4 * NA], ss[4 * NA];
+        if (MODE == KM_CFR) load_rows<NA>(tabR, true, c.pos4, nrp, none, g);
+        if (MODE != KM_BR) load_rows<NA>(tabS, true, c.pos4, nrp, none, ss);
+        float4 vn4 = f4zero();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float sg[NA];
+            float vn;
+            if (MODE == KM_BR) {
+                vn = -3.0e38f;
+#pragma unroll
+                for (int a = 0; a < NA; ++a) vn = fmaxf(vn, f4get(v[a], i));
+            } else {
+                if (MODE == KM_CFR) sigma_row<NA>(g, i, sg);
+                else sigma_row<NA>(ss, i, sg);
+                vn = 0.f;
+#pragma unroll
+                for (int a = 0; a < NA; ++a) vn += sg[a] * f4get(v[a], i);
+            }
+            const bool live = uint32_t(c.pos4 + i) < nl_p;
+            f4set(vn4, i, live ? vn : 0.f);
+            if (MODE == KM_CFR) {
+                const float w = f4get(mass, i) * scale;
+#pragma unroll
+                for (int a = 0; a < NA; ++a) {
+                    g[i * NA + a] += live ? f4get(v[a], i) - vn : 0.f;
+                    ss[i * NA + a] += live ? sg[a] * w : 0.f;
+                }
+            }
+        }
+        if (MODE == KM_CFR) {
+#pragma unroll
+            for (int q = 0; q < NA; ++q) {
+                *reinterpret_cast<float4*>(tabR + size_t(c.pos4) * NA + 4 * q) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+                *reinterpret_cast<float4*>(tabS + size_t(c.pos4) * NA + 4 * q) = make_float4(ss[4 * q], ss[4 * q + 1], ss[4 * q + 2], ss[4 * q + 3]);
+            }
+        }
+        stcg4(out + c.pos4, vn4);
+        return;
+    }
+    // bucketed rows: values and masses go through shared memory, one thread per row (CSR row -> positions)
+    float* M = c.X;
+    if (c.pos4 < c.HpP) {
+        *reinterpret_cast<float4*>(M + c.pos4) = mass;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) *reinterpret_cast<float4*>(c.X + (1 + a) * c.Hx + c.pos4) = v[a];
+        stcg4(out + c.pos4, f4zero());
+    }
+    __syncthreads();
+    const uint32_t n_rows = Pp.n_rows[b];
+    const uint16_t* __restrict__ rstart = Pp.row_start + size_t(b) * (c.HpP + 4);
+    const uint16_t* __restrict__ rpos = Pp.row_pos + size_t(b) * c.HpP;
+    const float* V1 = c.X + c.Hx;
+    for (uint32_t row = c.tid; row < n_rows; row += blockDim.x) {
+        float rg[NA], sr[NA], sg[NA], d[NA];
+        float norm = 0.f;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+            rg[a] = MODE == KM_CFR ? tabR[size_t(row) * NA + a] : 0.f;
+            sr[a] = MODE != KM_BR ? tabS[size_t(row) * NA + a] : 0.f;
+            sg[a] = fmaxf(MODE == KM_CFR ? rg[a] : sr[a], 0.f);
+            norm += sg[a];
+            d[a] = 0.f;
+        }
+        const float inv = norm > 0.f ? 1.0f / norm : 0.f;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) sg[a] = norm > 0.f ? sg[a] * inv : 1.0f / float(NA);
+        float msum = 0.f;
+        const int hs = rstart[row], he = rstart[row + 1];
+        for (int q = hs; q < he; ++q) {
+            const int h = rpos[q];
+            float va[NA];
+            float vn = (MODE == KM_BR) ? -3.0e38f : 0.f;
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                va[a] = V1[a * c.Hx + h];
+                if (MODE == KM_BR) vn = fmaxf(vn, va[a]);
+                else vn += sg[a] * va[a];
+            }
+            if (MODE == KM_CFR) {
+#pragma unroll
+                for (int a = 0; a < NA; ++a) d[a] += va[a] - vn;
+                msum += M[h];
+            }
+            __stcg(out + h, vn);
+        }
+        if (MODE == KM_CFR) {
+            const float w = msum * scale;
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                tabR[size_t(row) * NA + a] = rg[a] + d[a];
+                tabS[size_t(row) * NA + a] = sr[a] + sg[a] * w;
+            }
+        }
+    }
+}
+
+// wide nodes (more than FAST_ACTIONS actions): values in shared memory, dynamic loops over the actions
 template <int MODE>
-__global__ void __launch_bounds__(TASK_THREADS, RS_MIN_BLOCKS) task_kernel(const __grid_constant__ TaskArgs A) {
+__device__ __forceinline__ void task_trav_generic(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b) {
+    const DevRoundPlayer& Pp = Rk.rp[c.p];
+    const float scale = Rk.chance_scale[b];
+    const int n_act = nt.n_act;
+    bool need_sd = false;
+    for (int a = 0; a < n_act; ++a) {
+        const int ck = nt.child[a].kind;
+        if (ck == CK_VALUE && c.pos4 < c.HpP) *reinterpret_cast<float4*>(c.X + (1 + a) * c.Hx + c.pos4) = child_value4(A, c, Rk, nt.child[a], b);
+        need_sd |= (ck == CK_SHOWDOWN);
+    }
+    float4 mass, sd;
+    trav_terms(A, c, nt, Rk, k, b, need_sd, mass, sd);
+    float* out = Rk.cbuf + (size_t(nt.out) * Rk.n_boards + b) * c.HpP;
+    if (c.pos4 < c.HpP) {
+        *reinterpret_cast<float4*>(c.X + c.pos4) = mass;
+        for (int a = 0; a < n_act; ++a) {
+            const int ck = nt.child[a].kind;
+            const float cf = nt.child[a].coef * scale;
+            if (ck == CK_FOLD) *reinterpret_cast<float4*>(c.X + (1 + a) * c.Hx + c.pos4) = make_float4(cf * mass.x, cf * mass.y, cf * mass.z, cf * mass.w);
+            else if (ck == CK_SHOWDOWN) *reinterpret_cast<float4*>(c.X + (1 + a) * c.Hx + c.pos4) = make_float4(cf * sd.x, cf * sd.y, cf * sd.z, cf * sd.w);
+        }
+        stcg4(out + c.pos4, f4zero());
+    }
+    __syncthreads();
+    const uint32_t nrp = Pp.n_rows_pad[b];
+    const uint32_t n_rows = Pp.n_rows[b];
+    float* tabR = Pp.regrets + Pp.board_off[b] + size_t(nrp) * nt.cum_a;
+    float* tabS = Pp.ssum + Pp.board_off[b] + size_t(nrp) * nt.cum_a;
+    const uint16_t* __restrict__ rstart = Pp.row_start + size_t(b) * (c.HpP + 4);
+    const uint16_t* __restrict__ rpos = Pp.row_pos + size_t(b) * c.HpP;
+    const float* M = c.X;
+    const float* V1 = c.X + c.Hx;
+    for (uint32_t row = c.tid; row < n_rows; row += blockDim.x) {
+        const float* tsrc = (MODE == KM_EVAL ? tabS : tabR) + size_t(row) * n_act;
+        float norm = 0.f;
+        if (MODE != KM_BR)
+            for (int a = 0; a < n_act; ++a) norm += fmaxf(tsrc[a], 0.f);
+        const float inv = norm > 0.f ? 1.0f / norm : 0.f;
+        const float uni = 1.0f / float(n_act);
+        float msum = 0.f, vsum = 0.f;
+        const int hs = rstart[row], he = rstart[row + 1];
+        for (int q = hs; q < he; ++q) {
+            const int h = rpos[q];
+            float vn = (MODE == KM_BR) ? -3.0e38f : 0.f;
+            for (int a = 0; a < n_act; ++a) {
+                const float va = V1[a * c.Hx + h];
+                if (MODE == KM_BR) vn = fmaxf(vn, va);
+                else vn += (norm > 0.f ? fmaxf(tsrc[a], 0.f) * inv : uni) * va;
+            }
+            vsum += vn;
+            msum += M[h];
+            __stcg(out + h, vn);
+        }
+        if (MODE == KM_CFR) {
+            const float w = msum * scale;
+            for (int a = 0; a < n_act; ++a) {
+                float da = -vsum;
+                for (int q = hs; q < he; ++q) da += V1[a * c.Hx + rpos[q]];
+                const float old = tabR[size_t(row) * n_act + a];
+                const float sga = norm > 0.f ? fmaxf(old, 0.f) * inv : uni;
+                tabS[size_t(row) * n_act + a] += sga * w;
+                tabR[size_t(row) * n_act + a] = old + da;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the persistent kernel
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(MAX_TASK_THREADS, RS_MIN_BLOCKS) task_kernel(const __grid_constant__ TaskArgs A) {
     extern __shared__ __align__(16) float smem_raw[];
+    __shared__ __align__(16) NodeTask s_nt;
     __shared__ uint32_t s_ticket;
     __shared__ uint32_t s_task;
     __shared__ uint32_t s_epoch;
 
     Ctx c;
     c.tid = threadIdx.x;
-    c.T = blockDim.x;
     c.lane = c.tid & 31;
     c.warp = c.tid >> 5;
-    c.nwarps = c.T >> 5;
+    c.nwarps = blockDim.x >> 5;
+    c.pos4 = 4 * c.tid;
     c.p = A.trav;
     c.o = 1 - c.p;
-    c.Hp = A.pl[c.p].H;
-    c.Ho = A.pl[c.o].H;
-    c.HpP = A.pl[c.p].Hpad;
-    c.HoP = A.pl[c.o].Hpad;
+    c.Hp = A.H[c.p];
+    c.Ho = A.H[c.o];
+    c.HpP = A.Hpad[c.p];
+    c.HoP = A.Hpad[c.o];
     c.Hx = c.HpP > c.HoP ? c.HpP : c.HoP;
-    c.Rin = smem_raw;
-    c.X = c.Rin + c.HoP;
+    c.Rs = smem_raw;
+    c.X = c.Rs + c.HoP;
     c.P = c.X + A.slots * c.Hx;
-    c.CM = c.P + c.HoP + 4;
-    c.CS = c.CM + 52 * CM_STRIDE;
-    c.WS = c.CS + 64;
-    c.cards_p = A.pl[c.p].cards;
-    c.cards_o = A.pl[c.o].cards;
-    c.same_p = A.pl[c.p].same;
-    c.card_hands_o = A.pl[c.o].card_hands;
-    const int tid = c.tid, T = c.T, Hp = c.Hp, Ho = c.Ho, p = c.p, o = c.o;
-    c.hpt_p = (Hp + T - 1) / T;
-    c.hpt_o = (Ho + T - 1) / T;
+    c.GB = c.P + c.HoP + 4;
+    c.WSA = c.GB + 2 * c.HoP + 8;
+    c.WSB = c.WSA + 32;
+    const int tid = c.tid, T = blockDim.x;
 
     if (tid == 0) s_epoch = ld_acquire_u32(&A.ctl->epoch);
     uint32_t j0 = 0;  // thread 0 only: tickets are handed out in task order, so the search resumes where it stopped
@@ -212,384 +641,108 @@ __global__ void __launch_bounds__(TASK_THREADS, RS_MIN_BLOCKS) task_kernel(const
         const uint32_t t = s_ticket;
         const uint32_t epoch = s_epoch;
         if (t >= A.t1) break;
-        const NodeTask& nt = A.tasks[s_task];
-        const int kind = nt.kind;
-        const int k = nt.round_k;
-        const int b = int(t - nt.first);
+        const NodeTask* gt = A.tasks + s_task;
+        // copy the descriptor to shared memory while the dependency flags are polled
+        if (tid < int(sizeof(NodeTask) / 4)) reinterpret_cast<uint32_t*>(&s_nt)[tid] = __ldg(reinterpret_cast<const uint32_t*>(gt) + tid);
+        const int kind = gt->kind;
+        const int k = gt->round_k;
+        const int b = int(t - gt->first);
         const RoundArgs& Rk = A.rounds[k];
-        const int nb = Rk.n_boards;
-
-        // ---- wait for the producers of this instance's inputs ----
         if (kind == TK_GATHER) {
-            const NodeTask& dt = A.tasks[nt.dep[0]];
+            const NodeTask& dt = A.tasks[gt->dep[0]];
             const int cb0 = Rk.per_parent > 0 ? b * Rk.per_parent : 0;
             const int ncb = Rk.per_parent > 0 ? Rk.per_parent : Rk.n_boards_next;
             for (int i = tid; i < ncb; i += T) {
                 const uint32_t idx = dt.first + uint32_t(cb0 + i);
                 if (idx >= A.t0)
-                    while (ld_acquire_u32(A.flags + idx) != epoch) __nanosleep(40);
+                    while (ld_acquire_u32(A.flags + idx) != epoch) __nanosleep(20);
             }
-        } else if (tid < nt.n_dep) {
-            const NodeTask& dt = A.tasks[nt.dep[tid]];
-            const uint32_t idx = dt.first + uint32_t(nt.dep_kind[tid] == DK_PARENT_BOARD ? Rk.parent_board[b] : b);
-            if (idx >= A.t0)
-                while (ld_acquire_u32(A.flags + idx) != epoch) __nanosleep(40);
+        } else {
+            const int nd = gt->n_dep, total = nd + gt->n_src_all;
+            for (int i = tid; i < total; i += T) {
+                int dep, dk = DK_SAME_BOARD;
+                if (i < nd) {
+                    dep = gt->dep[i];
+                    dk = gt->dep_kind[i];
+                } else {
+                    dep = A.srcs[gt->src_all_first + (i - nd)].dep;
+                }
+                if (dep >= 0) {
+                    const uint32_t idx = A.tasks[dep].first + uint32_t(dk == DK_PARENT_BOARD ? Rk.parent_board[b] : b);
+                    if (idx >= A.t0)
+                        while (ld_acquire_u32(A.flags + idx) != epoch) __nanosleep(20);
+                }
+            }
         }
         __syncthreads();
-
-        const uint16_t* __restrict__ row_p = Rk.rp[p].row_of_hand + size_t(b) * Hp;
-        const uint16_t* __restrict__ row_o = Rk.rp[o].row_of_hand + size_t(b) * Ho;
-        const float scale = Rk.chance_scale[b];
-
-        // incoming opponent reach of this node on this board (masked by the hands the board removes)
-        auto rin_src = [&]() -> const float* {
-            if (nt.r_in == RIN_INITIAL) return A.root_weights[o];
-            if (nt.rin_parent_round) {
-                const RoundArgs& Rp = A.rounds[k - 1];
-                return Rp.rbuf + (size_t(nt.r_in) * Rp.n_boards + Rk.parent_board[b]) * Ho;
-            }
-            return Rk.rbuf + (size_t(nt.r_in) * nb + b) * Ho;
-        };
+        const NodeTask& nt = s_nt;
 
         switch (kind) {
-            case TK_DOWN: {  // cfr.rs:582-586 (+ terminal children, cfr.rs:523-558)
-                const float* src = rin_src();
-                const uint32_t nrows_o = Rk.rp[o].n_rows[b];
-                const float* __restrict__ tab =
-                    (MODE == KM_CFR ? Rk.rp[o].regrets : Rk.rp[o].ssum) + Rk.rp[o].board_off[b] + size_t(nrows_o) * nt.cum_a;
-                const int n_act = nt.n_act;
-                // child routing, decoded once: terminal children are staged in shared memory slots
-                int cslot[FAST_ACTIONS];
-                float* cdst[FAST_ACTIONS];
-                {
-                    int slot = 0;
-#pragma unroll
-                    for (int a = 0; a < FAST_ACTIONS; ++a) {
-                        cslot[a] = -1;
-                        cdst[a] = nullptr;
-                        if (a < n_act) {
-                            const int ck = nt.child[a].kind;
-                            if (ck == CK_FOLD || ck == CK_SHOWDOWN) cslot[a] = slot++;
-                            else cdst[a] = Rk.rbuf + (size_t(nt.child[a].buf) * nb + b) * Ho;
-                        }
-                    }
-                }
-                if (n_act <= FAST_ACTIONS) {
-                    // batched: all loads of a chunk of hands are in flight before any is used
-#pragma unroll 1
-                    for (int c0 = 0; c0 < MAX_HPT; c0 += HAND_CHUNK) {
-                        if (tid + c0 * T >= Ho) break;
-                        uint32_t row[HAND_CHUNK];
-                        float r[HAND_CHUNK];
-                        float g[HAND_CHUNK][FAST_ACTIONS];
-#pragma unroll
-                        for (int i = 0; i < HAND_CHUNK; ++i) {
-                            const int h = tid + (c0 + i) * T;
-                            row[i] = h < Ho ? row_o[h] : 0xFFFFu;
-                        }
-#pragma unroll
-                        for (int i = 0; i < HAND_CHUNK; ++i) {
-                            const int h = tid + (c0 + i) * T;
-                            r[i] = row[i] != 0xFFFF ? __ldcg(src + h) : 0.f;
-#pragma unroll
-                            for (int a = 0; a < FAST_ACTIONS; ++a)
-                                g[i][a] = (row[i] != 0xFFFF && a < n_act) ? tab[size_t(row[i]) * n_act + a] : 0.f;
-                        }
-#pragma unroll
-                        for (int i = 0; i < HAND_CHUNK; ++i) {
-                            const int h = tid + (c0 + i) * T;
-                            if (h >= Ho) continue;
-                            float norm = 0.f;
-#pragma unroll
-                            for (int a = 0; a < FAST_ACTIONS; ++a) {
-                                g[i][a] = fmaxf(g[i][a], 0.f);
-                                norm += g[i][a];
-                            }
-                            const float inv = norm > 0.f ? r[i] / norm : 0.f;
-                            const float uni = r[i] / float(n_act);
-#pragma unroll
-                            for (int a = 0; a < FAST_ACTIONS; ++a) {
-                                if (a < n_act) {
-                                    const float v = norm > 0.f ? g[i][a] * inv : uni;
-                                    if (cslot[a] >= 0) c.X[cslot[a] * c.Hx + h] = v;
-                                    else __stcg(cdst[a] + h, v);
-                                }
-                            }
-                        }
-                    }
-                } else {
-                    for (int h = tid; h < Ho; h += T) {
-                        const uint32_t row = row_o[h];
-                        float r = 0.f, norm = 0.f;
-                        if (row != 0xFFFF) {
-                            r = __ldcg(src + h);
-                            for (int a = 0; a < n_act; ++a) norm += fmaxf(tab[size_t(row) * n_act + a], 0.f);
-                        }
-                        int slot = 0;
-                        for (int a = 0; a < n_act; ++a) {
-                            float v = 0.f;
-                            if (row != 0xFFFF)
-                                v = norm > 0.f ? r * fmaxf(tab[size_t(row) * n_act + a], 0.f) / norm : r / float(n_act);
-                            const int ck = nt.child[a].kind;
-                            if (ck == CK_FOLD || ck == CK_SHOWDOWN) c.X[(slot++) * c.Hx + h] = v;
-                            else __stcg(Rk.rbuf + (size_t(nt.child[a].buf) * nb + b) * Ho + h, v);
-                        }
-                    }
-                }
-                if (nt.out >= 0) {
-                    float acc[MAX_HPT];
-#pragma unroll
-                    for (int i = 0; i < MAX_HPT; ++i) acc[i] = 0.f;
-                    int tslot = 0;
-                    for (int a = 0; a < n_act; ++a) {
-                        const int ck = nt.child[a].kind;
-                        if (ck != CK_FOLD && ck != CK_SHOWDOWN) continue;
-                        const float* r = c.X + (tslot++) * c.Hx;
-                        const float cf = nt.child[a].coef * scale;
-                        if (ck == CK_FOLD) {
-                            const float total = card_sums(c, r);
-#pragma unroll
-                            for (int i = 0; i < MAX_HPT; ++i) {
-                                const int h = tid + i * T;
-                                if (h < Hp && row_p[h] != 0xFFFF) acc[i] += cf * compat_mass(c, r, total, h);
-                            }
-                        } else {
-                            showdown_eval(c, A.sd[o], A.sd[p], b, row_o, row_p, r, cf, acc);
-                        }
-                    }
-                    float* out = Rk.cbuf + (size_t(nt.out) * nb + b) * Hp;
-#pragma unroll
-                    for (int i = 0; i < MAX_HPT; ++i) {
-                        const int h = tid + i * T;
-                        if (h < Hp) __stcg(out + h, acc[i]);
-                    }
+            case TK_DOWN: {
+                switch (nt.n_act) {
+                    case 2: task_down<MODE, 2>(A, c, nt, Rk, k, b); break;
+                    case 3: task_down<MODE, 3>(A, c, nt, Rk, k, b); break;
+                    case 4: task_down<MODE, 4>(A, c, nt, Rk, k, b); break;
+                    default: task_down_generic<MODE>(A, c, nt, Rk, k, b); break;
                 }
                 break;
             }
-            case TK_UP_OPP: {  // value of an opponent node = sum over its actions (sigma is already inside the reach)
-                float* out = Rk.cbuf + (size_t(nt.out) * nb + b) * Hp;
-                const int n_act = nt.n_act;
-                for (int h = tid; h < Hp; h += T) {
-                    float v = nt.aux >= 0 ? __ldcg(Rk.cbuf + (size_t(nt.aux) * nb + b) * Hp + h) : 0.f;
-                    for (int a = 0; a < n_act; ++a) {
-                        const int ck = nt.child[a].kind;
-                        if (ck == CK_ACTION) v += __ldcg(Rk.cbuf + (size_t(nt.child[a].buf) * nb + b) * Hp + h);
-                        else if (ck == CK_CHANCE) v += __ldcg(Rk.gathered + (size_t(nt.child[a].buf) * nb + b) * Hp + h);
-                    }
-                    __stcg(out + h, v);
+            case TK_UP_TRAV: {
+                switch (nt.n_act) {
+                    case 2: task_trav<MODE, 2>(A, c, nt, Rk, k, b); break;
+                    case 3: task_trav<MODE, 3>(A, c, nt, Rk, k, b); break;
+                    case 4: task_trav<MODE, 4>(A, c, nt, Rk, k, b); break;
+                    default: task_trav_generic<MODE>(A, c, nt, Rk, k, b); break;
                 }
                 break;
             }
-            case TK_UP_TRAV: {  // cfr.rs:588, 612-621
-                const float* src = rin_src();
-                const int n_act = nt.n_act;
-                // issue every vector load of the task up front: incoming reach + child value vectors
-                {
-                    float tmp[MAX_HPT];
-#pragma unroll
-                    for (int i = 0; i < MAX_HPT; ++i) {
-                        const int h = tid + i * T;
-                        tmp[i] = (h < Ho && row_o[h] != 0xFFFF) ? __ldcg(src + h) : 0.f;
-                    }
-                    for (int a = 0; a < n_act; ++a) {
-                        const int ck = nt.child[a].kind;
-                        if (ck != CK_ACTION && ck != CK_CHANCE) continue;
-                        const float* vsrc = (ck == CK_ACTION ? Rk.cbuf : Rk.gathered) + (size_t(nt.child[a].buf) * nb + b) * Hp;
-                        float* V = c.X + (1 + a) * c.Hx;
-                        float tv[MAX_HPT];
-#pragma unroll
-                        for (int i = 0; i < MAX_HPT; ++i) {
-                            const int h = tid + i * T;
-                            tv[i] = h < Hp ? __ldcg(vsrc + h) : 0.f;
-                        }
-#pragma unroll
-                        for (int i = 0; i < MAX_HPT; ++i) {
-                            const int h = tid + i * T;
-                            if (h < Hp) V[h] = tv[i];
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < MAX_HPT; ++i) {
-                        const int h = tid + i * T;
-                        if (h < Ho) c.Rin[h] = tmp[i];
-                    }
+            case TK_UP_OPP: {  // opponent node at a street root: terminal partial + children (sigma is inside the reach)
+                if (c.pos4 < c.HpP) {
+                    float4 v = nt.aux >= 0 ? ldcg4(Rk.cbuf + (size_t(nt.aux) * Rk.n_boards + b) * c.HpP + c.pos4) : f4zero();
+                    for (int a = 0; a < nt.n_act; ++a)
+                        if (nt.child[a].kind == CK_VALUE) v = f4add(v, child_value4(A, c, Rk, nt.child[a], b));
+                    stcg4(Rk.cbuf + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4, v);
                 }
-                float* M = c.X;  // slot 0
-                const float total = card_sums(c, c.Rin);
-                for (int h = tid; h < Hp; h += T) M[h] = compat_mass(c, c.Rin, total, h);
-                for (int a = 0; a < n_act; ++a) {
-                    float* V = c.X + (1 + a) * c.Hx;
-                    const int ck = nt.child[a].kind;
-                    if (ck == CK_FOLD) {
-                        const float cf = nt.child[a].coef * scale;
-                        for (int h = tid; h < Hp; h += T) V[h] = cf * M[h];
-                    } else if (ck == CK_SHOWDOWN) {
-                        float acc[MAX_HPT];
-#pragma unroll
-                        for (int i = 0; i < MAX_HPT; ++i) acc[i] = 0.f;
-                        showdown_eval(c, A.sd[o], A.sd[p], b, row_o, row_p, c.Rin, nt.child[a].coef * scale, acc);
-#pragma unroll
-                        for (int i = 0; i < MAX_HPT; ++i) {
-                            const int h = tid + i * T;
-                            if (h < Hp) V[h] = acc[i];
-                        }
-                    }
-                }
-                __syncthreads();
-                // one thread per infoset row: node value, regret and strategy-sum update
-                const uint32_t nrows_p = Rk.rp[p].n_rows[b];
-                float* tabR = Rk.rp[p].regrets + Rk.rp[p].board_off[b] + size_t(nrows_p) * nt.cum_a;
-                float* tabS = Rk.rp[p].ssum + Rk.rp[p].board_off[b] + size_t(nrows_p) * nt.cum_a;
-                const uint16_t* __restrict__ rstart = Rk.rp[p].row_start + size_t(b) * (Hp + 1);
-                const uint16_t* __restrict__ rhands = Rk.rp[p].row_hands + size_t(b) * Hp;
-                float* out = Rk.cbuf + (size_t(nt.out) * nb + b) * Hp;
-                const float* V1 = c.X + c.Hx;
-                if (n_act <= FAST_ACTIONS) {
-#pragma unroll 1
-                    for (uint32_t r0 = tid; r0 < nrows_p; r0 += HAND_CHUNK * T) {
-                        float rg[HAND_CHUNK][FAST_ACTIONS], ss[HAND_CHUNK][FAST_ACTIONS];
-                        int hs[HAND_CHUNK], he[HAND_CHUNK];
-                        // all table loads of the chunk first
-#pragma unroll
-                        for (int i = 0; i < HAND_CHUNK; ++i) {
-                            const uint32_t row = r0 + i * T;
-                            const bool ok = row < nrows_p;
-                            hs[i] = ok ? rstart[row] : 0;
-                            he[i] = ok ? rstart[row + 1] : 0;
-#pragma unroll
-                            for (int a = 0; a < FAST_ACTIONS; ++a) {
-                                const bool la = ok && a < n_act;
-                                rg[i][a] = (la && MODE == KM_CFR) ? tabR[size_t(row) * n_act + a] : 0.f;
-                                ss[i][a] = (la && MODE != KM_BR) ? tabS[size_t(row) * n_act + a] : 0.f;
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < HAND_CHUNK; ++i) {
-                            const uint32_t row = r0 + i * T;
-                            if (row >= nrows_p) continue;
-                            float sg[FAST_ACTIONS], d[FAST_ACTIONS];
-                            float norm = 0.f;
-#pragma unroll
-                            for (int a = 0; a < FAST_ACTIONS; ++a) {
-                                sg[a] = fmaxf(MODE == KM_EVAL ? ss[i][a] : rg[i][a], 0.f);
-                                norm += sg[a];
-                                d[a] = 0.f;
-                            }
-                            const float inv = norm > 0.f ? 1.0f / norm : 0.f;
-                            const float uni = 1.0f / float(n_act);
-#pragma unroll
-                            for (int a = 0; a < FAST_ACTIONS; ++a) sg[a] = a < n_act ? (norm > 0.f ? sg[a] * inv : uni) : 0.f;
-                            float msum = 0.f;
-                            for (int q = hs[i]; q < he[i]; ++q) {
-                                const int h = rhands[q];
-                                float v[FAST_ACTIONS];
-                                float vn = (MODE == KM_BR) ? -3.0e38f : 0.f;
-#pragma unroll
-                                for (int a = 0; a < FAST_ACTIONS; ++a) {
-                                    v[a] = 0.f;
-                                    if (a < n_act) {
-                                        v[a] = V1[a * c.Hx + h];
-                                        if (MODE == KM_BR) vn = fmaxf(vn, v[a]);
-                                        else vn += sg[a] * v[a];
-                                    }
-                                }
-                                if (MODE == KM_CFR) {
-#pragma unroll
-                                    for (int a = 0; a < FAST_ACTIONS; ++a) d[a] += v[a] - vn;
-                                    msum += M[h];
-                                }
-                                __stcg(out + h, vn);
-                            }
-                            if (MODE == KM_CFR) {
-                                const float w = msum * scale;
-#pragma unroll
-                                for (int a = 0; a < FAST_ACTIONS; ++a) {
-                                    if (a < n_act) {
-                                        tabR[size_t(row) * n_act + a] = rg[i][a] + d[a];
-                                        tabS[size_t(row) * n_act + a] = ss[i][a] + sg[a] * w;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                } else {
-                    // wide nodes (> FAST_ACTIONS actions): two passes over the actions, nothing kept in registers
-                    for (uint32_t row = tid; row < nrows_p; row += T) {
-                        const float* tsrc = (MODE == KM_EVAL ? tabS : tabR) + size_t(row) * n_act;
-                        float norm = 0.f;
-                        if (MODE != KM_BR)
-                            for (int a = 0; a < n_act; ++a) norm += fmaxf(tsrc[a], 0.f);
-                        const float inv = norm > 0.f ? 1.0f / norm : 0.f;
-                        const float uni = 1.0f / float(n_act);
-                        float msum = 0.f, vsum = 0.f;
-                        const int hs = rstart[row], he = rstart[row + 1];
-                        for (int q = hs; q < he; ++q) {
-                            const int h = rhands[q];
-                            float vn = (MODE == KM_BR) ? -3.0e38f : 0.f;
-                            for (int a = 0; a < n_act; ++a) {
-                                const float va = V1[a * c.Hx + h];
-                                if (MODE == KM_BR) vn = fmaxf(vn, va);
-                                else vn += (norm > 0.f ? fmaxf(tsrc[a], 0.f) * inv : uni) * va;
-                            }
-                            vsum += vn;
-                            msum += M[h];
-                            __stcg(out + h, vn);
-                        }
-                        if (MODE == KM_CFR) {
-                            const float w = msum * scale;
-                            for (int a = 0; a < n_act; ++a) {
-                                float da = -vsum;
-                                for (int q = hs; q < he; ++q) da += V1[a * c.Hx + rhands[q]];
-                                const float old = tabR[size_t(row) * n_act + a];
-                                const float sga = norm > 0.f ? fmaxf(old, 0.f) * inv : uni;
-                                tabS[size_t(row) * n_act + a] += sga * w;
-                                tabR[size_t(row) * n_act + a] = old + da;
-                            }
-                        }
-                    }
-                }
-                for (int h = tid; h < Hp; h += T)
-                    if (row_p[h] == 0xFFFF) __stcg(out + h, 0.f);
                 break;
             }
             case TK_GATHER: {  // cfr.rs:502-522: sum over the dealt cards, fixed board order
-                const RoundArgs& Rn = A.rounds[k + 1];
-                const int cb0 = Rk.per_parent > 0 ? b * Rk.per_parent : 0;
-                const int ncb = Rk.per_parent > 0 ? Rk.per_parent : Rk.n_boards_next;
-                const float* src = Rn.cbuf + (size_t(nt.aux) * Rn.n_boards + cb0) * Hp;
-                float* out = Rk.gathered + (size_t(nt.out) * nb + b) * Hp;
-                for (int h = tid; h < Hp; h += T) {
-                    float acc = 0.f;
-                    for (int i = 0; i < ncb; ++i) acc += __ldcg(src + size_t(i) * Hp + h);
-                    __stcg(out + h, acc);
+                if (c.pos4 < c.HpP) {
+                    const RoundArgs& Rn = A.rounds[k + 1];
+                    const int cb0 = Rk.per_parent > 0 ? b * Rk.per_parent : 0;
+                    const int ncb = Rk.per_parent > 0 ? Rk.per_parent : Rk.n_boards_next;
+                    const float* src = Rn.cbuf + (size_t(nt.aux) * Rn.n_boards + cb0) * c.HpP;
+                    const uint16_t* __restrict__ cp = Rn.rp[c.p].child_pos + size_t(cb0) * c.HpP + c.pos4;
+                    float4 acc = f4zero();
+                    for (int i = 0; i < ncb; ++i) {
+                        uint32_t q[4];
+                        unpack4(__ldg(reinterpret_cast<const uint2*>(cp + size_t(i) * c.HpP)), q);
+                        const float* s = src + size_t(i) * c.HpP;
+                        acc.x += q[0] != 0xffffu ? __ldcg(s + q[0]) : 0.f;
+                        acc.y += q[1] != 0xffffu ? __ldcg(s + q[1]) : 0.f;
+                        acc.z += q[2] != 0xffffu ? __ldcg(s + q[2]) : 0.f;
+                        acc.w += q[3] != 0xffffu ? __ldcg(s + q[3]) : 0.f;
+                    }
+                    stcg4(Rk.gathered + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4, acc);
                 }
                 break;
             }
             case TK_ROOT_SHOWDOWN: {
-                const float* src = rin_src();
-                for (int h = tid; h < Ho; h += T) c.Rin[h] = (row_o[h] != 0xFFFF) ? __ldcg(src + h) : 0.f;
-                float acc[MAX_HPT];
-#pragma unroll
-                for (int i = 0; i < MAX_HPT; ++i) acc[i] = 0.f;
-                showdown_eval(c, A.sd[o], A.sd[p], b, row_o, row_p, c.Rin, nt.child[0].coef * scale, acc);
-                float* out = Rk.cbuf + (size_t(nt.out) * nb + b) * Hp;
-#pragma unroll
-                for (int i = 0; i < MAX_HPT; ++i) {
-                    const int h = tid + i * T;
-                    if (h < Hp) __stcg(out + h, acc[i]);
-                }
+                float4 mass, sd;
+                trav_terms(A, c, nt, Rk, k, b, true, mass, sd);
+                const float cf = nt.child[0].coef * Rk.chance_scale[b];
+                if (c.pos4 < c.HpP)
+                    stcg4(Rk.cbuf + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4, make_float4(cf * sd.x, cf * sd.y, cf * sd.z, cf * sd.w));
                 break;
             }
             case TK_CHANCE_DOWN: {
-                const float* src = rin_src();
-                float* dst = Rk.rbuf + (size_t(nt.aux) * nb + b) * Ho;
-                for (int h = tid; h < Ho; h += T) __stcg(dst + h, (row_o[h] != 0xFFFF) ? __ldcg(src + h) : 0.f);
+                const float4 r4 = load_reach4(A, c, nt, Rk, k, b);
+                if (c.pos4 < c.HoP) stcg4(Rk.rbuf + (size_t(nt.aux) * Rk.n_boards + b) * c.HoP + c.pos4, r4);
                 break;
             }
             case TK_CHANCE_UP: {
-                const float* src = Rk.gathered + (size_t(nt.aux) * nb + b) * Hp;
-                float* out = Rk.cbuf + (size_t(nt.out) * nb + b) * Hp;
-                for (int h = tid; h < Hp; h += T) __stcg(out + h, __ldcg(src + h));
+                if (c.pos4 < c.HpP)
+                    stcg4(Rk.cbuf + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4,
+                          ldcg4(Rk.gathered + (size_t(nt.aux) * Rk.n_boards + b) * c.HpP + c.pos4));
                 break;
             }
             default: break;
@@ -642,11 +795,11 @@ __global__ void normalize_kernel(const float* __restrict__ in, float* __restrict
 
 size_t task_kernel_smem_bytes(int slots, int Hp_pad, int Ho_pad) {
     const int hx = Hp_pad > Ho_pad ? Hp_pad : Ho_pad;
-    size_t floats = size_t(Ho_pad) + size_t(slots) * hx + (Ho_pad + 4) + 52 * CM_STRIDE + 64 + 32;
+    size_t floats = size_t(Ho_pad) + size_t(slots) * hx + (Ho_pad + 4) + (2 * size_t(Ho_pad) + 8) + 64;
     return floats * sizeof(float);
 }
 
-cudaError_t configure_task_kernels(size_t smem, int* blocks_per_sm) {
+cudaError_t configure_task_kernels(size_t smem, int threads, int* blocks_per_sm) {
     cudaError_t e;
     e = cudaFuncSetAttribute(task_kernel<KM_CFR>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
@@ -655,20 +808,20 @@ cudaError_t configure_task_kernels(size_t smem, int* blocks_per_sm) {
     e = cudaFuncSetAttribute(task_kernel<KM_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     int n = 0, m = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, task_kernel<KM_CFR>, TASK_THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, task_kernel<KM_CFR>, threads, smem);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, task_kernel<KM_BR>, TASK_THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, task_kernel<KM_BR>, threads, smem);
     if (e != cudaSuccess) return e;
     *blocks_per_sm = n < m ? n : m;
     return cudaSuccess;
 }
 
-cudaError_t launch_task_kernel(const TaskArgs& a, int mode, int grid, size_t smem, cudaStream_t st) {
+cudaError_t launch_task_kernel(const TaskArgs& a, int mode, int grid, int threads, size_t smem, cudaStream_t st) {
     if (grid <= 0 || a.t1 <= a.t0) return cudaSuccess;
     switch (mode) {
-        case KM_CFR: task_kernel<KM_CFR><<<grid, TASK_THREADS, smem, st>>>(a); break;
-        case KM_BR: task_kernel<KM_BR><<<grid, TASK_THREADS, smem, st>>>(a); break;
-        default: task_kernel<KM_EVAL><<<grid, TASK_THREADS, smem, st>>>(a); break;
+        case KM_CFR: task_kernel<KM_CFR><<<grid, threads, smem, st>>>(a); break;
+        case KM_BR: task_kernel<KM_BR><<<grid, threads, smem, st>>>(a); break;
+        default: task_kernel<KM_EVAL><<<grid, threads, smem, st>>>(a); break;
     }
     return cudaGetLastError();
 }

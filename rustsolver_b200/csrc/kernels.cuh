@@ -1,8 +1,9 @@
 // Device side of the B200 CFR engine (sm_100a): a persistent dataflow kernel over the task graph
-// of one traversal (tasks.h).  One CTA executes one (node-task, board) instance at a time with
-// its working vectors in shared memory; instances exchange opponent-reach and counterfactual-
-// value vectors through L2-resident global buffers and order themselves with release/acquire
-// flags, so every SM stays busy on independent boards/nodes and a whole traversal is ONE launch.
+// of one traversal (tasks.h).  One CTA executes one (node-task, board) instance at a time; each
+// thread owns FOUR consecutive hands of the board-local hand order, so every vector and table
+// access is a 128-bit load/store.  Instances exchange opponent-reach and counterfactual-value
+// vectors through L2-resident global buffers and order themselves with release/acquire flags, so
+// every SM stays busy on independent boards/nodes and a whole traversal is ONE launch.
 //
 // Restates, in vector form:
 //   regret matching                Infoset::get_strategy          src/solver/infoset.rs:83-102
@@ -21,48 +22,37 @@
 namespace rs {
 
 constexpr int MAX_ACTIONS = MAX_TASK_CHILDREN;
-constexpr int CM_STRIDE = 53;   // per-card prefix row: entry 0 = 0, entries 1..n_c inclusive sums
-constexpr int TASK_THREADS = 256;
-constexpr int MAX_HPT = 6;      // hands per thread: ceil(1326 / 256)
-constexpr int HAND_CHUNK = 3;   // hands / rows whose loads are batched in registers
-constexpr int FAST_ACTIONS = 4; // nodes up to this many actions keep their table rows in registers
+constexpr int FAST_ACTIONS = 4;        // nodes up to this many actions keep their table rows in registers
+constexpr int MAX_TASK_THREADS = 352;  // ceil(1326 / 4) rounded up to a warp multiple
 
 enum KernelMode { KM_CFR = 0, KM_BR = 1, KM_EVAL = 2 };
 
-struct DevPlayer {
-    const uint8_t* cards;        // [H][2]
-    const uint16_t* same;        // [H]
-    const uint16_t* card_hands;  // [52][52]
-    int H;
-    int Hpad;  // H rounded up to 4
-};
-
-struct DevRoundPlayer {
-    const uint16_t* row_of_hand;  // [nb][H]
-    const uint16_t* row_start;    // [nb][H+1]
-    const uint16_t* row_hands;    // [nb][H]
+struct DevRoundPlayer {  // round k, player q; every array is indexed [board][...] in board-local hand order
+    const uint16_t* row_of_pos;   // [nb][Hpad]
+    const uint16_t* row_start;    // [nb][Hpad+4]
+    const uint16_t* row_pos;      // [nb][Hpad]
+    const uint16_t* cl_pos;       // [nb][2*Hpad]  per-card lists (q as opponent)
+    const uint16_t* parent_pos;   // [nb][Hpad]
+    const uint16_t* child_pos;    // [nb][Hpad(parent)]
+    const uint16_t* slot_of_pos;  // [nb][Hpad]  (round 0: initial range weights are given by hand slot)
+    const HandRec* hrec;          // [nb][Hpad]  (q as traverser)
     const uint32_t* n_rows;       // [nb]
+    const uint32_t* n_rows_pad;   // [nb]
+    const uint32_t* n_live;       // [nb]
     const uint64_t* board_off;    // [nb]
     float* regrets;
     float* ssum;
-};
-
-struct DevShowdown {
-    const uint16_t* sorted;  // [nb][H]
-    const uint32_t* n_live;  // [nb]
-    const uint8_t* cj;       // [nb][H][2]
-    const uint8_t* n_card;   // [nb][52]
-    const uint16_t* lohi;    // [nb][H][2]
-    const uint8_t* cpos;     // [nb][H][4]
+    int identity;
+    int pad;
 };
 
 struct RoundArgs {
     DevRoundPlayer rp[2];
     const float* chance_scale;    // [nb]
     const int32_t* parent_board;  // [nb] local id in the parent round
-    float* rbuf;                  // [n_rbuf][nb][H_opp]   opponent reach per buffer id
-    float* cbuf;                  // [n_cbuf][nb][H_trav]  counterfactual values per buffer id
-    float* gathered;              // [n_leaves][nb][H_trav]
+    float* rbuf;                  // [n_rbuf][nb][Hpad_opp]   opponent reach per buffer id
+    float* cbuf;                  // [n_cbuf][nb][Hpad_trav]  counterfactual values per buffer id
+    float* gathered;              // [n_leaves][nb][Hpad_trav]
     int n_boards;
     int per_parent;  // boards of the NEXT round per board of this one (0: every local next-round board hangs off board 0)
     int n_boards_next;
@@ -70,22 +60,22 @@ struct RoundArgs {
 };
 
 struct TaskArgs {
-    DevPlayer pl[2];
-    DevShowdown sd[2];  // final round
     RoundArgs rounds[3];
     const NodeTask* tasks;
+    const TaskSrc* srcs;
     uint32_t n_tasks;
     uint32_t* flags;  // [n_tickets] epoch of completion
     TaskCtl* ctl;
     const float* root_weights[2];
+    int H[2], Hpad[2];
     int trav;
     uint32_t t0, t1;  // ticket range of this launch
-    int slots;        // H-sized scratch vectors provisioned in shared memory
+    int slots;        // Hx-sized scratch vectors provisioned in shared memory
 };
 
 size_t task_kernel_smem_bytes(int slots, int Hp_pad, int Ho_pad);
-cudaError_t configure_task_kernels(size_t smem, int* blocks_per_sm);
-cudaError_t launch_task_kernel(const TaskArgs& a, int mode, int grid, size_t smem, cudaStream_t st);
+cudaError_t configure_task_kernels(size_t smem, int threads, int* blocks_per_sm);
+cudaError_t launch_task_kernel(const TaskArgs& a, int mode, int grid, int threads, size_t smem, cudaStream_t st);
 
 cudaError_t launch_scale(float* data, size_t n, float d, cudaStream_t st);
 // out[row][a] = regret-matched strategy of in[row][0..A)

@@ -347,6 +347,9 @@ struct TaskGen {
             }
         }
         // ---------------- up tasks, deepest street first ----------------
+        // Opponent nodes below a traverser node get no task of their own: the parent sums their terminal
+        // partial and their children's values itself (one hop less per tree level).  Opponent nodes that
+        // are street roots keep a TK_UP_OPP task because the gather / root read-out needs their value.
         tl.phase_cut = 0;
         for (int k = int(R) - 1; k >= 0; --k) {
             std::vector<Pending> pend;
@@ -367,36 +370,36 @@ struct TaskGen {
                         pend.push_back({t, id, n.depth});
                     } else if (n.kind == PK_ACTION) {
                         const bool opp = (n.player != trav);
+                        if (opp && !is_root && P->nodes[n.parent].kind == PK_ACTION && P->nodes[n.parent].player == trav) continue;
                         NodeTask t = blank(opp ? TK_UP_OPP : TK_UP_TRAV, uint32_t(k));
                         t.n_act = uint8_t(n.children.size());
                         t.cum_a = n.cum_a;
                         t.an_index = n.an_index;
                         t.out = cbuf[id];
-                        t.aux = opp ? tbuf[id] : -1;
-                        for (size_t a = 0; a < n.children.size(); ++a) {
-                            const int32_t c = n.children[a];
-                            const PNode& cn = P->nodes[c];
-                            TaskChild& tc = t.child[a];
-                            tc.buf = -1;
-                            if (cn.kind == PK_FOLD) {
-                                tc.kind = CK_FOLD;
-                                tc.coef = (trav == cn.last_to_act) ? -float(cn.value) : float(cn.value);
-                            } else if (cn.kind == PK_SHOWDOWN) {
-                                tc.kind = CK_SHOWDOWN;
-                                tc.coef = float(cn.value);
-                            } else if (cn.kind == PK_CHANCE) {
-                                tc.kind = CK_CHANCE;
-                                tc.buf = cn.leaf_id;
-                            } else {
-                                tc.kind = CK_ACTION;
-                                tc.buf = cbuf[c];
-                            }
-                        }
                         if (!opp) tl.max_children = std::max<uint32_t>(tl.max_children, t.n_act);
                         pend.push_back({t, id, n.depth});
                     }
                 }
             std::stable_sort(pend.begin(), pend.end(), [](const Pending& a, const Pending& b) { return a.depth > b.depth; });
+            // value sources of node `c` seen from its parent: c's own value buffer if c has an up task, else
+            // (opponent node folded into the parent) its terminal partial + its children's sources
+            std::function<bool(int32_t, std::vector<TaskSrc>&)> collect = [&](int32_t c, std::vector<TaskSrc>& out) -> bool {
+                const PNode& cn = P->nodes[c];
+                if (cn.kind == PK_CHANCE) {
+                    out.push_back(TaskSrc{cn.leaf_id, leaf_gather[k][cn.leaf_id], SK_GATHERED, {0, 0, 0}});
+                    return true;
+                }
+                if (cn.kind != PK_ACTION) return true;  // terminals are inside the terminal partial
+                if (up_task[c] >= 0) {
+                    out.push_back(TaskSrc{cbuf[c], up_task[c], SK_CBUF, {0, 0, 0}});
+                    return true;
+                }
+                // folded opponent node
+                if (tbuf[c] >= 0) out.push_back(TaskSrc{tbuf[c], down_task[c], SK_CBUF, {0, 0, 0}});
+                for (int32_t gc : cn.children)
+                    if (!collect(gc, out)) return false;
+                return true;
+            };
             for (Pending& pe : pend) {
                 NodeTask t = pe.t;
                 const PNode& n = P->nodes[pe.pnode];
@@ -409,16 +412,35 @@ struct TaskGen {
                         if (!add_rin_dep(t, rsrc[pe.pnode], uint32_t(k))) return false;
                     } else {
                         t.r_in = RIN_INITIAL;
+                        t.aux = tbuf[pe.pnode];
                         if (!add_dep(t, down_task[pe.pnode], DK_SAME_BOARD)) return false;
                     }
+                    t.src_all_first = uint32_t(tl.srcs.size());
                     for (size_t a = 0; a < n.children.size(); ++a) {
-                        const PNode& cn = P->nodes[n.children[a]];
-                        if (cn.kind == PK_ACTION) {
-                            if (!add_dep(t, up_task[n.children[a]], DK_SAME_BOARD)) return false;
-                        } else if (cn.kind == PK_CHANCE) {
-                            if (!add_dep(t, leaf_gather[k][cn.leaf_id], DK_SAME_BOARD)) return false;
+                        const int32_t c = n.children[a];
+                        const PNode& cn = P->nodes[c];
+                        TaskChild& tc = t.child[a];
+                        tc.buf = -1;
+                        if (cn.kind == PK_FOLD) {
+                            tc.kind = CK_FOLD;
+                            tc.coef = (trav == cn.last_to_act) ? -float(cn.value) : float(cn.value);  // cfr.rs:525-531
+                        } else if (cn.kind == PK_SHOWDOWN) {
+                            tc.kind = CK_SHOWDOWN;
+                            tc.coef = float(cn.value);  // cfr.rs:532-543
+                        } else {
+                            std::vector<TaskSrc> ss;
+                            if (!collect(c, ss)) return false;
+                            if (ss.size() > 255 || tl.srcs.size() + ss.size() > 65535) {
+                                err = "too many value sources for one task";
+                                return false;
+                            }
+                            tc.kind = CK_VALUE;
+                            tc.src_first = uint16_t(tl.srcs.size());
+                            tc.n_src = uint8_t(ss.size());
+                            tl.srcs.insert(tl.srcs.end(), ss.begin(), ss.end());
                         }
                     }
+                    t.n_src_all = uint16_t(tl.srcs.size() - t.src_all_first);
                 }
                 const uint32_t ti = emit(t);
                 up_task[pe.pnode] = int32_t(ti);
@@ -716,17 +738,10 @@ bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstrac
                     rh[rs_[r] + fill[r]++] = uint16_t(h);
                 }
             }
-            // local slab offsets: board b holds n_rows[b] * sum_a floats, [node][row][A]
-            uint64_t off = 0;
-            for (uint32_t b = 0; b < nB; ++b) {
-                T.board_off[b] = off;
-                if (b >= P->local_lo[k] && b < P->local_hi[k]) off += uint64_t(T.n_rows[b]) * T.sum_a;
-            }
-            T.board_off[nB] = off;
         }
     }
 
-    // ---- showdown permutations (final round must be the river) ----
+    // ---- showdown order (final round must be the river) ----
     bool any_showdown = false;
     for (auto& n : P->nodes)
         if (n.kind == PK_SHOWDOWN) {
@@ -734,85 +749,206 @@ bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstrac
             if (P->first_round + n.round_k != RS_ROUND_RIVER) return fail("showdown before the river");
         }
     if (any_showdown) {
-        uint32_t k = P->n_rounds - 1;
-        uint32_t nB = P->n_boards[k];
-        std::vector<uint32_t> str[2];
+        const uint32_t k = P->n_rounds - 1;
+        const uint32_t nB = P->n_boards[k];
         for (int q = 0; q < 2; ++q) {
-            uint32_t H = P->H[q];
+            const uint32_t H = P->H[q];
             ShowdownTables& S = P->sd[q];
             S.sorted.assign(size_t(nB) * H, 0xFFFF);
             S.n_live.assign(nB, 0);
             S.cls.assign(size_t(nB) * H, 0);
-            S.cj.assign(size_t(nB) * H * 2, 0);
-            S.n_card.assign(size_t(nB) * 52, 0);
-            S.lohi.assign(size_t(nB) * H * 2, 0);
-            S.cpos.assign(size_t(nB) * H * 4, 0);
-            str[q].resize(H);
-        }
-        std::vector<uint16_t> order[2];
-        for (uint32_t b = P->local_lo[k]; b < P->local_hi[k]; ++b) {
-            uint64_t bm = P->board_mask[k][b];
-            for (int q = 0; q < 2; ++q) {
-                uint32_t H = P->H[q];
-                ShowdownTables& S = P->sd[q];
-                order[q].clear();
+            S.strength.assign(size_t(nB) * H, 0);
+            std::vector<uint16_t> order;
+            for (uint32_t b = P->local_lo[k]; b < P->local_hi[k]; ++b) {
+                const uint64_t bm = P->board_mask[k][b];
+                uint32_t* str = &S.strength[size_t(b) * H];
+                order.clear();
                 for (uint32_t h = 0; h < H; ++h) {
-                    uint64_t hm = (1ull << P->hand_cards[q][2 * h]) | (1ull << P->hand_cards[q][2 * h + 1]);
-                    if (hm & bm) {
-                        str[q][h] = 0;
-                        continue;
-                    }
-                    str[q][h] = evaluate_mask(bm | hm) + 1;  // TrainHand::get_hand + evaluate (cfr.rs:38-46, 534)
-                    order[q].push_back(uint16_t(h));
+                    const uint64_t hm = (1ull << P->hand_cards[q][2 * h]) | (1ull << P->hand_cards[q][2 * h + 1]);
+                    if (hm & bm) continue;
+                    str[h] = evaluate_mask(bm | hm) + 1;  // TrainHand::get_hand + evaluate (cfr.rs:38-46, 534)
+                    order.push_back(uint16_t(h));
                 }
-                std::stable_sort(order[q].begin(), order[q].end(),
-                                 [&](uint16_t x, uint16_t y) { return str[q][x] < str[q][y]; });
-                uint32_t nl = uint32_t(order[q].size());
-                S.n_live[b] = nl;
+                std::stable_sort(order.begin(), order.end(), [&](uint16_t x, uint16_t y) { return str[x] < str[y]; });
+                S.n_live[b] = uint32_t(order.size());
                 uint32_t cls = 0;
-                uint32_t ccount[52] = {0};
-                for (uint32_t i = 0; i < nl; ++i) {
-                    uint16_t h = order[q][i];
-                    if (i > 0 && str[q][h] != str[q][order[q][i - 1]]) cls++;
-                    S.sorted[size_t(b) * H + i] = h;
+                for (size_t i = 0; i < order.size(); ++i) {
+                    if (i > 0 && str[order[i]] != str[order[i - 1]]) cls++;
+                    S.sorted[size_t(b) * H + i] = order[i];
                     S.cls[size_t(b) * H + i] = cls;
-                    uint8_t c0 = P->hand_cards[q][2 * h], c1 = P->hand_cards[q][2 * h + 1];
-                    S.cj[(size_t(b) * H + h) * 2 + 0] = uint8_t(ccount[c0]++);
-                    S.cj[(size_t(b) * H + h) * 2 + 1] = uint8_t(ccount[c1]++);
                 }
-                for (int c = 0; c < 52; ++c) S.n_card[size_t(b) * 52 + c] = uint8_t(ccount[c]);
             }
-            // traverser-role positions against the other player's sorted lists
-            for (int q = 0; q < 2; ++q) {
-                int o = 1 - q;
-                uint32_t H = P->H[q], Ho = P->H[o];
-                ShowdownTables& S = P->sd[q];
-                const std::vector<uint16_t>& oo = order[o];
-                // strengths of opp in sorted order
-                std::vector<uint32_t> os(oo.size());
-                for (size_t i = 0; i < oo.size(); ++i) os[i] = str[o][oo[i]];
-                // per-card sorted strength lists of the opponent
-                std::vector<uint32_t> cl[52];
-                for (size_t i = 0; i < oo.size(); ++i) {
-                    uint16_t h = oo[i];
-                    cl[P->hand_cards[o][2 * h]].push_back(os[i]);
-                    cl[P->hand_cards[o][2 * h + 1]].push_back(os[i]);
+        }
+    }
+
+    // ---- board-local hand order and the device tables indexed by it ----
+    for (uint32_t k = 0; k < P->n_rounds; ++k) {
+        const uint32_t nB = P->n_boards[k];
+        const bool final_round = any_showdown && k == P->n_rounds - 1;
+        for (int q = 0; q < 2; ++q) {
+            LocalTables& L = P->loc[k][q];
+            const RoundPlayerTables& T = P->tabs[k][q];
+            const uint32_t H = P->H[q];
+            L.Hpad = (H + 3) & ~3u;
+            L.slot_of_pos.assign(size_t(nB) * L.Hpad, 0xFFFF);
+            L.pos_of_slot.assign(size_t(nB) * H, 0xFFFF);
+            L.n_live.assign(nB, 0);
+            L.row_of_pos.assign(size_t(nB) * L.Hpad, 0xFFFF);
+            L.row_start.assign(size_t(nB) * (L.Hpad + 4), 0);
+            L.row_pos.assign(size_t(nB) * L.Hpad, 0xFFFF);
+            L.n_rows_pad.assign(nB, 0);
+            L.identity = true;
+            for (uint32_t b = P->local_lo[k]; b < P->local_hi[k]; ++b) {
+                uint16_t* sop = &L.slot_of_pos[size_t(b) * L.Hpad];
+                uint16_t* pos = &L.pos_of_slot[size_t(b) * H];
+                const uint16_t* roh = &T.row_of_hand[size_t(b) * H];
+                uint32_t n = 0;
+                if (final_round) {
+                    const ShowdownTables& S = P->sd[q];
+                    for (uint32_t i = 0; i < S.n_live[b]; ++i) sop[n++] = S.sorted[size_t(b) * H + i];
+                } else {
+                    for (uint32_t h = 0; h < H; ++h)
+                        if (roh[h] != 0xFFFF) sop[n++] = uint16_t(h);
                 }
-                (void)Ho;
-                for (uint32_t h = 0; h < H; ++h) {
-                    uint32_t s = str[q][h];
-                    if (s == 0) continue;
-                    uint32_t lo = uint32_t(std::lower_bound(os.begin(), os.end(), s) - os.begin());
-                    uint32_t hi = uint32_t(std::upper_bound(os.begin(), os.end(), s) - os.begin());
-                    S.lohi[(size_t(b) * H + h) * 2 + 0] = uint16_t(lo);
-                    S.lohi[(size_t(b) * H + h) * 2 + 1] = uint16_t(hi);
-                    for (int w = 0; w < 2; ++w) {
-                        const auto& L = cl[P->hand_cards[q][2 * h + w]];
-                        uint32_t clo = uint32_t(std::lower_bound(L.begin(), L.end(), s) - L.begin());
-                        uint32_t chi = uint32_t(std::upper_bound(L.begin(), L.end(), s) - L.begin());
-                        S.cpos[(size_t(b) * H + h) * 4 + 2 * w + 0] = uint8_t(clo);
-                        S.cpos[(size_t(b) * H + h) * 4 + 2 * w + 1] = uint8_t(chi);
+                L.n_live[b] = n;
+                for (uint32_t h = 0; h < H; ++h)
+                    if (roh[h] == 0xFFFF) sop[n++] = uint16_t(h);  // hands the board removes go last
+                for (uint32_t i = 0; i < H; ++i) pos[sop[i]] = uint16_t(i);
+                // rows by position; NONE-abstraction tables are renumbered so that row == position
+                uint16_t* rop = &L.row_of_pos[size_t(b) * L.Hpad];
+                for (uint32_t i = 0; i < L.n_live[b]; ++i) rop[i] = roh[sop[i]];
+            }
+        }
+    }
+    // The lossless tables (one row per live hand) use the local position as the row id, which makes every
+    // table access of a thread's four hands one contiguous run.  card_table (row_of_hand) reports that id.
+    for (uint32_t k = 0; k < P->n_rounds; ++k) {
+        uint32_t kind = (abs && k < abs->n_rounds) ? abs->rounds[k].kind : uint32_t(RS_ABS_NONE);
+        for (int q = 0; q < 2; ++q) {
+            LocalTables& L = P->loc[k][q];
+            RoundPlayerTables& T = P->tabs[k][q];
+            const uint32_t H = P->H[q];
+            const uint32_t nB = P->n_boards[k];
+            if (kind == RS_ABS_NONE) {
+                for (uint32_t b = P->local_lo[k]; b < P->local_hi[k]; ++b) {
+                    for (uint32_t i = 0; i < L.n_live[b]; ++i) {
+                        L.row_of_pos[size_t(b) * L.Hpad + i] = uint16_t(i);
+                        T.row_of_hand[size_t(b) * H + L.slot_of_pos[size_t(b) * L.Hpad + i]] = uint16_t(i);
                     }
+                }
+                L.identity = true;
+            } else {
+                L.identity = false;
+            }
+            uint64_t off = 0;
+            for (uint32_t b = 0; b < nB; ++b) {
+                T.board_off[b] = off;
+                if (b < P->local_lo[k] || b >= P->local_hi[k]) continue;
+                const uint32_t nr = T.n_rows[b];
+                L.n_rows_pad[b] = (nr + 3) & ~3u;
+                off += uint64_t(L.n_rows_pad[b]) * T.sum_a;  // [node][row_pad][A]: every slab starts 16-byte aligned
+                // CSR row -> positions
+                uint16_t* rs_ = &L.row_start[size_t(b) * (L.Hpad + 4)];
+                uint16_t* rp = &L.row_pos[size_t(b) * L.Hpad];
+                const uint16_t* rop = &L.row_of_pos[size_t(b) * L.Hpad];
+                std::vector<uint32_t> cnt(nr + 1, 0);
+                for (uint32_t i = 0; i < L.n_live[b]; ++i) cnt[rop[i] + 1]++;
+                for (uint32_t r = 0; r < nr; ++r) cnt[r + 1] += cnt[r];
+                for (uint32_t r = 0; r <= nr; ++r) rs_[r] = uint16_t(cnt[r]);
+                for (uint32_t r = nr + 1; r < L.Hpad + 4; ++r) rs_[r] = uint16_t(cnt[nr]);
+                std::vector<uint32_t> fill(cnt.begin(), cnt.end() - 1);
+                for (uint32_t i = 0; i < L.n_live[b]; ++i) rp[fill[rop[i]]++] = uint16_t(i);
+            }
+            T.board_off[nB] = off;
+        }
+    }
+    // per-card lists (opponent role), per-hand records (traverser role), street-transition maps
+    for (uint32_t k = 0; k < P->n_rounds; ++k) {
+        const uint32_t nB = P->n_boards[k];
+        const bool final_round = any_showdown && k == P->n_rounds - 1;
+        for (int q = 0; q < 2; ++q) {
+            LocalTables& L = P->loc[k][q];
+            L.cl_pos.assign(size_t(nB) * 2 * L.Hpad, 0xFFFF);
+            L.hrec.assign(size_t(nB) * L.Hpad, HandRec{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0xFFFF});
+            if (k > 0) {
+                L.parent_pos.assign(size_t(nB) * L.Hpad, 0xFFFF);
+                L.child_pos.assign(size_t(nB) * P->loc[k - 1][q].Hpad, 0xFFFF);
+            }
+        }
+        for (uint32_t b = P->local_lo[k]; b < P->local_hi[k]; ++b) {
+            uint32_t seg_start[2][53];
+            std::vector<uint32_t> seg_str[2][52];  // strengths inside each card segment (final round)
+            for (int q = 0; q < 2; ++q) {
+                LocalTables& L = P->loc[k][q];
+                const uint32_t H = P->H[q];
+                const uint16_t* sop = &L.slot_of_pos[size_t(b) * L.Hpad];
+                uint32_t cnt[53] = {0};
+                for (uint32_t i = 0; i < L.n_live[b]; ++i) {
+                    cnt[P->hand_cards[q][2 * sop[i]] + 1]++;
+                    cnt[P->hand_cards[q][2 * sop[i] + 1] + 1]++;
+                }
+                seg_start[q][0] = 0;
+                for (int c = 0; c < 52; ++c) seg_start[q][c + 1] = seg_start[q][c] + cnt[c + 1];
+                uint32_t fill[52];
+                for (int c = 0; c < 52; ++c) fill[c] = seg_start[q][c];
+                uint16_t* cl = &L.cl_pos[size_t(b) * 2 * L.Hpad];
+                for (uint32_t i = 0; i < L.n_live[b]; ++i) {  // ascending position = ascending strength on the river
+                    for (int w = 0; w < 2; ++w) {
+                        const int c = P->hand_cards[q][2 * sop[i] + w];
+                        cl[fill[c]++] = uint16_t(i);
+                        if (final_round) seg_str[q][c].push_back(P->sd[q].strength[size_t(b) * H + sop[i]]);
+                    }
+                }
+                if (k > 0) {
+                    const LocalTables& Lp = P->loc[k - 1][q];
+                    const uint32_t pb = uint32_t(P->board_parent[k][b]);
+                    uint16_t* pp = &L.parent_pos[size_t(b) * L.Hpad];
+                    uint16_t* cp = &L.child_pos[size_t(b) * Lp.Hpad];
+                    for (uint32_t i = 0; i < L.n_live[b]; ++i) {
+                        const uint16_t ppos = Lp.pos_of_slot[size_t(pb) * H + sop[i]];
+                        pp[i] = ppos;
+                        cp[ppos] = uint16_t(i);
+                    }
+                }
+            }
+            for (int q = 0; q < 2; ++q) {
+                const int o = 1 - q;
+                LocalTables& L = P->loc[k][q];
+                const LocalTables& Lo = P->loc[k][o];
+                const uint32_t H = P->H[q], Ho = P->H[o];
+                const uint16_t* sop = &L.slot_of_pos[size_t(b) * L.Hpad];
+                std::vector<uint32_t> ostr;  // opponent strengths in its local (sorted) order
+                if (final_round) {
+                    ostr.resize(Lo.n_live[b]);
+                    for (uint32_t i = 0; i < Lo.n_live[b]; ++i)
+                        ostr[i] = P->sd[o].strength[size_t(b) * Ho + Lo.slot_of_pos[size_t(b) * Lo.Hpad + i]];
+                }
+                for (uint32_t i = 0; i < L.n_live[b]; ++i) {
+                    const uint32_t h = sop[i];
+                    const int c0 = P->hand_cards[q][2 * h], c1 = P->hand_cards[q][2 * h + 1];
+                    HandRec r{};
+                    r.s0 = uint16_t(seg_start[o][c0]);
+                    r.n0 = uint8_t(seg_start[o][c0 + 1] - seg_start[o][c0]);
+                    r.s1 = uint16_t(seg_start[o][c1]);
+                    r.n1 = uint8_t(seg_start[o][c1 + 1] - seg_start[o][c1]);
+                    const uint16_t sm = P->same[q][h];
+                    r.same = 0xFFFF;
+                    if (sm != 0xFFFF) {
+                        const uint16_t op = Lo.pos_of_slot[size_t(b) * Ho + sm];
+                        if (op < Lo.n_live[b]) r.same = op;
+                    }
+                    if (final_round) {
+                        const uint32_t st = P->sd[q].strength[size_t(b) * H + h];
+                        r.lo = uint16_t(std::lower_bound(ostr.begin(), ostr.end(), st) - ostr.begin());
+                        r.hi = uint16_t(std::upper_bound(ostr.begin(), ostr.end(), st) - ostr.begin());
+                        const auto& l0 = seg_str[o][c0];
+                        const auto& l1 = seg_str[o][c1];
+                        r.dlo0 = uint8_t(std::lower_bound(l0.begin(), l0.end(), st) - l0.begin());
+                        r.dhi0 = uint8_t(std::upper_bound(l0.begin(), l0.end(), st) - l0.begin());
+                        r.dlo1 = uint8_t(std::lower_bound(l1.begin(), l1.end(), st) - l1.begin());
+                        r.dhi1 = uint8_t(std::upper_bound(l1.begin(), l1.end(), st) - l1.begin());
+                    }
+                    L.hrec[size_t(b) * L.Hpad + i] = r;
                 }
             }
         }

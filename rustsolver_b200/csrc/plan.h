@@ -19,6 +19,7 @@ namespace rs {
 
 struct TaskList {  // one traversal (one traverser) of the whole tree, in ticket order
     std::vector<NodeTask> tasks;
+    std::vector<TaskSrc> srcs;
     uint32_t n_tickets = 0;
     uint32_t phase_cut = 0;     // tickets [0, phase_cut) precede the cross-GPU all-reduce, [phase_cut, n) follow it
     uint32_t n_rbuf[3] = {0, 0, 0};  // reach buffers per round
@@ -59,17 +60,32 @@ struct RoundPlayerTables {  // per (round k, player q), boards are GLOBAL ids
     std::vector<uint16_t> row_start;      // [n_boards][H+1] CSR by row (entries past n_rows repeat the end)
     std::vector<uint16_t> row_hands;      // [n_boards][H] hand slots grouped by row (tail padded 0xFFFF)
     std::vector<uint32_t> n_rows;         // [n_boards]
-    std::vector<uint64_t> board_off;      // [n_boards+1] element offsets: board b occupies n_rows[b]*sum_a floats
+    std::vector<uint64_t> board_off;      // [n_boards+1] element offsets: board b occupies n_rows_pad[b]*sum_a floats
+};
+
+// Board-local hand order and the device tables indexed by it, per (round k, player q).  Live hands come first;
+// on the final round they are sorted by 7-card strength, weakest first, so a showdown prefix sum needs no gather.
+struct LocalTables {
+    uint32_t Hpad = 0;                    // H rounded up to 4
+    bool identity = true;                 // row == position for every live hand on every board (lossless, no merging)
+    std::vector<uint16_t> slot_of_pos;    // [nB][Hpad] hand slot at local position (0xFFFF padding)
+    std::vector<uint16_t> pos_of_slot;    // [nB][H]
+    std::vector<uint32_t> n_live;         // [nB]
+    std::vector<uint16_t> row_of_pos;     // [nB][Hpad] 0xFFFF = blocked / padding
+    std::vector<uint16_t> row_start;      // [nB][Hpad+4] CSR over positions (non-identity tables)
+    std::vector<uint16_t> row_pos;        // [nB][Hpad]
+    std::vector<uint32_t> n_rows_pad;     // [nB] rows rounded up to 4: slabs are 16-byte aligned
+    std::vector<HandRec> hrec;            // [nB][Hpad] q as traverser
+    std::vector<uint16_t> cl_pos;         // [nB][2*Hpad] q as opponent: positions of q's live hands, grouped by card
+    std::vector<uint16_t> parent_pos;     // [nB][Hpad] (k >= 1) position of the same hand on the parent board
+    std::vector<uint16_t> child_pos;      // [nB][Hpad] (k >= 1) indexed by PARENT position: position on this board / 0xFFFF
 };
 
 struct ShowdownTables {  // final round only, per player q, per GLOBAL board
     std::vector<uint16_t> sorted;   // [n_boards][H] live hand slots, weakest first (opp role)
     std::vector<uint32_t> n_live;   // [n_boards]
     std::vector<uint32_t> cls;      // [n_boards][H] strength-class id per sorted position
-    std::vector<uint8_t> cj;        // [n_boards][H][2] position of the hand inside its two per-card lists (opp role)
-    std::vector<uint8_t> n_card;    // [n_boards][52] live hands of q containing card c
-    std::vector<uint16_t> lohi;     // [n_boards][H][2] (trav role) #opp live hands weaker / weaker-or-equal
-    std::vector<uint8_t> cpos;      // [n_boards][H][4] (trav role) same, restricted to opp hands holding c0 / c1
+    std::vector<uint32_t> strength; // [n_boards][H] 7-card strength + 1 by hand slot, 0 = hand hits the board
 };
 
 struct Plan {
@@ -99,6 +115,7 @@ struct Plan {
     std::vector<Segment> segs[3];
     RoundPlayerTables tabs[3][2];
     ShowdownTables sd[2];
+    LocalTables loc[3][2];
     std::vector<int32_t> an_to_pnode;  // ActionNode.index -> PNode id
     TaskList tl[2];                    // per traverser
 

@@ -29,19 +29,34 @@ enum TaskKind : uint8_t {
     TK_CHANCE_DOWN = 5,
     TK_CHANCE_UP = 6
 };
-enum ChildKind : uint8_t { CK_ACTION = 0, CK_FOLD = 1, CK_SHOWDOWN = 2, CK_CHANCE = 3 };
+enum ChildKind : uint8_t {
+    CK_ACTION = 0,    // TK_DOWN: non-terminal child, buf = reach buffer written for it
+    CK_FOLD = 1,      // terminal, coef = +-pot
+    CK_SHOWDOWN = 2,  // terminal, coef = pot
+    CK_CHANCE = 3,    // TK_DOWN: chance child, buf = reach buffer the next street reads
+    CK_VALUE = 4      // TK_UP_*: child value = sum of the task's sources [src_first, src_first + n_src)
+};
 enum DepKind : uint8_t { DK_NONE = 0, DK_SAME_BOARD = 1, DK_PARENT_BOARD = 2, DK_CHILD_BOARDS = 3 };
+enum SrcKind : uint8_t { SK_CBUF = 0, SK_GATHERED = 1 };
 
 constexpr int32_t RIN_INITIAL = -1;  // reach source = the opponent's range weights (root round)
 constexpr int MAX_TASK_CHILDREN = 8;
-constexpr int MAX_TASK_DEPS = 10;
+constexpr int MAX_TASK_DEPS = 4;
 constexpr int MAX_TERMINAL_CHILDREN = 3;  // terminal children of one opponent node staged in shared memory
 
-struct TaskChild {
-    uint8_t kind;  // ChildKind
+struct TaskSrc {  // one value vector feeding a child value, with the task that produces it
+    int32_t buf;  // value buffer id (SK_CBUF) or chance-leaf id (SK_GATHERED) of the task's round
+    int32_t dep;  // node-task index of the producer (same board), -1 = none
+    uint8_t kind; // SrcKind
     uint8_t pad[3];
-    int32_t buf;   // TK_DOWN: reach buffer written for this child; TK_UP_*: value buffer read (CK_ACTION) or leaf id (CK_CHANCE)
-    float coef;    // +-pot of a terminal child (cfr.rs:525-556)
+};
+
+struct TaskChild {
+    uint8_t kind;        // ChildKind
+    uint8_t n_src;       // CK_VALUE
+    uint16_t src_first;  // CK_VALUE: index into the traverser's TaskSrc array
+    int32_t buf;         // TK_DOWN: reach buffer written for this child
+    float coef;          // +-pot of a terminal child (cfr.rs:525-556)
 };
 
 struct NodeTask {
@@ -50,21 +65,40 @@ struct NodeTask {
     uint8_t n_act;
     uint8_t n_dep;
     uint8_t rin_parent_round;  // 1: r_in names a reach buffer of the PARENT round, read at the parent board
-    uint8_t pad0[3];
+    uint8_t pad0;
+    uint16_t n_src_all;        // sources of all children, contiguous from src_all_first (waited on together)
     int32_t r_in;     // reach buffer id, or RIN_INITIAL
-    uint32_t cum_a;   // slab offset = n_rows(board) * cum_a inside the (round, player) table
+    uint32_t cum_a;   // slab offset = n_rows_pad(board) * cum_a inside the (round, player) table
     int32_t out;      // TK_DOWN: terminal-partial value buffer (-1: none); TK_UP_*, roots: value buffer; TK_GATHER: leaf id
     int32_t aux;      // TK_UP_OPP: terminal-partial buffer to add (-1 none); TK_GATHER: value buffer of the child street's root;
                       // TK_CHANCE_DOWN: reach buffer written; TK_CHANCE_UP: leaf id read
     uint32_t first;   // ticket of instance 0
     uint32_t count;   // instances = local boards of round_k
     uint32_t an_index;
+    uint32_t src_all_first;
     int32_t dep[MAX_TASK_DEPS];      // node-task index
     uint8_t dep_kind[MAX_TASK_DEPS]; // DepKind
-    uint8_t pad1[2];
     TaskChild child[MAX_TASK_CHILDREN];
 };
-static_assert(sizeof(NodeTask) == 4 + 4 + 4 * 7 + 4 * MAX_TASK_DEPS + MAX_TASK_DEPS + 2 + 12 * MAX_TASK_CHILDREN, "NodeTask layout");
+static_assert(sizeof(NodeTask) == 8 + 4 * 8 + 4 * MAX_TASK_DEPS + MAX_TASK_DEPS + 12 * MAX_TASK_CHILDREN, "NodeTask layout");
+static_assert(sizeof(NodeTask) % 4 == 0, "NodeTask is copied to shared memory as words");
+
+// Per-hand record of the traverser on one board (16 bytes, one 128-bit load), local hand order:
+//   u16 lo, hi      #opponent live hands strictly weaker / weaker-or-equal (final round only)
+//   u16 s0; u8 dlo0, dhi0   start of card c0's segment in the opponent's per-card list; #weaker / #weaker-or-equal inside it
+//   u16 s1; u8 dlo1, dhi1   same for card c1
+//   u8 n0, n1       lengths of the two segments
+//   u16 same        position of the identical combo in the opponent's order (0xFFFF: none)
+struct HandRec {
+    uint16_t lo, hi;
+    uint16_t s0;
+    uint8_t dlo0, dhi0;
+    uint16_t s1;
+    uint8_t dlo1, dhi1;
+    uint8_t n0, n1;
+    uint16_t same;
+};
+static_assert(sizeof(HandRec) == 16, "HandRec is one 128-bit load");
 
 struct TaskCtl {  // device-resident dispatcher state, reset by the last CTA to leave
     unsigned long long ticket;

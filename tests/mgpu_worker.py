@@ -64,8 +64,12 @@ def main():
             for s in range(lo, hi):
                 og = OracleGame(tree, ranges, board_masks[s])
                 og.iterate(n_iters)
+                from oracle import row_alignment
                 for an in range(tree.n_actions):
                     gr, gs = eng.read_infoset(an, s)
+                    q = int(tree.player[util.node_of(tree, an)])
+                    idx = row_alignment(eng.card_table(0, q, s), og.rows(0, q, 0), og.n_rows(0, q, 0))
+                    gr, gs = gr[idx], gs[idx]
                     orr, os_ = og.get_slab(an, 0)
                     assert np.abs(gr - orr).max() <= TOL * max(np.abs(orr).max(), 1e-12), (s, an)
                     assert np.abs(gs - os_).max() <= TOL * max(np.abs(os_).max(), 1e-12), (s, an)
@@ -83,13 +87,14 @@ def main():
                     return lo1 <= b < hi1
                 return lo1 * per2 <= b < hi1 * per2
 
+            al = util.RowAligner(eng, og, tree)
             for it in range(n_iters):
                 if it > 0:  # lock-step: restart from the oracle's state (see tests/util.py)
                     for an, b in util.all_slabs(tree, nb):
                         k = int(tree.round_idx[np.nonzero((tree.type == 0) & (tree.an_index == an))[0][0]])
                         if mine(k, b):
                             r, s = og.get_slab(an, b)
-                            eng.write_infoset(an, b, r.astype(np.float32), s.astype(np.float32))
+                            al.write(an, b, r, s)
                 eng.iterate(1)
                 og.iterate(1)
                 scales, diffs, table = {}, {}, {"R": 0.0, "S": 0.0}
@@ -103,7 +108,7 @@ def main():
                     k = int(tree.round_idx[np.nonzero((tree.type == 0) & (tree.an_index == an))[0][0]])
                     if not mine(k, b):
                         continue
-                    gr, gs = eng.read_infoset(an, b)
+                    gr, gs = al.read(an, b)
                     for g, oarr, nm in ((gr, orr, "R"), (gs, os_, "S")):
                         if oarr.size:
                             diffs[(an, b, nm)] = float(np.abs(g - oarr).max())

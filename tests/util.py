@@ -28,6 +28,47 @@ def bucket_keys_for(plan_or_oracle_boards, ranges, n_boards, K, seed):
     return out
 
 
+_node_cache = {}
+
+
+def node_of(tree, an):
+    key = id(tree)
+    if key not in _node_cache:
+        _node_cache[key] = {int(tree.an_index[i]): i for i in range(tree.n_nodes) if tree.type[i] == 0}
+    return _node_cache[key][an]
+
+
+class RowAligner:
+    """engine row <-> oracle row per (round, player, board), through the two card tables."""
+
+    def __init__(self, engine, oracle, tree):
+        self.engine, self.oracle, self.tree = engine, oracle, tree
+        self.cache = {}
+
+    def idx(self, an, b):
+        from oracle import row_alignment
+        node = node_of(self.tree, an)
+        k, q = int(self.tree.round_idx[node]), int(self.tree.player[node])
+        key = (k, q, b)
+        if key not in self.cache:
+            self.cache[key] = row_alignment(self.engine.card_table(k, q, b), self.oracle.rows(k, q, b), self.oracle.n_rows(k, q, b))
+        return self.cache[key]
+
+    def read(self, an, b):
+        """engine slabs with rows re-ordered to the oracle's row numbering"""
+        r, s = self.engine.read_infoset(an, b)
+        i = self.idx(an, b)
+        return r[i], s[i]
+
+    def write(self, an, b, regrets, ssum):
+        i = self.idx(an, b)
+        r = np.zeros_like(regrets, dtype=np.float32)
+        s = np.zeros_like(ssum, dtype=np.float32)
+        r[i] = regrets
+        s[i] = ssum
+        self.engine.write_infoset(an, b, r, s)
+
+
 def all_slabs(tree, n_boards_of_round):
     """(an_index, board) pairs of every infoset slab."""
     for i in range(tree.n_nodes):
@@ -40,7 +81,7 @@ def all_slabs(tree, n_boards_of_round):
 ABS_FLOOR = 1e-6  # of the whole table's max magnitude: fp32 cancellation noise floor
 
 
-def compare_tables(engine, oracle: OracleGame, tree, tol, boards=None):
+def compare_tables(engine, oracle: OracleGame, tree, tol, boards=None, aligner=None):
     """Norm-wise parity of every infoset slab, regrets and strategy sums.
 
     For each action node n and board b:
@@ -52,10 +93,11 @@ def compare_tables(engine, oracle: OracleGame, tree, tol, boards=None):
     st = engine.stats()
     nb = [st.n_boards[k] for k in range(st.n_rounds)]
     diffs, scales, table = {}, {}, {"regret": 0.0, "ssum": 0.0}
+    al = aligner or RowAligner(engine, oracle, tree)
     for an, b in all_slabs(tree, nb):
         if boards is not None and b not in boards:
             continue
-        gr, gs = engine.read_infoset(an, b)
+        gr, gs = al.read(an, b)
         orr, os_ = oracle.get_slab(an, b)
         assert gr.shape == orr.shape, (an, b, gr.shape, orr.shape)
         for g, o, name in ((gr, orr, "regret"), (gs, os_, "ssum")):
@@ -81,20 +123,22 @@ def lockstep(engine, oracle: OracleGame, tree, n_free, n_locked, tol):
     iterations where the engine is first reset to the oracle's state (cast to fp32).  Regret matching is
     discontinuous where a row's positive regret mass is rounding noise, so a free run diverges on such
     rows after a few iterations in ANY two arithmetics; lock-step isolates the one-iteration error."""
+    al = RowAligner(engine, oracle, tree)
     for _ in range(n_free):
         engine.iterate(1)
         oracle.iterate(1)
-        compare_tables(engine, oracle, tree, tol)
+        compare_tables(engine, oracle, tree, tol, aligner=al)
     for _ in range(n_locked):
-        copy_oracle_to_engine(engine, oracle, tree)
+        copy_oracle_to_engine(engine, oracle, tree, aligner=al)
         engine.iterate(1)
         oracle.iterate(1)
-        compare_tables(engine, oracle, tree, tol)
+        compare_tables(engine, oracle, tree, tol, aligner=al)
 
 
-def copy_oracle_to_engine(engine, oracle: OracleGame, tree):
+def copy_oracle_to_engine(engine, oracle: OracleGame, tree, aligner=None):
     st = engine.stats()
     nb = [st.n_boards[k] for k in range(st.n_rounds)]
+    al = aligner or RowAligner(engine, oracle, tree)
     for an, b in all_slabs(tree, nb):
         r, s = oracle.get_slab(an, b)
-        engine.write_infoset(an, b, r.astype(np.float32), s.astype(np.float32))
+        al.write(an, b, r, s)
