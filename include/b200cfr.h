@@ -202,6 +202,10 @@ typedef struct rs_kernel_time {
 } rs_kernel_time;
 int rs_profile_iteration(rs_engine* e, rs_kernel_time* out, size_t cap, uint32_t* n_out);
 
+/* Tuning aid: per task kind [count, wait cycles, body cycles, total cycles] accumulated by builds compiled with
+ * -DRS_TASK_TIMING (all zeros otherwise); out32 holds 8 kinds x 4 counters. */
+int rs_debug_task_timing(rs_engine* e, unsigned long long* out32, int reset);
+
 /* ---- host-only plan introspection (no GPU needed): integer parity surface ---- */
 typedef struct rs_plan rs_plan;
 int rs_plan_create(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs,

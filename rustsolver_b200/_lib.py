@@ -85,6 +85,7 @@ ENGINE_API = {
     "rs_stats_get": (C.c_int, [VP, C.POINTER(rs_stats)]),
     "rs_set_range_weights": (C.c_int, [VP, C.c_uint32, f32p, C.c_size_t]),
     "rs_profile_iteration": (C.c_int, [VP, C.POINTER(rs_kernel_time), C.c_size_t, u32p]),
+    "rs_debug_task_timing": (C.c_int, [VP, u64p, C.c_int]),
     "rs_plan_create": (C.c_int, [C.POINTER(rs_tree), C.POINTER(rs_ranges), C.POINTER(rs_abstraction),
                                  C.POINTER(rs_config), u64p, C.c_uint32, C.POINTER(VP)]),
     "rs_plan_destroy": (None, [VP]),

@@ -138,6 +138,7 @@ struct Engine {
     DevBuf<TaskSrc> srcs[2];
     DevBuf<uint32_t> flags;
     DevBuf<TaskCtl> ctl;
+    DevBuf<unsigned long long> timing;
     int slots = 1;
     size_t smem_bytes = 0;
     int blocks_per_sm = 1, n_sms = 148;
@@ -261,6 +262,8 @@ int Engine::init(const rs_config* cfg) {
         max_tickets = std::max(max_tickets, P.tl[p].n_tickets);
         slots = std::max(slots, int(std::max(P.tl[p].max_terminal, 1 + P.tl[p].max_children)));
     }
+    CU(timing.alloc(32));
+    CU(timing.zero());
     CU(flags.alloc(max_tickets));
     CU(flags.zero());
     {
@@ -361,6 +364,7 @@ void Engine::fill_args(TaskArgs* a, int trav) const {
     a->ctl = ctl.p;
     a->trav = trav;
     a->slots = slots;
+    a->timing = timing.p;
 }
 
 int Engine::prof_begin() {
@@ -893,6 +897,16 @@ int rs_profile_iteration(rs_engine* e, rs_kernel_time* out, size_t cap, uint32_t
         if (cap < rec.size()) return set_err(RS_ERR_CAPACITY, "output buffer too small");
         memcpy(out, rec.data(), rec.size() * sizeof(rs_kernel_time));
     }
+    return RS_OK;
+}
+
+int rs_debug_task_timing(rs_engine* e, unsigned long long* out32, int reset) {
+    if (!e || !out32) return set_err(RS_ERR_INVALID, "null argument");
+    Engine& E = e->e;
+    CU(cudaSetDevice(E.device));
+    CU(cudaStreamSynchronize(E.stream));
+    CU(cudaMemcpy(out32, E.timing.p, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) CU(E.timing.zero());
     return RS_OK;
 }
 

@@ -1,7 +1,11 @@
 #include "kernels.cuh"
 
-#ifndef RS_MIN_BLOCKS
-#define RS_MIN_BLOCKS 2  // resident CTAs per SM the register allocator must allow (at MAX_TASK_THREADS threads)
+// resident CTAs per SM the register allocator must allow, per block-size specialisation
+#ifndef RS_MIN_BLOCKS_288
+#define RS_MIN_BLOCKS_288 3  // ranges up to 1152 hands: 288 threads, <= 75 registers
+#endif
+#ifndef RS_MIN_BLOCKS_352
+#define RS_MIN_BLOCKS_352 2  // up to 1326 hands: 352 threads, <= 93 registers
 #endif
 
 namespace rs {
@@ -18,6 +22,10 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 }
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// bulk L2 prefetch (TMA unit, no destination): bytes must be a multiple of 16, p 16-byte aligned
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void stcg4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
@@ -37,7 +45,30 @@ __device__ __forceinline__ void unpack4(uint2 u, uint32_t (&o)[4]) {
     o[3] = u.y >> 16;
 }
 
+// barrier among the compute warps only (the dispatcher warp never joins it)
+__device__ __forceinline__ void csync(int n_compute) { asm volatile("bar.sync 2, %0;" ::"r"(n_compute) : "memory"); }
+// barrier between the compute warps and the dispatcher warp: one per task
+__device__ __forceinline__ void hsync(int n_all) { asm volatile("bar.sync 1, %0;" ::"r"(n_all) : "memory"); }
+
+// shared-memory mbarrier: the compute warps arrive when a task's body is finished, the dispatcher tests it
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(uint32_t(__cvta_generic_to_shared(bar))), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(uint32_t(__cvta_generic_to_shared(bar))) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(uint32_t(__cvta_generic_to_shared(bar))), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
 struct Ctx {
+    int nc;  // compute threads
     int tid, lane, warp, nwarps;
     int pos4;  // first of the four hands this thread owns
     int p, o, Hp, Ho, HpP, HoP, Hx;
@@ -55,7 +86,7 @@ struct Ctx {
 // One pass: every thread scans its 4 positions and its 8 list entries; warp shuffles + one cross-warp step.
 // Returns the total reach (all threads).
 __device__ __forceinline__ float scan_reach(const Ctx& c, const float* r, const uint16_t* __restrict__ cl_pos_b) {
-    __syncthreads();  // r is complete; previous readers of P / GB are done
+    csync(c.nc);  // r is complete; previous readers of P / GB are done
     float4 x = f4zero();
     if (c.pos4 < c.HoP) x = *reinterpret_cast<const float4*>(r + c.pos4);
     float y[8];
@@ -88,7 +119,7 @@ __device__ __forceinline__ float scan_reach(const Ctx& c, const float* r, const 
         c.WSA[c.warp] = ia;
         c.WSB[c.warp] = ib;
     }
-    __syncthreads();
+    csync(c.nc);
     // every warp scans the (<= 11) warp totals itself
     float wa = c.lane < c.nwarps ? c.WSA[c.lane] : 0.f;
     float wb = c.lane < c.nwarps ? c.WSB[c.lane] : 0.f;
@@ -131,7 +162,7 @@ __device__ __forceinline__ float scan_reach(const Ctx& c, const float* r, const 
         c.P[c.HoP] = total;
         c.GB[2 * c.HoP] = total_b;
     }
-    __syncthreads();
+    csync(c.nc);
     return total;
 }
 
@@ -468,12 +499,12 @@ __device__ __forceinline__ void task_trav(const TaskArgs& A, const Ctx& c, const
         for (int a = 0; a < NA; ++a) *reinterpret_cast<float4*>(c.X + (1 + a) * c.Hx + c.pos4) = v[a];
         stcg4(out + c.pos4, f4zero());
     }
-    __syncthreads();
+    csync(c.nc);
     const uint32_t n_rows = Pp.n_rows[b];
     const uint16_t* __restrict__ rstart = Pp.row_start + size_t(b) * (c.HpP + 4);
     const uint16_t* __restrict__ rpos = Pp.row_pos + size_t(b) * c.HpP;
     const float* V1 = c.X + c.Hx;
-    for (uint32_t row = c.tid; row < n_rows; row += blockDim.x) {
+    for (uint32_t row = c.tid; row < n_rows; row += c.nc) {
         float rg[NA], sr[NA], sg[NA], d[NA];
         float norm = 0.f;
 #pragma unroll
@@ -542,7 +573,7 @@ __device__ __forceinline__ void task_trav_generic(const TaskArgs& A, const Ctx& 
         }
         stcg4(out + c.pos4, f4zero());
     }
-    __syncthreads();
+    csync(c.nc);
     const uint32_t nrp = Pp.n_rows_pad[b];
     const uint32_t n_rows = Pp.n_rows[b];
     float* tabR = Pp.regrets + Pp.board_off[b] + size_t(nrp) * nt.cum_a;
@@ -551,7 +582,7 @@ __device__ __forceinline__ void task_trav_generic(const TaskArgs& A, const Ctx& 
     const uint16_t* __restrict__ rpos = Pp.row_pos + size_t(b) * c.HpP;
     const float* M = c.X;
     const float* V1 = c.X + c.Hx;
-    for (uint32_t row = c.tid; row < n_rows; row += blockDim.x) {
+    for (uint32_t row = c.tid; row < n_rows; row += c.nc) {
         const float* tsrc = (MODE == KM_EVAL ? tabS : tabR) + size_t(row) * n_act;
         float norm = 0.f;
         if (MODE != KM_BR)
@@ -589,20 +620,161 @@ __device__ __forceinline__ void task_trav_generic(const TaskArgs& A, const Ctx& 
 // ------------------------------------------------------------------------------------------------
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(MAX_TASK_THREADS, RS_MIN_BLOCKS) task_kernel(const __grid_constant__ TaskArgs A) {
-    extern __shared__ __align__(16) float smem_raw[];
-    __shared__ __align__(16) NodeTask s_nt;
-    __shared__ uint32_t s_ticket;
-    __shared__ uint32_t s_task;
-    __shared__ uint32_t s_epoch;
+// ticket -> node-task index; tickets are handed out in task order, so the search resumes at j0
+__device__ __forceinline__ uint32_t find_task(const TaskArgs& A, uint32_t tk, uint32_t j0) {
+    // node-tasks of one round sit in runs with the same instance count: jump, then fix up
+    uint32_t cnt = A.tasks[j0].count;
+    while (tk >= A.tasks[j0].first + cnt) {
+        const uint32_t skip = (tk - A.tasks[j0].first) / cnt;
+        const uint32_t jn = j0 + skip;
+        if (jn < A.n_tasks && A.tasks[jn].count == cnt && A.tasks[jn].first == A.tasks[j0].first + skip * cnt) j0 = jn;
+        else ++j0;
+        cnt = A.tasks[j0].count;
+    }
+    return j0;
+}
 
+// pull the table slab(s) the NEXT task of this CTA will read into L2 while the current task runs
+template <int MODE>
+__device__ __forceinline__ void prefetch_task_tables(const TaskArgs& A, uint32_t tk, uint32_t j) {
+    const NodeTask* g = A.tasks + j;
+    const int kind = g->kind;
+    if (kind != TK_DOWN && kind != TK_UP_TRAV) return;
+    const RoundArgs& Rk = A.rounds[g->round_k];
+    const int b = int(tk - g->first);
+    const int q = kind == TK_DOWN ? 1 - A.trav : A.trav;
+    const DevRoundPlayer& D = Rk.rp[q];
+    const uint32_t nrp = D.n_rows_pad[b];
+    const size_t off = D.board_off[b] + size_t(nrp) * g->cum_a;
+    const uint32_t bytes = nrp * uint32_t(g->n_act) * 4u;
+    if (kind == TK_DOWN) {
+        prefetch_l2_bulk((MODE == KM_CFR ? D.regrets : D.ssum) + off, bytes);
+    } else {
+        if (MODE == KM_CFR) prefetch_l2_bulk(D.regrets + off, bytes);
+        if (MODE != KM_BR) prefetch_l2_bulk(D.ssum + off, bytes);
+    }
+}
+
+struct TaskSlot {
+    uint32_t ticket;  // >= t1: no more work
+    uint32_t pad[3];
+    NodeTask nt;
+};
+
+template <int MODE, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_constant__ TaskArgs A) {
+    extern __shared__ __align__(16) float smem_raw[];
+    __shared__ __align__(16) TaskSlot s_slot[2];
+
+    __shared__ __align__(8) uint64_t s_done;  // phase i completes when every compute warp has finished task i
+
+    const int NC = blockDim.x - 32;  // compute threads; the last warp is the dispatcher
+    const int tid = threadIdx.x;
+    if (tid == 0) mbar_init(&s_done, uint32_t(NC >> 5));
+    __syncthreads();
+
+    if (tid >= NC) {
+        // ---------------- dispatcher warp ----------------
+        // Runs one task ahead of the compute warps: draws the ticket, finds the node-task, copies its descriptor to
+        // shared memory, pulls its table slabs into L2 and polls the producers' flags.  While polling it keeps
+        // testing the mbarrier and publishes the flag of the task the compute warps just finished the moment they
+        // are done: a finished task is never held back by the look-ahead (that would deadlock across CTAs).
+        const int lane = tid - NC;
+        uint32_t epoch = 0;
+        if (lane == 0) epoch = ld_acquire_u32(&A.ctl->epoch);
+        epoch = __shfl_sync(0xffffffffu, epoch, 0);
+        uint32_t j = 0, prev_tk = 0xffffffffu, parity = 0;
+        int buf = 0;
+        for (;;) {
+            bool published = (prev_tk == 0xffffffffu);  // meaningful on lane 0
+            auto try_publish = [&]() {
+                if (lane == 0 && !published && mbar_test(&s_done, parity)) {
+                    __threadfence();
+                    st_release_u32(A.flags + prev_tk, epoch);
+                    published = true;
+                }
+            };
+            uint32_t tk = 0;
+            if (lane == 0) tk = A.t0 + uint32_t(atomicAdd(&A.ctl->ticket, 1ull));
+            tk = __shfl_sync(0xffffffffu, tk, 0);
+            if (tk < A.t1) {
+                if (lane == 0) j = find_task(A, tk, j);
+                j = __shfl_sync(0xffffffffu, j, 0);
+                const NodeTask* gt = A.tasks + j;
+                for (int i = lane; i < int(sizeof(NodeTask) / 4); i += 32)
+                    reinterpret_cast<uint32_t*>(&s_slot[buf].nt)[i] = __ldg(reinterpret_cast<const uint32_t*>(gt) + i);
+                if (lane == 0) prefetch_task_tables<MODE>(A, tk, j);
+                try_publish();
+                const int kind = gt->kind;
+                const int b = int(tk - gt->first);
+                const RoundArgs& Rk = A.rounds[gt->round_k];
+                const int nd = gt->n_dep;
+                int total;
+                uint32_t gfirst = 0;
+                if (kind == TK_GATHER) {
+                    gfirst = uint32_t(gt->dep[0]) + uint32_t(Rk.per_parent > 0 ? b * Rk.per_parent : 0);
+                    total = Rk.per_parent > 0 ? Rk.per_parent : Rk.n_boards_next;
+                } else {
+                    total = nd + gt->n_src_all;
+                }
+                int i = lane;  // each lane walks its share of the producers, one flag test per round
+                for (;;) {
+                    if (i < total) {
+                        uint32_t idx;
+                        bool has = true;
+                        if (kind == TK_GATHER) {
+                            idx = gfirst + uint32_t(i);
+                        } else {
+                            int dfirst, dk = DK_SAME_BOARD;
+                            if (i < nd) {
+                                dfirst = gt->dep[i];
+                                dk = gt->dep_kind[i];
+                            } else {
+                                dfirst = A.srcs[gt->src_all_first + (i - nd)].dep;
+                            }
+                            has = dfirst >= 0;
+                            idx = uint32_t(dfirst) + uint32_t(dk == DK_PARENT_BOARD ? Rk.parent_board[b] : b);
+                        }
+                        if (!has || idx < A.t0 || ld_acquire_u32(A.flags + idx) == epoch) i += 32;
+                    }
+                    try_publish();
+                    if (__all_sync(0xffffffffu, i >= total)) break;
+                }
+            }
+            if (lane == 0) s_slot[buf].ticket = tk;
+            __syncwarp();
+            hsync(NC + 32);  // slot[buf] handed over; the compute warps are done with the previous task
+            if (lane == 0 && !published) {
+                __threadfence();
+                st_release_u32(A.flags + prev_tk, epoch);
+            }
+            if (prev_tk != 0xffffffffu) parity ^= 1;
+            if (tk >= A.t1) break;
+            prev_tk = tk;
+            buf ^= 1;
+        }
+        // the last CTA to leave re-arms the dispatcher state for the next launch
+        if (lane == 0) {
+            __threadfence();
+            const unsigned int e = atomicAdd(&A.ctl->exited, 1u);
+            if (e == gridDim.x - 1) {
+                A.ctl->ticket = 0ull;
+                A.ctl->exited = 0u;
+                __threadfence();
+                st_release_u32(&A.ctl->epoch, epoch + 1);
+            }
+        }
+        return;
+    }
+
+    // ---------------- compute warps ----------------
     Ctx c;
-    c.tid = threadIdx.x;
-    c.lane = c.tid & 31;
-    c.warp = c.tid >> 5;
-    c.nwarps = blockDim.x >> 5;
-    c.pos4 = 4 * c.tid;
+    c.nc = NC;
+    c.tid = tid;
+    c.lane = tid & 31;
+    c.warp = tid >> 5;
+    c.nwarps = NC >> 5;
+    c.pos4 = 4 * tid;
     c.p = A.trav;
     c.o = 1 - c.p;
     c.Hp = A.H[c.p];
@@ -616,67 +788,20 @@ __global__ void __launch_bounds__(MAX_TASK_THREADS, RS_MIN_BLOCKS) task_kernel(c
     c.GB = c.P + c.HoP + 4;
     c.WSA = c.GB + 2 * c.HoP + 8;
     c.WSB = c.WSA + 32;
-    const int tid = c.tid, T = blockDim.x;
 
-    if (tid == 0) s_epoch = ld_acquire_u32(&A.ctl->epoch);
-    uint32_t j0 = 0;  // thread 0 only: tickets are handed out in task order, so the search resumes where it stopped
+    int buf = 0;
     for (;;) {
-        if (tid == 0) {
-            const uint32_t tk = A.t0 + uint32_t(atomicAdd(&A.ctl->ticket, 1ull));
-            if (tk < A.t1) {
-                // node-tasks of one round sit in runs with the same instance count: jump, then fix up
-                uint32_t cnt = A.tasks[j0].count;
-                while (tk >= A.tasks[j0].first + cnt) {
-                    const uint32_t skip = (tk - A.tasks[j0].first) / cnt;
-                    const uint32_t jn = j0 + skip;
-                    if (jn < A.n_tasks && A.tasks[jn].count == cnt && A.tasks[jn].first == A.tasks[j0].first + skip * cnt) j0 = jn;
-                    else ++j0;
-                    cnt = A.tasks[j0].count;
-                }
-            }
-            s_ticket = tk;
-            s_task = j0;
-        }
-        __syncthreads();
-        const uint32_t t = s_ticket;
-        const uint32_t epoch = s_epoch;
+        hsync(NC + 32);
+        const uint32_t t = s_slot[buf].ticket;
         if (t >= A.t1) break;
-        const NodeTask* gt = A.tasks + s_task;
-        // copy the descriptor to shared memory while the dependency flags are polled
-        if (tid < int(sizeof(NodeTask) / 4)) reinterpret_cast<uint32_t*>(&s_nt)[tid] = __ldg(reinterpret_cast<const uint32_t*>(gt) + tid);
-        const int kind = gt->kind;
-        const int k = gt->round_k;
-        const int b = int(t - gt->first);
+        const NodeTask& nt = s_slot[buf].nt;
+        const int kind = nt.kind;
+        const int k = nt.round_k;
+        const int b = int(t - nt.first);
         const RoundArgs& Rk = A.rounds[k];
-        if (kind == TK_GATHER) {
-            const NodeTask& dt = A.tasks[gt->dep[0]];
-            const int cb0 = Rk.per_parent > 0 ? b * Rk.per_parent : 0;
-            const int ncb = Rk.per_parent > 0 ? Rk.per_parent : Rk.n_boards_next;
-            for (int i = tid; i < ncb; i += T) {
-                const uint32_t idx = dt.first + uint32_t(cb0 + i);
-                if (idx >= A.t0)
-                    while (ld_acquire_u32(A.flags + idx) != epoch) __nanosleep(20);
-            }
-        } else {
-            const int nd = gt->n_dep, total = nd + gt->n_src_all;
-            for (int i = tid; i < total; i += T) {
-                int dep, dk = DK_SAME_BOARD;
-                if (i < nd) {
-                    dep = gt->dep[i];
-                    dk = gt->dep_kind[i];
-                } else {
-                    dep = A.srcs[gt->src_all_first + (i - nd)].dep;
-                }
-                if (dep >= 0) {
-                    const uint32_t idx = A.tasks[dep].first + uint32_t(dk == DK_PARENT_BOARD ? Rk.parent_board[b] : b);
-                    if (idx >= A.t0)
-                        while (ld_acquire_u32(A.flags + idx) != epoch) __nanosleep(20);
-                }
-            }
-        }
-        __syncthreads();
-        const NodeTask& nt = s_nt;
-
+#ifdef RS_TASK_TIMING
+        const long long tm1 = clock64();
+#endif
         switch (kind) {
             case TK_DOWN: {
                 switch (nt.n_act) {
@@ -716,11 +841,11 @@ __global__ void __launch_bounds__(MAX_TASK_THREADS, RS_MIN_BLOCKS) task_kernel(c
                     for (int i = 0; i < ncb; ++i) {
                         uint32_t q[4];
                         unpack4(__ldg(reinterpret_cast<const uint2*>(cp + size_t(i) * c.HpP)), q);
-                        const float* s = src + size_t(i) * c.HpP;
-                        acc.x += q[0] != 0xffffu ? __ldcg(s + q[0]) : 0.f;
-                        acc.y += q[1] != 0xffffu ? __ldcg(s + q[1]) : 0.f;
-                        acc.z += q[2] != 0xffffu ? __ldcg(s + q[2]) : 0.f;
-                        acc.w += q[3] != 0xffffu ? __ldcg(s + q[3]) : 0.f;
+                        const float* sp = src + size_t(i) * c.HpP;
+                        acc.x += q[0] != 0xffffu ? __ldcg(sp + q[0]) : 0.f;
+                        acc.y += q[1] != 0xffffu ? __ldcg(sp + q[1]) : 0.f;
+                        acc.z += q[2] != 0xffffu ? __ldcg(sp + q[2]) : 0.f;
+                        acc.w += q[3] != 0xffffu ? __ldcg(sp + q[3]) : 0.f;
                     }
                     stcg4(Rk.gathered + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4, acc);
                 }
@@ -747,23 +872,15 @@ __global__ void __launch_bounds__(MAX_TASK_THREADS, RS_MIN_BLOCKS) task_kernel(c
             }
             default: break;
         }
-        // ---- publish ----
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            st_release_u32(A.flags + t, epoch);
+#ifdef RS_TASK_TIMING
+        if (tid == 0 && A.timing) {
+            atomicAdd(A.timing + kind * 4 + 0, 1ull);
+            atomicAdd(A.timing + kind * 4 + 2, (unsigned long long)(clock64() - tm1));  // body
         }
-    }
-    // the last CTA to leave re-arms the dispatcher for the next launch
-    if (tid == 0) {
-        __threadfence();
-        const unsigned int e = atomicAdd(&A.ctl->exited, 1u);
-        if (e == gridDim.x - 1) {
-            A.ctl->ticket = 0ull;
-            A.ctl->exited = 0u;
-            __threadfence();
-            st_release_u32(&A.ctl->epoch, s_epoch + 1);
-        }
+#endif
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(&s_done);  // this warp's part of the task is written
+        buf ^= 1;
     }
 }
 
@@ -799,30 +916,43 @@ size_t task_kernel_smem_bytes(int slots, int Hp_pad, int Ho_pad) {
     return floats * sizeof(float);
 }
 
-cudaError_t configure_task_kernels(size_t smem, int threads, int* blocks_per_sm) {
+template <int MAXT, int MINB>
+static cudaError_t configure_for(size_t smem, int threads, int* blocks_per_sm) {
     cudaError_t e;
-    e = cudaFuncSetAttribute(task_kernel<KM_CFR>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    e = cudaFuncSetAttribute(task_kernel<KM_CFR, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(task_kernel<KM_BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    e = cudaFuncSetAttribute(task_kernel<KM_BR, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(task_kernel<KM_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    e = cudaFuncSetAttribute(task_kernel<KM_EVAL, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     int n = 0, m = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, task_kernel<KM_CFR>, threads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, task_kernel<KM_CFR, MAXT, MINB>, threads + 32, smem);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, task_kernel<KM_BR>, threads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, task_kernel<KM_BR, MAXT, MINB>, threads + 32, smem);
     if (e != cudaSuccess) return e;
     *blocks_per_sm = n < m ? n : m;
     return cudaSuccess;
 }
 
+cudaError_t configure_task_kernels(size_t smem, int threads, int* blocks_per_sm) {
+    if (threads <= 288) return configure_for<288, RS_MIN_BLOCKS_288>(smem, threads, blocks_per_sm);
+    return configure_for<352, RS_MIN_BLOCKS_352>(smem, threads, blocks_per_sm);
+}
+
+template <int MAXT, int MINB>
+static void launch_for(const TaskArgs& a, int mode, int grid, int threads, size_t smem, cudaStream_t st) {
+    switch (mode) {
+        // one extra warp per CTA: the dispatcher
+        case KM_CFR: task_kernel<KM_CFR, MAXT, MINB><<<grid, threads + 32, smem, st>>>(a); break;
+        case KM_BR: task_kernel<KM_BR, MAXT, MINB><<<grid, threads + 32, smem, st>>>(a); break;
+        default: task_kernel<KM_EVAL, MAXT, MINB><<<grid, threads + 32, smem, st>>>(a); break;
+    }
+}
+
 cudaError_t launch_task_kernel(const TaskArgs& a, int mode, int grid, int threads, size_t smem, cudaStream_t st) {
     if (grid <= 0 || a.t1 <= a.t0) return cudaSuccess;
-    switch (mode) {
-        case KM_CFR: task_kernel<KM_CFR><<<grid, threads, smem, st>>>(a); break;
-        case KM_BR: task_kernel<KM_BR><<<grid, threads, smem, st>>>(a); break;
-        default: task_kernel<KM_EVAL><<<grid, threads, smem, st>>>(a); break;
-    }
+    if (threads <= 288) launch_for<288, RS_MIN_BLOCKS_288>(a, mode, grid, threads, smem, st);
+    else launch_for<352, RS_MIN_BLOCKS_352>(a, mode, grid, threads, smem, st);
     return cudaGetLastError();
 }
 

@@ -71,6 +71,7 @@ struct TaskArgs {
     int trav;
     uint32_t t0, t1;  // ticket range of this launch
     int slots;        // Hx-sized scratch vectors provisioned in shared memory
+    unsigned long long* timing;  // RS_TASK_TIMING builds: [8 kinds][count, wait cycles, body cycles, total cycles]
 };
 
 size_t task_kernel_smem_bytes(int slots, int Hp_pad, int Ho_pad);

@@ -100,11 +100,19 @@ def test_single_iteration_from_oracle_state():
 def test_discount_sweep():
     o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]], [[3.0]])
     tree, eng, orc = _pair(o)
-    eng.iterate(2)
-    orc.iterate(2)
+    util.lockstep(eng, orc, tree, n_free=1, n_locked=1, tol=TOL)
     eng.discount(0.5)
     orc.discount(0.5)
     util.compare_tables(eng, orc, tree, TOL)
+    # engine-side schedule of train()'s monitor thread (cfr.rs:248-261): d = p/(p+1) every `interval` iterations
+    n, tree2 = rb.build_game_tree(o)
+    e2 = rb.Engine(tree2, o.ranges(), o.board_mask, discount_interval=1, discount_cap=1)
+    e3 = rb.Engine(tree2, o.ranges(), o.board_mask)
+    e2.iterate(1)
+    e3.iterate(1)
+    for an in range(tree2.n_actions):
+        a, b = e2.read_infoset(an), e3.read_infoset(an)
+        assert np.allclose(a[0], 0.5 * b[0], rtol=1e-6, atol=0) and np.allclose(a[1], 0.5 * b[1], rtol=1e-6, atol=0)
 
 
 def test_exploitability_curve_matches_oracle():

@@ -28,14 +28,12 @@ def bucket_keys_for(plan_or_oracle_boards, ranges, n_boards, K, seed):
     return out
 
 
-_node_cache = {}
-
-
 def node_of(tree, an):
-    key = id(tree)
-    if key not in _node_cache:
-        _node_cache[key] = {int(tree.an_index[i]): i for i in range(tree.n_nodes) if tree.type[i] == 0}
-    return _node_cache[key][an]
+    m = getattr(tree, "_an_to_node", None)
+    if m is None:
+        m = {int(tree.an_index[i]): i for i in range(tree.n_nodes) if tree.type[i] == 0}
+        tree._an_to_node = m
+    return m[an]
 
 
 class RowAligner:
