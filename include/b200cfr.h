@@ -203,7 +203,8 @@ typedef struct rs_kernel_time {
 int rs_profile_iteration(rs_engine* e, rs_kernel_time* out, size_t cap, uint32_t* n_out);
 
 /* Tuning aid: per task kind [count, wait cycles, body cycles, total cycles] accumulated by builds compiled with
- * -DRS_TASK_TIMING (all zeros otherwise); out32 holds 8 kinds x 4 counters. */
+ * -DRS_TASK_TIMING (all zeros otherwise); out32 holds 96 words: 8 kinds x 4 counters, then per (kind, round)
+ * [earliest start, latest end] in globaltimer ns. */
 int rs_debug_task_timing(rs_engine* e, unsigned long long* out32, int reset);
 
 /* ---- host-only plan introspection (no GPU needed): integer parity surface ---- */

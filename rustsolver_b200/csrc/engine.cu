@@ -117,6 +117,7 @@ struct RoundDev {
     DevBuf<int32_t> parent_board;
     // transients of one traversal (shared by both traversers, sized for the larger)
     DevBuf<float> rbuf, cbuf, gathered;
+    DevBuf<float> sbuf[2];  // street-root values in parent-board order, one pool per traverser (unwritten entries must stay 0)
     uint32_t n_leaves = 0, n_boards = 0;
 };
 
@@ -251,6 +252,10 @@ int Engine::init(const rs_config* cfg) {
         CU(R.rbuf.alloc(n_r * nb * maxHP));
         CU(R.cbuf.alloc(n_c * nb * maxHP));
         CU(R.gathered.alloc(size_t(R.n_leaves) * nb * maxHP));
+        for (int p = 0; p < 2; ++p) {
+            CU(R.sbuf[p].alloc(size_t(P.tl[p].n_sbuf[k]) * nb * maxHP));
+            CU(R.sbuf[p].zero());
+        }
         CU(R.rbuf.zero());
         CU(R.cbuf.zero());
         CU(R.gathered.zero());
@@ -262,7 +267,7 @@ int Engine::init(const rs_config* cfg) {
         max_tickets = std::max(max_tickets, P.tl[p].n_tickets);
         slots = std::max(slots, int(std::max(P.tl[p].max_terminal, 1 + P.tl[p].max_children)));
     }
-    CU(timing.alloc(32));
+    CU(timing.alloc(96));
     CU(timing.zero());
     CU(flags.alloc(max_tickets));
     CU(flags.zero());
@@ -349,6 +354,7 @@ void Engine::fill_args(TaskArgs* a, int trav) const {
         ra.parent_board = R.parent_board.p;
         ra.rbuf = R.rbuf.p;
         ra.cbuf = R.cbuf.p;
+        ra.sbuf = R.sbuf[trav].p;
         ra.gathered = R.gathered.p;
         ra.n_boards = int(R.n_boards);
         if (k + 1 < P.n_rounds) {
@@ -905,8 +911,12 @@ int rs_debug_task_timing(rs_engine* e, unsigned long long* out32, int reset) {
     Engine& E = e->e;
     CU(cudaSetDevice(E.device));
     CU(cudaStreamSynchronize(E.stream));
-    CU(cudaMemcpy(out32, E.timing.p, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    if (reset) CU(E.timing.zero());
+    CU(cudaMemcpy(out32, E.timing.p, 96 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) {
+        std::vector<unsigned long long> init(96, 0);
+        for (int i = 0; i < 32; ++i) init[32 + 2 * i] = ~0ull;  // min-start slots
+        CU(cudaMemcpy(E.timing.p, init.data(), 96 * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
     return RS_OK;
 }
 

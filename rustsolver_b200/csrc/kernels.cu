@@ -220,6 +220,29 @@ __device__ __forceinline__ float4 child_value4(const TaskArgs& A, const Ctx& c, 
     return v;
 }
 
+// Store a node's value for the thread's four positions.  Street roots write in the parent board's hand order
+// (positions the child board removes are never written and stay zero), so the chance gather is a coalesced sum.
+__device__ __forceinline__ void store_value4(const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int b, float* out, float4 v) {
+    if (!nt.root_scatter) {
+        stcg4(out + c.pos4, v);
+        return;
+    }
+    uint32_t pp[4];
+    unpack4(__ldg(reinterpret_cast<const uint2*>(Rk.rp[c.p].parent_pos + size_t(b) * c.HpP + c.pos4)), pp);
+    if (pp[0] != 0xffffu) __stcg(out + pp[0], v.x);
+    if (pp[1] != 0xffffu) __stcg(out + pp[1], v.y);
+    if (pp[2] != 0xffffu) __stcg(out + pp[2], v.z);
+    if (pp[3] != 0xffffu) __stcg(out + pp[3], v.w);
+}
+__device__ __forceinline__ void store_value1(const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int b, float* out, int pos, float v) {
+    if (!nt.root_scatter) {
+        __stcg(out + pos, v);
+        return;
+    }
+    const uint32_t pp = Rk.rp[c.p].parent_pos[size_t(b) * c.HpP + pos];
+    if (pp != 0xffffu) __stcg(out + pp, v);
+}
+
 // Regret matching of one row held in registers (infoset.rs:83-123).
 template <int NA>
 __device__ __forceinline__ void sigma_row(const float (&g)[4 * NA], int i, float (&sg)[NA]) {
@@ -441,13 +464,13 @@ __device__ __forceinline__ void task_trav(const TaskArgs& A, const Ctx& c, const
     }
     const uint32_t nrp = Pp.n_rows_pad[b];
     const uint32_t nl_p = Pp.n_live[b];
-    float* out = Rk.cbuf + (size_t(nt.out) * Rk.n_boards + b) * c.HpP;
+    float* out = (nt.root_scatter ? Rk.sbuf : Rk.cbuf) + (size_t(nt.out) * Rk.n_boards + b) * c.HpP;
     float* tabR = Pp.regrets + Pp.board_off[b] + size_t(nrp) * nt.cum_a;
     float* tabS = Pp.ssum + Pp.board_off[b] + size_t(nrp) * nt.cum_a;
     if (Pp.identity) {
         // rows are the thread's own four positions: everything stays in registers
         if (uint32_t(c.pos4) >= nrp) {
-            if (c.pos4 < c.HpP) stcg4(out + c.pos4, f4zero());
+            if (c.pos4 < c.HpP && !nt.root_scatter) stcg4(out + c.pos4, f4zero());
             return;
         }
         const uint32_t none[4] = {0, 0, 0, 0};
@@ -488,7 +511,7 @@ __device__ __forceinline__ void task_trav(const TaskArgs& A, const Ctx& c, const
                 *reinterpret_cast<float4*>(tabS + size_t(c.pos4) * NA + 4 * q) = make_float4(ss[4 * q], ss[4 * q + 1], ss[4 * q + 2], ss[4 * q + 3]);
             }
         }
-        stcg4(out + c.pos4, vn4);
+        store_value4(c, nt, Rk, b, out, vn4);
         return;
     }
     // bucketed rows: values and masses go through shared memory, one thread per row (CSR row -> positions)
@@ -497,7 +520,7 @@ __device__ __forceinline__ void task_trav(const TaskArgs& A, const Ctx& c, const
         *reinterpret_cast<float4*>(M + c.pos4) = mass;
 #pragma unroll
         for (int a = 0; a < NA; ++a) *reinterpret_cast<float4*>(c.X + (1 + a) * c.Hx + c.pos4) = v[a];
-        stcg4(out + c.pos4, f4zero());
+        if (!nt.root_scatter) stcg4(out + c.pos4, f4zero());
     }
     csync(c.nc);
     const uint32_t n_rows = Pp.n_rows[b];
@@ -535,7 +558,7 @@ __device__ __forceinline__ void task_trav(const TaskArgs& A, const Ctx& c, const
                 for (int a = 0; a < NA; ++a) d[a] += va[a] - vn;
                 msum += M[h];
             }
-            __stcg(out + h, vn);
+            store_value1(c, nt, Rk, b, out, h, vn);
         }
         if (MODE == KM_CFR) {
             const float w = msum * scale;
@@ -562,7 +585,7 @@ __device__ __forceinline__ void task_trav_generic(const TaskArgs& A, const Ctx& 
     }
     float4 mass, sd;
     trav_terms(A, c, nt, Rk, k, b, need_sd, mass, sd);
-    float* out = Rk.cbuf + (size_t(nt.out) * Rk.n_boards + b) * c.HpP;
+    float* out = (nt.root_scatter ? Rk.sbuf : Rk.cbuf) + (size_t(nt.out) * Rk.n_boards + b) * c.HpP;
     if (c.pos4 < c.HpP) {
         *reinterpret_cast<float4*>(c.X + c.pos4) = mass;
         for (int a = 0; a < n_act; ++a) {
@@ -571,7 +594,7 @@ __device__ __forceinline__ void task_trav_generic(const TaskArgs& A, const Ctx& 
             if (ck == CK_FOLD) *reinterpret_cast<float4*>(c.X + (1 + a) * c.Hx + c.pos4) = make_float4(cf * mass.x, cf * mass.y, cf * mass.z, cf * mass.w);
             else if (ck == CK_SHOWDOWN) *reinterpret_cast<float4*>(c.X + (1 + a) * c.Hx + c.pos4) = make_float4(cf * sd.x, cf * sd.y, cf * sd.z, cf * sd.w);
         }
-        stcg4(out + c.pos4, f4zero());
+        if (!nt.root_scatter) stcg4(out + c.pos4, f4zero());
     }
     csync(c.nc);
     const uint32_t nrp = Pp.n_rows_pad[b];
@@ -601,7 +624,7 @@ __device__ __forceinline__ void task_trav_generic(const TaskArgs& A, const Ctx& 
             }
             vsum += vn;
             msum += M[h];
-            __stcg(out + h, vn);
+            store_value1(c, nt, Rk, b, out, h, vn);
         }
         if (MODE == KM_CFR) {
             const float w = msum * scale;
@@ -801,6 +824,11 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
         const RoundArgs& Rk = A.rounds[k];
 #ifdef RS_TASK_TIMING
         const long long tm1 = clock64();
+        if (tid == 0 && A.timing) {
+            unsigned long long gt0;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+            atomicMin(A.timing + 32 + (kind * 3 + k) * 2, gt0);
+        }
 #endif
         switch (kind) {
             case TK_DOWN: {
@@ -826,7 +854,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                     float4 v = nt.aux >= 0 ? ldcg4(Rk.cbuf + (size_t(nt.aux) * Rk.n_boards + b) * c.HpP + c.pos4) : f4zero();
                     for (int a = 0; a < nt.n_act; ++a)
                         if (nt.child[a].kind == CK_VALUE) v = f4add(v, child_value4(A, c, Rk, nt.child[a], b));
-                    stcg4(Rk.cbuf + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4, v);
+                    store_value4(c, nt, Rk, b, (nt.root_scatter ? Rk.sbuf : Rk.cbuf) + (size_t(nt.out) * Rk.n_boards + b) * c.HpP, v);
                 }
                 break;
             }
@@ -835,17 +863,15 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                     const RoundArgs& Rn = A.rounds[k + 1];
                     const int cb0 = Rk.per_parent > 0 ? b * Rk.per_parent : 0;
                     const int ncb = Rk.per_parent > 0 ? Rk.per_parent : Rk.n_boards_next;
-                    const float* src = Rn.cbuf + (size_t(nt.aux) * Rn.n_boards + cb0) * c.HpP;
-                    const uint16_t* __restrict__ cp = Rn.rp[c.p].child_pos + size_t(cb0) * c.HpP + c.pos4;
+                    // the child-street roots stored their values in THIS board's hand order (store_value4)
+                    const float* src = Rn.sbuf + (size_t(nt.aux) * Rn.n_boards + cb0) * c.HpP + c.pos4;
                     float4 acc = f4zero();
-                    for (int i = 0; i < ncb; ++i) {
-                        uint32_t q[4];
-                        unpack4(__ldg(reinterpret_cast<const uint2*>(cp + size_t(i) * c.HpP)), q);
-                        const float* sp = src + size_t(i) * c.HpP;
-                        acc.x += q[0] != 0xffffu ? __ldcg(sp + q[0]) : 0.f;
-                        acc.y += q[1] != 0xffffu ? __ldcg(sp + q[1]) : 0.f;
-                        acc.z += q[2] != 0xffffu ? __ldcg(sp + q[2]) : 0.f;
-                        acc.w += q[3] != 0xffffu ? __ldcg(sp + q[3]) : 0.f;
+                    for (int i0 = 0; i0 < ncb; i0 += 8) {  // eight loads in flight; summation order = board order
+                        float4 val[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) val[u] = (i0 + u < ncb) ? ldcg4(src + size_t(i0 + u) * c.HpP) : f4zero();
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) acc = f4add(acc, val[u]);
                     }
                     stcg4(Rk.gathered + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4, acc);
                 }
@@ -856,7 +882,8 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                 trav_terms(A, c, nt, Rk, k, b, true, mass, sd);
                 const float cf = nt.child[0].coef * Rk.chance_scale[b];
                 if (c.pos4 < c.HpP)
-                    stcg4(Rk.cbuf + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4, make_float4(cf * sd.x, cf * sd.y, cf * sd.z, cf * sd.w));
+                    store_value4(c, nt, Rk, b, (nt.root_scatter ? Rk.sbuf : Rk.cbuf) + (size_t(nt.out) * Rk.n_boards + b) * c.HpP,
+                                 make_float4(cf * sd.x, cf * sd.y, cf * sd.z, cf * sd.w));
                 break;
             }
             case TK_CHANCE_DOWN: {
@@ -866,8 +893,8 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
             }
             case TK_CHANCE_UP: {
                 if (c.pos4 < c.HpP)
-                    stcg4(Rk.cbuf + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4,
-                          ldcg4(Rk.gathered + (size_t(nt.aux) * Rk.n_boards + b) * c.HpP + c.pos4));
+                    store_value4(c, nt, Rk, b, (nt.root_scatter ? Rk.sbuf : Rk.cbuf) + (size_t(nt.out) * Rk.n_boards + b) * c.HpP,
+                                 ldcg4(Rk.gathered + (size_t(nt.aux) * Rk.n_boards + b) * c.HpP + c.pos4));
                 break;
             }
             default: break;
@@ -876,6 +903,9 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
         if (tid == 0 && A.timing) {
             atomicAdd(A.timing + kind * 4 + 0, 1ull);
             atomicAdd(A.timing + kind * 4 + 2, (unsigned long long)(clock64() - tm1));  // body
+            unsigned long long gt1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
+            atomicMax(A.timing + 32 + (kind * 3 + k) * 2 + 1, gt1);
         }
 #endif
         __syncwarp();

@@ -52,6 +52,7 @@ struct RoundArgs {
     const int32_t* parent_board;  // [nb] local id in the parent round
     float* rbuf;                  // [n_rbuf][nb][Hpad_opp]   opponent reach per buffer id
     float* cbuf;                  // [n_cbuf][nb][Hpad_trav]  counterfactual values per buffer id
+    float* sbuf;                  // [n_sbuf][nb][Hpad_trav]  street-root values in the PARENT board's hand order (this traverser's pool)
     float* gathered;              // [n_leaves][nb][Hpad_trav]
     int n_boards;
     int per_parent;  // boards of the NEXT round per board of this one (0: every local next-round board hangs off board 0)

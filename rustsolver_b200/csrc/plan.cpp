@@ -274,7 +274,8 @@ struct TaskGen {
                 }
                 const int32_t rootid = P->segs[k][s].root;
                 assign(k, rootid, root, seg_nodes[k][s]);
-                if (P->nodes[rootid].kind != PK_ACTION) cbuf[rootid] = new_cbuf(k);
+                if (k > 0) cbuf[rootid] = int32_t(tl.n_sbuf[k]++);  // street roots below the first round: scatter pool
+                else if (P->nodes[rootid].kind != PK_ACTION) cbuf[rootid] = new_cbuf(k);
                 segroot_cbuf[k][s] = cbuf[rootid];
             }
             // chance leaves whose inherited source is not a buffer of this round get a copy task
@@ -442,6 +443,8 @@ struct TaskGen {
                     }
                     t.n_src_all = uint16_t(tl.srcs.size() - t.src_all_first);
                 }
+                for (uint32_t s = 0; s < P->segs[k].size(); ++s)
+                    if (k > 0 && P->segs[k][s].root == pe.pnode) t.root_scatter = 1;
                 const uint32_t ti = emit(t);
                 up_task[pe.pnode] = int32_t(ti);
                 for (uint32_t s = 0; s < P->segs[k].size(); ++s)

@@ -24,6 +24,7 @@ struct TaskList {  // one traversal (one traverser) of the whole tree, in ticket
     uint32_t phase_cut = 0;     // tickets [0, phase_cut) precede the cross-GPU all-reduce, [phase_cut, n) follow it
     uint32_t n_rbuf[3] = {0, 0, 0};  // reach buffers per round
     uint32_t n_cbuf[3] = {0, 0, 0};  // value buffers per round
+    uint32_t n_sbuf[3] = {0, 0, 0};  // street-root value buffers per round (parent-board hand order, own pool per traverser)
     uint32_t max_children = 1;       // widest traverser node (value slots in shared memory)
     uint32_t max_terminal = 0;       // most terminal children under one opponent node
     int32_t root_cbuf = -1;          // value buffer (round 0) holding the root counterfactual values

@@ -65,7 +65,7 @@ struct NodeTask {
     uint8_t n_act;
     uint8_t n_dep;
     uint8_t rin_parent_round;  // 1: r_in names a reach buffer of the PARENT round, read at the parent board
-    uint8_t pad0;
+    uint8_t root_scatter;      // street root (round >= 1): the value is stored in the PARENT board's hand order
     uint16_t n_src_all;        // sources of all children, contiguous from src_all_first (waited on together)
     int32_t r_in;     // reach buffer id, or RIN_INITIAL
     uint32_t cum_a;   // slab offset = n_rows_pad(board) * cum_a inside the (round, player) table
