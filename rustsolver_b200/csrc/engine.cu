@@ -426,6 +426,9 @@ int Engine::enqueue_traversal(int trav, int mode, uint64_t* count) {
         a.t0 = cuts[phase];
         a.t1 = cuts[phase + 1];
         if (a.t1 <= a.t0) continue;
+        a.j0 = 0;
+        for (size_t j = 0; j < tl.tasks.size(); ++j)
+            if (tl.tasks[j].first <= a.t0) a.j0 = uint32_t(j);
         const int grid = int(std::min<uint64_t>(uint64_t(a.t1 - a.t0), uint64_t(n_sms) * blocks_per_sm));
         if ((rc = prof_begin()) != RS_OK) return rc;
         CU(launch_task_kernel(a, mode, grid, threads, smem_bytes, stream));

@@ -643,18 +643,25 @@ __device__ __forceinline__ void task_trav_generic(const TaskArgs& A, const Ctx& 
 // ------------------------------------------------------------------------------------------------
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------
-// ticket -> node-task index; tickets are handed out in task order, so the search resumes at j0
+// ticket -> node-task index.  Tickets are handed out in task order, so the answer is usually j0 or a few tasks
+// further (same-size runs let us jump); otherwise binary search over the first-ticket column.
 __device__ __forceinline__ uint32_t find_task(const TaskArgs& A, uint32_t tk, uint32_t j0) {
-    // node-tasks of one round sit in runs with the same instance count: jump, then fix up
-    uint32_t cnt = A.tasks[j0].count;
-    while (tk >= A.tasks[j0].first + cnt) {
-        const uint32_t skip = (tk - A.tasks[j0].first) / cnt;
-        const uint32_t jn = j0 + skip;
-        if (jn < A.n_tasks && A.tasks[jn].count == cnt && A.tasks[jn].first == A.tasks[j0].first + skip * cnt) j0 = jn;
-        else ++j0;
-        cnt = A.tasks[j0].count;
+    {
+        const uint32_t f = A.tasks[j0].first, cnt = A.tasks[j0].count;
+        if (tk < f + cnt) return j0;
+        const uint32_t jn = j0 + (tk - f) / cnt;  // exact when the tasks in between all have `cnt` instances
+        if (jn < A.n_tasks) {
+            const uint32_t fn = A.tasks[jn].first;
+            if (fn <= tk && tk < fn + A.tasks[jn].count) return jn;
+        }
     }
-    return j0;
+    uint32_t lo = j0, hi = A.n_tasks - 1;  // last task with first <= tk
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (A.tasks[mid].first <= tk) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
 }
 
 // pull the table slab(s) the NEXT task of this CTA will read into L2 while the current task runs
@@ -706,7 +713,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
         uint32_t epoch = 0;
         if (lane == 0) epoch = ld_acquire_u32(&A.ctl->epoch);
         epoch = __shfl_sync(0xffffffffu, epoch, 0);
-        uint32_t j = 0, prev_tk = 0xffffffffu, parity = 0;
+        uint32_t j = A.j0, prev_tk = 0xffffffffu, parity = 0;
         int buf = 0;
         for (;;) {
             bool published = (prev_tk == 0xffffffffu);  // meaningful on lane 0

@@ -71,6 +71,7 @@ struct TaskArgs {
     int H[2], Hpad[2];
     int trav;
     uint32_t t0, t1;  // ticket range of this launch
+    uint32_t j0;      // node-task holding ticket t0 (search hint)
     int slots;        // Hx-sized scratch vectors provisioned in shared memory
     unsigned long long* timing;  // RS_TASK_TIMING builds: [8 kinds][count, wait cycles, body cycles, total cycles]
 };
