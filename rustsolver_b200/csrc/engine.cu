@@ -226,7 +226,17 @@ int Engine::init(const rs_config* cfg) {
             CU(R.row_pos[q].upload(slice(L.row_pos, lo, hi, hp)));
             CU(R.cl_pos[q].upload(slice(L.cl_pos, lo, hi, 2 * hp)));
             CU(R.slot_of_pos[q].upload(slice(L.slot_of_pos, lo, hi, hp)));
-            CU(R.hrec[q].upload(slice(L.hrec, lo, hi, hp)));
+            {
+                // four word planes per board: [board][word][pos] (see load_recs4)
+                std::vector<HandRec> aos = slice(L.hrec, lo, hi, hp);
+                std::vector<HandRec> soa(aos.size());
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(aos.data());
+                uint32_t* dst = reinterpret_cast<uint32_t*>(soa.data());
+                for (size_t b = 0; b < size_t(nb); ++b)
+                    for (size_t i = 0; i < hp; ++i)
+                        for (int wd = 0; wd < 4; ++wd) dst[(b * 4 + wd) * hp + i] = src[(b * hp + i) * 4 + wd];
+                CU(R.hrec[q].upload(soa));
+            }
             if (k > 0) {
                 CU(R.parent_pos[q].upload(slice(L.parent_pos, lo, hi, hp)));
                 CU(R.child_pos[q].upload(slice(L.child_pos, lo, hi, size_t(P.loc[k - 1][q].Hpad))));

@@ -166,6 +166,19 @@ __device__ __forceinline__ float scan_reach(const Ctx& c, const float* r, const 
     return total;
 }
 
+// The per-hand records of a board are stored as four word planes [4][Hpad]: one 128-bit load per plane gives the
+// thread the same word of its four hands, fully coalesced across the warp.
+__device__ __forceinline__ void load_recs4(const uint32_t* __restrict__ planes, int HpP, int pos4, uint4 (&rec)[4]) {
+    const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(planes + pos4));
+    const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(planes + HpP + pos4));
+    const uint4 w2 = __ldg(reinterpret_cast<const uint4*>(planes + 2 * HpP + pos4));
+    const uint4 w3 = __ldg(reinterpret_cast<const uint4*>(planes + 3 * HpP + pos4));
+    rec[0] = make_uint4(w0.x, w1.x, w2.x, w3.x);
+    rec[1] = make_uint4(w0.y, w1.y, w2.y, w3.y);
+    rec[2] = make_uint4(w0.z, w1.z, w2.z, w3.z);
+    rec[3] = make_uint4(w0.w, w1.w, w2.w, w3.w);
+}
+
 // After scan_reach: for the traverser's hand record `rec`
 //   mass = opponent reach compatible with the hand (total - both cards' sums + the identical combo)
 //   sd   = weaker minus stronger compatible opponent reach (showdown, cfr.rs:532-556)
@@ -324,10 +337,7 @@ __device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const
     const uint16_t* __restrict__ cl = O.cl_pos + size_t(b) * 2 * c.HoP;
     float4 acc = f4zero();
     uint4 rec[4];
-    if (c.pos4 < c.HpP) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rec[i] = __ldg(reinterpret_cast<const uint4*>(Pp.hrec + size_t(b) * c.HpP + c.pos4 + i));
-    }
+    if (c.pos4 < c.HpP) load_recs4(reinterpret_cast<const uint32_t*>(Pp.hrec) + size_t(b) * 4 * c.HpP, c.HpP, c.pos4, rec);
     slot = 0;
     for (int a = 0; a < NA; ++a) {
         const int ck = nt.child[a].kind;
@@ -389,6 +399,8 @@ __device__ __forceinline__ void task_down_generic(const TaskArgs& A, const Ctx& 
     const float scale = Rk.chance_scale[b];
     const uint16_t* __restrict__ cl = O.cl_pos + size_t(b) * 2 * c.HoP;
     float4 acc = f4zero();
+    uint4 rec[4];
+    if (c.pos4 < c.HpP) load_recs4(reinterpret_cast<const uint32_t*>(Pp.hrec) + size_t(b) * 4 * c.HpP, c.HpP, c.pos4, rec);
     int slot = 0;
     for (int a = 0; a < n_act; ++a) {
         const int ck = nt.child[a].kind;
@@ -398,11 +410,11 @@ __device__ __forceinline__ void task_down_generic(const TaskArgs& A, const Ctx& 
         const float cf = nt.child[a].coef * scale;
         const float total = scan_reach(c, r, cl);
         if (c.pos4 < c.HpP) {
+#pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (uint32_t(c.pos4 + i) < nl_p) {
-                    const uint4 rec = __ldg(reinterpret_cast<const uint4*>(Pp.hrec + size_t(b) * c.HpP + c.pos4 + i));
                     float m, sd;
-                    hand_terms(c, r, total, rec, m, sd);
+                    hand_terms(c, r, total, rec[i], m, sd);
                     f4set(acc, i, f4get(acc, i) + cf * (ck == CK_FOLD ? m : sd));
                 }
             }
@@ -425,13 +437,14 @@ __device__ __forceinline__ void trav_terms(const TaskArgs& A, const Ctx& c, cons
     const DevRoundPlayer& Pp = Rk.rp[c.p];
     const uint32_t nl_p = Pp.n_live[b];
     if (c.pos4 < c.HpP) {
+        uint4 rec[4];
+        load_recs4(reinterpret_cast<const uint32_t*>(Pp.hrec) + size_t(b) * 4 * c.HpP, c.HpP, c.pos4, rec);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (uint32_t(c.pos4 + i) < nl_p) {
-                const uint4 rec = __ldg(reinterpret_cast<const uint4*>(Pp.hrec + size_t(b) * c.HpP + c.pos4 + i));
                 float m, s = 0.f;
-                if (need_sd) hand_terms(c, c.Rs, total, rec, m, s);
-                else m = hand_mass(c, c.Rs, total, rec);
+                if (need_sd) hand_terms(c, c.Rs, total, rec[i], m, s);
+                else m = hand_mass(c, c.Rs, total, rec[i]);
                 f4set(mass, i, m);
                 f4set(sd, i, s);
             }
