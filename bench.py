@@ -10,9 +10,9 @@ NCCL every traversal (strong scaling: the job is the same subgame at every N).
 
 Rank 0 prints ONE JSON line (keys documented in the task contract): value = iterations/s with all
 inputs resident in HBM (CUDA events around each step, L2 flushed between steps, max over ranks),
-e2e = the same through the C ABI from host buffers, roofline = the dominant kernel (river-street
-segment kernel) from CUDA events on the engine's stream, cpu_baseline = the literal scalar port of
-the reference's cfr() on this box's host cores.
+e2e = the same through the C ABI from host buffers, roofline = the dominant kernel (task_kernel<CFR>,
+one launch per player traversal) from CUDA events on the engine's stream, cpu_baseline = the literal
+scalar port of the reference's cfr() on this box's host cores.
 `--impl reference` times that port alone (the reference itself cannot be built: no Rust toolchain).
 """
 from __future__ import annotations
@@ -319,7 +319,7 @@ def run_ours(args):
                        "table_bytes_per_gpu": int(st.table_bytes),
                        "parallelism": "single GPU" if world == 1 else f"river boards sharded over {world} GPUs + NCCL all-reduce at the chance nodes",
                        "l2": "flushed between timed steps (256 MiB device write); each step timed by CUDA events on the launch stream",
-                       "threads_per_block": 256},
+                       "threads_per_block": "4 hands per thread + 1 dispatcher warp (320 for 1128 hands)"},
             "updates_per_sec": value * upd_global,
             "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
