@@ -137,6 +137,7 @@ struct Engine {
     DevBuf<float> root_weights[2];
     DevBuf<NodeTask> tasks[2];
     DevBuf<TaskSrc> srcs[2];
+    DevBuf<uint32_t> task_of_ticket[2];
     DevBuf<uint32_t> flags;
     DevBuf<TaskCtl> ctl;
     DevBuf<unsigned long long> timing;
@@ -274,6 +275,12 @@ int Engine::init(const rs_config* cfg) {
     for (int p = 0; p < 2; ++p) {
         CU(tasks[p].upload(P.tl[p].tasks));
         CU(srcs[p].upload(P.tl[p].srcs));
+        {
+            std::vector<uint32_t> tix(P.tl[p].n_tickets);
+            for (size_t j = 0; j < P.tl[p].tasks.size(); ++j)
+                for (uint32_t i = 0; i < P.tl[p].tasks[j].count; ++i) tix[P.tl[p].tasks[j].first + i] = uint32_t(j);
+            CU(task_of_ticket[p].upload(tix));
+        }
         max_tickets = std::max(max_tickets, P.tl[p].n_tickets);
         slots = std::max(slots, int(std::max(P.tl[p].max_terminal, 1 + P.tl[p].max_children)));
     }
@@ -375,6 +382,7 @@ void Engine::fill_args(TaskArgs* a, int trav) const {
     }
     a->tasks = tasks[trav].p;
     a->srcs = srcs[trav].p;
+    a->task_of_ticket = task_of_ticket[trav].p;
     a->n_tasks = uint32_t(P.tl[trav].tasks.size());
     a->flags = flags.p;
     a->ctl = ctl.p;

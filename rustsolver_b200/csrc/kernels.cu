@@ -726,8 +726,12 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
         uint32_t epoch = 0;
         if (lane == 0) epoch = ld_acquire_u32(&A.ctl->epoch);
         epoch = __shfl_sync(0xffffffffu, epoch, 0);
-        uint32_t j = A.j0, prev_tk = 0xffffffffu, parity = 0;
+        uint32_t prev_tk = 0xffffffffu, parity = 0;
         int buf = 0;
+        // the ticket for the task prepared in iteration i was drawn in iteration i-1: its round trip is hidden
+        uint32_t tk_next = 0;
+        if (lane == 0) tk_next = A.t0 + uint32_t(atomicAdd(&A.ctl->ticket, 1ull));
+        tk_next = __shfl_sync(0xffffffffu, tk_next, 0);
         for (;;) {
             bool published = (prev_tk == 0xffffffffu);  // meaningful on lane 0
             auto try_publish = [&]() {
@@ -737,52 +741,60 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                     published = true;
                 }
             };
-            uint32_t tk = 0;
-            if (lane == 0) tk = A.t0 + uint32_t(atomicAdd(&A.ctl->ticket, 1ull));
-            tk = __shfl_sync(0xffffffffu, tk, 0);
+            const uint32_t tk = tk_next;
             if (tk < A.t1) {
-                if (lane == 0) j = find_task(A, tk, j);
-                j = __shfl_sync(0xffffffffu, j, 0);
+                unsigned long long pend = 0;
+                if (lane == 0) pend = atomicAdd(&A.ctl->ticket, 1ull);  // consumed at the end of this iteration
+                const uint32_t j = __ldg(A.task_of_ticket + tk);
                 const NodeTask* gt = A.tasks + j;
+                NodeTask& st = s_slot[buf].nt;
                 for (int i = lane; i < int(sizeof(NodeTask) / 4); i += 32)
-                    reinterpret_cast<uint32_t*>(&s_slot[buf].nt)[i] = __ldg(reinterpret_cast<const uint32_t*>(gt) + i);
-                if (lane == 0) prefetch_task_tables<MODE>(A, tk, j);
-                try_publish();
-                const int kind = gt->kind;
-                const int b = int(tk - gt->first);
-                const RoundArgs& Rk = A.rounds[gt->round_k];
-                const int nd = gt->n_dep;
+                    reinterpret_cast<uint32_t*>(&st)[i] = __ldg(reinterpret_cast<const uint32_t*>(gt) + i);
+                __syncwarp();
+                const int kind = st.kind;
+                const int b = int(tk - st.first);
+                const RoundArgs& Rk = A.rounds[st.round_k];
+                const int nd = st.n_dep;
                 int total;
                 uint32_t gfirst = 0;
                 if (kind == TK_GATHER) {
-                    gfirst = uint32_t(gt->dep[0]) + uint32_t(Rk.per_parent > 0 ? b * Rk.per_parent : 0);
+                    gfirst = uint32_t(st.dep[0]) + uint32_t(Rk.per_parent > 0 ? b * Rk.per_parent : 0);
                     total = Rk.per_parent > 0 ? Rk.per_parent : Rk.n_boards_next;
                 } else {
-                    total = nd + gt->n_src_all;
+                    total = nd + st.n_src_all;
                 }
-                int i = lane;  // each lane walks its share of the producers, one flag test per round
-                for (;;) {
+                // each lane resolves the flag index of its first producer now (loads overlap the prefetch setup)
+                auto flag_index = [&](int i, bool& has) -> uint32_t {
+                    has = true;
+                    if (kind == TK_GATHER) return gfirst + uint32_t(i);
+                    int dfirst, dk = DK_SAME_BOARD;
+                    if (i < nd) {
+                        dfirst = st.dep[i];
+                        dk = st.dep_kind[i];
+                    } else {
+                        dfirst = __ldg(&A.srcs[st.src_all_first + (i - nd)].dep);
+                    }
+                    has = dfirst >= 0;
+                    return uint32_t(dfirst) + uint32_t(dk == DK_PARENT_BOARD ? Rk.parent_board[b] : b);
+                };
+                int i = lane;
+                bool has = false;
+                uint32_t idx = 0;
+                if (i < total) idx = flag_index(i, has);
+                if (lane == 0) prefetch_task_tables<MODE>(A, tk, j);
+                try_publish();
+                for (;;) {  // one flag test per lane per round
                     if (i < total) {
-                        uint32_t idx;
-                        bool has = true;
-                        if (kind == TK_GATHER) {
-                            idx = gfirst + uint32_t(i);
-                        } else {
-                            int dfirst, dk = DK_SAME_BOARD;
-                            if (i < nd) {
-                                dfirst = gt->dep[i];
-                                dk = gt->dep_kind[i];
-                            } else {
-                                dfirst = A.srcs[gt->src_all_first + (i - nd)].dep;
-                            }
-                            has = dfirst >= 0;
-                            idx = uint32_t(dfirst) + uint32_t(dk == DK_PARENT_BOARD ? Rk.parent_board[b] : b);
+                        if (!has || idx < A.t0 || ld_acquire_u32(A.flags + idx) == epoch) {
+                            i += 32;
+                            if (i < total) idx = flag_index(i, has);
                         }
-                        if (!has || idx < A.t0 || ld_acquire_u32(A.flags + idx) == epoch) i += 32;
                     }
                     try_publish();
                     if (__all_sync(0xffffffffu, i >= total)) break;
+                    __nanosleep(64);
                 }
+                tk_next = A.t0 + uint32_t(__shfl_sync(0xffffffffu, pend, 0));
             }
             if (lane == 0) s_slot[buf].ticket = tk;
             __syncwarp();

@@ -64,6 +64,7 @@ struct TaskArgs {
     RoundArgs rounds[3];
     const NodeTask* tasks;
     const TaskSrc* srcs;
+    const uint32_t* task_of_ticket;  // [n_tickets] node-task index of every ticket
     uint32_t n_tasks;
     uint32_t* flags;  // [n_tickets] epoch of completion
     TaskCtl* ctl;
