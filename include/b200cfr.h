@@ -144,6 +144,13 @@ void rs_destroy(rs_engine* e);
 
 /* train(): run n_iters synchronous full-tree CFR iterations; returns after the device is idle */
 int rs_iterate(rs_engine* e, uint64_t n_iters);
+/* MCCFR-style iteration: train() samples the run-out of the board for every iteration (generate_hand,
+ * cfr.rs:100-143, 209) and traverses only that deal.  Here the host keeps the RNG and passes n_paths sampled
+ * run-outs, `dealt[n_paths][n_rounds-1]` cards in deal order; paths must start with distinct cards.  One call =
+ * one iteration (player 0 then player 1) over the root street and the sampled boards, for ALL hands at once
+ * (public chance sampling); values are importance-weighted by (#possible deals)/(#sampled) so the update is an
+ * unbiased estimate of the full iteration's. */
+int rs_iterate_sampled(rs_engine* e, const uint8_t* dealt, uint32_t n_paths);
 /* discount sweep of train()'s monitor thread (cfr.rs:248-261): every table *= d */
 int rs_discount(rs_engine* e, float d);
 int rs_reset(rs_engine* e);

@@ -70,6 +70,7 @@ def load():
     lib.orc_literal_mccfr.argtypes = [VP, C.c_long, C.c_int, C.c_uint64, C.c_long, C.c_long, C.c_long]
     lib.orc_literal_to_double.argtypes = [VP, C.c_double]
     lib.orc_num_threads.restype = C.c_int
+    lib.orc_iterate_sampled.argtypes = [VP, C.c_int, i32p, i32p]
     lib.orc_chance_partials.restype = C.c_int
     lib.orc_chance_partials.argtypes = [VP, C.c_int, C.c_int, C.c_int, f64p, C.c_int]
     _lib = lib
@@ -143,6 +144,25 @@ class OracleGame:
     # --- vector-form fp64 CFR ---
     def iterate(self, n: int = 1):
         self.lib.orc_iterate(self.h, n)
+
+    def board_id_of(self, dealt) -> list:
+        """board ids per round (1..) of a run-out given as dealt cards in deal order (ascending-card board table)."""
+        ids, mask, bid = [], self.board_mask(0, 0), 0
+        for k, c in enumerate(dealt, start=1):
+            per = 52 - bin(mask).count("1")
+            idx = sum(1 for x in range(int(c)) if not (mask >> x) & 1)
+            bid = bid * per + idx
+            mask |= 1 << int(c)
+            ids.append(bid)
+        return ids
+
+    def iterate_sampled(self, paths):
+        """One MCCFR-style iteration on sampled run-outs (paths = [[turn, river], ...] dealt cards)."""
+        paths = [list(p) for p in paths]
+        ids = [self.board_id_of(p) for p in paths]
+        r1 = np.ascontiguousarray([i[0] for i in ids], dtype=np.int32)
+        r2 = np.ascontiguousarray([i[1] if len(i) > 1 else 0 for i in ids], dtype=np.int32)
+        self.lib.orc_iterate_sampled(self.h, len(paths), r1.ctypes.data_as(i32p), r2.ctypes.data_as(i32p))
 
     def traverse_player(self, p: int):
         self.lib.orc_traverse_player(self.h, p)

@@ -163,6 +163,10 @@ typedef struct orc_game {
     int shard_lo, shard_hi;
     double* rec;
     int rec_n, rec_cap;
+    /* sampled run-outs (MCCFR-style board sampling, generate_hand cfr.rs:100-143): when samp_n > 0 chance nodes only
+     * deal the boards listed in samp[k+1] and weight them by (#possible deals)/(#sampled children) */
+    int samp_n;
+    int* samp[3];
 } orc_game;
 
 static void* xcalloc(size_t n, size_t sz) {
@@ -549,6 +553,18 @@ static void showdown_values(const orc_game* g, int p, int b, const double* reach
 
 static void walk(walk_ctx* c, int node, int k, int b, const double* reach, double pi, double* out);
 
+/* sampled mode: is child board cb (round k1) one of the sampled run-outs? */
+static int samp_allowed(const orc_game* g, int k1, int cb) {
+    if (g->samp_n <= 0) return 1;
+    for (int i = 0; i < g->samp_n; ++i)
+        if (g->samp[k1][i] == cb) return 1;
+    return 0;
+}
+static double samp_weight(const orc_game* g, int k, int per) {
+    if (g->samp_n <= 0) return 1.0;
+    return (double)per / (double)(k == 0 ? g->samp_n : 1);
+}
+
 /* expected showdown over run-outs from board (k,b) */
 static void runout_showdown(walk_ctx* c, int k, int b, const double* reach, double pi, double value, double* out) {
     orc_game* g = c->g;
@@ -564,10 +580,16 @@ static void runout_showdown(walk_ctx* c, int k, int b, const double* reach, doub
     int per = g->deal_count[k + 1];
     for (int i = 0; i < per; ++i) {
         int cb = b * per + i;
+        if (!samp_allowed(g, k + 1, cb)) continue;
         for (int j = 0; j < Ho; ++j) r2[j] = (g->hmask[o][j] & g->bmask[k + 1][cb]) ? 0.0 : reach[j];
         runout_showdown(c, k + 1, cb, r2, pi / len, value, tmp);
         for (int h = 0; h < Hp; ++h)
             if (!(g->hmask[p][h] & g->bmask[k + 1][cb])) out[h] += tmp[h];
+    }
+    {
+        const double w = samp_weight(g, k, per);
+        if (w != 1.0)
+            for (int h = 0; h < Hp; ++h) out[h] *= w;
     }
     free(r2);
     free(tmp);
@@ -592,10 +614,16 @@ static void walk(walk_ctx* c, int node, int k, int b, const double* reach, doubl
             for (int i = 0; i < per; ++i) {
                 int cb = b * per + i;
                 if (k == 0 && g->shard_hi > 0 && (cb < g->shard_lo || cb >= g->shard_hi)) continue; /* another rank's board */
+                if (!samp_allowed(g, k + 1, cb)) continue;
                 for (int j = 0; j < Ho; ++j) r2[j] = (g->hmask[o][j] & g->bmask[k + 1][cb]) ? 0.0 : reach[j];
                 walk(c, g->children[g->child_off[node]], k + 1, cb, r2, pi / len, tmp);
                 for (int h = 0; h < Hp; ++h)
                     if (!(g->hmask[p][h] & g->bmask[k + 1][cb])) out[h] += tmp[h];
+            }
+            {
+                const double w = samp_weight(g, k, per);
+                if (w != 1.0)
+                    for (int h = 0; h < Hp; ++h) out[h] *= w;
             }
             free(r2);
             free(tmp);
@@ -719,6 +747,15 @@ void orc_iterate(orc_game* g, int n_iters) {
 }
 
 void orc_traverse_player(orc_game* g, int p) { traverse(g, p, MODE_CFR); }
+
+/* One iteration on sampled run-outs: board_ids[k-1][i] = board id of path i in round k (k = 1 .. n_rounds-1). */
+void orc_iterate_sampled(orc_game* g, int n_paths, const int* ids_round1, const int* ids_round2) {
+    g->samp_n = n_paths;
+    g->samp[1] = (int*)ids_round1;
+    g->samp[2] = (int*)ids_round2;
+    for (int p = 0; p < 2; ++p) traverse(g, p, MODE_CFR);
+    g->samp_n = 0;
+}
 
 void orc_best_response(orc_game* g, double out[2]) {
     for (int p = 0; p < 2; ++p) {

@@ -71,6 +71,7 @@ ENGINE_API = {
                                   C.POINTER(rs_config), u64p, C.c_uint32, C.POINTER(VP)]),
     "rs_destroy": (None, [VP]),
     "rs_iterate": (C.c_int, [VP, C.c_uint64]),
+    "rs_iterate_sampled": (C.c_int, [VP, u8p, C.c_uint32]),
     "rs_discount": (C.c_int, [VP, C.c_float]),
     "rs_reset": (C.c_int, [VP]),
     "rs_read_infoset": (C.c_int, [VP, C.c_uint32, C.c_uint32, f32p, f32p, C.c_size_t, u32p, u32p]),

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -121,6 +122,14 @@ struct RoundDev {
     uint32_t n_leaves = 0, n_boards = 0;
 };
 
+// a traversal's task list with ticket numbering materialised for a given number of instances per round
+struct TaskSet {
+    DevBuf<NodeTask> tasks;
+    DevBuf<TaskSrc> srcs;
+    DevBuf<uint32_t> tix;  // ticket -> node-task index
+    uint32_t n_tickets = 0, phase_cut = 0, n_tasks = 0;
+};
+
 struct Engine {
     Plan plan;
     int device = 0;
@@ -135,9 +144,10 @@ struct Engine {
     RoundDev rd[3];
     DevBuf<float> scratch;  // strategy read-outs
     DevBuf<float> root_weights[2];
-    DevBuf<NodeTask> tasks[2];
-    DevBuf<TaskSrc> srcs[2];
-    DevBuf<uint32_t> task_of_ticket[2];
+    TaskSet full[2];                                        // every board of every round (rs_iterate)
+    std::map<int, std::unique_ptr<TaskSet[]>> sampled_sets;  // by number of sampled paths (rs_iterate_sampled)
+    DevBuf<int32_t> sample_board[3];
+    int sample_cap = 0;
     DevBuf<uint32_t> flags;
     DevBuf<TaskCtl> ctl;
     DevBuf<unsigned long long> timing;
@@ -166,8 +176,10 @@ struct Engine {
     }
 
     int init(const rs_config* cfg);
-    void fill_args(TaskArgs* a, int trav) const;
-    int enqueue_traversal(int trav, int mode, uint64_t* count);
+    void fill_args(TaskArgs* a, int trav, const TaskSet& set) const;
+    int materialize(int trav, const uint32_t counts[3], TaskSet* out);
+    int enqueue_sampled(int n_paths, uint64_t* count);
+    int enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet* set = nullptr, int n_paths = 0);
     int enqueue_iteration(uint64_t* count);
     int iterate(uint64_t n);
     int root_sum(int player, double* out);
@@ -273,15 +285,11 @@ int Engine::init(const rs_config* cfg) {
     }
     uint32_t max_tickets = 0;
     for (int p = 0; p < 2; ++p) {
-        CU(tasks[p].upload(P.tl[p].tasks));
-        CU(srcs[p].upload(P.tl[p].srcs));
-        {
-            std::vector<uint32_t> tix(P.tl[p].n_tickets);
-            for (size_t j = 0; j < P.tl[p].tasks.size(); ++j)
-                for (uint32_t i = 0; i < P.tl[p].tasks[j].count; ++i) tix[P.tl[p].tasks[j].first + i] = uint32_t(j);
-            CU(task_of_ticket[p].upload(tix));
-        }
-        max_tickets = std::max(max_tickets, P.tl[p].n_tickets);
+        uint32_t counts[3] = {0, 0, 0};
+        for (uint32_t k = 0; k < P.n_rounds; ++k) counts[k] = rd[k].n_boards;
+        int rc = materialize(p, counts, &full[p]);
+        if (rc != RS_OK) return rc;
+        max_tickets = std::max(max_tickets, full[p].n_tickets);
         slots = std::max(slots, int(std::max(P.tl[p].max_terminal, 1 + P.tl[p].max_children)));
     }
     CU(timing.alloc(96));
@@ -338,7 +346,40 @@ int Engine::init(const rs_config* cfg) {
     return RS_OK;
 }
 
-void Engine::fill_args(TaskArgs* a, int trav) const {
+int Engine::materialize(int trav, const uint32_t counts[3], TaskSet* out) {
+    const TaskList& tl = plan.tl[trav];
+    std::vector<NodeTask> t = tl.tasks;
+    std::vector<TaskSrc> sr = tl.srcs;
+    uint32_t first = 0;
+    out->phase_cut = 0;
+    bool cut_set = false;
+    for (size_t j = 0; j < t.size(); ++j) {
+        if (!cut_set && tl.tasks[j].first >= tl.phase_cut) {
+            out->phase_cut = first;
+            cut_set = true;
+        }
+        t[j].first = first;
+        t[j].count = counts[t[j].round_k];
+        first += t[j].count;
+    }
+    if (!cut_set) out->phase_cut = first;
+    out->n_tickets = first;
+    out->n_tasks = uint32_t(t.size());
+    for (NodeTask& x : t)
+        for (int i = 0; i < x.n_dep; ++i)
+            if (x.dep[i] >= 0) x.dep[i] = int32_t(t[x.dep[i]].first);
+    for (TaskSrc& x : sr)
+        if (x.dep >= 0) x.dep = int32_t(t[x.dep].first);
+    std::vector<uint32_t> tix(first);
+    for (size_t j = 0; j < t.size(); ++j)
+        for (uint32_t i = 0; i < t[j].count; ++i) tix[t[j].first + i] = uint32_t(j);
+    CU(out->tasks.upload(t));
+    CU(out->srcs.upload(sr));
+    CU(out->tix.upload(tix));
+    return RS_OK;
+}
+
+void Engine::fill_args(TaskArgs* a, int trav, const TaskSet& set) const {
     const Plan& P = plan;
     memset(a, 0, sizeof(*a));
     for (int q = 0; q < 2; ++q) {
@@ -380,10 +421,10 @@ void Engine::fill_args(TaskArgs* a, int trav) const {
             ra.n_boards_next = int(rd[k + 1].n_boards);
         }
     }
-    a->tasks = tasks[trav].p;
-    a->srcs = srcs[trav].p;
-    a->task_of_ticket = task_of_ticket[trav].p;
-    a->n_tasks = uint32_t(P.tl[trav].tasks.size());
+    a->tasks = set.tasks.p;
+    a->srcs = set.srcs.p;
+    a->task_of_ticket = set.tix.p;
+    a->n_tasks = set.n_tasks;
     a->flags = flags.p;
     a->ctl = ctl.p;
     a->trav = trav;
@@ -422,7 +463,7 @@ int Engine::prof_end(uint32_t kind, uint32_t phase, int trav, uint32_t grid, uin
 uint64_t Engine::table_bytes_of(int trav, int phase) const {
     const Plan& P = plan;
     uint64_t bytes = 0;
-    const bool split = P.tl[trav].phase_cut < P.tl[trav].n_tickets;
+    const bool split = full[trav].phase_cut < full[trav].n_tickets;
     for (uint32_t k = 0; k < P.n_rounds; ++k) {
         const uint64_t own = P.tabs[k][trav].board_off[P.n_boards[k]];
         const uint64_t opp = P.tabs[k][1 - trav].board_off[P.n_boards[k]];
@@ -433,20 +474,25 @@ uint64_t Engine::table_bytes_of(int trav, int phase) const {
     return bytes;
 }
 
-int Engine::enqueue_traversal(int trav, int mode, uint64_t* count) {
+int Engine::enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet* set, int n_paths) {
     const Plan& P = plan;
     const TaskList& tl = P.tl[trav];
+    if (!set) set = &full[trav];
     TaskArgs a;
-    fill_args(&a, trav);
+    fill_args(&a, trav, *set);
+    if (n_paths > 0) {
+        a.n_paths = n_paths;
+        for (uint32_t k = 1; k < P.n_rounds; ++k) {
+            a.sample_board[k] = sample_board[k].p;
+            a.gather_scale[k - 1] = float(P.deal_count[k]) / float(k == 1 ? n_paths : 1);
+        }
+    }
     int rc;
-    const uint32_t cuts[3] = {0, tl.phase_cut, tl.n_tickets};
+    const uint32_t cuts[3] = {0, set->phase_cut, set->n_tickets};
     for (int phase = 0; phase < 2; ++phase) {
         a.t0 = cuts[phase];
         a.t1 = cuts[phase + 1];
         if (a.t1 <= a.t0) continue;
-        a.j0 = 0;
-        for (size_t j = 0; j < tl.tasks.size(); ++j)
-            if (tl.tasks[j].first <= a.t0) a.j0 = uint32_t(j);
         const int grid = int(std::min<uint64_t>(uint64_t(a.t1 - a.t0), uint64_t(n_sms) * blocks_per_sm));
         if ((rc = prof_begin()) != RS_OK) return rc;
         CU(launch_task_kernel(a, mode, grid, threads, smem_bytes, stream));
@@ -456,7 +502,7 @@ int Engine::enqueue_traversal(int trav, int mode, uint64_t* count) {
         if ((rc = prof_end(RS_KERNEL_TRAVERSAL, uint32_t(phase), trav, uint32_t(grid), table_bytes_of(trav, phase), vec)) != RS_OK)
             return rc;
         ++*count;
-        if (phase == 0 && tl.phase_cut < tl.n_tickets) {
+        if (phase == 0 && set->phase_cut < set->n_tickets) {
             // the one exchange step of the path: counterfactual values at the shared chance nodes
             RoundDev& Par = rd[P.shard_round - 1];
             if ((rc = prof_begin()) != RS_OK) return rc;
@@ -466,6 +512,25 @@ int Engine::enqueue_traversal(int trav, int mode, uint64_t* count) {
             if ((rc = prof_end(RS_KERNEL_ALLREDUCE, 0, trav, 0, 0, n * 4)) != RS_OK) return rc;
             ++*count;
         }
+    }
+    return RS_OK;
+}
+
+// one iteration on sampled run-outs: sample_board[] already holds the board ids
+int Engine::enqueue_sampled(int n_paths, uint64_t* count) {
+    auto it = sampled_sets.find(n_paths);
+    if (it == sampled_sets.end()) {
+        std::unique_ptr<TaskSet[]> sets(new TaskSet[2]);
+        for (int p = 0; p < 2; ++p) {
+            uint32_t counts[3] = {rd[0].n_boards, uint32_t(n_paths), uint32_t(n_paths)};
+            int rc = materialize(p, counts, &sets[p]);
+            if (rc != RS_OK) return rc;
+        }
+        it = sampled_sets.emplace(n_paths, std::move(sets)).first;
+    }
+    for (int p = 0; p < 2; ++p) {
+        int rc = enqueue_traversal(p, KM_CFR, count, &it->second[p], n_paths);
+        if (rc != RS_OK) return rc;
     }
     return RS_OK;
 }
@@ -655,6 +720,52 @@ void rs_destroy(rs_engine* e) {
 int rs_iterate(rs_engine* e, uint64_t n_iters) {
     if (!e) return set_err(RS_ERR_INVALID, "null engine");
     return e->e.iterate(n_iters);
+}
+
+int rs_iterate_sampled(rs_engine* e, const uint8_t* dealt, uint32_t n_paths) {
+    if (!e || !dealt) return set_err(RS_ERR_INVALID, "null argument");
+    Engine& E = e->e;
+    const Plan& P = E.plan;
+    if (P.n_rounds < 2) return set_err(RS_ERR_INVALID, "a single-street tree has no chance node to sample");
+    if (P.n_sub != 1 || P.world != 1) return set_err(RS_ERR_UNSUPPORTED, "sampled iterations need one root board on one GPU");
+    if (n_paths == 0 || n_paths > P.n_boards[1]) return set_err(RS_ERR_INVALID, "n_paths must be in 1..#first-street deals");
+    const uint32_t L = P.n_rounds - 1;  // cards per path
+    std::vector<int32_t> ids[3];
+    std::vector<uint8_t> seen(52, 0);
+    for (uint32_t s = 0; s < n_paths; ++s) {
+        uint32_t id = 0;
+        uint64_t mask = P.board_mask[0][0];
+        for (uint32_t k = 1; k <= L; ++k) {
+            const int c = dealt[s * L + (k - 1)];
+            if (c >= 52 || (mask & (1ull << c))) return set_err(RS_ERR_INVALID, "sampled card already on the board");
+            if (k == 1) {
+                if (seen[c]) return set_err(RS_ERR_INVALID, "sampled paths must start with distinct cards");
+                seen[c] = 1;
+            }
+            id = id * P.deal_count[k] + uint32_t(__builtin_popcountll(~mask & ((1ull << c) - 1)));
+            mask |= 1ull << c;
+            ids[k].push_back(int32_t(id));
+        }
+    }
+    CU(cudaSetDevice(E.device));
+    if (int(n_paths) > E.sample_cap) {
+        for (uint32_t k = 1; k <= L; ++k) CU(E.sample_board[k].alloc(n_paths));
+        E.sample_cap = int(n_paths);
+    }
+    for (uint32_t k = 1; k <= L; ++k)
+        CU(cudaMemcpyAsync(E.sample_board[k].p, ids[k].data(), n_paths * sizeof(int32_t), cudaMemcpyHostToDevice, E.stream));
+    CU(cudaEventRecord(E.ev0, E.stream));
+    uint64_t cnt = 0;
+    int rc = E.enqueue_sampled(int(n_paths), &cnt);
+    if (rc != RS_OK) return rc;
+    CU(cudaEventRecord(E.ev1, E.stream));
+    CU(cudaStreamSynchronize(E.stream));  // ids[] are host temporaries
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, E.ev0, E.ev1));
+    E.device_ms += ms;
+    E.launches += cnt;
+    E.iterations += 1;
+    return RS_OK;
 }
 
 int rs_discount(rs_engine* e, float d) {

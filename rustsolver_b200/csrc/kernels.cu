@@ -656,25 +656,15 @@ __device__ __forceinline__ void task_trav_generic(const TaskArgs& A, const Ctx& 
 // ------------------------------------------------------------------------------------------------
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------
-// ticket -> node-task index.  Tickets are handed out in task order, so the answer is usually j0 or a few tasks
-// further (same-size runs let us jump); otherwise binary search over the first-ticket column.
-__device__ __forceinline__ uint32_t find_task(const TaskArgs& A, uint32_t tk, uint32_t j0) {
-    {
-        const uint32_t f = A.tasks[j0].first, cnt = A.tasks[j0].count;
-        if (tk < f + cnt) return j0;
-        const uint32_t jn = j0 + (tk - f) / cnt;  // exact when the tasks in between all have `cnt` instances
-        if (jn < A.n_tasks) {
-            const uint32_t fn = A.tasks[jn].first;
-            if (fn <= tk && tk < fn + A.tasks[jn].count) return jn;
-        }
-    }
-    uint32_t lo = j0, hi = A.n_tasks - 1;  // last task with first <= tk
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if (A.tasks[mid].first <= tk) lo = mid;
-        else hi = mid - 1;
-    }
-    return lo;
+// instance -> board.  Full traversal: the instance number IS the (local) board.  Sampled mode: round 0 keeps its
+// boards, deeper rounds run on the sampled run-outs only.
+__device__ __forceinline__ int board_of(const TaskArgs& A, int k, int inst) {
+    return (k > 0 && A.sample_board[k] != nullptr) ? A.sample_board[k][inst] : inst;
+}
+// instance of the PARENT-round task that feeds instance `inst` of round k (flags are indexed by instance)
+__device__ __forceinline__ int parent_instance(const TaskArgs& A, const RoundArgs& Rk, int k, int inst, int b) {
+    if (A.sample_board[k] == nullptr) return Rk.parent_board[b];
+    return k - 1 == 0 ? Rk.parent_board[b] : inst;  // path i of round k hangs off path i of round k-1
 }
 
 // pull the table slab(s) the NEXT task of this CTA will read into L2 while the current task runs
@@ -684,7 +674,7 @@ __device__ __forceinline__ void prefetch_task_tables(const TaskArgs& A, uint32_t
     const int kind = g->kind;
     if (kind != TK_DOWN && kind != TK_UP_TRAV) return;
     const RoundArgs& Rk = A.rounds[g->round_k];
-    const int b = int(tk - g->first);
+    const int b = board_of(A, g->round_k, int(tk - g->first));
     const int q = kind == TK_DOWN ? 1 - A.trav : A.trav;
     const DevRoundPlayer& D = Rk.rp[q];
     const uint32_t nrp = D.n_rows_pad[b];
@@ -752,14 +742,22 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                     reinterpret_cast<uint32_t*>(&st)[i] = __ldg(reinterpret_cast<const uint32_t*>(gt) + i);
                 __syncwarp();
                 const int kind = st.kind;
-                const int b = int(tk - st.first);
-                const RoundArgs& Rk = A.rounds[st.round_k];
+                const int k = st.round_k;
+                const int inst = int(tk - st.first);
+                const int b = board_of(A, k, inst);
+                const RoundArgs& Rk = A.rounds[k];
                 const int nd = st.n_dep;
+                const bool sampled = A.sample_board[1] != nullptr;
                 int total;
                 uint32_t gfirst = 0;
                 if (kind == TK_GATHER) {
-                    gfirst = uint32_t(st.dep[0]) + uint32_t(Rk.per_parent > 0 ? b * Rk.per_parent : 0);
-                    total = Rk.per_parent > 0 ? Rk.per_parent : Rk.n_boards_next;
+                    if (sampled) {  // children = the sampled paths: all of them below the root board, else this path's own
+                        gfirst = uint32_t(st.dep[0]) + uint32_t(k == 0 ? 0 : inst);
+                        total = k == 0 ? A.n_paths : 1;
+                    } else {
+                        gfirst = uint32_t(st.dep[0]) + uint32_t(Rk.per_parent > 0 ? b * Rk.per_parent : 0);
+                        total = Rk.per_parent > 0 ? Rk.per_parent : Rk.n_boards_next;
+                    }
                 } else {
                     total = nd + st.n_src_all;
                 }
@@ -775,7 +773,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                         dfirst = __ldg(&A.srcs[st.src_all_first + (i - nd)].dep);
                     }
                     has = dfirst >= 0;
-                    return uint32_t(dfirst) + uint32_t(dk == DK_PARENT_BOARD ? Rk.parent_board[b] : b);
+                    return uint32_t(dfirst) + uint32_t(dk == DK_PARENT_BOARD ? parent_instance(A, Rk, k, inst, b) : inst);
                 };
                 int i = lane;
                 bool has = false;
@@ -783,6 +781,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                 if (i < total) idx = flag_index(i, has);
                 if (lane == 0) prefetch_task_tables<MODE>(A, tk, j);
                 try_publish();
+                (void)b;
                 for (;;) {  // one flag test per lane per round
                     if (i < total) {
                         if (!has || idx < A.t0 || ld_acquire_u32(A.flags + idx) == epoch) {
@@ -852,7 +851,8 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
         const NodeTask& nt = s_slot[buf].nt;
         const int kind = nt.kind;
         const int k = nt.round_k;
-        const int b = int(t - nt.first);
+        const int inst = int(t - nt.first);
+        const int b = board_of(A, k, inst);
         const RoundArgs& Rk = A.rounds[k];
 #ifdef RS_TASK_TIMING
         const long long tm1 = clock64();
@@ -893,17 +893,28 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
             case TK_GATHER: {  // cfr.rs:502-522: sum over the dealt cards, fixed board order
                 if (c.pos4 < c.HpP) {
                     const RoundArgs& Rn = A.rounds[k + 1];
-                    const int cb0 = Rk.per_parent > 0 ? b * Rk.per_parent : 0;
-                    const int ncb = Rk.per_parent > 0 ? Rk.per_parent : Rk.n_boards_next;
                     // the child-street roots stored their values in THIS board's hand order (store_value4)
-                    const float* src = Rn.sbuf + (size_t(nt.aux) * Rn.n_boards + cb0) * c.HpP + c.pos4;
+                    const float* base = Rn.sbuf + size_t(nt.aux) * Rn.n_boards * c.HpP + c.pos4;
                     float4 acc = f4zero();
-                    for (int i0 = 0; i0 < ncb; i0 += 8) {  // eight loads in flight; summation order = board order
-                        float4 val[8];
+                    if (A.sample_board[k + 1] != nullptr) {
+                        // sampled run-outs (generate_hand, cfr.rs:100-143): uniform sampling of the next card, weight
+                        // = (#possible deals) / (#sampled children)
+                        const int32_t* sb = A.sample_board[k + 1];
+                        const int s0 = k == 0 ? 0 : inst, ns = k == 0 ? A.n_paths : 1;
+                        for (int i = 0; i < ns; ++i) acc = f4add(acc, ldcg4(base + size_t(sb[s0 + i]) * c.HpP));
+                        const float w = A.gather_scale[k];
+                        acc = make_float4(acc.x * w, acc.y * w, acc.z * w, acc.w * w);
+                    } else {
+                        const int cb0 = Rk.per_parent > 0 ? b * Rk.per_parent : 0;
+                        const int ncb = Rk.per_parent > 0 ? Rk.per_parent : Rk.n_boards_next;
+                        const float* src = base + size_t(cb0) * c.HpP;
+                        for (int i0 = 0; i0 < ncb; i0 += 8) {  // eight loads in flight; summation order = board order
+                            float4 val[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) val[u] = (i0 + u < ncb) ? ldcg4(src + size_t(i0 + u) * c.HpP) : f4zero();
+                            for (int u = 0; u < 8; ++u) val[u] = (i0 + u < ncb) ? ldcg4(src + size_t(i0 + u) * c.HpP) : f4zero();
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) acc = f4add(acc, val[u]);
+                            for (int u = 0; u < 8; ++u) acc = f4add(acc, val[u]);
+                        }
                     }
                     stcg4(Rk.gathered + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4, acc);
                 }

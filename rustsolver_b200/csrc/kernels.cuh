@@ -72,7 +72,12 @@ struct TaskArgs {
     int H[2], Hpad[2];
     int trav;
     uint32_t t0, t1;  // ticket range of this launch
-    uint32_t j0;      // node-task holding ticket t0 (search hint)
+    // sampled-board mode (rs_iterate_sampled): rounds >= 1 only run on n_paths sampled run-outs.  Instance i of a
+    // round-k task works on board sample_board[k][i]; the chance gather sums the sampled children only and
+    // multiplies by gather_scale[k] = (#possible deals) / (#sampled children) (importance weight of uniform sampling)
+    const int32_t* sample_board[3];  // null = every board (full traversal)
+    int n_paths;
+    float gather_scale[3];
     int slots;        // Hx-sized scratch vectors provisioned in shared memory
     unsigned long long* timing;  // RS_TASK_TIMING builds: [8 kinds][count, wait cycles, body cycles, total cycles]
 };

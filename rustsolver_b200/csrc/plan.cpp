@@ -464,12 +464,8 @@ struct TaskGen {
         }
         if (!(P->world > 1 && P->shard_round >= 1)) tl.phase_cut = tl.n_tickets;
         tl.root_cbuf = segroot_cbuf[0][0];
-        // the kernel polls flags[first ticket of the producer + board]: store the ticket, not the task index
-        for (NodeTask& t : tl.tasks)
-            for (int i = 0; i < t.n_dep; ++i)
-                if (t.dep[i] >= 0) t.dep[i] = int32_t(tl.tasks[t.dep[i]].first);
-        for (TaskSrc& sr : tl.srcs)
-            if (sr.dep >= 0) sr.dep = int32_t(tl.tasks[sr.dep].first);
+        // NOTE: dep fields hold node-task INDICES here; the engine converts them to first tickets when it
+        // materialises the ticket numbering for a given instance count per round (engine.cu: materialize)
         if (tl.max_terminal > MAX_TERMINAL_CHILDREN) {
             err = "more than 3 terminal children under one action node";
             return false;

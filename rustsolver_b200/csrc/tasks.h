@@ -46,7 +46,7 @@ constexpr int MAX_TERMINAL_CHILDREN = 3;  // terminal children of one opponent n
 
 struct TaskSrc {  // one value vector feeding a child value, with the task that produces it
     int32_t buf;  // value buffer id (SK_CBUF) or chance-leaf id (SK_GATHERED) of the task's round
-    int32_t dep;  // first ticket of the producer task (same board), -1 = none
+    int32_t dep;  // producer: node-task index in the plan, first ticket of that task once uploaded; -1 = none
     uint8_t kind; // SrcKind
     uint8_t pad[3];
 };
@@ -76,7 +76,7 @@ struct NodeTask {
     uint32_t count;   // instances = local boards of round_k
     uint32_t an_index;
     uint32_t src_all_first;
-    int32_t dep[MAX_TASK_DEPS];      // first ticket of the producer task
+    int32_t dep[MAX_TASK_DEPS];      // producers: node-task index in the plan, first ticket once uploaded
     uint8_t dep_kind[MAX_TASK_DEPS]; // DepKind
     TaskChild child[MAX_TASK_CHILDREN];
 };

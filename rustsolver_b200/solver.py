@@ -423,6 +423,13 @@ class Engine(_PlanOrEngine):
     def iterate(self, n: int = 1):
         check(self._lib.rs_iterate(self._h, n))
 
+    def iterate_sampled(self, paths):
+        """One MCCFR-style iteration on sampled run-outs: paths = [[turn, river], ...] dealt cards in deal order."""
+        a = np.ascontiguousarray(paths, dtype=np.uint8)
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        check(self._lib.rs_iterate_sampled(self._h, _ptr(a, u8p), a.shape[0]))
+
     def discount(self, d: float):
         check(self._lib.rs_discount(self._h, d))
 

@@ -149,3 +149,68 @@ def test_batch_of_river_subgames():
             assert gr.shape == orr.shape
             assert np.abs(gr - orr).max() <= TOL * max(np.abs(orr).max(), 1e-12)
             assert np.abs(gs - os_).max() <= TOL * max(np.abs(os_).max(), 1e-12)
+
+
+def _sample_paths(rng, board_mask, n_paths, n_cards):
+    live = [c for c in range(52) if not (board_mask >> c) & 1]
+    firsts = rng.choice(live, n_paths, replace=False)
+    paths = []
+    for f in firsts:
+        p = [int(f)]
+        while len(p) < n_cards:
+            c = int(rng.choice(live))
+            if c not in p:
+                p.append(c)
+        paths.append(p)
+    return paths
+
+
+@pytest.mark.parametrize("board,n_cards,n_paths", [("4d5dAs3c", 1, 1), ("4d5dAs3c", 1, 5), ("4d5dAs", 2, 1), ("4d5dAs", 2, 4)])
+def test_sampled_board_iterations_match_oracle(board, n_cards, n_paths):
+    """MCCFR-style board sampling (generate_hand, cfr.rs:100-143): the host samples run-outs, the engine traverses
+    only those boards.  Both sides restart from the same state (the oracle after two full iterations) for every
+    draw, run ONE sampled iteration on the same paths, and must agree on every slab."""
+    rounds = n_cards + 1
+    stacks = (500, 500) if n_cards == 1 else (60, 60)
+    ranges = [util.RANGE_A, util.RANGE_B] if n_cards == 1 else ["AA,KK,AKs,76s,54s", "QQ,JJ,AQs,65s,32s"]
+    o = util.small_options(board, ranges, [[0.5, 1.0]] * rounds if n_cards == 1 else [[1.0]] * rounds, [[3.0]] * rounds,
+                           pot=35 if n_cards == 1 else 40, stacks=stacks)
+    tree, eng, orc = _pair(o)
+    orc.iterate(2)
+    st = eng.stats()
+    nb = [st.n_boards[k] for k in range(st.n_rounds)]
+    state = {key: orc.get_slab(*key) for key in util.all_slabs(tree, nb)}
+    al = util.RowAligner(eng, orc, tree)
+    rng = np.random.RandomState(100 + n_paths)
+    for draw in range(3):
+        paths = _sample_paths(rng, o.board_mask, n_paths, n_cards)
+        for key, (r, s_) in state.items():
+            orc.set_slab(key[0], key[1], r, s_)
+        util.copy_oracle_to_engine(eng, orc, tree, aligner=al)
+        eng.iterate_sampled(paths)
+        orc.iterate_sampled(paths)
+        util.compare_tables(eng, orc, tree, TOL, aligner=al)
+    # sampling every possible first card is the full iteration (importance weight 1), bit for bit on the engine
+    if n_cards == 1:
+        live = [c for c in range(52) if not (o.board_mask >> c) & 1]
+        e1 = rb.Engine(tree, o.ranges(), o.board_mask)
+        e2 = rb.Engine(tree, o.ranges(), o.board_mask)
+        for _ in range(2):
+            e1.iterate(1)
+            e2.iterate_sampled([[c] for c in live])
+        for key in util.all_slabs(tree, nb):
+            x, y = e1.read_infoset(*key), e2.read_infoset(*key)
+            assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1])
+
+
+def test_sampled_iterations_converge():
+    """Chance-sampled CFR drives exploitability down (sanity of the importance weights)."""
+    o = util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[1.0]] * 2, [[3.0]] * 2)
+    n, tree = rb.build_game_tree(o)
+    eng = rb.Engine(tree, o.ranges(), o.board_mask)
+    e0 = sum(eng.best_response()) / 2
+    rng = np.random.RandomState(9)
+    for it in range(600):
+        eng.iterate_sampled(_sample_paths(rng, o.board_mask, 4, 1))
+    e1 = sum(eng.best_response()) / 2
+    assert e1 < 0.25 * e0, (e0, e1)

@@ -94,3 +94,31 @@ def test_chance_sum_switch_documents_the_reference_quirk():
     _, ua = a.literal_cfr(1)
     _, ub = b.literal_cfr(1)
     assert ua != ub
+
+
+def test_sampled_runouts_are_an_unbiased_estimate_of_the_full_traversal():
+    """MCCFR-style board sampling (generate_hand, cfr.rs:100-143) in vector form: one uniformly sampled next card,
+    weighted by the number of possible deals.  Averaged over every card it must equal the full traversal exactly,
+    and sampling all cards at once IS the full traversal."""
+    o = util.small_options("4d5dAs3c", ["AA,KK,AKs,76s", "QQ,JJ,AQs,65s"], [[1.0]] * 2, [[3.0]] * 2)
+    _, tree = rb.build_game_tree(o)
+    live = [c for c in range(52) if not (o.board_mask >> c) & 1]
+    full = OracleGame(tree, o.ranges(), o.board_mask)
+    full.iterate(1)
+    acc = None
+    for c in live:
+        g = OracleGame(tree, o.ranges(), o.board_mask)
+        g.iterate_sampled([[c]])
+        r = g.get_slab(0, 0)[0]
+        acc = r if acc is None else acc + r
+    assert np.allclose(acc / len(live), full.get_slab(0, 0)[0], rtol=1e-12, atol=1e-15)
+    a = OracleGame(tree, o.ranges(), o.board_mask)
+    b = OracleGame(tree, o.ranges(), o.board_mask)
+    for _ in range(2):
+        a.iterate(1)
+        b.iterate_sampled([[c] for c in live])
+    for an in a.action_nodes:
+        k = int(tree.round_idx[a.action_nodes[an]])
+        for bd in range(a.n_boards(k)):
+            x, y = a.get_slab(an, bd), b.get_slab(an, bd)
+            assert np.allclose(x[0], y[0], rtol=1e-12, atol=1e-18) and np.allclose(x[1], y[1], rtol=1e-12, atol=1e-20)
