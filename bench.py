@@ -192,6 +192,10 @@ def run_ours(args):
     t0 = time.perf_counter()
     eng = rb.Engine(tree, ranges, w.options.board_mask, w.card_abs, board_masks=w.board_masks, device=local_rank,
                     rank=rank, world_size=world, nccl_id=nccl_id)
+    fused = False
+    if world > 1 and os.environ.get("RS_NO_FUSED", "0") != "1" and eng.stats().n_rounds > 1:
+        eng.enable_fused_exchange(dist, dev)  # the kernel exchanges the chance-node sums itself over NVLink peer memory
+        fused = True
     create_s = time.perf_counter() - t0
     st = eng.stats()
     upd_global = int(st.updates_per_iteration_global)
@@ -317,7 +321,9 @@ def run_ours(args):
                        "hands": [int(st.n_hands[0]), int(st.n_hands[1])],
                        "updates_per_iteration": upd_global,
                        "table_bytes_per_gpu": int(st.table_bytes),
-                       "parallelism": "single GPU" if world == 1 else f"river boards sharded over {world} GPUs + NCCL all-reduce at the chance nodes",
+                       "parallelism": "single GPU" if world == 1 else (
+                           f"boards sharded over {world} GPUs, chance-node sums exchanged inside the traversal kernel over NVLink peer memory"
+                           if fused else f"boards sharded over {world} GPUs + NCCL all-reduce at the chance nodes"),
                        "l2": "flushed between timed steps (256 MiB device write); each step timed by CUDA events on the launch stream",
                        "threads_per_block": "4 hands per thread + 1 dispatcher warp (320 for 1128 hands)"},
             "updates_per_sec": value * upd_global,

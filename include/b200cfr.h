@@ -132,6 +132,17 @@ int rs_device_count(void);
 /* fills RS_NCCL_ID_BYTES bytes; call on rank 0 and broadcast */
 int rs_nccl_unique_id(uint8_t* out);
 
+/* Board-sharded engines (world_size > 1) exchange the counterfactual values of the shared chance nodes once per
+ * traversal (cfr.rs:512-521 sums over the dealt cards).  By default that is an ncclAllReduce between two launches.
+ * With the buffers below mapped into every rank the traversal kernel does the exchange itself: each GPU stores its
+ * partial sums into its peers' buffers over NVLink and adds the arrived partials in rank order, one launch per
+ * traversal.  Every rank exports a handle (a CUDA IPC handle, one process per GPU), the host gathers them, every
+ * rank imports all of them in rank order; all ranks must do so at the same point of their call sequence. */
+#define RS_EXCHANGE_HANDLE_BYTES 64
+int rs_exchange_export(rs_engine* e, uint8_t* out /* RS_EXCHANGE_HANDLE_BYTES */);
+int rs_exchange_import(rs_engine* e, const uint8_t* handles /* n_ranks * RS_EXCHANGE_HANDLE_BYTES */, uint32_t n_ranks);
+
+
 int rs_create(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs,
               const rs_config* cfg, rs_engine** out);
 /* Batch of independent subgames sharing one tree shape and abstraction kind but with their own

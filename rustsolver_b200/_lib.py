@@ -17,6 +17,7 @@ f32p = C.POINTER(C.c_float)
 f64p = C.POINTER(C.c_double)
 
 RS_NCCL_ID_BYTES = 128
+RS_EXCHANGE_HANDLE_BYTES = 64
 
 
 class rs_tree(C.Structure):
@@ -65,6 +66,8 @@ ENGINE_API = {
     "rs_version": (C.c_int, []),
     "rs_device_count": (C.c_int, []),
     "rs_nccl_unique_id": (C.c_int, [u8p]),
+    "rs_exchange_export": (C.c_int, [VP, u8p]),
+    "rs_exchange_import": (C.c_int, [VP, u8p, C.c_uint32]),
     "rs_create": (C.c_int, [C.POINTER(rs_tree), C.POINTER(rs_ranges), C.POINTER(rs_abstraction),
                             C.POINTER(rs_config), C.POINTER(VP)]),
     "rs_create_batch": (C.c_int, [C.POINTER(rs_tree), C.POINTER(rs_ranges), C.POINTER(rs_abstraction),

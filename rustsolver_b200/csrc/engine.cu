@@ -151,6 +151,12 @@ struct Engine {
     DevBuf<uint32_t> flags;
     DevBuf<TaskCtl> ctl;
     DevBuf<unsigned long long> timing;
+    // in-kernel exchange of the chance-node partial sums (board-sharded engines): one allocation per rank,
+    // [flags: 2 * vectors u32, padded to 256 B][data: 2 * vectors * Hpad floats], vectors = leaves * parent boards * world
+    DevBuf<unsigned char> xch;
+    size_t xch_flag_bytes = 0, xch_vectors = 0;
+    void* xch_peer_base[RS_MAX_PEERS] = {nullptr};
+    bool fused_exchange = false;
     int slots = 1;
     size_t smem_bytes = 0;
     int blocks_per_sm = 1, n_sms = 148;
@@ -167,6 +173,8 @@ struct Engine {
     uint64_t discount_interval = 0, discount_cap = 0;
 
     ~Engine() {
+        for (int r = 0; r < RS_MAX_PEERS; ++r)
+            if (xch_peer_base[r] && r != plan.rank) cudaIpcCloseMemHandle(xch_peer_base[r]);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph) cudaGraphDestroy(graph);
         if (comm && nccl::g_api.CommDestroy) nccl::g_api.CommDestroy(comm);
@@ -342,6 +350,13 @@ int Engine::init(const rs_config* cfg) {
         CU(cudaMemcpy(parts, tmp.p, sizeof(parts), cudaMemcpyDeviceToHost));
         updates_global = uint64_t(parts[0]) + (uint64_t(parts[1]) << 20) + (uint64_t(parts[2]) << 40);
     }
+    if (P.world > 1 && P.shard_round >= 1) {
+        const RoundDev& Par = rd[P.shard_round - 1];
+        xch_vectors = size_t(Par.n_leaves) * Par.n_boards * size_t(P.world);
+        xch_flag_bytes = (2 * xch_vectors * sizeof(uint32_t) + 255) & ~size_t(255);
+        CU(xch.alloc(xch_flag_bytes + 2 * xch_vectors * maxHP * sizeof(float)));
+        CU(xch.zero());
+    }
     CU(cudaDeviceSynchronize());
     return RS_OK;
 }
@@ -428,6 +443,16 @@ void Engine::fill_args(TaskArgs* a, int trav, const TaskSet& set) const {
     a->flags = flags.p;
     a->ctl = ctl.p;
     a->trav = trav;
+    if (fused_exchange) {
+        a->xch_world = P.world;
+        a->xch_rank = P.rank;
+        a->xch_round = int(P.shard_round);
+        a->xch_leaves = int(rd[P.shard_round - 1].n_leaves);
+        for (int r = 0; r < P.world; ++r) {
+            a->xflag_peer[r] = reinterpret_cast<uint32_t*>(xch_peer_base[r]);
+            a->xch_peer[r] = reinterpret_cast<float*>(static_cast<unsigned char*>(xch_peer_base[r]) + xch_flag_bytes);
+        }
+    }
     a->slots = slots;
     a->timing = timing.p;
 }
@@ -488,7 +513,8 @@ int Engine::enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet
         }
     }
     int rc;
-    const uint32_t cuts[3] = {0, set->phase_cut, set->n_tickets};
+    // with the in-kernel exchange the whole traversal is one launch; else it is cut at the shared chance nodes
+    const uint32_t cuts[3] = {0, fused_exchange ? set->n_tickets : set->phase_cut, set->n_tickets};
     for (int phase = 0; phase < 2; ++phase) {
         a.t0 = cuts[phase];
         a.t1 = cuts[phase + 1];
@@ -502,7 +528,7 @@ int Engine::enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet
         if ((rc = prof_end(RS_KERNEL_TRAVERSAL, uint32_t(phase), trav, uint32_t(grid), table_bytes_of(trav, phase), vec)) != RS_OK)
             return rc;
         ++*count;
-        if (phase == 0 && set->phase_cut < set->n_tickets) {
+        if (phase == 0 && !fused_exchange && set->phase_cut < set->n_tickets) {
             // the one exchange step of the path: counterfactual values at the shared chance nodes
             RoundDev& Par = rd[P.shard_round - 1];
             if ((rc = prof_begin()) != RS_OK) return rc;
@@ -655,6 +681,51 @@ int rs_nccl_unique_id(uint8_t* out) {
     int rc = nccl::g_api.GetUniqueId(&id);
     if (rc != 0) return set_err(RS_ERR_NCCL, "ncclGetUniqueId failed");
     memcpy(out, &id, RS_NCCL_ID_BYTES);
+    return RS_OK;
+}
+
+int rs_exchange_export(rs_engine* e, uint8_t* out) {
+    if (!e || !out) return set_err(RS_ERR_INVALID, "null argument");
+    Engine& E = e->e;
+    if (!E.xch.p || E.xch_vectors == 0) return set_err(RS_ERR_INVALID, "engine is not board-sharded: nothing to exchange");
+    CU(cudaSetDevice(E.device));
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == RS_EXCHANGE_HANDLE_BYTES, "IPC handle size");
+    CU(cudaIpcGetMemHandle(&h, E.xch.p));
+    memcpy(out, &h, sizeof(h));
+    return RS_OK;
+}
+
+int rs_exchange_import(rs_engine* e, const uint8_t* handles, uint32_t n_ranks) {
+    if (!e || !handles) return set_err(RS_ERR_INVALID, "null argument");
+    Engine& E = e->e;
+    if (!E.xch.p || E.xch_vectors == 0) return set_err(RS_ERR_INVALID, "engine is not board-sharded: nothing to exchange");
+    if (int(n_ranks) != E.plan.world || n_ranks > uint32_t(RS_MAX_PEERS))
+        return set_err(RS_ERR_INVALID, "rs_exchange_import needs one handle per rank (at most 8 ranks)");
+    if (E.fused_exchange) return set_err(RS_ERR_INVALID, "exchange buffers already imported");
+    CU(cudaSetDevice(E.device));
+    CU(cudaStreamSynchronize(E.stream));
+    for (uint32_t r = 0; r < n_ranks; ++r) {
+        if (int(r) == E.plan.rank) {
+            E.xch_peer_base[r] = E.xch.p;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + size_t(r) * RS_EXCHANGE_HANDLE_BYTES, sizeof(h));
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        E.xch_peer_base[r] = p;
+    }
+    E.fused_exchange = true;
+    // the iteration graph was captured with the two-launch + all-reduce schedule: capture again on the next call
+    if (E.graph_exec) {
+        cudaGraphExecDestroy(E.graph_exec);
+        E.graph_exec = nullptr;
+    }
+    if (E.graph) {
+        cudaGraphDestroy(E.graph);
+        E.graph = nullptr;
+    }
     return RS_OK;
 }
 

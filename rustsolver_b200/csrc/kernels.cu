@@ -20,6 +20,15 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// system scope: flags that live in a peer GPU's memory
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -690,7 +699,8 @@ __device__ __forceinline__ void prefetch_task_tables(const TaskArgs& A, uint32_t
 
 struct TaskSlot {
     uint32_t ticket;  // >= t1: no more work
-    uint32_t pad[3];
+    uint32_t epoch;   // launch number: the value that marks flags "done" in this launch
+    uint32_t pad[2];
     NodeTask nt;
 };
 
@@ -795,7 +805,10 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                 }
                 tk_next = A.t0 + uint32_t(__shfl_sync(0xffffffffu, pend, 0));
             }
-            if (lane == 0) s_slot[buf].ticket = tk;
+            if (lane == 0) {
+                s_slot[buf].ticket = tk;
+                s_slot[buf].epoch = epoch;
+            }
             __syncwarp();
             hsync(NC + 32);  // slot[buf] handed over; the compute warps are done with the previous task
             if (lane == 0 && !published) {
@@ -917,6 +930,35 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                         }
                     }
                     stcg4(Rk.gathered + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4, acc);
+                }
+                if (A.xch_world > 1 && k + 1 == A.xch_round) {
+                    // Board-sharded traversal: the sum above only covers this GPU's boards.  Every rank writes its
+                    // partial vector straight into the peers' exchange buffers (NVLink stores), raises one flag per
+                    // peer, waits for the partials of all ranks to land in its own buffer and adds them up in rank
+                    // order (bit-identical on every GPU).  This is the one exchange step of the path, inside the
+                    // traversal kernel: no second launch, no NCCL call.  Buffers alternate with the launch parity: a
+                    // rank can be at most one traversal ahead of a peer that still reads.
+                    const uint32_t ep = s_slot[buf].epoch;
+                    const size_t vec = ((size_t(ep & 1u) * A.xch_leaves + nt.out) * Rk.n_boards + b) * A.xch_world;
+                    if (c.pos4 < c.HpP) {
+                        const float4 part = ldcg4(Rk.gathered + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4);
+                        for (int peer = 0; peer < A.xch_world; ++peer)
+                            *reinterpret_cast<float4*>(A.xch_peer[peer] + (vec + A.xch_rank) * c.HpP + c.pos4) = part;
+                    }
+                    __threadfence_system();
+                    csync(c.nc);
+                    if (tid < A.xch_world) {
+                        st_release_sys_u32(A.xflag_peer[tid] + vec + A.xch_rank, ep);
+                        const uint32_t* mine = A.xflag_peer[A.xch_rank] + vec + tid;
+                        while (ld_acquire_sys_u32(mine) != ep) __nanosleep(100);
+                    }
+                    csync(c.nc);
+                    if (c.pos4 < c.HpP) {
+                        const float* src = A.xch_peer[A.xch_rank] + vec * c.HpP + c.pos4;
+                        float4 acc = f4zero();
+                        for (int r = 0; r < A.xch_world; ++r) acc = f4add(acc, ldcg4(src + size_t(r) * c.HpP));
+                        stcg4(Rk.gathered + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4, acc);
+                    }
                 }
                 break;
             }

@@ -22,6 +22,7 @@
 namespace rs {
 
 constexpr int MAX_ACTIONS = MAX_TASK_CHILDREN;
+constexpr int RS_MAX_PEERS = 8;        // GPUs of one NVSwitch box
 constexpr int FAST_ACTIONS = 4;        // nodes up to this many actions keep their table rows in registers
 constexpr int MAX_TASK_THREADS = 352;  // ceil(1326 / 4) rounded up to a warp multiple
 
@@ -79,6 +80,14 @@ struct TaskArgs {
     int n_paths;
     float gather_scale[3];
     int slots;        // Hx-sized scratch vectors provisioned in shared memory
+    // In-kernel exchange of the chance-node partial sums between the GPUs of a board-sharded traversal (peer memory
+    // over NVLink, engine.cu: rs_exchange_import).  xch_world <= 1: not used (single GPU, or the NCCL path).
+    // Layout of every rank's buffer: [parity][leaf][parent board][rank][Hpad] floats and one flag per vector.
+    float* xch_peer[RS_MAX_PEERS];
+    uint32_t* xflag_peer[RS_MAX_PEERS];
+    int xch_world, xch_rank;
+    int xch_round;    // the sharded round: the gathers of round xch_round - 1 exchange their sums
+    int xch_leaves;   // chance leaves of round xch_round - 1
     unsigned long long* timing;  // RS_TASK_TIMING builds: [8 kinds][count, wait cycles, body cycles, total cycles]
 };
 

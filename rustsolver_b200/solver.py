@@ -486,6 +486,29 @@ class Engine(_PlanOrEngine):
         return [dict(kind=kinds[buf[i].kind], phase=buf[i].phase, traverser=buf[i].traverser, grid=buf[i].grid,
                      ms=buf[i].ms, table_bytes=buf[i].table_bytes, vector_bytes=buf[i].vector_bytes) for i in range(n.value)]
 
+    def exchange_export(self) -> bytes:
+        """Handle of this rank's exchange buffer (board-sharded engines): gather one per rank, then exchange_import."""
+        buf = (C.c_uint8 * _lib.RS_EXCHANGE_HANDLE_BYTES)()
+        check(self._lib.rs_exchange_export(self._h, buf))
+        return bytes(buf)
+
+    def exchange_import(self, handles: Sequence[bytes]):
+        """Map every rank's exchange buffer: the traversal kernel then exchanges the chance-node sums itself over
+        NVLink peer memory (one launch per traversal, no NCCL call).  Collective: every rank, same point."""
+        blob = b"".join(handles)
+        assert len(blob) == len(handles) * _lib.RS_EXCHANGE_HANDLE_BYTES
+        arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        check(self._lib.rs_exchange_import(self._h, arr, len(handles)))
+
+    def enable_fused_exchange(self, dist, device):
+        """All-gather the exchange handles over a torch.distributed group and import them (see exchange_import)."""
+        import torch
+        mine = torch.tensor(list(self.exchange_export()), dtype=torch.uint8, device=device)
+        allh = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(allh, mine)
+        self.exchange_import([bytes(h.cpu().tolist()) for h in allh])
+        dist.barrier()
+
     def best_response(self):
         out = (C.c_double * 2)()
         check(self._lib.rs_best_response(self._h, out))

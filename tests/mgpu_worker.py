@@ -51,6 +51,8 @@ def main():
     ranges = configs.workload_ranges(w) if case == "batch" else o.ranges()
     eng = rb.Engine(tree, ranges, o.board_mask, [], board_masks=board_masks, device=local, rank=rank, world_size=world,
                     nccl_id=nccl_id)
+    if os.environ.get("RS_FUSED", "0") == "1" and case != "batch":
+        eng.enable_fused_exchange(dist, dev)  # in-kernel exchange over peer memory instead of the NCCL all-reduce
     st = eng.stats()
     n_iters = 3
     ok = True

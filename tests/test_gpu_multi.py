@@ -17,14 +17,17 @@ def _n_gpus():
         return 0
 
 
-@pytest.mark.parametrize("case", ["turn", "flop", "batch"])
-def test_sharded_engine_matches_oracle(case):
+@pytest.mark.parametrize("case,fused", [("turn", 0), ("flop", 0), ("batch", 0), ("turn", 1), ("flop", 1)])
+def test_sharded_engine_matches_oracle(case, fused):
+    """fused = 1: the traversal kernel exchanges the chance-node sums itself over peer memory (rs_exchange_import);
+    fused = 0: two launches with an ncclAllReduce between them."""
+    import os
     n = _n_gpus()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29641", str(ROOT / "tests" / "mgpu_worker.py"), case]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT), env=dict(os.environ, RS_FUSED=str(fused)))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert f"mgpu_worker {case} world={world}: OK" in r.stdout
