@@ -138,6 +138,13 @@ int rs_nccl_unique_id(uint8_t* out);
  * partial sums into its peers' buffers over NVLink and adds the arrived partials in rank order, one launch per
  * traversal.  Every rank exports a handle (a CUDA IPC handle, one process per GPU), the host gathers them, every
  * rank imports all of them in rank order; all ranks must do so at the same point of their call sequence. */
+/* Batched suit-isomorphic hand indexing on the device: out[i] = hand_indexer_s::get_index of the (2 + n_board_cards)
+ * cards at cards + i * (2 + n_board_cards), hole cards first (indexer init(2, [2, n_board_cards]),
+ * card_abstraction.rs:88-90,205).  This is what rs_create uses to build the card tables (generate_maps,
+ * card_abstraction.rs:75-184); exported so that the host can index hands in bulk, e.g. to apply a cluster_arr.
+ * kernel_ms may be NULL. */
+int rs_gpu_index_hands(uint32_t n_board_cards, const uint8_t* cards, size_t n, uint64_t* out, float* kernel_ms);
+
 #define RS_EXCHANGE_HANDLE_BYTES 64
 int rs_exchange_export(rs_engine* e, uint8_t* out /* RS_EXCHANGE_HANDLE_BYTES */);
 int rs_exchange_import(rs_engine* e, const uint8_t* handles /* n_ranks * RS_EXCHANGE_HANDLE_BYTES */, uint32_t n_ranks);
@@ -164,6 +171,12 @@ int rs_iterate(rs_engine* e, uint64_t n_iters);
 int rs_iterate_sampled(rs_engine* e, const uint8_t* dealt, uint32_t n_paths);
 /* discount sweep of train()'s monitor thread (cfr.rs:248-261): every table *= d */
 int rs_discount(rs_engine* e, float d);
+/* Pruning as train() switches it on for an iteration (cfr.rs:219): a traverser action whose regret is <= threshold
+ * is not explored, i.e. its regret is left alone by the update (cfr.rs:352,379-386,419-440); the node value is
+ * unaffected (regret matching gives it probability 0).  The reference's -10 000 000 is in units of S = 100
+ * (cfr.rs:424): pass -1e5 for the same cut on this engine's unscaled fp32 regrets.  -INFINITY (the default)
+ * switches pruning off.  Applies to rs_iterate and rs_iterate_sampled from the next call on. */
+int rs_set_prune_threshold(rs_engine* e, float threshold);
 int rs_reset(rs_engine* e);
 
 /* infoset_table[round,player][board][action node] -> [row][n_actions] (README.md:45-47).

@@ -38,6 +38,7 @@ def load():
                                C.c_uint64, C.POINTER(u32p)]
     lib.orc_destroy.argtypes = [VP]
     lib.orc_set_options.argtypes = [VP, C.c_int, C.c_int, C.c_int]
+    lib.orc_set_prune_threshold.argtypes = [VP, C.c_double]
     lib.orc_iterate.argtypes = [VP, C.c_int]
     lib.orc_traverse_player.argtypes = [VP, C.c_int]
     lib.orc_best_response.argtypes = [VP, f64p]
@@ -140,6 +141,10 @@ class OracleGame:
 
     def set_options(self, chance_sum=False, fast_terminals=True):
         self.lib.orc_set_options(self.h, int(chance_sum), 0, int(fast_terminals))
+
+    def set_prune_threshold(self, thr: float):
+        """Freeze the regrets of actions at or below `thr` (cfr.rs:352,379-386); -inf switches pruning off."""
+        self.lib.orc_set_prune_threshold(self.h, float(thr))
 
     # --- vector-form fp64 CFR ---
     def iterate(self, n: int = 1):

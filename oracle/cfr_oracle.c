@@ -152,6 +152,7 @@ typedef struct orc_game {
     int chance_sum; /* 1 = literal cfr.rs:511-521 (sum), 0 = mean (default) */
     int own_reach_avg;
     int fast_terminals;
+    double prune_threshold; /* regrets <= this are frozen by the traverser's update (cfr.rs:352,379-386,419); -inf = off */
     double root_value[2];
     double* root_cfv[2];
     size_t** boff;      /* [an][board] element offset of the slab inside the node's table */
@@ -188,6 +189,7 @@ orc_game* orc_create(int n_nodes, const uint8_t* type, const uint32_t* child_off
                      int H0, const uint8_t* hands0, int H1, const uint8_t* hands1, uint64_t board_mask,
                      const uint32_t* const* keys /* [3*2] index k*2+q, entries may be NULL */) {
     orc_game* g = (orc_game*)xcalloc(1, sizeof(orc_game));
+    g->prune_threshold = -INFINITY;
     g->n_nodes = n_nodes;
     g->type = (uint8_t*)xcalloc(n_nodes, 1);
     g->child_off = (int*)xcalloc(n_nodes + 1, sizeof(int));
@@ -425,6 +427,11 @@ static void ensure_strength(orc_game* g) {
         }
     }
 }
+
+/* Pruning as train() switches it on (cfr.rs:219): an action whose regret is <= the threshold is not explored, so its
+ * regret (and strategy sum, whose increment is 0 for such an action anyway) is left alone (cfr.rs:379-386,419-440).
+ * The node value is unaffected because regret matching gives the action probability 0. */
+void orc_set_prune_threshold(orc_game* g, double thr) { g->prune_threshold = thr; }
 
 void orc_set_options(orc_game* g, int chance_sum, int own_reach_avg, int fast_terminals) {
     g->chance_sum = chance_sum;
@@ -708,14 +715,18 @@ static void walk(walk_ctx* c, int node, int k, int b, const double* reach, doubl
         if (c->mode == MODE_CFR) {
             /* cfr.rs:612-621 summed over every hand mapped to the row; sigma is the strategy at the
              * start of the traversal (each (node, board) slab is visited once per traversal) */
+            unsigned char* frozen = (unsigned char*)xcalloc((size_t)nr * A, 1);
+            for (int i = 0; i < nr * A; ++i) frozen[i] = R[i] <= g->prune_threshold; /* tested on the regrets the node started with */
             for (int h = 0; h < Hp; ++h) {
                 if (rows[h] < 0) continue;
                 int r = rows[h];
                 for (int a = 0; a < A; ++a) {
+                    if (frozen[(size_t)r * A + a]) continue;
                     R[(size_t)r * A + a] += cv[(size_t)a * Hp + h] - out[h];
                     S[(size_t)r * A + a] += sigma[(size_t)r * A + a] * m[h] * pi;
                 }
             }
+            free(frozen);
             free(m);
         }
     }

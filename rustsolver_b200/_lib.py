@@ -66,6 +66,7 @@ ENGINE_API = {
     "rs_version": (C.c_int, []),
     "rs_device_count": (C.c_int, []),
     "rs_nccl_unique_id": (C.c_int, [u8p]),
+    "rs_gpu_index_hands": (C.c_int, [C.c_uint32, u8p, C.c_size_t, u64p, f32p]),
     "rs_exchange_export": (C.c_int, [VP, u8p]),
     "rs_exchange_import": (C.c_int, [VP, u8p, C.c_uint32]),
     "rs_create": (C.c_int, [C.POINTER(rs_tree), C.POINTER(rs_ranges), C.POINTER(rs_abstraction),
@@ -76,6 +77,7 @@ ENGINE_API = {
     "rs_iterate": (C.c_int, [VP, C.c_uint64]),
     "rs_iterate_sampled": (C.c_int, [VP, u8p, C.c_uint32]),
     "rs_discount": (C.c_int, [VP, C.c_float]),
+    "rs_set_prune_threshold": (C.c_int, [VP, C.c_float]),
     "rs_reset": (C.c_int, [VP]),
     "rs_read_infoset": (C.c_int, [VP, C.c_uint32, C.c_uint32, f32p, f32p, C.c_size_t, u32p, u32p]),
     "rs_write_infoset": (C.c_int, [VP, C.c_uint32, C.c_uint32, f32p, f32p, C.c_size_t]),

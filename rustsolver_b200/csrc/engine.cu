@@ -15,6 +15,9 @@
 #include <vector>
 
 #include "../../include/b200cfr.h"
+#include <cmath>
+
+#include "indexer_kernel.h"
 #include "kernels.cuh"
 #include "plan.h"
 
@@ -85,6 +88,11 @@ static bool load(std::string* err) {
         if (e__ != cudaSuccess)                                                                    \
             return set_err(RS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));      \
     } while (0)
+
+// plan.h: BatchIndexFn backed by the device indexer
+static bool device_batch_index(const HandIndexer& ix, const uint8_t* cards, size_t n, uint64_t* out, std::string* err) {
+    return gpu_index_hands(ix, ix.rounds() - 1, cards, n, out, nullptr, err);
+}
 
 template <class T>
 struct DevBuf {
@@ -157,6 +165,7 @@ struct Engine {
     size_t xch_flag_bytes = 0, xch_vectors = 0;
     void* xch_peer_base[RS_MAX_PEERS] = {nullptr};
     bool fused_exchange = false;
+    float prune_threshold = -INFINITY;  // rs_set_prune_threshold
     int slots = 1;
     size_t smem_bytes = 0;
     int blocks_per_sm = 1, n_sms = 148;
@@ -454,6 +463,7 @@ void Engine::fill_args(TaskArgs* a, int trav, const TaskSet& set) const {
         }
     }
     a->slots = slots;
+    a->prune_threshold = prune_threshold;
     a->timing = timing.p;
 }
 
@@ -684,6 +694,37 @@ int rs_nccl_unique_id(uint8_t* out) {
     return RS_OK;
 }
 
+int rs_gpu_index_hands(uint32_t n_board_cards, const uint8_t* cards, size_t n, uint64_t* out, float* kernel_ms) {
+    if (!cards || !out) return set_err(RS_ERR_INVALID, "null argument");
+    if (n_board_cards < 3 || n_board_cards > 5) return set_err(RS_ERR_INVALID, "n_board_cards must be 3, 4 or 5");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(RS_ERR_CUDA, "no CUDA device available (no CPU fallback)");
+    HandIndexer ix;
+    if (!ix.init(2, {2, uint8_t(n_board_cards)})) return set_err(RS_ERR_INVALID, "hand indexer init failed");
+    std::string err;
+    if (!gpu_index_hands(ix, 1, cards, n, out, kernel_ms, &err)) return set_err(RS_ERR_CUDA, err);
+    return RS_OK;
+}
+
+int rs_set_prune_threshold(rs_engine* e, float threshold) {
+    if (!e) return set_err(RS_ERR_INVALID, "null engine");
+    if (threshold != threshold) return set_err(RS_ERR_INVALID, "threshold is NaN (use -INFINITY to switch pruning off)");
+    Engine& E = e->e;
+    E.prune_threshold = threshold;
+    // the threshold is a kernel argument baked into the captured iteration graph: capture again on the next call
+    CU(cudaSetDevice(E.device));
+    CU(cudaStreamSynchronize(E.stream));
+    if (E.graph_exec) {
+        cudaGraphExecDestroy(E.graph_exec);
+        E.graph_exec = nullptr;
+    }
+    if (E.graph) {
+        cudaGraphDestroy(E.graph);
+        E.graph = nullptr;
+    }
+    return RS_OK;
+}
+
 int rs_exchange_export(rs_engine* e, uint8_t* out) {
     if (!e || !out) return set_err(RS_ERR_INVALID, "null argument");
     Engine& E = e->e;
@@ -759,7 +800,11 @@ static int create_impl(const rs_tree* tree, const rs_ranges* ranges, const rs_ab
     if (!h) return set_err(RS_ERR_INVALID, "out of memory");
     std::string err;
     try {
-        if (!compile_plan(tree, ranges, abs, cfg, board_masks, n_sub, &h->e.plan, &err)) return set_err(RS_ERR_INVALID, err);
+        // card tables: the canonical hand indices come from the device indexer (bit-identical to the host one)
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) == cudaSuccess && cfg && cfg->device >= 0 && cfg->device < ndev) cudaSetDevice(cfg->device);
+        if (!compile_plan(tree, ranges, abs, cfg, board_masks, n_sub, &h->e.plan, &err, ndev > 0 ? &device_batch_index : nullptr))
+            return set_err(RS_ERR_INVALID, err);
         int rc = h->e.init(cfg);
         if (rc != RS_OK) return rc;
     } catch (const std::exception& ex) {

@@ -317,6 +317,22 @@ uint64_t HandIndexer::index_round(const uint8_t* cards, int round) const {
     return index;
 }
 
+void HandIndexer::flatten(int round, FlatTables* out) const {
+    const Tables& T = tables();
+    out->rounds = rounds_;
+    for (int r = 0; r < MAX_ROUNDS; ++r) {
+        out->cards_per_round[r] = cards_per_round_[r];
+        out->round_start[r] = round_start_[r];
+    }
+    out->rank_set_to_index.assign(T.rank_set_to_index, T.rank_set_to_index + (1 << RANKS));
+    out->ncr_ranks.assign(&T.ncr_ranks[0][0], &T.ncr_ranks[0][0] + (RANKS + 1) * (RANKS + 1));
+    out->suit_perms.assign(&T.suit_perms[0][0], &T.suit_perms[0][0] + 24 * SUITS);
+    out->perm_to_config = perm_to_config_[round];
+    out->perm_to_pi = perm_to_pi_[round];
+    out->config_to_equal = config_to_equal_[round];
+    out->config_to_offset = config_to_offset_[round];
+}
+
 bool HandIndexer::get_hand(int round, uint64_t index, uint8_t* cards) const {
     const Tables& T = tables();
     if (round < 0 || round >= rounds_ || index >= round_size_[round]) return false;

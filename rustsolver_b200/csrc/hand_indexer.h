@@ -39,6 +39,19 @@ public:
     int rounds() const { return rounds_; }
     int total_cards(int round) const { return round_start_[round] + cards_per_round_[round]; }
 
+    // Flat copy of everything index_round needs, for the device indexer (indexer_kernel.cu).
+    struct FlatTables {
+        int rounds = 0;
+        uint8_t cards_per_round[MAX_ROUNDS] = {0};
+        int round_start[MAX_ROUNDS] = {0};
+        std::vector<uint32_t> rank_set_to_index;  // [1 << 13]
+        std::vector<uint32_t> ncr_ranks;          // [14][14]
+        std::vector<uint8_t> suit_perms;          // [24][4]
+        std::vector<uint32_t> perm_to_config, perm_to_pi, config_to_equal;  // of `round`
+        std::vector<uint64_t> config_to_offset;
+    };
+    void flatten(int round, FlatTables* out) const;
+
 private:
     int rounds_ = 0;
     uint8_t cards_per_round_[MAX_ROUNDS] = {0};

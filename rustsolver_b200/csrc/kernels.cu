@@ -521,7 +521,7 @@ __device__ __forceinline__ void task_trav(const TaskArgs& A, const Ctx& c, const
                 const float w = f4get(mass, i) * scale;
 #pragma unroll
                 for (int a = 0; a < NA; ++a) {
-                    g[i * NA + a] += live ? f4get(v[a], i) - vn : 0.f;
+                    g[i * NA + a] += (live && g[i * NA + a] > A.prune_threshold) ? f4get(v[a], i) - vn : 0.f;
                     ss[i * NA + a] += live ? sg[a] * w : 0.f;
                 }
             }
@@ -586,7 +586,7 @@ __device__ __forceinline__ void task_trav(const TaskArgs& A, const Ctx& c, const
             const float w = msum * scale;
 #pragma unroll
             for (int a = 0; a < NA; ++a) {
-                tabR[size_t(row) * NA + a] = rg[a] + d[a];
+                tabR[size_t(row) * NA + a] = rg[a] + (rg[a] > A.prune_threshold ? d[a] : 0.f);
                 tabS[size_t(row) * NA + a] = sr[a] + sg[a] * w;
             }
         }
@@ -656,7 +656,7 @@ __device__ __forceinline__ void task_trav_generic(const TaskArgs& A, const Ctx& 
                 const float old = tabR[size_t(row) * n_act + a];
                 const float sga = norm > 0.f ? fmaxf(old, 0.f) * inv : uni;
                 tabS[size_t(row) * n_act + a] += sga * w;
-                tabR[size_t(row) * n_act + a] = old + da;
+                tabR[size_t(row) * n_act + a] = old + (old > A.prune_threshold ? da : 0.f);
             }
         }
     }

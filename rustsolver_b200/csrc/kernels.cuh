@@ -80,6 +80,7 @@ struct TaskArgs {
     int n_paths;
     float gather_scale[3];
     int slots;        // Hx-sized scratch vectors provisioned in shared memory
+    float prune_threshold;  // traverser actions with regret <= this keep their regret (cfr.rs:352,379-386); -inf = off
     // In-kernel exchange of the chance-node partial sums between the GPUs of a board-sharded traversal (peer memory
     // over NVLink, engine.cu: rs_exchange_import).  xch_world <= 1: not used (single GPU, or the NCCL path).
     // Layout of every rank's buffer: [parity][leaf][parent board][rank][Hpad] floats and one flag per vector.

@@ -478,7 +478,7 @@ struct TaskGen {
 
 bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs,
                   const rs_config* cfg, const uint64_t* board_masks, uint32_t n_sub, Plan* P,
-                  std::string* err) {
+                  std::string* err, BatchIndexFn batch_index) {
     auto fail = [&](const std::string& m) {
         if (err) *err = m;
         return false;
@@ -684,19 +684,44 @@ bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstrac
             T.row_hands.assign(size_t(nB) * H, 0xFFFF);
             T.n_rows.assign(nB, 0);
             T.board_off.assign(size_t(nB) + 1, 0);
+            // canonical hand indices of every live (board, hand) of this player, in one batch: the device indexer
+            // when the engine provides it (indexer_kernel.cu), the host indexer otherwise
+            std::vector<uint64_t> canon;  // [(b - local_lo) * H + h]
+            if (kind == RS_ABS_ISOMORPHIC || kind == RS_ABS_CLUSTER_ARR) {
+                const uint32_t lo = P->local_lo[k], hi = P->local_hi[k];
+                const int nc = 2 + nbc;
+                std::vector<uint8_t> cards_all;
+                std::vector<uint32_t> where;
+                cards_all.reserve(size_t(hi - lo) * H * nc);
+                where.reserve(size_t(hi - lo) * H);
+                for (uint32_t b = lo; b < hi; ++b) {
+                    const uint64_t bm = P->board_mask[k][b];
+                    uint8_t bc[5];
+                    int nbd = 0;
+                    for (uint64_t m = bm; m; m &= m - 1) bc[nbd++] = uint8_t(__builtin_ctzll(m));  // ascending (cfr.rs:78-82)
+                    for (uint32_t h = 0; h < H; ++h) {
+                        const uint8_t a = P->hand_cards[q][2 * h], c = P->hand_cards[q][2 * h + 1];
+                        if (bm & ((1ull << a) | (1ull << c))) continue;
+                        cards_all.push_back(a);
+                        cards_all.push_back(c);
+                        for (int i = 0; i < nbd; ++i) cards_all.push_back(bc[i]);
+                        where.push_back((b - lo) * H + h);
+                    }
+                }
+                std::vector<uint64_t> idx(where.size());
+                if (batch_index) {
+                    std::string berr;
+                    if (!batch_index(indexer, cards_all.data(), where.size(), idx.data(), &berr)) return fail("device indexer: " + berr);
+                } else {
+                    for (size_t i = 0; i < where.size(); ++i) idx[i] = indexer.get_index(&cards_all[i * nc]);
+                }
+                canon.assign(size_t(hi - lo) * H, 0);
+                for (size_t i = 0; i < where.size(); ++i) canon[where[i]] = idx[i];
+            }
             std::unordered_map<uint64_t, uint32_t> dense;
             std::vector<uint32_t> row_count;
             for (uint32_t b = P->local_lo[k]; b < P->local_hi[k]; ++b) {
                 uint64_t bm = P->board_mask[k][b];
-                uint8_t cards[7];
-                {
-                    int i = 2;
-                    uint64_t m = bm;
-                    while (m) {  // ascending-card order via trailing_zeros (cfr.rs:78-82)
-                        cards[i++] = uint8_t(__builtin_ctzll(m));
-                        m &= m - 1;
-                    }
-                }
                 dense.clear();
                 row_count.clear();
                 uint16_t* roh = &T.row_of_hand[size_t(b) * H];
@@ -709,9 +734,7 @@ bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstrac
                     } else if (kind == RS_ABS_BUCKET_TABLE) {
                         key = ra->bucket_table[q][size_t(b) * H + h];
                     } else {
-                        cards[0] = a;
-                        cards[1] = c;
-                        key = indexer.get_index(cards);
+                        key = canon[size_t(b - P->local_lo[k]) * H + h];  // hand_indexer.get_index (card_abstraction.rs:205)
                         if (kind == RS_ABS_CLUSTER_ARR) key = ra->cluster_arr[key];  // index_to_cluster, card_abstraction.rs:20-29
                     }
                     auto it = dense.find(key);

@@ -126,8 +126,13 @@ struct Plan {
     uint32_t boards_local(uint32_t k) const { return local_hi[k] - local_lo[k]; }
 };
 
+// Optional batch indexer: out[i] = ix.get_index(cards + i * n_cards) for i < n.  The engine passes the device
+// implementation (indexer_kernel.cu); without one the host indexer is used.  Both are bit-identical.
+class HandIndexer;
+typedef bool (*BatchIndexFn)(const HandIndexer& ix, const uint8_t* cards, size_t n, uint64_t* out, std::string* err);
+
 bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs,
                   const rs_config* cfg, const uint64_t* board_masks, uint32_t n_sub, Plan* out,
-                  std::string* err);
+                  std::string* err, BatchIndexFn batch_index = nullptr);
 
 }  // namespace rs

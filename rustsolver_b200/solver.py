@@ -248,6 +248,16 @@ class HandIndexer:
         self._lib.rsh_indexer_index_many(self._h, _ptr(a, u8p), len(a), _ptr(out, u64p))
         return out
 
+    def index_many_gpu(self, cards: np.ndarray, return_ms: bool = False):
+        """index_many on the device (rs_gpu_index_hands): indexer must be [2, 3|4|5]; fails without a GPU."""
+        assert len(self.cards_per_round) == 2 and self.cards_per_round[0] == 2
+        a = np.ascontiguousarray(cards, dtype=np.uint8)
+        assert a.ndim == 2 and a.shape[1] == sum(self.cards_per_round)
+        out = np.zeros(len(a), dtype=np.uint64)
+        ms = C.c_float(0.0)
+        check(self._lib.rs_gpu_index_hands(self.cards_per_round[1], _ptr(a, u8p), len(a), _ptr(out, u64p), C.byref(ms)))
+        return (out, float(ms.value)) if return_ms else out
+
     def get_hand(self, round: int, index: int) -> List[int]:
         n = sum(self.cards_per_round[:round + 1])
         out = np.zeros(n, dtype=np.uint8)
@@ -485,6 +495,10 @@ class Engine(_PlanOrEngine):
         kinds = {0: "traversal", 3: "allreduce"}
         return [dict(kind=kinds[buf[i].kind], phase=buf[i].phase, traverser=buf[i].traverser, grid=buf[i].grid,
                      ms=buf[i].ms, table_bytes=buf[i].table_bytes, vector_bytes=buf[i].vector_bytes) for i in range(n.value)]
+
+    def set_prune_threshold(self, threshold: float):
+        """Traverser actions with regret <= threshold keep their regret (cfr.rs:352,379-386); -inf = off."""
+        check(self._lib.rs_set_prune_threshold(self._h, float(threshold)))
 
     def exchange_export(self) -> bytes:
         """Handle of this rank's exchange buffer (board-sharded engines): gather one per rank, then exchange_import."""

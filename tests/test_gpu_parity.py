@@ -115,6 +115,59 @@ def test_discount_sweep():
         assert np.allclose(a[0], 0.5 * b[0], rtol=1e-6, atol=0) and np.allclose(a[1], 0.5 * b[1], rtol=1e-6, atol=0)
 
 
+def _safe_prune_threshold(orc, tree, nb, q=0.35):
+    """A threshold at quantile q of the negative regrets, moved into the middle of the widest nearby gap so that no
+    regret sits within fp32 rounding of it (the engine restarts from the oracle's state cast to fp32)."""
+    vals = np.concatenate([orc.get_slab(an, b)[0].ravel() for an, b in util.all_slabs(tree, nb)])
+    neg = np.sort(vals[vals < 0])
+    assert neg.size > 50
+    i0 = int(q * neg.size)
+    window = neg[max(i0 - 500, 0):i0 + 500]
+    gaps = np.diff(window)
+    j = int(np.argmax(gaps))
+    thr = 0.5 * (window[j] + window[j + 1])
+    # fp32 rounding moves a regret or the threshold by at most 6e-8 relative: a gap of 1e-6 keeps every cell on its side
+    assert gaps[j] > 1e-6 * abs(thr), "no safe gap near the quantile"
+    return float(thr), float((vals <= thr).mean())
+
+
+@pytest.mark.parametrize("bucketed", [False, True])
+def test_pruning_matches_oracle(bucketed):
+    """rs_set_prune_threshold (cfr.rs:219,352,379-386): regrets at or below the threshold are frozen."""
+    o = util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]] * 2, [[3.0]] * 2)
+    if bucketed:
+        n, tree = rb.build_game_tree(o)
+        r = o.ranges()
+        k0 = util.bucket_keys_for(None, r, 1, 7, seed=3)
+        k1 = util.bucket_keys_for(None, r, 48, 11, seed=4)
+        abs_ = [rb.CardAbstraction(rb.RS_ABS_BUCKET_TABLE, bucket_table=k0), rb.CardAbstraction(rb.RS_ABS_BUCKET_TABLE, bucket_table=k1)]
+        eng = rb.Engine(tree, r, o.board_mask, abs_)
+        orc = OracleGame(tree, r, o.board_mask, keys=[k0, k1])
+    else:
+        tree, eng, orc = _pair(o)
+    orc.iterate(6)
+    st = eng.stats()
+    nb = [st.n_boards[k] for k in range(st.n_rounds)]
+    al = util.RowAligner(eng, orc, tree)
+    for _ in range(3):
+        thr, frac = _safe_prune_threshold(orc, tree, nb)
+        assert 0.05 < frac < 0.6, frac  # the threshold really freezes a good part of the table
+        before = {(an, b): orc.get_slab(an, b)[0].copy() for an, b in util.all_slabs(tree, nb)}
+        eng.set_prune_threshold(thr)
+        orc.set_prune_threshold(thr)
+        util.copy_oracle_to_engine(eng, orc, tree, aligner=al)
+        eng.iterate(1)
+        orc.iterate(1)
+        util.compare_tables(eng, orc, tree, TOL, aligner=al)
+        for (an, b), r0 in before.items():  # frozen cells are bit-identical on the GPU too
+            g = al.read(an, b)[0]
+            m = r0 <= thr
+            assert np.array_equal(g[m], r0[m].astype(np.float32)), (an, b)
+    eng.set_prune_threshold(float("-inf"))
+    orc.set_prune_threshold(float("-inf"))
+    util.lockstep(eng, orc, tree, n_free=0, n_locked=1, tol=TOL)
+
+
 def test_exploitability_curve_matches_oracle():
     o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]], [[3.0]])
     tree, eng, orc = _pair(o)

@@ -122,3 +122,27 @@ def test_sampled_runouts_are_an_unbiased_estimate_of_the_full_traversal():
         for bd in range(a.n_boards(k)):
             x, y = a.get_slab(an, bd), b.get_slab(an, bd)
             assert np.allclose(x[0], y[0], rtol=1e-12, atol=1e-18) and np.allclose(x[1], y[1], rtol=1e-12, atol=1e-20)
+
+
+def test_pruning_freezes_regrets_at_or_below_the_threshold():
+    """cfr.rs:352,379-386,419: a pruned action is not explored, so its regret is left alone; -inf = no pruning."""
+    o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]], [[3.0]])
+    n, tree = rb.build_game_tree(o)
+    a, b = OracleGame(tree, o.ranges(), o.board_mask), OracleGame(tree, o.ranges(), o.board_mask)
+    a.iterate(5)
+    b.iterate(5)
+    vals = np.concatenate([a.get_slab(an, 0)[0].ravel() for an in range(tree.n_actions)])
+    thr = float(np.quantile(vals[vals < 0], 0.4))
+    before = [a.get_slab(an, 0)[0].copy() for an in range(tree.n_actions)]
+    a.set_prune_threshold(thr)
+    b.set_prune_threshold(float("-inf"))
+    a.iterate(1)
+    b.iterate(1)
+    n_frozen = n_moved = 0
+    for an in range(tree.n_actions):
+        ra, rb_ = a.get_slab(an, 0)[0], b.get_slab(an, 0)[0]
+        m = before[an] <= thr
+        assert np.array_equal(ra[m], before[an][m])  # frozen exactly
+        n_frozen += int(m.sum())
+        n_moved += int((rb_[m] != before[an][m]).sum())
+    assert n_frozen > 10 and n_moved > 0  # without pruning those cells do move
