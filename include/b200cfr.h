@@ -145,6 +145,23 @@ int rs_nccl_unique_id(uint8_t* out);
  * kernel_ms may be NULL. */
 int rs_gpu_index_hands(uint32_t n_board_cards, const uint8_t* cards, size_t n, uint64_t* out, float* kernel_ms);
 
+/* Abstraction generation, the data-parallel part (src/gen_abstraction): distances between hand-strength histograms
+ * and the k-means assignment step.  Host buffers in and out; histograms are row-major [n][dim], dim <= 128.
+ *   RS_DIST_EMD_1D  emd::emd_1d  (gen_abstraction/emd.rs:54-113), the linear-time EMD approximation
+ *   RS_DIST_L2      kmeans::l2_dist (gen_abstraction/kmeans.rs:622-630)
+ * rs_kmeans_assign            = Kmeans::predict (kmeans.rs:173-211): cluster[i] = first nearest centre; min_dist,
+ *                               inertia (sum of the minima, fp64, point order) and kernel_ms may be NULL
+ * rs_histogram_distances      = out[i] = dist(p_i, q_i)
+ * rs_kmeans_update_min_dists  = update_min_dists (kmeans.rs:603-619): min_dists[i] = min(min_dists[i], dist(x_i, c)^2)
+ * Distances are bit-identical to the fp32 arithmetic of the reference evaluated in its order. */
+#define RS_DIST_EMD_1D 0u
+#define RS_DIST_L2 1u
+int rs_kmeans_assign(const float* points, size_t n, uint32_t dim, const float* centers, uint32_t k, uint32_t dist_kind,
+                     uint32_t* cluster, float* min_dist, double* inertia, float* kernel_ms);
+int rs_histogram_distances(const float* p, const float* q, size_t n, uint32_t dim, uint32_t dist_kind, float* out);
+int rs_kmeans_update_min_dists(const float* points, size_t n, uint32_t dim, const float* new_center, uint32_t dist_kind,
+                               float* min_dists);
+
 #define RS_EXCHANGE_HANDLE_BYTES 64
 int rs_exchange_export(rs_engine* e, uint8_t* out /* RS_EXCHANGE_HANDLE_BYTES */);
 int rs_exchange_import(rs_engine* e, const uint8_t* handles /* n_ranks * RS_EXCHANGE_HANDLE_BYTES */, uint32_t n_ranks);

@@ -19,6 +19,7 @@ u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
 i32p = C.POINTER(C.c_int32)
 f64p = C.POINTER(C.c_double)
+f32p = C.POINTER(C.c_float)
 VP = C.c_void_p
 
 _lib = None
@@ -76,6 +77,54 @@ def load():
     lib.orc_chance_partials.argtypes = [VP, C.c_int, C.c_int, C.c_int, f64p, C.c_int]
     _lib = lib
     return lib
+
+
+def _abs_lib():
+    lib = load()
+    if not getattr(lib, "_abs_ready", False):
+        lib.orc_emd_1d.restype = C.c_float
+        lib.orc_emd_1d.argtypes = [f32p, f32p, C.c_int]
+        lib.orc_l2_dist.restype = C.c_float
+        lib.orc_l2_dist.argtypes = [f32p, f32p, C.c_int]
+        lib.orc_kmeans_predict.restype = C.c_double
+        lib.orc_kmeans_predict.argtypes = [f32p, C.c_int64, C.c_int, f32p, C.c_int, C.c_int, u32p, f32p]
+        lib.orc_update_min_dists.argtypes = [f32p, C.c_int64, C.c_int, f32p, C.c_int, f32p]
+        lib._abs_ready = True
+    return lib
+
+
+def emd_1d(p, q) -> float:
+    """emd::emd_1d (gen_abstraction/emd.rs:54-113), fp32, reference operation order."""
+    a = np.ascontiguousarray(p, dtype=np.float32)
+    b = np.ascontiguousarray(q, dtype=np.float32)
+    assert a.shape == b.shape and a.ndim == 1
+    return float(_abs_lib().orc_emd_1d(a.ctypes.data_as(f32p), b.ctypes.data_as(f32p), len(a)))
+
+
+def l2_dist(p, q) -> float:
+    a = np.ascontiguousarray(p, dtype=np.float32)
+    b = np.ascontiguousarray(q, dtype=np.float32)
+    return float(_abs_lib().orc_l2_dist(a.ctypes.data_as(f32p), b.ctypes.data_as(f32p), len(a)))
+
+
+def kmeans_predict(points, centers, kind: int = 0):
+    """Kmeans::predict (kmeans.rs:173-211): (cluster[n] u32, min_dist[n] f32, inertia)."""
+    x = np.ascontiguousarray(points, dtype=np.float32)
+    c = np.ascontiguousarray(centers, dtype=np.float32)
+    cl = np.zeros(len(x), dtype=np.uint32)
+    md = np.zeros(len(x), dtype=np.float32)
+    inertia = _abs_lib().orc_kmeans_predict(x.ctypes.data_as(f32p), len(x), x.shape[1], c.ctypes.data_as(f32p), len(c), kind,
+                                           cl.ctypes.data_as(u32p), md.ctypes.data_as(f32p))
+    return cl, md, float(inertia)
+
+
+def update_min_dists(points, new_center, min_dists, kind: int = 0):
+    """update_min_dists (kmeans.rs:603-619), in place on a copy that is returned."""
+    x = np.ascontiguousarray(points, dtype=np.float32)
+    c = np.ascontiguousarray(new_center, dtype=np.float32)
+    md = np.array(min_dists, dtype=np.float32, copy=True)
+    _abs_lib().orc_update_min_dists(x.ctypes.data_as(f32p), len(x), x.shape[1], c.ctypes.data_as(f32p), kind, md.ctypes.data_as(f32p))
+    return md
 
 
 def row_alignment(engine_rows_of_slot: np.ndarray, oracle_rows_of_slot: np.ndarray, n_rows: int) -> np.ndarray:

@@ -1,0 +1,236 @@
+// Device side of the abstraction generator's data-parallel hot loop: the k-means assignment
+// step over hand-strength histograms with the reference's linear-time EMD approximation as the distance.
+//
+//   emd_1d            /root/reference/src/gen_abstraction/emd.rs:54-113   (bins: emd.rs:24-49, 91-93)
+//   l2_dist           /root/reference/src/gen_abstraction/kmeans.rs:622-630
+//   Kmeans::predict   /root/reference/src/gen_abstraction/kmeans.rs:173-211
+//   update_min_dists  /root/reference/src/gen_abstraction/kmeans.rs:603-619
+//
+// One thread owns one data point; its two working histograms live in shared memory with the thread index as the
+// fastest dimension ([bin][thread]: conflict-free), the centre being compared is staged once per block and read as a
+// broadcast.  Every fp32 operation uses a round-to-nearest intrinsic in the reference's order (no FMA contraction),
+// so distances are bit-identical to the CPU restatement (oracle/abstraction_oracle.c) and the argmin is exact.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/b200cfr.h"
+#include "abstraction_kernels.h"
+
+namespace rs {
+
+namespace {
+
+constexpr int ABS_THREADS = 64;
+
+// emd.rs:54-113.  pin/qin: the two histograms (element i at pin[i * sp] / qin[i * sq]); p/q: scratch, element i at [i * ABS_THREADS]
+__device__ __forceinline__ float emd_1d_dev(const float* pin, int sp, const float* qin, int sq, int n, float* p, float* q) {
+    float p_sum = 0.0f, q_sum = 0.0f;
+    for (int i = 0; i < n; ++i) p_sum = __fadd_rn(p_sum, pin[i * sp]);
+    for (int i = 0; i < n; ++i) q_sum = __fadd_rn(q_sum, qin[i * sq]);
+    if (p_sum == 0.0f || q_sum == 0.0f) return 0.0f;
+    float cost = 0.0f, w = 0.0f;
+    for (int i = 0; i < n; ++i) {  // normalise, then the corresponding bins (no cost), emd.rs:63-77
+        const float a = __fdiv_rn(pin[i * sp], p_sum), b = __fdiv_rn(qin[i * sq], q_sum);
+        const float mass = a < b ? a : b;
+        w = __fadd_rn(w, mass);
+        p[i * ABS_THREADS] = __fsub_rn(a, mass);
+        q[i * ABS_THREADS] = __fsub_rn(b, mass);
+    }
+    float factor = __fsub_rn(__fmul_rn(4.45f, w), 1.5f);  // emd.rs:83-88
+    if (factor < 1.0f) factor = 1.0f;
+    else if (factor > 4.0f) factor = 4.0f;
+    const int u = int(roundf(__fdiv_rn(float(n), factor)));
+    // reachable bins in the order of the reference's stable sort by |b|: -1, +1, -2, +2, ... (emd.rs:91-93)
+    for (int d = 1; d < u; ++d) {
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+            const int b = sgn * d;
+            const int j0 = b < 0 ? -b : 0, j1 = b > 0 ? n - b : n;  // j + b inside [0, n)
+            for (int j = j0; j < j1; ++j) {
+                const float pj = p[j * ABS_THREADS];
+                if (pj != 0.0f) {
+                    const float qk = q[(j + b) * ABS_THREADS];
+                    if (qk != 0.0f) {
+                        const float mass = pj < qk ? pj : qk;
+                        w = __fadd_rn(w, mass);
+                        cost = __fadd_rn(cost, __fmul_rn(mass, float(d)));  // |j - k| = d
+                        p[j * ABS_THREADS] = __fsub_rn(pj, mass);
+                        q[(j + b) * ABS_THREADS] = __fsub_rn(qk, mass);
+                    }
+                }
+            }
+        }
+    }
+    return fabsf(__fadd_rn(cost, __fmul_rn(__fsub_rn(1.0f, w), float(u))));
+}
+
+// kmeans.rs:622-630
+__device__ __forceinline__ float l2_dist_dev(const float* a, int sa, const float* b, int sb, int n) {
+    float sum = 0.0f;
+    for (int i = 0; i < n; ++i) {
+        const float d = __fsub_rn(a[i * sa], b[i * sb]);
+        sum = __fadd_rn(sum, __fmul_rn(d, d));
+    }
+    return __fsqrt_rn(sum);
+}
+
+// shared memory of a block: [centre: dim][point copies: dim * T][p scratch: dim * T][q scratch: dim * T]
+struct Smem {
+    float *centre, *x, *p, *q;
+};
+__device__ __forceinline__ Smem carve(float* raw, int dim) {
+    Smem s;
+    s.centre = raw;
+    s.x = raw + ((dim + 3) & ~3);
+    s.p = s.x + dim * ABS_THREADS;
+    s.q = s.p + dim * ABS_THREADS;
+    return s;
+}
+
+// Kmeans::predict: cluster[i] = first centre at minimal distance (strict <, kmeans.rs:197-203)
+__global__ void __launch_bounds__(ABS_THREADS) kmeans_assign_kernel(const float* __restrict__ points, size_t n, int dim,
+                                                                     const float* __restrict__ centers, int k, int kind,
+                                                                     uint32_t* __restrict__ cluster, float* __restrict__ min_dist) {
+    extern __shared__ __align__(16) float raw[];
+    const Smem s = carve(raw, dim);
+    const int t = threadIdx.x;
+    const size_t i = size_t(blockIdx.x) * ABS_THREADS + t;
+    const bool live = i < n;
+    // the block's points: coalesced read of ABS_THREADS * dim consecutive floats, transposed into [bin][thread]
+    const size_t base = size_t(blockIdx.x) * ABS_THREADS * dim;
+    const size_t avail = (n - size_t(blockIdx.x) * ABS_THREADS < size_t(ABS_THREADS) ? n - size_t(blockIdx.x) * ABS_THREADS : size_t(ABS_THREADS)) * dim;
+    for (size_t e = t; e < avail; e += ABS_THREADS) s.x[(e % dim) * ABS_THREADS + e / dim] = __ldg(points + base + e);
+    int best = 0;
+    float best_d = 0.0f;
+    for (int c = 0; c < k; ++c) {
+        __syncthreads();  // the previous centre is no longer read (and, first time, the points are in place)
+        for (int e = t; e < dim; e += ABS_THREADS) s.centre[e] = __ldg(centers + size_t(c) * dim + e);
+        __syncthreads();
+        if (live) {
+            const float d = kind == RS_DIST_EMD_1D ? emd_1d_dev(s.x + t, ABS_THREADS, s.centre, 1, dim, s.p + t, s.q + t)
+                                                   : l2_dist_dev(s.x + t, ABS_THREADS, s.centre, 1, dim);
+            if (c == 0 || d < best_d) {
+                best_d = d;
+                best = c;
+            }
+        }
+    }
+    if (live) {
+        cluster[i] = uint32_t(best);
+        if (min_dist) min_dist[i] = best_d;
+    }
+}
+
+// out[i] = dist(p_i, q_i) (q_stride = 0: every point against the same histogram)
+__global__ void __launch_bounds__(ABS_THREADS) pair_dist_kernel(const float* __restrict__ p, const float* __restrict__ q, size_t q_stride,
+                                                                 size_t n, int dim, int kind, float* __restrict__ out) {
+    extern __shared__ __align__(16) float raw[];
+    const Smem s = carve(raw, dim);
+    const int t = threadIdx.x;
+    const size_t i = size_t(blockIdx.x) * ABS_THREADS + t;
+    if (i >= n) return;
+    const float* a = p + i * dim;
+    const float* b = q + i * q_stride;
+    out[i] = kind == RS_DIST_EMD_1D ? emd_1d_dev(a, 1, b, 1, dim, s.p + t, s.q + t) : l2_dist_dev(a, 1, b, 1, dim);
+}
+
+// update_min_dists (kmeans.rs:603-619): md[i] = min(md[i], d^2)
+__global__ void square_min_kernel(const float* __restrict__ d, size_t n, float* __restrict__ md) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = __fmul_rn(d[i], d[i]);
+    if (v < md[i]) md[i] = v;
+}
+
+size_t smem_bytes(int dim) { return (size_t((dim + 3) & ~3) + 3 * size_t(dim) * ABS_THREADS) * sizeof(float); }
+
+template <class T>
+struct Dev {
+    T* p = nullptr;
+    ~Dev() { cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+};
+
+#define ABS_CU(call)                                                      \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) {                                         \
+            *err = std::string(#call) + ": " + cudaGetErrorString(e__);  \
+            return false;                                                 \
+        }                                                                 \
+    } while (0)
+
+}  // namespace
+
+bool gpu_kmeans_assign(const float* points, size_t n, uint32_t dim, const float* centers, uint32_t k, uint32_t kind,
+                       uint32_t* cluster, float* min_dist, double* inertia, float* kernel_ms, std::string* err) {
+    Dev<float> d_pts, d_ctr, d_md;
+    Dev<uint32_t> d_cl;
+    ABS_CU(d_pts.alloc(n * dim));
+    ABS_CU(d_ctr.alloc(size_t(k) * dim));
+    ABS_CU(d_md.alloc(n));
+    ABS_CU(d_cl.alloc(n));
+    if (n == 0) {
+        if (inertia) *inertia = 0.0;
+        if (kernel_ms) *kernel_ms = 0.f;
+        return true;
+    }
+    ABS_CU(cudaMemcpy(d_pts.p, points, n * dim * sizeof(float), cudaMemcpyHostToDevice));
+    ABS_CU(cudaMemcpy(d_ctr.p, centers, size_t(k) * dim * sizeof(float), cudaMemcpyHostToDevice));
+    const size_t smem = smem_bytes(int(dim));
+    ABS_CU(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    cudaEvent_t e0, e1;
+    ABS_CU(cudaEventCreate(&e0));
+    ABS_CU(cudaEventCreate(&e1));
+    const unsigned blocks = unsigned((n + ABS_THREADS - 1) / ABS_THREADS);
+    cudaEventRecord(e0);
+    kmeans_assign_kernel<<<blocks, ABS_THREADS, smem>>>(d_pts.p, n, int(dim), d_ctr.p, int(k), int(kind), d_cl.p, d_md.p);
+    cudaEventRecord(e1);
+    cudaError_t le = cudaGetLastError();
+    std::vector<float> md(n);
+    cudaError_t ce = cudaMemcpy(cluster, d_cl.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess) ce = cudaMemcpy(md.data(), d_md.p, n * sizeof(float), cudaMemcpyDeviceToHost);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ABS_CU(le);
+    ABS_CU(ce);
+    if (kernel_ms) *kernel_ms = ms;
+    if (min_dist) std::copy(md.begin(), md.end(), min_dist);
+    if (inertia) {
+        double s = 0.0;
+        for (float v : md) s += double(v);  // fixed order (the reference adds into an f32 from racing threads)
+        *inertia = s;
+    }
+    return true;
+}
+
+bool gpu_pair_dist(const float* p, const float* q, bool q_shared, size_t n, uint32_t dim, uint32_t kind, float* out, float* min_dists_io,
+                   std::string* err) {
+    Dev<float> d_p, d_q, d_out, d_md;
+    ABS_CU(d_p.alloc(n * dim));
+    ABS_CU(d_q.alloc(q_shared ? dim : n * dim));
+    ABS_CU(d_out.alloc(n));
+    if (n == 0) return true;
+    ABS_CU(cudaMemcpy(d_p.p, p, n * dim * sizeof(float), cudaMemcpyHostToDevice));
+    ABS_CU(cudaMemcpy(d_q.p, q, (q_shared ? size_t(dim) : n * dim) * sizeof(float), cudaMemcpyHostToDevice));
+    const size_t smem = smem_bytes(int(dim));
+    ABS_CU(cudaFuncSetAttribute(pair_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const unsigned blocks = unsigned((n + ABS_THREADS - 1) / ABS_THREADS);
+    pair_dist_kernel<<<blocks, ABS_THREADS, smem>>>(d_p.p, d_q.p, q_shared ? 0 : dim, n, int(dim), int(kind), d_out.p);
+    ABS_CU(cudaGetLastError());
+    if (min_dists_io) {
+        ABS_CU(d_md.alloc(n));
+        ABS_CU(cudaMemcpy(d_md.p, min_dists_io, n * sizeof(float), cudaMemcpyHostToDevice));
+        square_min_kernel<<<unsigned((n + 255) / 256), 256>>>(d_out.p, n, d_md.p);
+        ABS_CU(cudaGetLastError());
+        ABS_CU(cudaMemcpy(min_dists_io, d_md.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    if (out) ABS_CU(cudaMemcpy(out, d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return true;
+}
+
+}  // namespace rs

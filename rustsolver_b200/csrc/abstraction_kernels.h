@@ -1,0 +1,18 @@
+// Device k-means assignment / EMD distance of the abstraction generator (abstraction_kernels.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+namespace rs {
+
+constexpr uint32_t ABS_MAX_BINS = 128;
+
+// Kmeans::predict (kmeans.rs:173-211) on host buffers; min_dist, inertia, kernel_ms may be null
+bool gpu_kmeans_assign(const float* points, size_t n, uint32_t dim, const float* centers, uint32_t k, uint32_t kind,
+                       uint32_t* cluster, float* min_dist, double* inertia, float* kernel_ms, std::string* err);
+// out[i] = dist(p_i, q_i), or dist(p_i, q) when q_shared; min_dists_io (optional): update_min_dists (kmeans.rs:603-619)
+bool gpu_pair_dist(const float* p, const float* q, bool q_shared, size_t n, uint32_t dim, uint32_t kind, float* out, float* min_dists_io,
+                   std::string* err);
+
+}  // namespace rs

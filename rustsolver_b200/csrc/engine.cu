@@ -17,6 +17,7 @@
 #include "../../include/b200cfr.h"
 #include <cmath>
 
+#include "abstraction_kernels.h"
 #include "indexer_kernel.h"
 #include "kernels.cuh"
 #include "plan.h"
@@ -691,6 +692,44 @@ int rs_nccl_unique_id(uint8_t* out) {
     int rc = nccl::g_api.GetUniqueId(&id);
     if (rc != 0) return set_err(RS_ERR_NCCL, "ncclGetUniqueId failed");
     memcpy(out, &id, RS_NCCL_ID_BYTES);
+    return RS_OK;
+}
+
+static int abstraction_args_ok(const void* a, const void* b, uint32_t dim, uint32_t dist_kind) {
+    if (!a || !b) return set_err(RS_ERR_INVALID, "null argument");
+    if (dim == 0 || dim > ABS_MAX_BINS) return set_err(RS_ERR_INVALID, "histograms have 1..128 bins");
+    if (dist_kind != RS_DIST_EMD_1D && dist_kind != RS_DIST_L2) return set_err(RS_ERR_INVALID, "unknown distance");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(RS_ERR_CUDA, "no CUDA device available (no CPU fallback)");
+    return RS_OK;
+}
+
+int rs_kmeans_assign(const float* points, size_t n, uint32_t dim, const float* centers, uint32_t k, uint32_t dist_kind,
+                     uint32_t* cluster, float* min_dist, double* inertia, float* kernel_ms) {
+    int rc = abstraction_args_ok(points, centers, dim, dist_kind);
+    if (rc != RS_OK) return rc;
+    if (!cluster) return set_err(RS_ERR_INVALID, "null argument");
+    if (k == 0) return set_err(RS_ERR_INVALID, "no centres");
+    std::string err;
+    if (!gpu_kmeans_assign(points, n, dim, centers, k, dist_kind, cluster, min_dist, inertia, kernel_ms, &err)) return set_err(RS_ERR_CUDA, err);
+    return RS_OK;
+}
+
+int rs_histogram_distances(const float* p, const float* q, size_t n, uint32_t dim, uint32_t dist_kind, float* out) {
+    int rc = abstraction_args_ok(p, q, dim, dist_kind);
+    if (rc != RS_OK) return rc;
+    if (!out) return set_err(RS_ERR_INVALID, "null argument");
+    std::string err;
+    if (!gpu_pair_dist(p, q, false, n, dim, dist_kind, out, nullptr, &err)) return set_err(RS_ERR_CUDA, err);
+    return RS_OK;
+}
+
+int rs_kmeans_update_min_dists(const float* points, size_t n, uint32_t dim, const float* new_center, uint32_t dist_kind, float* min_dists) {
+    int rc = abstraction_args_ok(points, new_center, dim, dist_kind);
+    if (rc != RS_OK) return rc;
+    if (!min_dists) return set_err(RS_ERR_INVALID, "null argument");
+    std::string err;
+    if (!gpu_pair_dist(points, new_center, true, n, dim, dist_kind, nullptr, min_dists, &err)) return set_err(RS_ERR_CUDA, err);
     return RS_OK;
 }
 

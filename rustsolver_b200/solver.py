@@ -218,6 +218,44 @@ def build_game_tree(options: Options):
         lib.rsh_tree_free(th)
 
 
+RS_DIST_EMD_1D, RS_DIST_L2 = 0, 1
+
+
+def kmeans_assign(points: np.ndarray, centers: np.ndarray, dist: int = RS_DIST_EMD_1D, return_ms: bool = False):
+    """Kmeans::predict (gen_abstraction/kmeans.rs:173-211) on the GPU: (cluster[n], min_dist[n], inertia[, kernel ms])."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(points, dtype=np.float32)
+    c = np.ascontiguousarray(centers, dtype=np.float32)
+    assert x.ndim == 2 and c.ndim == 2 and x.shape[1] == c.shape[1]
+    cl = np.zeros(len(x), dtype=np.uint32)
+    md = np.zeros(len(x), dtype=np.float32)
+    inertia, ms = C.c_double(0.0), C.c_float(0.0)
+    check(lib.rs_kmeans_assign(_ptr(x, f32p), len(x), x.shape[1], _ptr(c, f32p), len(c), dist, _ptr(cl, u32p), _ptr(md, f32p),
+                               C.byref(inertia), C.byref(ms)))
+    return (cl, md, float(inertia.value), float(ms.value)) if return_ms else (cl, md, float(inertia.value))
+
+
+def histogram_distances(p: np.ndarray, q: np.ndarray, dist: int = RS_DIST_EMD_1D) -> np.ndarray:
+    """out[i] = emd_1d(p[i], q[i]) (emd.rs:54-113) or l2_dist (kmeans.rs:622-630) on the GPU."""
+    lib = _lib.load()
+    a = np.ascontiguousarray(p, dtype=np.float32)
+    b = np.ascontiguousarray(q, dtype=np.float32)
+    assert a.shape == b.shape and a.ndim == 2
+    out = np.zeros(len(a), dtype=np.float32)
+    check(lib.rs_histogram_distances(_ptr(a, f32p), _ptr(b, f32p), len(a), a.shape[1], dist, _ptr(out, f32p)))
+    return out
+
+
+def kmeans_update_min_dists(points: np.ndarray, new_center: np.ndarray, min_dists: np.ndarray, dist: int = RS_DIST_EMD_1D) -> np.ndarray:
+    """update_min_dists (kmeans.rs:603-619) on the GPU; returns the updated copy."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(points, dtype=np.float32)
+    c = np.ascontiguousarray(new_center, dtype=np.float32)
+    md = np.array(min_dists, dtype=np.float32, copy=True)
+    check(lib.rs_kmeans_update_min_dists(_ptr(x, f32p), len(x), x.shape[1], _ptr(c, f32p), dist, _ptr(md, f32p)))
+    return md
+
+
 class HandIndexer:
     """rust_poker::hand_indexer_s (card_abstraction.rs:88-90)."""
 

@@ -1,0 +1,70 @@
+"""CPU: the oracle's restatement of emd_1d / l2_dist / Kmeans::predict against the reference's own known answers."""
+import numpy as np
+
+import oracle
+from tests import abstraction_kats as K
+
+
+def test_emd_1d_reference_known_answers():
+    """emd.rs:122-180: identical histograms -> 0; 66 vs JT and 72 vs AA within ERROR = 0.01 of the exact EMD."""
+    for p, q, want, exact in K.KATS:
+        got = oracle.emd_1d(p, q)
+        if exact:
+            assert got == want
+        else:
+            assert abs(got - want) < K.ERROR, (got, want)
+    assert oracle.emd_1d(K.H_66, K.H_66) == 0.0  # identical, normalised sum exactly 1: exactly 0
+    # the one-ulp residue of test_same, step by step in numpy float32 (see tests/abstraction_kats.py)
+    p = np.array(K.H_SAME, dtype=np.float32)
+    s = np.float32(0)
+    for v in p:
+        s = np.float32(s + v)
+    w = np.float32(0)
+    for v in p:
+        w = np.float32(w + np.float32(v / s))
+    factor = min(max(np.float32(np.float32(4.45) * w) - np.float32(1.5), 1.0), 4.0)
+    u = int(np.round(np.float32(len(p)) / np.float32(factor)))
+    assert oracle.emd_1d(p, p) == float(np.float32(np.float32(1) - w) * np.float32(u))
+
+
+def test_emd_1d_edge_cases():
+    z = np.zeros(30, dtype=np.float32)
+    assert oracle.emd_1d(z, K.H_66) == 0.0 and oracle.emd_1d(K.H_66, z) == 0.0  # emd.rs:60-62: an empty histogram
+    one_hot = lambda i: np.eye(30, dtype=np.float32)[i]
+    # all mass moves i -> j: the cross-bin search finds it at distance |i - j| while it is within reach (u = 30 here)
+    assert oracle.emd_1d(one_hot(3), one_hot(10)) == 7.0
+    assert oracle.emd_1d(one_hot(0), one_hot(29)) == 29.0
+    # unnormalised input is normalised first (emd.rs:57-66)
+    a = np.array(K.H_66, dtype=np.float32)
+    assert abs(oracle.emd_1d(4 * a, K.H_JT) - oracle.emd_1d(a, K.H_JT)) < 1e-5
+
+
+def test_l2_dist():
+    a, b = np.array(K.H_66, dtype=np.float32), np.array(K.H_JT, dtype=np.float32)
+    assert abs(oracle.l2_dist(a, b) - float(np.sqrt(((a - b) ** 2).sum()))) < 1e-6
+    assert oracle.l2_dist(a, a) == 0.0
+
+
+def test_kmeans_predict_is_the_first_nearest_centre():
+    rng = np.random.default_rng(3)
+    x = K.random_histograms(rng, 200, 30)
+    c = K.random_histograms(rng, 17, 30)
+    c[5] = c[11]  # a duplicated centre: the strict < of kmeans.rs:199 keeps the first
+    for kind in (0, 1):
+        cl, md, inertia = oracle.kmeans_predict(x, c, kind)
+        f = oracle.emd_1d if kind == 0 else oracle.l2_dist
+        for i in range(0, 200, 13):
+            d = np.array([f(x[i], c[k]) for k in range(17)], dtype=np.float32)
+            assert cl[i] == int(np.argmin(d)) and md[i] == d.min()
+        assert not (cl == 11).any()
+        assert abs(inertia - float(md.astype(np.float64).sum())) < 1e-9
+
+
+def test_update_min_dists():
+    rng = np.random.default_rng(4)
+    x = K.random_histograms(rng, 50, 30)
+    c = K.random_histograms(rng, 1, 30)[0]
+    md0 = rng.random(50).astype(np.float32) * 20
+    md = oracle.update_min_dists(x, c, md0, 0)
+    want = np.minimum(md0, np.array([np.float32(oracle.emd_1d(x[i], c)) ** 2 for i in range(50)], dtype=np.float32))
+    assert np.array_equal(md, want)

@@ -1,0 +1,55 @@
+"""GPU: emd_1d / l2_dist / k-means assignment kernels (abstraction_kernels.cu) through the C ABI against the
+reference's known answers and, bit for bit, against the CPU restatement (same fp32 operations in the same order)."""
+import numpy as np
+import pytest
+
+import oracle
+import rustsolver_b200 as rb
+from tests import abstraction_kats as K
+
+pytestmark = pytest.mark.gpu
+
+
+def test_emd_1d_reference_known_answers_on_the_device():
+    for p, q, want, exact in K.KATS:
+        got = float(rb.histogram_distances(np.array([p], np.float32), np.array([q], np.float32))[0])
+        assert (got == want) if exact else (abs(got - want) < K.ERROR), (got, want)
+        assert got == oracle.emd_1d(p, q)  # and identical to the CPU restatement
+
+
+@pytest.mark.parametrize("dim", [8, 30, 50, 128])
+def test_distances_are_bit_exact(dim):
+    rng = np.random.default_rng(dim)
+    p = K.random_histograms(rng, 4000, dim)
+    q = K.random_histograms(rng, 4000, dim)
+    p[7] = 0.0  # an empty histogram: distance 0 (emd.rs:60-62)
+    q[9] = p[9]
+    for kind, f in ((rb.RS_DIST_EMD_1D, oracle.emd_1d), (rb.RS_DIST_L2, oracle.l2_dist)):
+        dev = rb.histogram_distances(p, q, kind)
+        host = np.array([f(p[i], q[i]) for i in range(len(p))], dtype=np.float32)
+        assert np.array_equal(dev, host), np.abs(dev - host).max()
+    assert rb.histogram_distances(p, q, rb.RS_DIST_EMD_1D)[7] == 0.0
+
+
+@pytest.mark.parametrize("n,k,dim", [(1, 1, 30), (63, 5, 30), (5000, 200, 50), (4097, 33, 8)])
+def test_kmeans_assignment_matches_predict(n, k, dim):
+    rng = np.random.default_rng(n + k)
+    x = K.random_histograms(rng, n, dim)
+    c = K.random_histograms(rng, k, dim)
+    if k > 3:
+        c[k - 1] = c[1]  # duplicated centre: the first one wins (strict <, kmeans.rs:199)
+    for kind in (rb.RS_DIST_EMD_1D, rb.RS_DIST_L2):
+        cl, md, inertia = rb.kmeans_assign(x, c, kind)
+        ocl, omd, oin = oracle.kmeans_predict(x, c, kind)
+        assert np.array_equal(cl, ocl)
+        assert np.array_equal(md, omd)
+        assert abs(inertia - oin) <= 1e-9 * max(abs(oin), 1.0)
+    assert len(rb.kmeans_assign(x[:0], c)[0]) == 0  # empty data set
+
+
+def test_update_min_dists_matches():
+    rng = np.random.default_rng(11)
+    x = K.random_histograms(rng, 3000, 30)
+    c = K.random_histograms(rng, 1, 30)[0]
+    md0 = (rng.random(3000) * 30).astype(np.float32)
+    assert np.array_equal(rb.kmeans_update_min_dists(x, c, md0), oracle.update_min_dists(x, c, md0, 0))
