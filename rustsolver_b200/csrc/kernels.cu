@@ -81,13 +81,23 @@ struct Ctx {
     int tid, lane, warp, nwarps;
     int pos4;  // first of the four hands this thread owns
     int p, o, Hp, Ho, HpP, HoP, Hx;
-    float* Rs;   // [HoP]        opponent reach being scanned
-    float* X;    // [slots][Hx]
-    float* P;    // [HoP + 4]    exclusive prefix of reach by position (strength order on the river)
-    float* GB;   // [2*HoP + 8]  exclusive prefix of reach over the opponent's per-card lists
-    float* WSA;  // [32]
-    float* WSB;  // [32]
 };
+
+// Shared memory of a CTA at COMPILE-TIME offsets (capacity = the largest range, 1326 hands padded to a warp multiple of
+// four-hand threads): the arrays need no pointer registers and every access is base + immediate.
+//   SM_RS  [HCAP]        opponent reach being scanned
+//   SM_P   [HCAP + 4]    exclusive prefix of reach by position (strength order on the river)
+//   SM_GB  [2*HCAP + 8]  exclusive prefix of reach over the opponent's per-card lists
+//   SM_WSA / SM_WSB [32] warp totals of the two scans
+//   SM_X   [slots][Hx]   scratch vectors (terminal-child reach, bucketed rows), Hx known at run time
+constexpr int HCAP = MAX_TASK_THREADS * 4;
+extern __shared__ __align__(16) float smem_raw[];
+#define SM_RS (smem_raw)
+#define SM_P (smem_raw + HCAP)
+#define SM_GB (smem_raw + 2 * HCAP + 4)
+#define SM_WSA (smem_raw + 4 * HCAP + 12)
+#define SM_WSB (smem_raw + 4 * HCAP + 44)
+#define SM_X (smem_raw + 4 * HCAP + 76)
 
 // Exclusive prefix sums of opponent reach r (shared memory, HoP floats, zero past the live hands):
 //   P[i]  = reach of the i weakest hands           (position order)
@@ -125,13 +135,13 @@ __device__ __forceinline__ float scan_reach(const Ctx& c, const float* r, const 
         }
     }
     if (c.lane == 31) {
-        c.WSA[c.warp] = ia;
-        c.WSB[c.warp] = ib;
+        SM_WSA[c.warp] = ia;
+        SM_WSB[c.warp] = ib;
     }
     csync(c.nc);
     // every warp scans the (<= 11) warp totals itself
-    float wa = c.lane < c.nwarps ? c.WSA[c.lane] : 0.f;
-    float wb = c.lane < c.nwarps ? c.WSB[c.lane] : 0.f;
+    float wa = c.lane < c.nwarps ? SM_WSA[c.lane] : 0.f;
+    float wb = c.lane < c.nwarps ? SM_WSB[c.lane] : 0.f;
 #pragma unroll
     for (int d = 1; d < 16; d <<= 1) {
         const float ta = __shfl_up_sync(0xffffffffu, wa, d);
@@ -152,7 +162,7 @@ __device__ __forceinline__ float scan_reach(const Ctx& c, const float* r, const 
         o.y = ea + x.x;
         o.z = o.y + x.y;
         o.w = o.z + x.z;
-        *reinterpret_cast<float4*>(c.P + c.pos4) = o;
+        *reinterpret_cast<float4*>(SM_P + c.pos4) = o;
     }
     if (8 * c.tid < 2 * c.HoP) {
         float4 o0, o1;
@@ -164,12 +174,12 @@ __device__ __forceinline__ float scan_reach(const Ctx& c, const float* r, const 
         o1.y = o1.x + y[4];
         o1.z = o1.y + y[5];
         o1.w = o1.z + y[6];
-        *reinterpret_cast<float4*>(c.GB + 8 * c.tid) = o0;
-        *reinterpret_cast<float4*>(c.GB + 8 * c.tid + 4) = o1;
+        *reinterpret_cast<float4*>(SM_GB + 8 * c.tid) = o0;
+        *reinterpret_cast<float4*>(SM_GB + 8 * c.tid + 4) = o1;
     }
     if (c.tid == 0) {
-        c.P[c.HoP] = total;
-        c.GB[2 * c.HoP] = total_b;
+        SM_P[c.HoP] = total;
+        SM_GB[2 * c.HoP] = total_b;
     }
     csync(c.nc);
     return total;
@@ -196,14 +206,14 @@ __device__ __forceinline__ void hand_terms(const Ctx& c, const float* r, float t
     const uint32_t s0 = rec.y & 0xffffu, dlo0 = (rec.y >> 16) & 0xffu, dhi0 = rec.y >> 24;
     const uint32_t s1 = rec.z & 0xffffu, dlo1 = (rec.z >> 16) & 0xffu, dhi1 = rec.z >> 24;
     const uint32_t n0 = rec.w & 0xffu, n1 = (rec.w >> 8) & 0xffu, same = rec.w >> 16;
-    const float g0s = c.GB[s0], g0e = c.GB[s0 + n0], g1s = c.GB[s1], g1e = c.GB[s1 + n1];
+    const float g0s = SM_GB[s0], g0e = SM_GB[s0 + n0], g1s = SM_GB[s1], g1e = SM_GB[s1 + n1];
     mass = total - (g0e - g0s) - (g1e - g1s) + (same != 0xffffu ? r[same] : 0.f);
-    sd = c.P[lo] + c.P[hi] - total - c.GB[s0 + dlo0] - c.GB[s0 + dhi0] + g0s + g0e - c.GB[s1 + dlo1] - c.GB[s1 + dhi1] + g1s + g1e;
+    sd = SM_P[lo] + SM_P[hi] - total - SM_GB[s0 + dlo0] - SM_GB[s0 + dhi0] + g0s + g0e - SM_GB[s1 + dlo1] - SM_GB[s1 + dhi1] + g1s + g1e;
 }
 __device__ __forceinline__ float hand_mass(const Ctx& c, const float* r, float total, const uint4& rec) {
     const uint32_t s0 = rec.y & 0xffffu, s1 = rec.z & 0xffffu;
     const uint32_t n0 = rec.w & 0xffu, n1 = (rec.w >> 8) & 0xffu, same = rec.w >> 16;
-    return total - (c.GB[s0 + n0] - c.GB[s0]) - (c.GB[s1 + n1] - c.GB[s1]) + (same != 0xffffu ? r[same] : 0.f);
+    return total - (SM_GB[s0 + n0] - SM_GB[s0]) - (SM_GB[s1 + n1] - SM_GB[s1]) + (same != 0xffffu ? r[same] : 0.f);
 }
 
 // Opponent reach of the thread's four positions for this task (masked by what the board removes).
@@ -274,7 +284,7 @@ __device__ __forceinline__ void sigma_row(const float (&g)[4 * NA], int i, float
         sg[a] = fmaxf(g[i * NA + a], 0.f);
         norm += sg[a];
     }
-    const float inv = norm > 0.f ? 1.0f / norm : 0.f;
+    const float inv = __fdividef(1.0f, norm);  // MUFU.RCP + one multiply (2 ulp), not the IEEE division sequence; only used when norm > 0
 #pragma unroll
     for (int a = 0; a < NA; ++a) sg[a] = norm > 0.f ? sg[a] * inv : 1.0f / float(NA);
 }
@@ -333,7 +343,7 @@ __device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const
     for (int a = 0; a < NA; ++a) {
         const int ck = nt.child[a].kind;
         if (c.pos4 < c.HoP) {
-            if (ck == CK_FOLD || ck == CK_SHOWDOWN) *reinterpret_cast<float4*>(c.X + slot * c.Hx + c.pos4) = v[a];
+            if (ck == CK_FOLD || ck == CK_SHOWDOWN) *reinterpret_cast<float4*>(SM_X + slot * c.Hx + c.pos4) = v[a];
             else stcg4(Rk.rbuf + (size_t(nt.child[a].buf) * Rk.n_boards + b) * c.HoP + c.pos4, v[a]);
         }
         if (ck == CK_FOLD || ck == CK_SHOWDOWN) ++slot;
@@ -351,7 +361,7 @@ __device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const
     for (int a = 0; a < NA; ++a) {
         const int ck = nt.child[a].kind;
         if (ck != CK_FOLD && ck != CK_SHOWDOWN) continue;
-        const float* r = c.X + slot * c.Hx;
+        const float* r = SM_X + slot * c.Hx;
         ++slot;
         const float cf = nt.child[a].coef * scale;
         const float total = scan_reach(c, r, cl);
@@ -397,7 +407,7 @@ __device__ __forceinline__ void task_down_generic(const TaskArgs& A, const Ctx& 
                 float v = 0.f;
                 if (live) v = norm > 0.f ? r * fmaxf(slab[size_t(rows[i]) * n_act + a], 0.f) / norm : r / float(n_act);
                 const int ck = nt.child[a].kind;
-                if (ck == CK_FOLD || ck == CK_SHOWDOWN) c.X[(slot++) * c.Hx + c.pos4 + i] = v;
+                if (ck == CK_FOLD || ck == CK_SHOWDOWN) SM_X[(slot++) * c.Hx + c.pos4 + i] = v;
                 else __stcg(Rk.rbuf + (size_t(nt.child[a].buf) * Rk.n_boards + b) * c.HoP + c.pos4 + i, v);
             }
         }
@@ -414,7 +424,7 @@ __device__ __forceinline__ void task_down_generic(const TaskArgs& A, const Ctx& 
     for (int a = 0; a < n_act; ++a) {
         const int ck = nt.child[a].kind;
         if (ck != CK_FOLD && ck != CK_SHOWDOWN) continue;
-        const float* r = c.X + slot * c.Hx;
+        const float* r = SM_X + slot * c.Hx;
         ++slot;
         const float cf = nt.child[a].coef * scale;
         const float total = scan_reach(c, r, cl);
@@ -439,8 +449,8 @@ __device__ __forceinline__ void task_down_generic(const TaskArgs& A, const Ctx& 
 __device__ __forceinline__ void trav_terms(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b,
                                            bool need_sd, float4& mass, float4& sd) {
     const float4 r4 = load_reach4(A, c, nt, Rk, k, b);
-    if (c.pos4 < c.HoP) *reinterpret_cast<float4*>(c.Rs + c.pos4) = r4;
-    const float total = scan_reach(c, c.Rs, Rk.rp[c.o].cl_pos + size_t(b) * 2 * c.HoP);
+    if (c.pos4 < c.HoP) *reinterpret_cast<float4*>(SM_RS + c.pos4) = r4;
+    const float total = scan_reach(c, SM_RS, Rk.rp[c.o].cl_pos + size_t(b) * 2 * c.HoP);
     mass = f4zero();
     sd = f4zero();
     const DevRoundPlayer& Pp = Rk.rp[c.p];
@@ -452,8 +462,8 @@ __device__ __forceinline__ void trav_terms(const TaskArgs& A, const Ctx& c, cons
         for (int i = 0; i < 4; ++i) {
             if (uint32_t(c.pos4 + i) < nl_p) {
                 float m, s = 0.f;
-                if (need_sd) hand_terms(c, c.Rs, total, rec[i], m, s);
-                else m = hand_mass(c, c.Rs, total, rec[i]);
+                if (need_sd) hand_terms(c, SM_RS, total, rec[i], m, s);
+                else m = hand_mass(c, SM_RS, total, rec[i]);
                 f4set(mass, i, m);
                 f4set(sd, i, s);
             }
@@ -537,18 +547,18 @@ __device__ __forceinline__ void task_trav(const TaskArgs& A, const Ctx& c, const
         return;
     }
     // bucketed rows: values and masses go through shared memory, one thread per row (CSR row -> positions)
-    float* M = c.X;
+    float* M = SM_X;
     if (c.pos4 < c.HpP) {
         *reinterpret_cast<float4*>(M + c.pos4) = mass;
 #pragma unroll
-        for (int a = 0; a < NA; ++a) *reinterpret_cast<float4*>(c.X + (1 + a) * c.Hx + c.pos4) = v[a];
+        for (int a = 0; a < NA; ++a) *reinterpret_cast<float4*>(SM_X + (1 + a) * c.Hx + c.pos4) = v[a];
         if (!nt.root_scatter) stcg4(out + c.pos4, f4zero());
     }
     csync(c.nc);
     const uint32_t n_rows = Pp.n_rows[b];
     const uint16_t* __restrict__ rstart = Pp.row_start + size_t(b) * (c.HpP + 4);
     const uint16_t* __restrict__ rpos = Pp.row_pos + size_t(b) * c.HpP;
-    const float* V1 = c.X + c.Hx;
+    const float* V1 = SM_X + c.Hx;
     for (uint32_t row = c.tid; row < n_rows; row += c.nc) {
         float rg[NA], sr[NA], sg[NA], d[NA];
         float norm = 0.f;
@@ -602,19 +612,19 @@ __device__ __forceinline__ void task_trav_generic(const TaskArgs& A, const Ctx& 
     bool need_sd = false;
     for (int a = 0; a < n_act; ++a) {
         const int ck = nt.child[a].kind;
-        if (ck == CK_VALUE && c.pos4 < c.HpP) *reinterpret_cast<float4*>(c.X + (1 + a) * c.Hx + c.pos4) = child_value4(A, c, Rk, nt.child[a], b);
+        if (ck == CK_VALUE && c.pos4 < c.HpP) *reinterpret_cast<float4*>(SM_X + (1 + a) * c.Hx + c.pos4) = child_value4(A, c, Rk, nt.child[a], b);
         need_sd |= (ck == CK_SHOWDOWN);
     }
     float4 mass, sd;
     trav_terms(A, c, nt, Rk, k, b, need_sd, mass, sd);
     float* out = (nt.root_scatter ? Rk.sbuf : Rk.cbuf) + (size_t(nt.out) * Rk.n_boards + b) * c.HpP;
     if (c.pos4 < c.HpP) {
-        *reinterpret_cast<float4*>(c.X + c.pos4) = mass;
+        *reinterpret_cast<float4*>(SM_X + c.pos4) = mass;
         for (int a = 0; a < n_act; ++a) {
             const int ck = nt.child[a].kind;
             const float cf = nt.child[a].coef * scale;
-            if (ck == CK_FOLD) *reinterpret_cast<float4*>(c.X + (1 + a) * c.Hx + c.pos4) = make_float4(cf * mass.x, cf * mass.y, cf * mass.z, cf * mass.w);
-            else if (ck == CK_SHOWDOWN) *reinterpret_cast<float4*>(c.X + (1 + a) * c.Hx + c.pos4) = make_float4(cf * sd.x, cf * sd.y, cf * sd.z, cf * sd.w);
+            if (ck == CK_FOLD) *reinterpret_cast<float4*>(SM_X + (1 + a) * c.Hx + c.pos4) = make_float4(cf * mass.x, cf * mass.y, cf * mass.z, cf * mass.w);
+            else if (ck == CK_SHOWDOWN) *reinterpret_cast<float4*>(SM_X + (1 + a) * c.Hx + c.pos4) = make_float4(cf * sd.x, cf * sd.y, cf * sd.z, cf * sd.w);
         }
         if (!nt.root_scatter) stcg4(out + c.pos4, f4zero());
     }
@@ -625,8 +635,8 @@ __device__ __forceinline__ void task_trav_generic(const TaskArgs& A, const Ctx& 
     float* tabS = Pp.ssum + Pp.board_off[b] + size_t(nrp) * nt.cum_a;
     const uint16_t* __restrict__ rstart = Pp.row_start + size_t(b) * (c.HpP + 4);
     const uint16_t* __restrict__ rpos = Pp.row_pos + size_t(b) * c.HpP;
-    const float* M = c.X;
-    const float* V1 = c.X + c.Hx;
+    const float* M = SM_X;
+    const float* V1 = SM_X + c.Hx;
     for (uint32_t row = c.tid; row < n_rows; row += c.nc) {
         const float* tsrc = (MODE == KM_EVAL ? tabS : tabR) + size_t(row) * n_act;
         float norm = 0.f;
@@ -706,7 +716,6 @@ struct TaskSlot {
 
 template <int MODE, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_constant__ TaskArgs A) {
-    extern __shared__ __align__(16) float smem_raw[];
     __shared__ __align__(16) TaskSlot s_slot[2];
 
     __shared__ __align__(8) uint64_t s_done;  // phase i completes when every compute warp has finished task i
@@ -736,7 +745,9 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
             bool published = (prev_tk == 0xffffffffu);  // meaningful on lane 0
             auto try_publish = [&]() {
                 if (lane == 0 && !published && mbar_test(&s_done, parity)) {
+#ifndef RS_NO_PUBLISH_FENCE
                     __threadfence();
+#endif
                     st_release_u32(A.flags + prev_tk, epoch);
                     published = true;
                 }
@@ -812,7 +823,9 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
             __syncwarp();
             hsync(NC + 32);  // slot[buf] handed over; the compute warps are done with the previous task
             if (lane == 0 && !published) {
+#ifndef RS_NO_PUBLISH_FENCE
                 __threadfence();
+#endif
                 st_release_u32(A.flags + prev_tk, epoch);
             }
             if (prev_tk != 0xffffffffu) parity ^= 1;
@@ -849,12 +862,6 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
     c.HpP = A.Hpad[c.p];
     c.HoP = A.Hpad[c.o];
     c.Hx = c.HpP > c.HoP ? c.HpP : c.HoP;
-    c.Rs = smem_raw;
-    c.X = c.Rs + c.HoP;
-    c.P = c.X + A.slots * c.Hx;
-    c.GB = c.P + c.HoP + 4;
-    c.WSA = c.GB + 2 * c.HoP + 8;
-    c.WSB = c.WSA + 32;
 
     int buf = 0;
     for (;;) {
@@ -1027,7 +1034,7 @@ __global__ void normalize_kernel(const float* __restrict__ in, float* __restrict
 
 size_t task_kernel_smem_bytes(int slots, int Hp_pad, int Ho_pad) {
     const int hx = Hp_pad > Ho_pad ? Hp_pad : Ho_pad;
-    size_t floats = size_t(Ho_pad) + size_t(slots) * hx + (Ho_pad + 4) + (2 * size_t(Ho_pad) + 8) + 64;
+    size_t floats = size_t(4 * HCAP + 76) + size_t(slots) * hx;  // fixed-offset arrays (SM_*), then the scratch vectors
     return floats * sizeof(float);
 }
 
