@@ -453,6 +453,9 @@ void Engine::fill_args(TaskArgs* a, int trav, const TaskSet& set) const {
     a->flags = flags.p;
     a->ctl = ctl.p;
     a->trav = trav;
+    a->HpP = a->Hpad[trav];
+    a->HoP = a->Hpad[1 - trav];
+    a->Hx = std::max(a->HpP, a->HoP);
     if (fused_exchange) {
         a->xch_world = P.world;
         a->xch_rank = P.rank;

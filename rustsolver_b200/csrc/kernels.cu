@@ -475,18 +475,20 @@ template <int MODE, int NA>
 __device__ __forceinline__ void task_trav(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b) {
     const DevRoundPlayer& Pp = Rk.rp[c.p];
     const float scale = Rk.chance_scale[b];
-    // child values that come from other tasks: issue the loads first
     float4 v[NA];
     bool need_sd = false;
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
         v[a] = f4zero();
-        const int ck = nt.child[a].kind;
-        if (ck == CK_VALUE) v[a] = child_value4(A, c, Rk, nt.child[a], b);
-        need_sd |= (ck == CK_SHOWDOWN);
+        need_sd |= (nt.child[a].kind == CK_SHOWDOWN);
     }
     float4 mass, sd;
     trav_terms(A, c, nt, Rk, k, b, need_sd, mass, sd);
+    // child values that come from other tasks: loaded after the scan (held across it they cost registers the
+    // 64-register build does not have: measured +2 %)
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+        if (nt.child[a].kind == CK_VALUE) v[a] = child_value4(A, c, Rk, nt.child[a], b);
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
         const int ck = nt.child[a].kind;
@@ -859,9 +861,9 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
     c.o = 1 - c.p;
     c.Hp = A.H[c.p];
     c.Ho = A.H[c.o];
-    c.HpP = A.Hpad[c.p];
-    c.HoP = A.Hpad[c.o];
-    c.Hx = c.HpP > c.HoP ? c.HpP : c.HoP;
+    c.HpP = A.HpP;
+    c.HoP = A.HoP;
+    c.Hx = A.Hx;
 
     int buf = 0;
     for (;;) {

@@ -72,6 +72,8 @@ struct TaskArgs {
     const float* root_weights[2];
     int H[2], Hpad[2];
     int trav;
+    int HpP, HoP, Hx;  // padded range sizes of the traverser / the opponent / the larger: scalar kernel parameters are
+                       // constant-bank operands, no registers and no indexed parameter loads in the kernel
     uint32_t t0, t1;  // ticket range of this launch
     // sampled-board mode (rs_iterate_sampled): rounds >= 1 only run on n_paths sampled run-outs.  Instance i of a
     // round-k task works on board sample_board[k][i]; the chance gather sums the sampled children only and
