@@ -89,6 +89,7 @@ struct Ctx {
 //   SM_P   [HCAP + 4]    exclusive prefix of reach by position (strength order on the river)
 //   SM_GB  [2*HCAP + 8]  exclusive prefix of reach over the opponent's per-card lists
 //   SM_WSA / SM_WSB [32] warp totals of the two scans
+//   SM_REC [4][HCAP]     the traverser's per-hand records of the board, staged by cp.async at the start of a task
 //   SM_X   [slots][Hx]   scratch vectors (terminal-child reach, bucketed rows), Hx known at run time
 constexpr int HCAP = MAX_TASK_THREADS * 4;
 extern __shared__ __align__(16) float smem_raw[];
@@ -97,7 +98,8 @@ extern __shared__ __align__(16) float smem_raw[];
 #define SM_GB (smem_raw + 2 * HCAP + 4)
 #define SM_WSA (smem_raw + 4 * HCAP + 12)
 #define SM_WSB (smem_raw + 4 * HCAP + 44)
-#define SM_X (smem_raw + 4 * HCAP + 76)
+#define SM_REC (reinterpret_cast<uint32_t*>(smem_raw + 4 * HCAP + 76))
+#define SM_X (smem_raw + 8 * HCAP + 76)
 
 // Exclusive prefix sums of opponent reach r (shared memory, HoP floats, zero past the live hands):
 //   P[i]  = reach of the i weakest hands           (position order)
@@ -192,6 +194,32 @@ __device__ __forceinline__ void load_recs4(const uint32_t* __restrict__ planes, 
     const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(planes + HpP + pos4));
     const uint4 w2 = __ldg(reinterpret_cast<const uint4*>(planes + 2 * HpP + pos4));
     const uint4 w3 = __ldg(reinterpret_cast<const uint4*>(planes + 3 * HpP + pos4));
+    rec[0] = make_uint4(w0.x, w1.x, w2.x, w3.x);
+    rec[1] = make_uint4(w0.y, w1.y, w2.y, w3.y);
+    rec[2] = make_uint4(w0.z, w1.z, w2.z, w3.z);
+    rec[3] = make_uint4(w0.w, w1.w, w2.w, w3.w);
+}
+
+// The records are needed only after the first scan of a task.  Loading them into registers up front would cost 16
+// registers across the scan, loading them afterwards exposes an L2 round trip: instead every thread copies its own
+// 4 x 16 bytes into shared memory with cp.async when the task starts and reads them back when it needs them (no
+// barrier: a thread only ever reads what it copied itself).
+__device__ __forceinline__ void stage_recs(const Ctx& c, const uint32_t* __restrict__ planes) {
+    if (c.pos4 < c.HpP) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(SM_REC + w * HCAP + c.pos4))),
+                         "l"(planes + size_t(w) * c.HpP + c.pos4)
+                         : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void staged_recs_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void staged_recs4(const Ctx& c, uint4 (&rec)[4]) {
+    const uint4 w0 = *reinterpret_cast<const uint4*>(SM_REC + c.pos4);
+    const uint4 w1 = *reinterpret_cast<const uint4*>(SM_REC + HCAP + c.pos4);
+    const uint4 w2 = *reinterpret_cast<const uint4*>(SM_REC + 2 * HCAP + c.pos4);
+    const uint4 w3 = *reinterpret_cast<const uint4*>(SM_REC + 3 * HCAP + c.pos4);
     rec[0] = make_uint4(w0.x, w1.x, w2.x, w3.x);
     rec[1] = make_uint4(w0.y, w1.y, w2.y, w3.y);
     rec[2] = make_uint4(w0.z, w1.z, w2.z, w3.z);
@@ -324,6 +352,7 @@ __device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const
     const DevRoundPlayer& O = Rk.rp[c.o];
     const uint32_t nrp = O.n_rows_pad[b];
     const float* __restrict__ slab = (MODE == KM_CFR ? O.regrets : O.ssum) + O.board_off[b] + size_t(nrp) * nt.cum_a;
+    if (nt.out >= 0) stage_recs(c, reinterpret_cast<const uint32_t*>(Rk.rp[c.p].hrec) + size_t(b) * 4 * c.HpP);
     const float4 r4 = load_reach4(A, c, nt, Rk, k, b);
     uint32_t rows[4] = {0xffffu, 0xffffu, 0xffffu, 0xffffu};
     if (!O.identity && c.pos4 < c.HoP) unpack4(__ldg(reinterpret_cast<const uint2*>(O.row_of_pos + size_t(b) * c.HoP + c.pos4)), rows);
@@ -355,8 +384,6 @@ __device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const
     const float scale = Rk.chance_scale[b];
     const uint16_t* __restrict__ cl = O.cl_pos + size_t(b) * 2 * c.HoP;
     float4 acc = f4zero();
-    uint4 rec[4];
-    if (c.pos4 < c.HpP) load_recs4(reinterpret_cast<const uint32_t*>(Pp.hrec) + size_t(b) * 4 * c.HpP, c.HpP, c.pos4, rec);
     slot = 0;
     for (int a = 0; a < NA; ++a) {
         const int ck = nt.child[a].kind;
@@ -365,7 +392,10 @@ __device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const
         ++slot;
         const float cf = nt.child[a].coef * scale;
         const float total = scan_reach(c, r, cl);
+        staged_recs_wait();
         if (c.pos4 < c.HpP) {
+            uint4 rec[4];
+            staged_recs4(c, rec);  // read back for every terminal child instead of held in registers across the scans
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (uint32_t(c.pos4 + i) < nl_p) {
@@ -448,16 +478,18 @@ __device__ __forceinline__ void task_down_generic(const TaskArgs& A, const Ctx& 
 // common front part: stage the reach, run the scan, produce per-hand mass and showdown term
 __device__ __forceinline__ void trav_terms(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b,
                                            bool need_sd, float4& mass, float4& sd) {
+    const DevRoundPlayer& Pp = Rk.rp[c.p];
+    stage_recs(c, reinterpret_cast<const uint32_t*>(Pp.hrec) + size_t(b) * 4 * c.HpP);
     const float4 r4 = load_reach4(A, c, nt, Rk, k, b);
     if (c.pos4 < c.HoP) *reinterpret_cast<float4*>(SM_RS + c.pos4) = r4;
     const float total = scan_reach(c, SM_RS, Rk.rp[c.o].cl_pos + size_t(b) * 2 * c.HoP);
     mass = f4zero();
     sd = f4zero();
-    const DevRoundPlayer& Pp = Rk.rp[c.p];
     const uint32_t nl_p = Pp.n_live[b];
+    staged_recs_wait();
     if (c.pos4 < c.HpP) {
         uint4 rec[4];
-        load_recs4(reinterpret_cast<const uint32_t*>(Pp.hrec) + size_t(b) * 4 * c.HpP, c.HpP, c.pos4, rec);
+        staged_recs4(c, rec);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (uint32_t(c.pos4 + i) < nl_p) {
@@ -1036,7 +1068,7 @@ __global__ void normalize_kernel(const float* __restrict__ in, float* __restrict
 
 size_t task_kernel_smem_bytes(int slots, int Hp_pad, int Ho_pad) {
     const int hx = Hp_pad > Ho_pad ? Hp_pad : Ho_pad;
-    size_t floats = size_t(4 * HCAP + 76) + size_t(slots) * hx;  // fixed-offset arrays (SM_*), then the scratch vectors
+    size_t floats = size_t(8 * HCAP + 76) + size_t(slots) * hx;  // fixed-offset arrays (SM_*), then the scratch vectors
     return floats * sizeof(float);
 }
 
