@@ -90,6 +90,7 @@ struct Ctx {
 //   SM_GB  [2*HCAP + 8]  exclusive prefix of reach over the opponent's per-card lists
 //   SM_WSA / SM_WSB [32] warp totals of the two scans
 //   SM_REC [4][HCAP]     the traverser's per-hand records of the board, staged by cp.async at the start of a task
+//   SM_CL  [HCAP] words  the opponent's per-card lists of the board (u16 pairs), staged the same way
 //   SM_X   [slots][Hx]   scratch vectors (terminal-child reach, bucketed rows), Hx known at run time
 constexpr int HCAP = MAX_TASK_THREADS * 4;
 extern __shared__ __align__(16) float smem_raw[];
@@ -99,21 +100,34 @@ extern __shared__ __align__(16) float smem_raw[];
 #define SM_WSA (smem_raw + 4 * HCAP + 12)
 #define SM_WSB (smem_raw + 4 * HCAP + 44)
 #define SM_REC (reinterpret_cast<uint32_t*>(smem_raw + 4 * HCAP + 76))
-#define SM_X (smem_raw + 8 * HCAP + 76)
+#define SM_CL (reinterpret_cast<uint32_t*>(smem_raw + 8 * HCAP + 76))
+#define SM_X (smem_raw + 9 * HCAP + 76)
+
+// Copy the thread's eight entries of the opponent's per-card lists (cl_pos of the board, u16) into shared memory with
+// cp.async; scan_reach reads them back.  Like the hand records (stage_recs) this is issued when a task starts, so the
+// L2 round trip overlaps the reach load instead of following it, and costs no registers.
+__device__ __forceinline__ void stage_lists_raw(int tid, int HoP, const uint16_t* __restrict__ cl_pos_b) {
+    if (8 * tid < 2 * HoP)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(SM_CL + 4 * tid))), "l"(cl_pos_b + 8 * tid)
+                     : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 // Exclusive prefix sums of opponent reach r (shared memory, HoP floats, zero past the live hands):
 //   P[i]  = reach of the i weakest hands           (position order)
 //   GB[e] = reach of the first e entries of the opponent's concatenated per-card lists
 // One pass: every thread scans its 4 positions and its 8 list entries; warp shuffles + one cross-warp step.
 // Returns the total reach (all threads).
-__device__ __forceinline__ float scan_reach(const Ctx& c, const float* r, const uint16_t* __restrict__ cl_pos_b) {
+__device__ __forceinline__ float scan_reach(const Ctx& c, const float* r) {
     csync(c.nc);  // r is complete; previous readers of P / GB are done
     float4 x = f4zero();
     if (c.pos4 < c.HoP) x = *reinterpret_cast<const float4*>(r + c.pos4);
     float y[8];
     {
+        // the thread's eight list entries were staged by stage_lists when the task started
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         uint4 u = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        if (8 * c.tid < 2 * c.HoP) u = __ldg(reinterpret_cast<const uint4*>(cl_pos_b) + c.tid);
+        if (8 * c.tid < 2 * c.HoP) u = *reinterpret_cast<const uint4*>(SM_CL + 4 * c.tid);
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -352,7 +366,10 @@ __device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const
     const DevRoundPlayer& O = Rk.rp[c.o];
     const uint32_t nrp = O.n_rows_pad[b];
     const float* __restrict__ slab = (MODE == KM_CFR ? O.regrets : O.ssum) + O.board_off[b] + size_t(nrp) * nt.cum_a;
-    if (nt.out >= 0) stage_recs(c, reinterpret_cast<const uint32_t*>(Rk.rp[c.p].hrec) + size_t(b) * 4 * c.HpP);
+    if (nt.out >= 0) {
+        stage_lists_raw(c.tid, c.HoP, O.cl_pos + size_t(b) * 2 * c.HoP);
+        stage_recs(c, reinterpret_cast<const uint32_t*>(Rk.rp[c.p].hrec) + size_t(b) * 4 * c.HpP);
+    }
     const float4 r4 = load_reach4(A, c, nt, Rk, k, b);
     uint32_t rows[4] = {0xffffu, 0xffffu, 0xffffu, 0xffffu};
     if (!O.identity && c.pos4 < c.HoP) unpack4(__ldg(reinterpret_cast<const uint2*>(O.row_of_pos + size_t(b) * c.HoP + c.pos4)), rows);
@@ -382,7 +399,6 @@ __device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const
     const DevRoundPlayer& Pp = Rk.rp[c.p];
     const uint32_t nl_p = Pp.n_live[b];
     const float scale = Rk.chance_scale[b];
-    const uint16_t* __restrict__ cl = O.cl_pos + size_t(b) * 2 * c.HoP;
     float4 acc = f4zero();
     slot = 0;
     for (int a = 0; a < NA; ++a) {
@@ -391,7 +407,7 @@ __device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const
         const float* r = SM_X + slot * c.Hx;
         ++slot;
         const float cf = nt.child[a].coef * scale;
-        const float total = scan_reach(c, r, cl);
+        const float total = scan_reach(c, r);
         staged_recs_wait();
         if (c.pos4 < c.HpP) {
             uint4 rec[4];
@@ -446,7 +462,7 @@ __device__ __forceinline__ void task_down_generic(const TaskArgs& A, const Ctx& 
     const DevRoundPlayer& Pp = Rk.rp[c.p];
     const uint32_t nl_p = Pp.n_live[b];
     const float scale = Rk.chance_scale[b];
-    const uint16_t* __restrict__ cl = O.cl_pos + size_t(b) * 2 * c.HoP;
+    stage_lists_raw(c.tid, c.HoP, O.cl_pos + size_t(b) * 2 * c.HoP);  // generic path: staged right before the scans
     float4 acc = f4zero();
     uint4 rec[4];
     if (c.pos4 < c.HpP) load_recs4(reinterpret_cast<const uint32_t*>(Pp.hrec) + size_t(b) * 4 * c.HpP, c.HpP, c.pos4, rec);
@@ -457,7 +473,7 @@ __device__ __forceinline__ void task_down_generic(const TaskArgs& A, const Ctx& 
         const float* r = SM_X + slot * c.Hx;
         ++slot;
         const float cf = nt.child[a].coef * scale;
-        const float total = scan_reach(c, r, cl);
+        const float total = scan_reach(c, r);
         if (c.pos4 < c.HpP) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -479,10 +495,11 @@ __device__ __forceinline__ void task_down_generic(const TaskArgs& A, const Ctx& 
 __device__ __forceinline__ void trav_terms(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b,
                                            bool need_sd, float4& mass, float4& sd) {
     const DevRoundPlayer& Pp = Rk.rp[c.p];
+    stage_lists_raw(c.tid, c.HoP, Rk.rp[c.o].cl_pos + size_t(b) * 2 * c.HoP);
     stage_recs(c, reinterpret_cast<const uint32_t*>(Pp.hrec) + size_t(b) * 4 * c.HpP);
     const float4 r4 = load_reach4(A, c, nt, Rk, k, b);
     if (c.pos4 < c.HoP) *reinterpret_cast<float4*>(SM_RS + c.pos4) = r4;
-    const float total = scan_reach(c, SM_RS, Rk.rp[c.o].cl_pos + size_t(b) * 2 * c.HoP);
+    const float total = scan_reach(c, SM_RS);
     mass = f4zero();
     sd = f4zero();
     const uint32_t nl_p = Pp.n_live[b];
@@ -1068,7 +1085,7 @@ __global__ void normalize_kernel(const float* __restrict__ in, float* __restrict
 
 size_t task_kernel_smem_bytes(int slots, int Hp_pad, int Ho_pad) {
     const int hx = Hp_pad > Ho_pad ? Hp_pad : Ho_pad;
-    size_t floats = size_t(8 * HCAP + 76) + size_t(slots) * hx;  // fixed-offset arrays (SM_*), then the scratch vectors
+    size_t floats = size_t(9 * HCAP + 76) + size_t(slots) * hx;  // fixed-offset arrays (SM_*), then the scratch vectors
     return floats * sizeof(float);
 }
 
