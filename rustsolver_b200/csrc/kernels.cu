@@ -8,6 +8,10 @@
 #define RS_MIN_BLOCKS_352 2  // up to 1326 hands: 352 threads, <= 93 registers
 #endif
 
+#ifndef RS_POLL_SLEEP_NS
+#define RS_POLL_SLEEP_NS 64  // pause between two rounds of flag polls of the dispatcher
+#endif
+
 namespace rs {
 
 namespace {
@@ -863,7 +867,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                     }
                     try_publish();
                     if (__all_sync(0xffffffffu, i >= total)) break;
-                    __nanosleep(64);
+                    __nanosleep(RS_POLL_SLEEP_NS);
                 }
                 tk_next = A.t0 + uint32_t(__shfl_sync(0xffffffffu, pend, 0));
             }
