@@ -210,6 +210,12 @@ int rs_average_strategy(rs_engine* e, uint32_t an_index, uint32_t board_id, floa
 /* Infoset::get_strategy (infoset.rs:83-102) for every row of the slab */
 int rs_current_strategy(rs_engine* e, uint32_t an_index, uint32_t board_id, float* out,
                         size_t cap_floats, uint32_t* n_rows_out, uint32_t* n_actions_out);
+/* Headerless little-endian dump of the average strategy in the style of the reference's abstraction files
+ * (gen_abstraction/main.rs:372-380, read back by card_abstraction.rs:227-229): for every action node in
+ * ActionNode.index order, for every board of its round this rank owns in board-id order, the fp32 slab
+ * [row][n_actions] of Infoset::get_final_strategy (infoset.rs:104-123).  The reference's calc_br / strategy export
+ * is a stub (cfr.rs:629-744).  n_floats_out may be NULL. */
+int rs_dump_average_strategy(rs_engine* e, const char* path, uint64_t* n_floats_out);
 
 /* board table (README.md:41-43): dealt cards beyond the root board, in deal order -> board id */
 int rs_board_id(rs_engine* e, uint32_t round_idx, const uint8_t* dealt, uint32_t n_dealt,

@@ -85,6 +85,7 @@ ENGINE_API = {
     "rs_read_infoset": (C.c_int, [VP, C.c_uint32, C.c_uint32, f32p, f32p, C.c_size_t, u32p, u32p]),
     "rs_write_infoset": (C.c_int, [VP, C.c_uint32, C.c_uint32, f32p, f32p, C.c_size_t]),
     "rs_average_strategy": (C.c_int, [VP, C.c_uint32, C.c_uint32, f32p, C.c_size_t, u32p, u32p]),
+    "rs_dump_average_strategy": (C.c_int, [VP, C.c_char_p, u64p]),
     "rs_current_strategy": (C.c_int, [VP, C.c_uint32, C.c_uint32, f32p, C.c_size_t, u32p, u32p]),
     "rs_board_id": (C.c_int, [VP, C.c_uint32, u8p, C.c_uint32, u32p]),
     "rs_card_table": (C.c_int, [VP, C.c_uint32, C.c_uint32, C.c_uint32, u16p, C.c_size_t, u32p]),

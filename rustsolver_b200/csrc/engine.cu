@@ -1053,6 +1053,40 @@ int rs_current_strategy(rs_engine* e, uint32_t an_index, uint32_t board_id, floa
     return strategy_impl(e, an_index, board_id, out, cap_floats, n_rows_out, n_actions_out, false);
 }
 
+// Headerless little-endian dump of the average strategy, the style of the reference's abstraction files
+// (gen_abstraction/main.rs:372-380 packs u32 after u32, card_abstraction.rs:227-229 reads them back): for every action
+// node in ActionNode.index order, for every board of the node's round this rank owns in board-id order, the slab
+// [row][n_actions] of fp32 probabilities (Infoset::get_final_strategy, infoset.rs:104-123).
+int rs_dump_average_strategy(rs_engine* e, const char* path, uint64_t* n_floats_out) {
+    if (!e || !path) return set_err(RS_ERR_INVALID, "null argument");
+    Engine& E = e->e;
+    const Plan& P = E.plan;
+    FILE* f = fopen(path, "wb");
+    if (!f) return set_err(RS_ERR_INVALID, std::string("cannot open ") + path);
+    uint64_t total = 0;
+    std::vector<float> buf;
+    int rc = RS_OK;
+    for (uint32_t an = 0; an < P.an_to_pnode.size() && rc == RS_OK; ++an) {
+        if (P.an_to_pnode[an] < 0) continue;
+        const uint32_t k = P.nodes[P.an_to_pnode[an]].round_k;
+        for (uint32_t b = P.local_lo[k]; b < P.local_hi[k]; ++b) {
+            uint32_t nr = 0, na = 0;
+            if ((rc = strategy_impl(e, an, b, nullptr, 0, &nr, &na, true)) != RS_OK) break;
+            buf.resize(size_t(nr) * na);
+            if (buf.empty()) continue;
+            if ((rc = strategy_impl(e, an, b, buf.data(), buf.size(), &nr, &na, true)) != RS_OK) break;
+            if (fwrite(buf.data(), sizeof(float), buf.size(), f) != buf.size()) {
+                rc = set_err(RS_ERR_INVALID, std::string("short write to ") + path);
+                break;
+            }
+            total += buf.size();
+        }
+    }
+    fclose(f);
+    if (rc == RS_OK && n_floats_out) *n_floats_out = total;
+    return rc;
+}
+
 static int board_id_impl(const Plan& P, uint32_t round_idx, const uint8_t* dealt, uint32_t n_dealt, uint32_t* out) {
     if (round_idx >= P.n_rounds) return set_err(RS_ERR_INVALID, "round_idx out of range");
     if (n_dealt != round_idx) return set_err(RS_ERR_INVALID, "need exactly round_idx dealt cards");

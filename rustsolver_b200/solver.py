@@ -534,6 +534,12 @@ class Engine(_PlanOrEngine):
         return [dict(kind=kinds[buf[i].kind], phase=buf[i].phase, traverser=buf[i].traverser, grid=buf[i].grid,
                      ms=buf[i].ms, table_bytes=buf[i].table_bytes, vector_bytes=buf[i].vector_bytes) for i in range(n.value)]
 
+    def dump_average_strategy(self, path: str) -> int:
+        """Headerless LE fp32 dump of the average strategy (rs_dump_average_strategy); returns the number of floats."""
+        n = C.c_uint64(0)
+        check(self._lib.rs_dump_average_strategy(self._h, str(path).encode(), C.byref(n)))
+        return int(n.value)
+
     def set_prune_threshold(self, threshold: float):
         """Traverser actions with regret <= threshold keep their regret (cfr.rs:352,379-386); -inf = off."""
         check(self._lib.rs_set_prune_threshold(self._h, float(threshold)))

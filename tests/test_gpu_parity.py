@@ -168,6 +168,26 @@ def test_pruning_matches_oracle(bucketed):
     util.lockstep(eng, orc, tree, n_free=0, n_locked=1, tol=TOL)
 
 
+def test_average_strategy_dump(tmp_path):
+    """rs_dump_average_strategy: headerless LE fp32, action nodes in index order, boards in id order, [row][A]."""
+    o = util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]] * 2, [[3.0]] * 2)
+    tree, eng, orc = _pair(o)
+    eng.iterate(3)
+    path = tmp_path / "avg_strategy.dat"
+    n = eng.dump_average_strategy(path)
+    data = np.fromfile(path, dtype="<f4")
+    assert len(data) == n and path.stat().st_size == 4 * n
+    st = eng.stats()
+    nb = [st.n_boards[k] for k in range(st.n_rounds)]
+    off = 0
+    for an, b in util.all_slabs(tree, nb):  # action nodes ascending, boards ascending inside a node
+        s = eng.average_strategy(an, b)
+        assert np.array_equal(data[off:off + s.size], s.ravel())
+        assert np.allclose(s.sum(axis=1), 1.0, atol=1e-5)
+        off += s.size
+    assert off == n
+
+
 def test_exploitability_curve_matches_oracle():
     o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]], [[3.0]])
     tree, eng, orc = _pair(o)
