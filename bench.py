@@ -306,6 +306,13 @@ def run_ours(args):
                 "per_kernel_ms": {k: round(v, 5) for k, v in shares.items()},
                 "whole_iteration_frac": (upd_global * BYTES_PER_UPDATE / world) / (ms_per_step * 1e-3) / 1e9 / peak}
 
+    # exploitability of the average strategy after everything run so far (rs_best_response: two best-response
+    # traversals, same kernel; parity of this number against the oracle is tests/test_gpu_parity.py's job)
+    st_end = eng.stats()
+    br = eng.best_response()
+    exploit = {"iterations": int(st_end.iterations), "chips": 0.5 * (br[0] + br[1]),
+               "best_response_values": [br[0], br[1]], "starting_pot_chips": int(w.options.starting_pot)}
+
     line = None
     if rank == 0:
         cpu = None
@@ -332,6 +339,7 @@ def run_ours(args):
                     "what": "per step: rs_set_range_weights x2 from pinned host memory, rs_iterate(1), rs_root_values x2"},
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "exploitability": exploit,
             "clocks": clocks,
             "back_to_back_iter_per_sec": back_to_back,
             "engine_create_s": create_s,
