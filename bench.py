@@ -194,8 +194,9 @@ def run_ours(args):
                     rank=rank, world_size=world, nccl_id=nccl_id)
     fused = False
     if world > 1 and os.environ.get("RS_NO_FUSED", "0") != "1" and eng.stats().n_rounds > 1:
-        eng.enable_fused_exchange(dist, dev)  # the kernel exchanges the chance-node sums itself over NVLink peer memory
-        fused = True
+        # the kernel exchanges the chance-node sums itself over NVLink peer memory (False: some rank could not map
+        # its peers, every rank stays on the NCCL all-reduce)
+        fused = eng.enable_fused_exchange(dist, dev)
     create_s = time.perf_counter() - t0
     st = eng.stats()
     upd_global = int(st.updates_per_iteration_global)

@@ -165,6 +165,9 @@ int rs_kmeans_update_min_dists(const float* points, size_t n, uint32_t dim, cons
 #define RS_EXCHANGE_HANDLE_BYTES 64
 int rs_exchange_export(rs_engine* e, uint8_t* out /* RS_EXCHANGE_HANDLE_BYTES */);
 int rs_exchange_import(rs_engine* e, const uint8_t* handles /* n_ranks * RS_EXCHANGE_HANDLE_BYTES */, uint32_t n_ranks);
+/* rs_exchange_import is all-or-nothing on one rank (a failed mapping leaves that rank on the NCCL path).  The switch
+ * must be unanimous: when any rank failed, the others call rs_exchange_disable to return to the NCCL path too. */
+int rs_exchange_disable(rs_engine* e);
 
 
 int rs_create(const rs_tree* tree, const rs_ranges* ranges, const rs_abstraction* abs,

@@ -72,6 +72,7 @@ ENGINE_API = {
     "rs_gpu_index_hands": (C.c_int, [C.c_uint32, u8p, C.c_size_t, u64p, f32p]),
     "rs_exchange_export": (C.c_int, [VP, u8p]),
     "rs_exchange_import": (C.c_int, [VP, u8p, C.c_uint32]),
+    "rs_exchange_disable": (C.c_int, [VP]),
     "rs_create": (C.c_int, [C.POINTER(rs_tree), C.POINTER(rs_ranges), C.POINTER(rs_abstraction),
                             C.POINTER(rs_config), C.POINTER(VP)]),
     "rs_create_batch": (C.c_int, [C.POINTER(rs_tree), C.POINTER(rs_ranges), C.POINTER(rs_abstraction),

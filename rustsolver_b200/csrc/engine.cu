@@ -182,9 +182,15 @@ struct Engine {
     uint64_t updates_global = 0;
     uint64_t discount_interval = 0, discount_cap = 0;
 
-    ~Engine() {
-        for (int r = 0; r < RS_MAX_PEERS; ++r)
+    void close_peers() {
+        for (int r = 0; r < RS_MAX_PEERS; ++r) {
             if (xch_peer_base[r] && r != plan.rank) cudaIpcCloseMemHandle(xch_peer_base[r]);
+            xch_peer_base[r] = nullptr;
+        }
+    }
+
+    ~Engine() {
+        close_peers();
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph) cudaGraphDestroy(graph);
         if (comm && nccl::g_api.CommDestroy) nccl::g_api.CommDestroy(comm);
@@ -796,7 +802,12 @@ int rs_exchange_import(rs_engine* e, const uint8_t* handles, uint32_t n_ranks) {
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + size_t(r) * RS_EXCHANGE_HANDLE_BYTES, sizeof(h));
         void* p = nullptr;
-        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        const cudaError_t ce = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) {  // all or nothing: unmap what was mapped, the engine keeps the NCCL path
+            cudaGetLastError();
+            E.close_peers();
+            return set_err(RS_ERR_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(ce));
+        }
         E.xch_peer_base[r] = p;
     }
     E.fused_exchange = true;
@@ -808,6 +819,26 @@ int rs_exchange_import(rs_engine* e, const uint8_t* handles, uint32_t n_ranks) {
     if (E.graph) {
         cudaGraphDestroy(E.graph);
         E.graph = nullptr;
+    }
+    return RS_OK;
+}
+
+int rs_exchange_disable(rs_engine* e) {
+    if (!e) return set_err(RS_ERR_INVALID, "null engine");
+    Engine& E = e->e;
+    CU(cudaSetDevice(E.device));
+    CU(cudaStreamSynchronize(E.stream));
+    E.close_peers();
+    if (E.fused_exchange) {  // back to two launches + ncclAllReduce: the captured graph has to go
+        E.fused_exchange = false;
+        if (E.graph_exec) {
+            cudaGraphExecDestroy(E.graph_exec);
+            E.graph_exec = nullptr;
+        }
+        if (E.graph) {
+            cudaGraphDestroy(E.graph);
+            E.graph = nullptr;
+        }
     }
     return RS_OK;
 }

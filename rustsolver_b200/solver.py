@@ -564,8 +564,18 @@ class Engine(_PlanOrEngine):
         mine = torch.tensor(list(self.exchange_export()), dtype=torch.uint8, device=device)
         allh = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
         dist.all_gather(allh, mine)
-        self.exchange_import([bytes(h.cpu().tolist()) for h in allh])
-        dist.barrier()
+        ok = 1
+        try:
+            self.exchange_import([bytes(h.cpu().tolist()) for h in allh])
+        except EngineError as e:  # no peer access between some pair of GPUs: every rank stays on the NCCL path
+            print(f"[rustsolver_b200] in-kernel exchange unavailable on this rank: {e}", flush=True)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            check(self._lib.rs_exchange_disable(self._h))
+            return False
+        return True
 
     def best_response(self):
         out = (C.c_double * 2)()
