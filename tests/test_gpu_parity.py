@@ -89,6 +89,36 @@ def test_bucketed_rows_many_to_one():
     util.lockstep(eng, orc, tree, n_free=1, n_locked=4, tol=TOL)
 
 
+@pytest.mark.parametrize("bucketed", [False, True])
+def test_wide_nodes_take_the_generic_path(bucketed):
+    """Three bet sizes and three raise sizes (config 3's action abstraction): nodes with five actions, more than the
+    four the register-resident task bodies are specialised for (task_down_generic / task_trav_generic)."""
+    o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.33, 0.66, 1.0]], [[2.0, 3.0, 4.0]])
+    n, tree = rb.build_game_tree(o)
+    widths = np.diff(tree.child_offset)[tree.type == 0]
+    assert widths.max() >= 5, widths.max()
+    r = o.ranges()
+    if bucketed:
+        k0 = util.bucket_keys_for(None, r, 1, 9, seed=8)
+        eng = rb.Engine(tree, r, o.board_mask, [rb.CardAbstraction(rb.RS_ABS_BUCKET_TABLE, bucket_table=k0)])
+        orc = OracleGame(tree, r, o.board_mask, keys=[k0])
+    else:
+        eng = rb.Engine(tree, r, o.board_mask)
+        orc = OracleGame(tree, r, o.board_mask)
+    util.lockstep(eng, orc, tree, n_free=2, n_locked=3, tol=TOL)
+    assert np.allclose(eng.best_response(), orc.best_response(), rtol=1e-4, atol=1e-4)
+    assert np.allclose(eng.average_value(), orc.average_value(), rtol=1e-4, atol=1e-4)
+
+
+def test_degenerate_ranges():
+    """One hand against three, one of them blocked by the other's cards on some run-outs; and identical one-hand ranges
+    that always collide (no compatible deal: every value is 0)."""
+    o = util.small_options("4d5dAs3c", ["AhAc", "KhKc,AhKd,7h6h"], [[0.5, 1.0]] * 2, [[3.0]] * 2)
+    tree, eng, orc = _pair(o)
+    util.lockstep(eng, orc, tree, n_free=2, n_locked=2, tol=TOL)
+    assert np.allclose(eng.best_response(), orc.best_response(), rtol=1e-4, atol=1e-4)
+
+
 def test_single_iteration_from_oracle_state():
     """Restart the GPU from the oracle's state every iteration: isolates one-step error from drift."""
     o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]], [[3.0]])
