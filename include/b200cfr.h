@@ -106,6 +106,9 @@ typedef struct rs_config {
     uint64_t discount_cap;
 } rs_config;
 #define RS_FLAG_NO_GRAPH 1u     /* launch kernels directly instead of replaying a CUDA graph */
+#define RS_FLAG_NO_CHAIN_SPLIT 2u /* keep one task per node on rounds with one or two boards (default: such rounds are
+                                     chains of dependent tasks and their node tasks are split so that each level of
+                                     the chain only waits for what it needs; results are identical either way) */
 #define RS_FLAG_OWN_REACH_AVG 2u /* weight strategy_sum by the player's own reach instead of the
                                     reference's counterfactual reach (cfr.rs:618-619) */
 

@@ -394,7 +394,7 @@ __device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const
         const int ck = nt.child[a].kind;
         if (c.pos4 < c.HoP) {
             if (ck == CK_FOLD || ck == CK_SHOWDOWN) *reinterpret_cast<float4*>(SM_X + slot * c.Hx + c.pos4) = v[a];
-            else stcg4(Rk.rbuf + (size_t(nt.child[a].buf) * Rk.n_boards + b) * c.HoP + c.pos4, v[a]);
+            else if (nt.child[a].buf >= 0) stcg4(Rk.rbuf + (size_t(nt.child[a].buf) * Rk.n_boards + b) * c.HoP + c.pos4, v[a]);
         }
         if (ck == CK_FOLD || ck == CK_SHOWDOWN) ++slot;
     }
@@ -458,7 +458,7 @@ __device__ __forceinline__ void task_down_generic(const TaskArgs& A, const Ctx& 
                 if (live) v = norm > 0.f ? r * fmaxf(slab[size_t(rows[i]) * n_act + a], 0.f) / norm : r / float(n_act);
                 const int ck = nt.child[a].kind;
                 if (ck == CK_FOLD || ck == CK_SHOWDOWN) SM_X[(slot++) * c.Hx + c.pos4 + i] = v;
-                else __stcg(Rk.rbuf + (size_t(nt.child[a].buf) * Rk.n_boards + b) * c.HoP + c.pos4 + i, v);
+                else if (nt.child[a].buf >= 0) __stcg(Rk.rbuf + (size_t(nt.child[a].buf) * Rk.n_boards + b) * c.HoP + c.pos4 + i, v);
             }
         }
     }
@@ -524,6 +524,23 @@ __device__ __forceinline__ void trav_terms(const TaskArgs& A, const Ctx& c, cons
     }
 }
 
+// mass / showdown terms of a traverser node: computed here (scan + per-hand terms), or, on chain rounds, read from the
+// two value buffers the node's TK_TRAV_TERMS task left
+__device__ __forceinline__ void trav_terms_or_load(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b,
+                                                   bool need_sd, float4& mass, float4& sd) {
+    if (!nt.pre_terms) {
+        trav_terms(A, c, nt, Rk, k, b, need_sd, mass, sd);
+        return;
+    }
+    mass = f4zero();
+    sd = f4zero();
+    if (c.pos4 < c.HpP) {
+        const float* m = Rk.cbuf + (size_t(nt.aux) * Rk.n_boards + b) * c.HpP + c.pos4;
+        mass = ldcg4(m);
+        if (need_sd) sd = ldcg4(m + size_t(Rk.n_boards) * c.HpP);
+    }
+}
+
 template <int MODE, int NA>
 __device__ __forceinline__ void task_trav(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b) {
     const DevRoundPlayer& Pp = Rk.rp[c.p];
@@ -536,7 +553,7 @@ __device__ __forceinline__ void task_trav(const TaskArgs& A, const Ctx& c, const
         need_sd |= (nt.child[a].kind == CK_SHOWDOWN);
     }
     float4 mass, sd;
-    trav_terms(A, c, nt, Rk, k, b, need_sd, mass, sd);
+    trav_terms_or_load(A, c, nt, Rk, k, b, need_sd, mass, sd);
     // child values that come from other tasks: loaded after the scan (held across it they cost registers the
     // 64-register build does not have: measured +2 %)
 #pragma unroll
@@ -671,7 +688,7 @@ __device__ __forceinline__ void task_trav_generic(const TaskArgs& A, const Ctx& 
         need_sd |= (ck == CK_SHOWDOWN);
     }
     float4 mass, sd;
-    trav_terms(A, c, nt, Rk, k, b, need_sd, mass, sd);
+    trav_terms_or_load(A, c, nt, Rk, k, b, need_sd, mass, sd);
     float* out = (nt.root_scatter ? Rk.sbuf : Rk.cbuf) + (size_t(nt.out) * Rk.n_boards + b) * c.HpP;
     if (c.pos4 < c.HpP) {
         *reinterpret_cast<float4*>(SM_X + c.pos4) = mass;
@@ -1021,6 +1038,18 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                         for (int r = 0; r < A.xch_world; ++r) acc = f4add(acc, ldcg4(src + size_t(r) * c.HpP));
                         stcg4(Rk.gathered + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4, acc);
                     }
+                }
+                break;
+            }
+            case TK_TRAV_TERMS: {  // chain rounds: the reach-only part of a traverser node, ahead of its children
+                bool need_sd = false;
+                for (int a = 0; a < nt.n_act; ++a) need_sd |= (nt.child[a].kind == CK_SHOWDOWN);
+                float4 mass, sd;
+                trav_terms(A, c, nt, Rk, k, b, need_sd, mass, sd);
+                if (c.pos4 < c.HpP) {
+                    float* m = Rk.cbuf + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4;
+                    stcg4(m, mass);
+                    stcg4(m + size_t(Rk.n_boards) * c.HpP, sd);
                 }
                 break;
             }

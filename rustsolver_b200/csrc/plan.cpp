@@ -163,6 +163,7 @@ struct TaskGen {
     std::vector<RSrc> rsrc;                 // per PNode: where its incoming opponent reach lives
     std::vector<int32_t> cbuf, tbuf;        // per PNode: value buffer / terminal-partial buffer
     std::vector<int32_t> down_task, up_task;  // per PNode: node-task index
+    std::vector<int32_t> terms_task, terms_buf;  // per PNode (traverser nodes of chain rounds): TK_TRAV_TERMS task, its first value buffer
     std::vector<int32_t> rbuf_producer[3];  // reach buffer id -> node-task index writing it
     std::vector<int32_t> leaf_rbuf[3];      // leaf id -> reach buffer (of the leaf's round) the child street reads
     std::vector<int32_t> leaf_gather[3];    // leaf id -> node-task index of its gather
@@ -173,6 +174,9 @@ struct TaskGen {
         int32_t pnode;
         int depth;
     };
+
+    // a round with one or two local boards is a chain of dependent tasks (tasks.h: TK_TRAV_TERMS)
+    bool chain_round(uint32_t k) const { return P->boards_local(k) <= 2 && !(P->flags & RS_FLAG_NO_CHAIN_SPLIT); }
 
     int32_t new_rbuf(uint32_t k) {
         rbuf_producer[k].push_back(-1);
@@ -250,6 +254,8 @@ struct TaskGen {
         tbuf.assign(N, -1);
         down_task.assign(N, -1);
         up_task.assign(N, -1);
+        terms_task.assign(N, -1);
+        terms_buf.assign(N, -1);
         const uint32_t R = P->n_rounds;
         std::vector<std::vector<int32_t>> seg_nodes[3];
         for (uint32_t k = 0; k < R; ++k) {
@@ -324,6 +330,29 @@ struct TaskGen {
                             }
                         }
                         tl.max_terminal = std::max(tl.max_terminal, nterm);
+                        if (chain_round(k) && nterm > 0 && nterm < n.children.size()) {
+                            // chain round: the next level only waits for the child reach, so that goes first and
+                            // alone; a second task values the terminal children
+                            NodeTask reach = t;
+                            reach.out = -1;
+                            pend.push_back({reach, id, n.depth});
+                            for (size_t a = 0; a < n.children.size(); ++a)
+                                if (t.child[a].kind == CK_ACTION || t.child[a].kind == CK_CHANCE) t.child[a].buf = -1;  // not written again
+                        }
+                        pend.push_back({t, id, n.depth});
+                    } else if (n.kind == PK_ACTION && n.player == trav && chain_round(k)) {
+                        // chain round: scan + per-hand terms of the traverser node as soon as its reach exists
+                        NodeTask t = blank(TK_TRAV_TERMS, k);
+                        t.n_act = uint8_t(n.children.size());
+                        t.an_index = n.an_index;
+                        t.out = new_cbuf(k);  // mass; the showdown terms go to the next buffer
+                        (void)new_cbuf(k);
+                        for (size_t a = 0; a < n.children.size(); ++a) {
+                            const PNode& cn = P->nodes[n.children[a]];
+                            t.child[a].buf = -1;
+                            t.child[a].kind = cn.kind == PK_FOLD ? CK_FOLD : (cn.kind == PK_SHOWDOWN ? CK_SHOWDOWN : CK_VALUE);
+                        }
+                        terms_buf[id] = t.out;
                         pend.push_back({t, id, n.depth});
                     }
                 }
@@ -338,10 +367,13 @@ struct TaskGen {
                     const uint32_t ti = emit(t);
                     rbuf_producer[k][t.aux] = int32_t(ti);
                     down_task[pe.pnode] = int32_t(ti);
+                } else if (t.kind == TK_TRAV_TERMS) {
+                    if (!add_rin_dep(t, rsrc[pe.pnode], k)) return false;
+                    terms_task[pe.pnode] = int32_t(emit(t));
                 } else {
                     if (!add_rin_dep(t, rsrc[pe.pnode], k)) return false;
                     const uint32_t ti = emit(t);
-                    down_task[pe.pnode] = int32_t(ti);
+                    down_task[pe.pnode] = int32_t(ti);  // of a split node: the task emitted last, the one with the terminal values
                     for (int a = 0; a < t.n_act; ++a)
                         if (t.child[a].buf >= 0) rbuf_producer[k][t.child[a].buf] = int32_t(ti);
                 }
@@ -410,7 +442,13 @@ struct TaskGen {
                     if (!add_dep(t, leaf_gather[k][n.leaf_id], DK_SAME_BOARD)) return false;
                 } else {
                     if (t.kind == TK_UP_TRAV) {
-                        if (!add_rin_dep(t, rsrc[pe.pnode], uint32_t(k))) return false;
+                        if (terms_task[pe.pnode] >= 0) {  // chain round: the scan and the terms were done by TK_TRAV_TERMS
+                            t.pre_terms = 1;
+                            t.aux = terms_buf[pe.pnode];
+                            if (!add_dep(t, terms_task[pe.pnode], DK_SAME_BOARD)) return false;
+                        } else if (!add_rin_dep(t, rsrc[pe.pnode], uint32_t(k))) {
+                            return false;
+                        }
                     } else {
                         t.r_in = RIN_INITIAL;
                         t.aux = tbuf[pe.pnode];

@@ -15,6 +15,12 @@
 //                  (cfr.rs:502-522)
 //   TK_ROOT_SHOWDOWN / TK_CHANCE_DOWN / TK_CHANCE_UP   street roots created by the all-in run-out
 //                  expansion (a bare showdown, or a pass-through chance node)
+//   TK_TRAV_TERMS  traverser action node of a CHAIN round (a round with one or two boards, where the traversal is
+//                  a chain of dependent tasks): the part of TK_UP_TRAV that only needs the opponent reach -- the
+//                  scan and the per-hand mass / showdown terms -- runs as its own task during the down pass and
+//                  leaves two vectors for the TK_UP_TRAV task, which is then short.  On chain rounds opponent nodes
+//                  are split the same way: one TK_DOWN task writes the child reach (what the next level waits
+//                  for), a second one values the terminal children.
 #pragma once
 #include <cstdint>
 
@@ -27,7 +33,8 @@ enum TaskKind : uint8_t {
     TK_GATHER = 3,
     TK_ROOT_SHOWDOWN = 4,
     TK_CHANCE_DOWN = 5,
-    TK_CHANCE_UP = 6
+    TK_CHANCE_UP = 6,
+    TK_TRAV_TERMS = 7
 };
 enum ChildKind : uint8_t {
     CK_ACTION = 0,    // TK_DOWN: non-terminal child, buf = reach buffer written for it
@@ -79,8 +86,9 @@ struct NodeTask {
     int32_t dep[MAX_TASK_DEPS];      // producers: node-task index in the plan, first ticket once uploaded
     uint8_t dep_kind[MAX_TASK_DEPS]; // DepKind
     TaskChild child[MAX_TASK_CHILDREN];
+    uint32_t pre_terms;  // TK_UP_TRAV: 1 = mass and showdown terms come from value buffers aux, aux + 1 (TK_TRAV_TERMS)
 };
-static_assert(sizeof(NodeTask) == 8 + 4 * 8 + 4 * MAX_TASK_DEPS + MAX_TASK_DEPS + 12 * MAX_TASK_CHILDREN, "NodeTask layout");
+static_assert(sizeof(NodeTask) == 8 + 4 * 8 + 4 * MAX_TASK_DEPS + MAX_TASK_DEPS + 12 * MAX_TASK_CHILDREN + 4, "NodeTask layout");
 static_assert(sizeof(NodeTask) % 4 == 0, "NodeTask is copied to shared memory as words");
 
 // Per-hand record of the traverser on one board (16 bytes, one 128-bit load), local hand order:

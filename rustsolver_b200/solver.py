@@ -24,6 +24,7 @@ from ._lib import (EngineError, check, f32p, f64p, i32p, rs_abstraction, rs_conf
 
 RS_ABS_NONE, RS_ABS_ISOMORPHIC, RS_ABS_CLUSTER_ARR, RS_ABS_BUCKET_TABLE = 0, 1, 2, 3
 RS_FLAG_NO_GRAPH = 1
+RS_FLAG_NO_CHAIN_SPLIT = 2
 NODE_ACTION, NODE_TERMINAL, NODE_PUBLIC_CHANCE, NODE_PRIVATE_CHANCE = 0, 1, 2, 3
 TERM_ALLIN, TERM_SHOWDOWN, TERM_UNCONTESTED = 0, 1, 2
 ACTION_NAMES = {0: "Bet", 1: "Raise", 2: "Check", 3: "Call", 4: "Fold"}

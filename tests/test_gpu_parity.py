@@ -61,6 +61,24 @@ def test_no_graph_matches_graph():
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])  # bit-reproducible
 
 
+def test_chain_split_is_bit_identical():
+    """Rounds with one or two boards run with split node tasks (TK_TRAV_TERMS, reach-first TK_DOWN); the flag
+    RS_FLAG_NO_CHAIN_SPLIT keeps one task per node.  Same arithmetic in the same order: identical tables."""
+    o = util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]] * 2, [[3.0]] * 2)
+    n, tree = rb.build_game_tree(o)
+    r = o.ranges()
+    e1 = rb.Engine(tree, r, o.board_mask)
+    e2 = rb.Engine(tree, r, o.board_mask, flags=rb.RS_FLAG_NO_CHAIN_SPLIT)
+    e1.iterate(5)
+    e2.iterate(5)
+    st = e1.stats()
+    nb = [st.n_boards[k] for k in range(st.n_rounds)]
+    for an, b in util.all_slabs(tree, nb):
+        x, y = e1.read_infoset(an, b), e2.read_infoset(an, b)
+        assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]), (an, b)
+    assert e1.best_response() == e2.best_response()
+
+
 def test_turn_river_small_ranges():
     o = util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]] * 2, [[3.0]] * 2)
     tree, eng, orc = _pair(o)
