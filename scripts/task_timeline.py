@@ -17,7 +17,7 @@ eng._lib.rs_debug_task_timing(eng._h, p64, 1)
 # so profile a single EVAL traversal pair is not the CFR kernel; instead run iterate(1) and report both traversals merged
 eng.iterate(1)
 eng._lib.rs_debug_task_timing(eng._h, p64, 1)
-kinds = ['DOWN', 'UP_OPP', 'UP_TRAV', 'GATHER', 'ROOT_SD', 'CH_DOWN', 'CH_UP', '?']
+kinds = ['DOWN', 'UP_OPP', 'UP_TRAV', 'GATHER', 'ROOT_SD', 'CH_DOWN', 'CH_UP', 'TRAV_TERMS']
 rows = []
 for k in range(8):
     for r in range(3):

@@ -16,7 +16,7 @@ iters = 10
 eng.iterate(iters)
 eng._lib.rs_debug_task_timing(eng._h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), 1)
 st = eng.stats()
-kinds = ['DOWN', 'UP_OPP', 'UP_TRAV', 'GATHER', 'ROOT_SD', 'CH_DOWN', 'CH_UP', '?']
+kinds = ['DOWN', 'UP_OPP', 'UP_TRAV', 'GATHER', 'ROOT_SD', 'CH_DOWN', 'CH_UP', 'TRAV_TERMS']
 print(name, 'ms/iter', st.device_ms / st.iterations)
 tot = 0
 for k in range(8):

@@ -14,7 +14,7 @@ p64 = buf.ctypes.data_as(C.POINTER(C.c_uint64))
 eng._lib.rs_debug_task_timing(eng._h, p64, 1)
 eng.iterate(1)
 eng._lib.rs_debug_task_timing(eng._h, p64, 1)
-kinds = ['DOWN', 'UP_OPP', 'UP_TRAV', 'GATHER', 'ROOT_SD', 'CH_DOWN', 'CH_UP', '?']
+kinds = ['DOWN', 'UP_OPP', 'UP_TRAV', 'GATHER', 'ROOT_SD', 'CH_DOWN', 'CH_UP', 'TRAV_TERMS']
 st = eng.stats()
 print(name, 'ms/iter', st.device_ms / st.iterations, 'n action nodes', tree.n_actions)
 for k in range(8):
