@@ -6,6 +6,8 @@
 #include <numeric>
 #include <unordered_map>
 
+#include <cstdlib>
+
 #include "hand_indexer.h"
 #include "poker.h"
 
@@ -176,7 +178,14 @@ struct TaskGen {
     };
 
     // a round with one or two local boards is a chain of dependent tasks (tasks.h: TK_TRAV_TERMS)
-    bool chain_round(uint32_t k) const { return P->boards_local(k) <= 2 && !(P->flags & RS_FLAG_NO_CHAIN_SPLIT); }
+    // RS_CHAIN_BOARDS overrides the board count up to which a round is treated as a chain (tuning)
+    bool chain_round(uint32_t k) const {
+        static const uint32_t limit = [] {
+            const char* e = getenv("RS_CHAIN_BOARDS");
+            return e ? uint32_t(atoi(e)) : 2u;
+        }();
+        return P->boards_local(k) <= limit && !(P->flags & RS_FLAG_NO_CHAIN_SPLIT);
+    }
 
     int32_t new_rbuf(uint32_t k) {
         rbuf_producer[k].push_back(-1);
