@@ -162,6 +162,13 @@ int rs_gpu_index_hands(uint32_t n_board_cards, const uint8_t* cards, size_t n, u
 int rs_kmeans_assign(const float* points, size_t n, uint32_t dim, const float* centers, uint32_t k, uint32_t dist_kind,
                      uint32_t* cluster, float* min_dist, double* inertia, float* kernel_ms);
 int rs_histogram_distances(const float* p, const float* q, size_t n, uint32_t dim, uint32_t dist_kind, float* out);
+/* Kmeans::fit_regular (kmeans.rs:497-599): `rounds` rounds (the reference runs 10) of Lloyd's algorithm with its
+ * Hamerly-style bounds -- init_s (265-284) and reassign_clusters (285-334) on the device, the centre update on the host
+ * in the reference's summation order.  centers [k][dim] in/out (k >= 2), cluster [n] out, inertia (may be NULL) = the
+ * reference's final figure, the mean upper bound.  Deterministic where the reference races (its s vector and bounds
+ * are restated as written, including s not being reset between rounds). */
+int rs_kmeans_fit_regular(const float* points, size_t n, uint32_t dim, float* centers, uint32_t k, uint32_t dist_kind,
+                          uint32_t rounds, uint32_t* cluster, float* inertia);
 int rs_kmeans_update_min_dists(const float* points, size_t n, uint32_t dim, const float* new_center, uint32_t dist_kind,
                                float* min_dists);
 

@@ -89,6 +89,8 @@ def _abs_lib():
         lib.orc_kmeans_predict.restype = C.c_double
         lib.orc_kmeans_predict.argtypes = [f32p, C.c_int64, C.c_int, f32p, C.c_int, C.c_int, u32p, f32p]
         lib.orc_update_min_dists.argtypes = [f32p, C.c_int64, C.c_int, f32p, C.c_int, f32p]
+        lib.orc_kmeans_fit_regular.restype = C.c_float
+        lib.orc_kmeans_fit_regular.argtypes = [f32p, C.c_int64, C.c_int, f32p, C.c_int, C.c_int, C.c_int, u32p]
         lib._abs_ready = True
     return lib
 
@@ -116,6 +118,16 @@ def kmeans_predict(points, centers, kind: int = 0):
     inertia = _abs_lib().orc_kmeans_predict(x.ctypes.data_as(f32p), len(x), x.shape[1], c.ctypes.data_as(f32p), len(c), kind,
                                            cl.ctypes.data_as(u32p), md.ctypes.data_as(f32p))
     return cl, md, float(inertia)
+
+
+def kmeans_fit_regular(points, centers, kind: int = 0, rounds: int = 10):
+    """Kmeans::fit_regular (kmeans.rs:497-599): (cluster[n], new centers, inertia = mean upper bound)."""
+    x = np.ascontiguousarray(points, dtype=np.float32)
+    c = np.array(centers, dtype=np.float32, copy=True, order="C")
+    cl = np.zeros(len(x), dtype=np.uint32)
+    inertia = _abs_lib().orc_kmeans_fit_regular(x.ctypes.data_as(f32p), len(x), x.shape[1], c.ctypes.data_as(f32p), len(c), kind, rounds,
+                                               cl.ctypes.data_as(u32p))
+    return cl, c, float(inertia)
 
 
 def update_min_dists(points, new_center, min_dists, kind: int = 0):

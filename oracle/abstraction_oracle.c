@@ -113,3 +113,109 @@ void orc_update_min_dists(const float* points, int64_t n, int dim, const float* 
         if (d < min_dists[i]) min_dists[i] = d;
     }
 }
+
+/* Kmeans::fit_regular (kmeans.rs:497-599): ten rounds of Lloyd's algorithm with Hamerly-style bounds.
+ *   init_s             kmeans.rs:265-284   s[i] = min(s[i], min_{j != i} dist(c_i, c_j)) / 2 -- s is NOT reset between
+ *                                          rounds in the reference (it is created once, kmeans.rs:513), restated as is
+ *   reassign_clusters  kmeans.rs:285-334   per point: skip when the upper bound is within max(s[c], lower bound); else
+ *                                          tighten the upper bound, else scan every other centre
+ *   centre update      kmeans.rs:522-543   sums in point order (f32), bins with positive mass divided by the count
+ *   bounds update      kmeans.rs:545-575   upper += movement of the own centre, lower -= the largest movement (the
+ *                                          second largest for the points of the centre that moved most)
+ * centers [k][dim] in/out; cluster [n] out (starts at 0 like the reference, kmeans.rs:511); returns the reference's
+ * final "inertia" = mean upper bound (f32 sum in point order / n). */
+float orc_kmeans_fit_regular(const float* points, int64_t n, int dim, float* centers, int k, int kind, int rounds, uint32_t* cluster) {
+    float* s = (float*)malloc(sizeof(float) * (size_t)k);
+    float* lo = (float*)malloc(sizeof(float) * (size_t)n);
+    float* hi = (float*)malloc(sizeof(float) * (size_t)n);
+    float* mass = (float*)malloc(sizeof(float) * (size_t)k * dim);
+    float* count = (float*)malloc(sizeof(float) * (size_t)k);
+    float* move = (float*)malloc(sizeof(float) * (size_t)k);
+    for (int i = 0; i < k; ++i) s[i] = 3.40282347e+38f; /* f32::MAX */
+    for (int64_t i = 0; i < n; ++i) {
+        cluster[i] = 0;
+        lo[i] = 0.0f;
+        hi[i] = 3.40282347e+38f;
+    }
+    for (int t = 0; t < rounds; ++t) {
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < k; ++i) { /* init_s */
+            float v = s[i];
+            for (int j = 0; j < k; ++j) {
+                if (i == j) continue;
+                float d = dist(centers + (size_t)i * dim, centers + (size_t)j * dim, dim, kind);
+                if (d < v) v = d;
+            }
+            s[i] = v / 2.0f;
+        }
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int64_t i = 0; i < n; ++i) { /* reassign_clusters */
+            const float* x = points + i * dim;
+            int min_cluster = (int)cluster[i];
+            float ucb = s[min_cluster] > lo[i] ? s[min_cluster] : lo[i]; /* f32::max */
+            if (hi[i] <= ucb) continue;
+            float u2 = dist(x, centers + (size_t)min_cluster * dim, dim, kind);
+            hi[i] = u2;
+            if (hi[i] <= ucb) continue;
+            float l2 = 3.40282347e+38f;
+            for (int j = 0; j < k; ++j) {
+                if (j == min_cluster) continue;
+                float d2 = dist(x, centers + (size_t)j * dim, dim, kind);
+                if (d2 < u2) {
+                    l2 = u2;
+                    u2 = d2;
+                    min_cluster = j;
+                } else if (d2 < l2) {
+                    l2 = d2;
+                }
+            }
+            lo[i] = l2;
+            if ((int)cluster[i] != min_cluster) {
+                hi[i] = u2;
+                cluster[i] = (uint32_t)min_cluster;
+            }
+        }
+        memset(mass, 0, sizeof(float) * (size_t)k * dim);
+        memset(count, 0, sizeof(float) * (size_t)k);
+        for (int64_t j = 0; j < n; ++j) { /* sequential, like the reference */
+            count[cluster[j]] += 1.0f;
+            float* m = mass + (size_t)cluster[j] * dim;
+            const float* x = points + j * dim;
+            for (int b = 0; b < dim; ++b) m[b] += x[b];
+        }
+        for (int j = 0; j < k; ++j)
+            for (int b = 0; b < dim; ++b)
+                if (mass[(size_t)j * dim + b] > 0.0f) mass[(size_t)j * dim + b] /= count[j];
+        for (int j = 0; j < k; ++j) move[j] = dist(mass + (size_t)j * dim, centers + (size_t)j * dim, dim, kind);
+        int longest_idx = 0;
+        float longest = move[0], second = k > 1 ? move[1] : 0.0f;
+        if (k > 1 && longest < second) {
+            longest = move[1];
+            second = move[0];
+            longest_idx = 1;
+        }
+        for (int j = 2; j < k; ++j) {
+            if (longest < move[j]) {
+                second = longest;
+                longest = move[j];
+                longest_idx = j;
+            } else if (second < move[j]) {
+                second = move[j];
+            }
+        }
+        for (int64_t i = 0; i < n; ++i) {
+            hi[i] += move[cluster[i]];
+            lo[i] -= ((int)cluster[i] == longest_idx) ? second : longest;
+        }
+        memcpy(centers, mass, sizeof(float) * (size_t)k * dim);
+    }
+    float total = 0.0f;
+    for (int64_t i = 0; i < n; ++i) total += hi[i];
+    free(s);
+    free(lo);
+    free(hi);
+    free(mass);
+    free(count);
+    free(move);
+    return total / (float)n;
+}

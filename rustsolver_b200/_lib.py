@@ -67,6 +67,7 @@ ENGINE_API = {
     "rs_device_count": (C.c_int, []),
     "rs_nccl_unique_id": (C.c_int, [u8p]),
     "rs_kmeans_assign": (C.c_int, [f32p, C.c_size_t, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u32p, f32p, f64p, f32p]),
+    "rs_kmeans_fit_regular": (C.c_int, [f32p, C.c_size_t, C.c_uint32, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f32p]),
     "rs_histogram_distances": (C.c_int, [f32p, f32p, C.c_size_t, C.c_uint32, C.c_uint32, f32p]),
     "rs_kmeans_update_min_dists": (C.c_int, [f32p, C.c_size_t, C.c_uint32, f32p, C.c_uint32, f32p]),
     "rs_gpu_index_hands": (C.c_int, [C.c_uint32, u8p, C.c_size_t, u64p, f32p]),

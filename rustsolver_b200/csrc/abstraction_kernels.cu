@@ -144,6 +144,102 @@ __global__ void square_min_kernel(const float* __restrict__ d, size_t n, float* 
     if (v < md[i]) md[i] = v;
 }
 
+__device__ __forceinline__ float dist_dev(int kind, const float* a, int sa, const float* b, int sb, int n, float* p, float* q) {
+    return kind == RS_DIST_EMD_1D ? emd_1d_dev(a, sa, b, sb, n, p, q) : l2_dist_dev(a, sa, b, sb, n);
+}
+
+// init_s (kmeans.rs:265-284): s[i] = min(s[i], min_{j != i} dist(c_i, c_j)) / 2; one thread per centre
+__global__ void __launch_bounds__(ABS_THREADS) centre_half_min_kernel(const float* __restrict__ centers, int k, int dim, int kind,
+                                                                       float* __restrict__ s_io) {
+    extern __shared__ __align__(16) float raw[];
+    const Smem s = carve(raw, dim);
+    const int t = threadIdx.x;
+    const int i = blockIdx.x * ABS_THREADS + t;
+    const bool live = i < k;
+    if (live)
+        for (int e = 0; e < dim; ++e) s.x[e * ABS_THREADS + t] = __ldg(centers + size_t(i) * dim + e);
+    float v = live ? s_io[i] : 0.0f;
+    for (int j = 0; j < k; ++j) {
+        __syncthreads();
+        for (int e = t; e < dim; e += ABS_THREADS) s.centre[e] = __ldg(centers + size_t(j) * dim + e);
+        __syncthreads();
+        if (live && j != i) {
+            const float d = dist_dev(kind, s.x + t, ABS_THREADS, s.centre, 1, dim, s.p + t, s.q + t);
+            if (d < v) v = d;
+        }
+    }
+    if (live) s_io[i] = __fdiv_rn(v, 2.0f);
+}
+
+// reassign_clusters (kmeans.rs:285-334): Hamerly-style bounds; one thread per point
+__global__ void __launch_bounds__(ABS_THREADS) kmeans_reassign_kernel(const float* __restrict__ points, size_t n, int dim,
+                                                                       const float* __restrict__ centers, int k, int kind,
+                                                                       const float* __restrict__ s_half, uint32_t* __restrict__ cluster,
+                                                                       float* __restrict__ lo, float* __restrict__ hi) {
+    extern __shared__ __align__(16) float raw[];
+    const Smem s = carve(raw, dim);
+    const int t = threadIdx.x;
+    const size_t i = size_t(blockIdx.x) * ABS_THREADS + t;
+    const bool live = i < n;
+    const size_t base = size_t(blockIdx.x) * ABS_THREADS * dim;
+    const size_t avail = (n - size_t(blockIdx.x) * ABS_THREADS < size_t(ABS_THREADS) ? n - size_t(blockIdx.x) * ABS_THREADS : size_t(ABS_THREADS)) * dim;
+    for (size_t e = t; e < avail; e += ABS_THREADS) s.x[(e % dim) * ABS_THREADS + e / dim] = __ldg(points + base + e);
+    __syncthreads();
+    int min_cluster = 0;
+    const int ci = live ? int(cluster[i]) : 0;
+    float u2 = 0.0f, l2 = 3.40282347e+38f, hi_i = 0.0f;
+    bool scan = false;
+    if (live) {
+        min_cluster = ci;
+        const float lo_i = lo[i];
+        hi_i = hi[i];
+        const float sc = s_half[ci];
+        const float ucb = sc > lo_i ? sc : lo_i;
+        if (!(hi_i <= ucb)) {
+            u2 = dist_dev(kind, s.x + t, ABS_THREADS, centers + size_t(ci) * dim, 1, dim, s.p + t, s.q + t);  // own centre: straight from memory
+            hi_i = u2;
+            scan = !(hi_i <= ucb);
+        }
+    }
+    if (__syncthreads_or(scan ? 1 : 0)) {  // somebody in the block has to look at every other centre
+        for (int j = 0; j < k; ++j) {
+            __syncthreads();
+            for (int e = t; e < dim; e += ABS_THREADS) s.centre[e] = __ldg(centers + size_t(j) * dim + e);
+            __syncthreads();
+            if (scan && j != min_cluster) {
+                const float d2 = dist_dev(kind, s.x + t, ABS_THREADS, s.centre, 1, dim, s.p + t, s.q + t);
+                if (d2 < u2) {
+                    l2 = u2;
+                    u2 = d2;
+                    min_cluster = j;
+                } else if (d2 < l2) {
+                    l2 = d2;
+                }
+            }
+        }
+    }
+    if (live) {
+        if (scan) {
+            lo[i] = l2;
+            if (ci != min_cluster) {
+                hi_i = u2;
+                cluster[i] = uint32_t(min_cluster);
+            }
+        }
+        hi[i] = hi_i;
+    }
+}
+
+// bounds update after the centres moved (kmeans.rs:566-575)
+__global__ void bounds_update_kernel(const uint32_t* __restrict__ cluster, size_t n, const float* __restrict__ move, int longest_idx,
+                                     float longest, float second, float* __restrict__ lo, float* __restrict__ hi) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = int(cluster[i]);
+    hi[i] = __fadd_rn(hi[i], move[c]);
+    lo[i] = __fsub_rn(lo[i], c == longest_idx ? second : longest);
+}
+
 size_t smem_bytes(int dim) { return (size_t((dim + 3) & ~3) + 3 * size_t(dim) * ABS_THREADS) * sizeof(float); }
 
 template <class T>
@@ -230,6 +326,84 @@ bool gpu_pair_dist(const float* p, const float* q, bool q_shared, size_t n, uint
         ABS_CU(cudaMemcpy(min_dists_io, d_md.p, n * sizeof(float), cudaMemcpyDeviceToHost));
     }
     if (out) ABS_CU(cudaMemcpy(out, d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return true;
+}
+
+bool gpu_kmeans_fit_regular(const float* points, size_t n, uint32_t dim, float* centers, uint32_t k, uint32_t kind, uint32_t rounds,
+                            uint32_t* cluster, float* inertia, std::string* err) {
+    Dev<float> d_pts, d_ctr, d_new, d_s, d_lo, d_hi, d_move;
+    Dev<uint32_t> d_cl;
+    ABS_CU(d_pts.alloc(n * dim));
+    ABS_CU(d_ctr.alloc(size_t(k) * dim));
+    ABS_CU(d_new.alloc(size_t(k) * dim));
+    ABS_CU(d_s.alloc(k));
+    ABS_CU(d_lo.alloc(n));
+    ABS_CU(d_hi.alloc(n));
+    ABS_CU(d_move.alloc(k));
+    ABS_CU(d_cl.alloc(n));
+    const float fmax = 3.40282347e+38f;
+    std::vector<float> h_s(k, fmax), h_hi(n, fmax), h_mass(size_t(k) * dim), h_count(k), h_move(k);
+    std::vector<uint32_t> h_cl(n, 0);
+    ABS_CU(cudaMemcpy(d_pts.p, points, n * dim * sizeof(float), cudaMemcpyHostToDevice));
+    ABS_CU(cudaMemcpy(d_ctr.p, centers, size_t(k) * dim * sizeof(float), cudaMemcpyHostToDevice));
+    ABS_CU(cudaMemcpy(d_s.p, h_s.data(), k * sizeof(float), cudaMemcpyHostToDevice));
+    ABS_CU(cudaMemcpy(d_hi.p, h_hi.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    ABS_CU(cudaMemset(d_lo.p, 0, std::max<size_t>(n, 1) * sizeof(float)));
+    ABS_CU(cudaMemset(d_cl.p, 0, std::max<size_t>(n, 1) * sizeof(uint32_t)));
+    const size_t smem = smem_bytes(int(dim));
+    ABS_CU(cudaFuncSetAttribute(centre_half_min_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    ABS_CU(cudaFuncSetAttribute(kmeans_reassign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    ABS_CU(cudaFuncSetAttribute(pair_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const unsigned pblocks = unsigned((n + ABS_THREADS - 1) / ABS_THREADS), cblocks = unsigned((k + ABS_THREADS - 1) / ABS_THREADS);
+    for (uint32_t t = 0; t < rounds; ++t) {
+        centre_half_min_kernel<<<cblocks, ABS_THREADS, smem>>>(d_ctr.p, int(k), int(dim), int(kind), d_s.p);
+        if (n) kmeans_reassign_kernel<<<pblocks, ABS_THREADS, smem>>>(d_pts.p, n, int(dim), d_ctr.p, int(k), int(kind), d_s.p, d_cl.p, d_lo.p, d_hi.p);
+        ABS_CU(cudaGetLastError());
+        ABS_CU(cudaMemcpy(h_cl.data(), d_cl.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        // centre update: f32 sums in point order like the reference (kmeans.rs:522-543); O(n * dim), not the hot part
+        std::fill(h_mass.begin(), h_mass.end(), 0.0f);
+        std::fill(h_count.begin(), h_count.end(), 0.0f);
+        for (size_t j = 0; j < n; ++j) {
+            h_count[h_cl[j]] += 1.0f;
+            float* m = &h_mass[size_t(h_cl[j]) * dim];
+            const float* x = points + j * dim;
+            for (uint32_t b = 0; b < dim; ++b) m[b] += x[b];
+        }
+        for (uint32_t j = 0; j < k; ++j)
+            for (uint32_t b = 0; b < dim; ++b)
+                if (h_mass[size_t(j) * dim + b] > 0.0f) h_mass[size_t(j) * dim + b] /= h_count[j];
+        ABS_CU(cudaMemcpy(d_new.p, h_mass.data(), size_t(k) * dim * sizeof(float), cudaMemcpyHostToDevice));
+        pair_dist_kernel<<<cblocks, ABS_THREADS, smem>>>(d_new.p, d_ctr.p, dim, k, int(dim), int(kind), d_move.p);  // movement of every centre
+        ABS_CU(cudaGetLastError());
+        ABS_CU(cudaMemcpy(h_move.data(), d_move.p, k * sizeof(float), cudaMemcpyDeviceToHost));
+        int longest_idx = 0;
+        float longest = h_move[0], second = h_move[1];
+        if (longest < second) {
+            longest = h_move[1];
+            second = h_move[0];
+            longest_idx = 1;
+        }
+        for (uint32_t j = 2; j < k; ++j) {
+            if (longest < h_move[j]) {
+                second = longest;
+                longest = h_move[j];
+                longest_idx = int(j);
+            } else if (second < h_move[j]) {
+                second = h_move[j];
+            }
+        }
+        if (n) bounds_update_kernel<<<unsigned((n + 255) / 256), 256>>>(d_cl.p, n, d_move.p, longest_idx, longest, second, d_lo.p, d_hi.p);
+        ABS_CU(cudaGetLastError());
+        ABS_CU(cudaMemcpy(d_ctr.p, d_new.p, size_t(k) * dim * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+    ABS_CU(cudaMemcpy(centers, d_ctr.p, size_t(k) * dim * sizeof(float), cudaMemcpyDeviceToHost));
+    ABS_CU(cudaMemcpy(cluster, d_cl.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    ABS_CU(cudaMemcpy(h_hi.data(), d_hi.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (inertia) {
+        float total = 0.0f;  // f32, point order (kmeans.rs:590)
+        for (size_t i = 0; i < n; ++i) total += h_hi[i];
+        *inertia = n ? total / float(n) : 0.0f;
+    }
     return true;
 }
 

@@ -15,4 +15,9 @@ bool gpu_kmeans_assign(const float* points, size_t n, uint32_t dim, const float*
 bool gpu_pair_dist(const float* p, const float* q, bool q_shared, size_t n, uint32_t dim, uint32_t kind, float* out, float* min_dists_io,
                    std::string* err);
 
+// Kmeans::fit_regular (kmeans.rs:497-599): `rounds` (the reference: 10) rounds of init_s + reassign_clusters on the
+// device, centre update on the host in the reference's summation order; centers in/out, cluster out (k >= 2)
+bool gpu_kmeans_fit_regular(const float* points, size_t n, uint32_t dim, float* centers, uint32_t k, uint32_t kind, uint32_t rounds,
+                            uint32_t* cluster, float* inertia, std::string* err);
+
 }  // namespace rs

@@ -724,6 +724,17 @@ int rs_kmeans_assign(const float* points, size_t n, uint32_t dim, const float* c
     return RS_OK;
 }
 
+int rs_kmeans_fit_regular(const float* points, size_t n, uint32_t dim, float* centers, uint32_t k, uint32_t dist_kind, uint32_t rounds,
+                          uint32_t* cluster, float* inertia) {
+    int rc = abstraction_args_ok(points, centers, dim, dist_kind);
+    if (rc != RS_OK) return rc;
+    if (!cluster) return set_err(RS_ERR_INVALID, "null argument");
+    if (k < 2) return set_err(RS_ERR_INVALID, "fit_regular needs at least two centres (kmeans.rs:547-548 reads center_movement[1])");
+    std::string err;
+    if (!gpu_kmeans_fit_regular(points, n, dim, centers, k, dist_kind, rounds, cluster, inertia, &err)) return set_err(RS_ERR_CUDA, err);
+    return RS_OK;
+}
+
 int rs_histogram_distances(const float* p, const float* q, size_t n, uint32_t dim, uint32_t dist_kind, float* out) {
     int rc = abstraction_args_ok(p, q, dim, dist_kind);
     if (rc != RS_OK) return rc;

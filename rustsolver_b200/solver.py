@@ -236,6 +236,19 @@ def kmeans_assign(points: np.ndarray, centers: np.ndarray, dist: int = RS_DIST_E
     return (cl, md, float(inertia.value), float(ms.value)) if return_ms else (cl, md, float(inertia.value))
 
 
+def kmeans_fit_regular(points: np.ndarray, centers: np.ndarray, dist: int = RS_DIST_EMD_1D, rounds: int = 10):
+    """Kmeans::fit_regular (gen_abstraction/kmeans.rs:497-599) on the GPU: (cluster[n], new centers[k][dim], inertia)."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(points, dtype=np.float32)
+    c = np.array(centers, dtype=np.float32, copy=True, order="C")
+    assert x.ndim == 2 and c.ndim == 2 and x.shape[1] == c.shape[1]
+    cl = np.zeros(len(x), dtype=np.uint32)
+    inertia = C.c_float(0.0)
+    check(lib.rs_kmeans_fit_regular(_ptr(x, f32p), len(x), x.shape[1], _ptr(c, f32p), len(c), dist, rounds, _ptr(cl, u32p),
+                                    C.byref(inertia)))
+    return cl, c, float(inertia.value)
+
+
 def histogram_distances(p: np.ndarray, q: np.ndarray, dist: int = RS_DIST_EMD_1D) -> np.ndarray:
     """out[i] = emd_1d(p[i], q[i]) (emd.rs:54-113) or l2_dist (kmeans.rs:622-630) on the GPU."""
     lib = _lib.load()

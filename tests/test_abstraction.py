@@ -68,3 +68,46 @@ def test_update_min_dists():
     md = oracle.update_min_dists(x, c, md0, 0)
     want = np.minimum(md0, np.array([np.float32(oracle.emd_1d(x[i], c)) ** 2 for i in range(50)], dtype=np.float32))
     assert np.array_equal(md, want)
+
+
+def _lloyd_reference(x, c, kind, rounds):
+    """Plain Lloyd rounds with the reference's centre update (f32 sums in point order, kmeans.rs:522-543)."""
+    c = c.copy()
+    for _ in range(rounds):
+        cl, _, _ = oracle.kmeans_predict(x, c, kind)
+        mass = np.zeros_like(c)
+        count = np.zeros(len(c), dtype=np.float32)
+        for j in range(len(x)):
+            count[cl[j]] += np.float32(1.0)
+            mass[cl[j]] += x[j]
+        for j in range(len(c)):
+            pos = mass[j] > 0
+            mass[j][pos] = mass[j][pos] / count[j]
+        c = mass
+    return cl, c
+
+
+def test_fit_regular_first_round_is_a_full_assignment():
+    """Round one: every upper bound is f32::MAX, so every point scans every centre -> Kmeans::predict, then the means."""
+    rng = np.random.default_rng(21)
+    x = K.random_histograms(rng, 300, 30)
+    c0 = K.random_histograms(rng, 12, 30)
+    for kind in (0, 1):
+        cl, c1, inertia = oracle.kmeans_fit_regular(x, c0, kind, rounds=1)
+        want_cl, want_c = _lloyd_reference(x, c0, kind, 1)
+        assert np.array_equal(cl, want_cl)
+        assert np.array_equal(c1, want_c)
+        assert np.isfinite(inertia)
+
+
+def test_fit_regular_with_a_metric_equals_plain_lloyd():
+    """With l2_dist (a metric) the Hamerly bounds of kmeans.rs:285-334 only skip work: ten rounds give the assignments
+    and centres of ten plain Lloyd rounds."""
+    rng = np.random.default_rng(22)
+    x = K.random_histograms(rng, 250, 16)
+    c0 = x[rng.choice(len(x), 9, replace=False)].copy()
+    cl, c, inertia = oracle.kmeans_fit_regular(x, c0, 1, rounds=10)
+    want_cl, want_c = _lloyd_reference(x, c0, 1, 10)
+    assert np.array_equal(cl, want_cl)
+    assert np.allclose(c, want_c, rtol=0, atol=0)
+    assert inertia >= 0

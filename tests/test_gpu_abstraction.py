@@ -53,3 +53,17 @@ def test_update_min_dists_matches():
     c = K.random_histograms(rng, 1, 30)[0]
     md0 = (rng.random(3000) * 30).astype(np.float32)
     assert np.array_equal(rb.kmeans_update_min_dists(x, c, md0), oracle.update_min_dists(x, c, md0, 0))
+
+
+@pytest.mark.parametrize("kind", [rb.RS_DIST_EMD_1D, rb.RS_DIST_L2])
+def test_fit_regular_matches_the_cpu_restatement(kind):
+    """Kmeans::fit_regular (kmeans.rs:497-599): ten rounds with the reference's bounds, device vs CPU, bit for bit."""
+    rng = np.random.default_rng(31 + kind)
+    x = K.random_histograms(rng, 3000, 30)
+    c0 = x[rng.choice(len(x), 20, replace=False)].copy()
+    cl, c, inertia = rb.kmeans_fit_regular(x, c0, kind, rounds=10)
+    ocl, oc, oin = oracle.kmeans_fit_regular(x, c0, kind, rounds=10)
+    assert np.array_equal(cl, ocl)
+    assert np.array_equal(c, oc)
+    assert inertia == oin
+    assert len(np.unique(cl)) > 5
