@@ -109,8 +109,13 @@ typedef struct rs_config {
 #define RS_FLAG_NO_CHAIN_SPLIT 2u /* keep one task per node on rounds with one or two boards (default: such rounds are
                                      chains of dependent tasks and their node tasks are split so that each level of
                                      the chain only waits for what it needs; results are identical either way) */
-#define RS_FLAG_OWN_REACH_AVG 2u /* weight strategy_sum by the player's own reach instead of the
-                                    reference's counterfactual reach (cfr.rs:618-619) */
+#define RS_FLAG_STREET_KERNEL 4u /* EXPERIMENTAL: walk the final betting round with the fused street kernel (one CTA per board
+                                    and run of street segments, terminals valued by one sorted sweep with running per-card
+                                    sums, csrc/street_kernel.cu) instead of the per-(node, board) dataflow tasks.  Same
+                                    values up to fp32 rounding; measured slower than the task kernel,
+                                    so it is off by default.  Lossy (bucketed) final rounds and nodes wider than 5 actions
+                                    always take the task path */
+#define RS_FLAG_ALL (RS_FLAG_NO_GRAPH | RS_FLAG_NO_CHAIN_SPLIT | RS_FLAG_STREET_KERNEL) /* rs_create rejects other bits */
 
 typedef struct rs_engine rs_engine;
 
@@ -255,11 +260,14 @@ int rs_set_range_weights(rs_engine* e, uint32_t player, const float* weights, si
 
 /* Kernel-level profile of ONE iteration launched kernel by kernel (no graph) with a CUDA event pair
  * around every launch on the engine's stream.  The iteration is a real one (tables are updated). */
-#define RS_KERNEL_TRAVERSAL 0 /* persistent task kernel: one traversal (or one phase of it when sharded) */
+#define RS_KERNEL_TRAVERSAL 0 /* persistent task kernel: the rounds above the final one (or one phase of them);
+                                 the whole traversal when the final round is not eligible for the street kernel */
+#define RS_KERNEL_STREET 1    /* fused final-street kernel: every board and street segment of the last betting round */
 #define RS_KERNEL_ALLREDUCE 3
 typedef struct rs_kernel_time {
     uint32_t kind;      /* RS_KERNEL_* */
-    uint32_t phase;     /* 0, or 1 for the part of a sharded traversal after the all-reduce */
+    uint32_t phase;     /* RS_KERNEL_TRAVERSAL: 0 = down pass above the final round, 1 = gathers + up pass,
+                           2 = the part of a sharded traversal after the all-reduce */
     uint32_t traverser;
     uint32_t grid;      /* CTAs launched */
     float ms;           /* CUDA-event duration */
@@ -293,6 +301,20 @@ int rs_plan_infoset_offset(const rs_plan* p, uint32_t an_index, uint32_t board_i
 int rs_plan_showdown_order(const rs_plan* p, uint32_t player, uint32_t board_id,
                            uint16_t* order_out, uint32_t* class_out, size_t cap,
                            uint32_t* n_live_out);
+
+/* The final betting round as the fused street kernel sees it (csrc/street.h): out = {eligible, unit templates, max sweep
+ * warps per unit, max reach rows per unit, max value slots, segments, opponent-node ops, traverser-node ops}.  When the
+ * round is not eligible rs_last_error() says why (bucketed tables, a node wider than 5 actions, the flag). */
+int rs_plan_street_info(const rs_plan* p, uint32_t traverser, uint32_t out[8]);
+/* The event stream that drives the sorted sweep of `traverser` on a final-round board: per strength class, weakest
+ * first, a header word (n_read | n_add << 11), the traverser's hands of the class (reads), the opponent's (adds); an
+ * entry is position | card_a << 11 | card_b << 17 in the owner's board-local (strength-sorted) order.
+ * out == NULL: only the count. */
+int rs_plan_street_events(const rs_plan* p, uint32_t traverser, uint32_t board_id, uint32_t* out, size_t cap, uint32_t* n_out);
+/* The eight pieces the sweep of that board is cut into (several warps sweep one board): out[0..8] = first event word of
+ * piece q (out[8] = the word count), out[9..17] = first opponent position added, out[18..26] = first traverser position
+ * read.  Cuts fall on class boundaries. */
+int rs_plan_street_segments(const rs_plan* p, uint32_t traverser, uint32_t board_id, uint32_t out[27]);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ CSRC = ROOT / "rustsolver_b200" / "csrc"
 ENGINE_SO = ROOT / "rustsolver_b200" / "libb200cfr.so"
 ORACLE_SO = ROOT / "oracle" / "liborc.so"
 
-ENGINE_SOURCES = ["kernels.cu", "indexer_kernel.cu", "abstraction_kernels.cu", "engine.cu", "plan.cpp", "poker.cpp", "game.cpp", "hand_indexer.cpp",
+ENGINE_SOURCES = ["kernels.cu", "street_kernel.cu", "indexer_kernel.cu", "abstraction_kernels.cu", "engine.cu", "plan.cpp", "poker.cpp", "game.cpp", "hand_indexer.cpp",
                   "trainer.cpp", "host_api.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall,-O3"]
@@ -74,7 +74,7 @@ def build_oracle(force: bool = False) -> Path:
     if not force and not _stale(ORACLE_SO, [src, ROOT / "oracle" / "abstraction_oracle.c"]):
         return ORACLE_SO
     # -ffp-contract=off: no FMA contraction, the fp32 restatements must keep the reference's operation order
-    cmd = ["gcc", "-O3", "-std=gnu11", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-Wall",
+    cmd = ["gcc", "-O3", "-march=native", "-std=gnu11", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-Wall",
            str(src), str(ROOT / "oracle" / "abstraction_oracle.c"), "-o", str(ORACLE_SO), "-lm"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:

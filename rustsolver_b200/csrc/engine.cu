@@ -21,6 +21,7 @@
 #include "indexer_kernel.h"
 #include "kernels.cuh"
 #include "plan.h"
+#include "street_kernel.cuh"
 
 namespace rs {
 
@@ -137,6 +138,19 @@ struct TaskSet {
     DevBuf<TaskSrc> srcs;
     DevBuf<uint32_t> tix;  // ticket -> node-task index
     uint32_t n_tickets = 0, phase_cut = 0, n_tasks = 0;
+    uint32_t street_lo = 0, street_hi = 0;  // tickets of the final round's node tasks (replaced by the street kernel)
+    uint32_t street_inst = 0;               // instances (boards or sampled run-outs) of the final round
+};
+
+// device copy of one traverser's final-street programs (street.h)
+struct StreetDev {
+    DevBuf<SwUnit> units;
+    DevBuf<SwSeg> segs;
+    DevBuf<SwDown> downs;
+    DevBuf<SwUp> ups;
+    DevBuf<SwTerm> terms;
+    DevBuf<uint32_t> ev, ev_off, seg;
+    uint32_t n_tmpl = 0;
 };
 
 struct Engine {
@@ -167,6 +181,13 @@ struct Engine {
     void* xch_peer_base[RS_MAX_PEERS] = {nullptr};
     bool fused_exchange = false;
     float prune_threshold = -INFINITY;  // rs_set_prune_threshold
+    // fused final-street kernel (street_kernel.cu); off: the final round runs as node tasks like the others
+    bool street_on = false;
+    StreetDev street[2];
+    DevBuf<uint16_t> st_pcards[2], st_same[2];
+    DevBuf<float> st_scratch;
+    size_t st_stride = 0, st_smem = 0;
+    int st_XP = 0, st_YP = 0, st_rows = 0, st_slots = 0, st_threads = 0, st_blocks_per_sm = 1, st_sweep_warps = 1;
     int slots = 1;
     size_t smem_bytes = 0;
     int blocks_per_sm = 1, n_sms = 148;
@@ -204,13 +225,15 @@ struct Engine {
     int materialize(int trav, const uint32_t counts[3], TaskSet* out);
     int enqueue_sampled(int n_paths, uint64_t* count);
     int enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet* set = nullptr, int n_paths = 0);
+    int init_street();
+    int enqueue_street(int trav, int mode, const TaskSet& set, int n_paths);
     int enqueue_iteration(uint64_t* count);
     int iterate(uint64_t n);
     int root_sum(int player, double* out);
     int root_values(int player, std::vector<float>* out);
     int prof_begin();
     int prof_end(uint32_t kind, uint32_t k, int trav, uint32_t grid, uint64_t table_bytes, uint64_t vector_bytes);
-    uint64_t table_bytes_of(int trav, int phase) const;
+    uint64_t table_bytes_of(int trav, int phase, bool street) const;
 };
 
 template <class T>
@@ -233,6 +256,7 @@ int Engine::init(const rs_config* cfg) {
     if (prop.major < 10) return set_err(RS_ERR_UNSUPPORTED, "kernels are built for sm_100a only; found an older device");
     if (cfg->threads_per_block)
         return set_err(RS_ERR_INVALID, "threads_per_block is derived from the range size (4 hands per thread) and cannot be set");
+    if (cfg->flags & ~uint32_t(RS_FLAG_ALL)) return set_err(RS_ERR_INVALID, "unknown bits in rs_config.flags");
     use_graph = !(cfg->flags & RS_FLAG_NO_GRAPH);
     discount_interval = cfg->discount_interval;
     discount_cap = cfg->discount_cap;
@@ -247,8 +271,14 @@ int Engine::init(const rs_config* cfg) {
     }
     const int HP[2] = {int((P.H[0] + 3) & ~3u), int((P.H[1] + 3) & ~3u)};
     const size_t maxHP = size_t(std::max(HP[0], HP[1]));
+    const bool street_wanted = P.street[0].eligible && P.street[1].eligible;
     threads = int(((maxHP / 4) + 31) / 32 * 32);
     if (threads > MAX_TASK_THREADS) return set_err(RS_ERR_UNSUPPORTED, "range larger than 1326 hands");
+    n_sms = prop.multiProcessorCount;
+    if (street_wanted) {  // sets street_on when the fused street kernel fits
+        int rc = init_street();
+        if (rc != RS_OK) return rc;
+    }
     for (uint32_t k = 0; k < P.n_rounds; ++k) {
         RoundDev& R = rd[k];
         const uint32_t lo = P.local_lo[k], hi = P.local_hi[k], nb = hi - lo;
@@ -294,8 +324,11 @@ int Engine::init(const rs_config* cfg) {
         if (k > 0)
             for (uint32_t b = 0; b < nb; ++b) pb[b] = P.board_parent[k][lo + b] - int32_t(P.local_lo[k - 1]);
         CU(R.parent_board.upload(pb));
-        const size_t n_r = std::max(P.tl[0].n_rbuf[k], P.tl[1].n_rbuf[k]);
-        const size_t n_c = std::max(P.tl[0].n_cbuf[k], P.tl[1].n_cbuf[k]);
+        // the fused street kernel keeps the final round's vectors in its own per-CTA scratch; only the root round's
+        // value buffers are read from outside (rs_root_values)
+        const bool fused_round = street_on && k + 1 == P.n_rounds;
+        const size_t n_r = fused_round ? 0 : std::max(P.tl[0].n_rbuf[k], P.tl[1].n_rbuf[k]);
+        const size_t n_c = (fused_round && k > 0) ? 0 : std::max(P.tl[0].n_cbuf[k], P.tl[1].n_cbuf[k]);
         CU(R.rbuf.alloc(n_r * nb * maxHP));
         CU(R.cbuf.alloc(n_c * nb * maxHP));
         CU(R.gathered.alloc(size_t(R.n_leaves) * nb * maxHP));
@@ -377,6 +410,129 @@ int Engine::init(const rs_config* cfg) {
     return RS_OK;
 }
 
+
+// Upload the final-street programs and size the per-CTA scratch of the fused street kernel.
+int Engine::init_street() {
+    const Plan& P = plan;
+    const uint32_t k = P.n_rounds - 1;
+    const uint32_t lo = P.local_lo[k], hi = P.local_hi[k];
+    uint32_t max_batches = 1, max_rows = 1, max_slots = 1;
+    for (int p = 0; p < 2; ++p) {
+        const StreetPlan& S = P.street[p];
+        StreetDev& D = street[p];
+        CU(D.units.upload(S.units));
+        CU(D.segs.upload(S.segs));
+        CU(D.downs.upload(S.downs));
+        CU(D.ups.upload(S.ups));
+        CU(D.terms.upload(S.terms));
+        {
+            std::vector<uint32_t> ev = S.ev;
+            ev.resize(ev.size() + 64, 0u);  // the sweep's event window prefetches up to 64 words past a board's last event
+            CU(D.ev.upload(ev));
+        }
+        CU(D.seg.upload(slice(S.seg, lo, hi, 3 * (SW_SEGS + 1))));
+        CU(D.ev_off.upload(std::vector<uint32_t>(S.ev_off.begin() + lo, S.ev_off.begin() + hi + 1)));
+        D.n_tmpl = uint32_t(S.units.size());
+        max_batches = std::max(max_batches, S.max_batches);
+        max_rows = std::max(max_rows, S.max_rows);
+        max_slots = std::max(max_slots, S.max_slots);
+        const LocalTables& L = P.loc[k][p];
+        CU(st_pcards[p].upload(slice(L.pcards, lo, hi, L.Hpad)));
+        std::vector<uint16_t> same(size_t(hi - lo) * L.Hpad, 0xFFFF);
+        for (size_t i = 0; i < same.size(); ++i) same[i] = L.hrec[size_t(lo) * L.Hpad + i].same;
+        CU(st_same[p].upload(same));
+    }
+    const int HPmax = int(std::max((P.H[0] + 3) & ~3u, (P.H[1] + 3) & ~3u));
+    st_XP = (HPmax + 31) & ~31;
+    st_YP = st_XP;
+    st_rows = int(max_batches) * SW_LANES;
+    st_slots = int(max_slots);
+    st_stride = size_t(st_rows) * st_XP + size_t(st_rows) * st_YP + size_t(st_slots) * HPmax;
+    st_threads = threads;  // 4 hands per thread in one pass
+    if (const char* e = getenv("RS_STREET_THREADS")) st_threads = std::max(32, std::min(352, atoi(e) / 32 * 32));
+    st_threads = std::max(st_threads, int(max_batches) * 32);
+    // sweep warps per batch of 32 rows: the sweep of a board is cut into that many segments (street.h)
+    int want_sw = 4;
+    if (const char* e = getenv("RS_SWEEP_WARPS")) want_sw = atoi(e);
+    st_sweep_warps = 1;
+    while (st_sweep_warps * 2 <= want_sw && st_sweep_warps * 2 <= SW_SEGS && int(max_batches) * st_sweep_warps * 2 * 32 <= st_threads)
+        st_sweep_warps *= 2;
+    st_smem = street_smem_bytes(int(max_batches), st_sweep_warps);
+    int max_optin = 0;
+    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (st_smem > size_t(max_optin)) return RS_OK;  // too many sweep warps for one CTA: stay on the task kernel
+    CU(configure_street_kernels(st_smem, st_threads, &st_blocks_per_sm));
+    if (st_blocks_per_sm < 1) return RS_OK;
+    if (const char* e = getenv("RS_STREET_BLOCKS")) st_blocks_per_sm = std::max(1, std::min(st_blocks_per_sm, atoi(e)));
+    CU(st_scratch.alloc(st_stride * size_t(n_sms) * st_blocks_per_sm));
+    CU(st_scratch.zero());
+    street_on = true;
+    return RS_OK;
+}
+
+int Engine::enqueue_street(int trav, int mode, const TaskSet& set, int n_paths) {
+    const Plan& P = plan;
+    const uint32_t k = P.n_rounds - 1;
+    const RoundDev& R = rd[k];
+    const StreetDev& D = street[trav];
+    StreetArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int q = 0; q < 2; ++q) {
+        DevRoundPlayer& d = a.rp[q];
+        d.row_of_pos = R.row_of_pos[q].p;
+        d.row_start = R.row_start[q].p;
+        d.row_pos = R.row_pos[q].p;
+        d.cl_pos = R.cl_pos[q].p;
+        d.parent_pos = R.parent_pos[q].p;
+        d.child_pos = R.child_pos[q].p;
+        d.slot_of_pos = R.slot_of_pos[q].p;
+        d.hrec = R.hrec[q].p;
+        d.n_rows = R.n_rows[q].p;
+        d.n_rows_pad = R.n_rows_pad[q].p;
+        d.n_live = R.n_live[q].p;
+        d.board_off = R.board_off[q].p;
+        d.regrets = R.regrets[q].p;
+        d.ssum = R.ssum[q].p;
+        d.identity = 1;
+    }
+    a.chance_scale = R.chance_scale.p;
+    a.parent_board = R.parent_board.p;
+    a.parent_rbuf = k > 0 ? rd[k - 1].rbuf.p : nullptr;
+    a.parent_n_boards = k > 0 ? int(rd[k - 1].n_boards) : 0;
+    a.n_boards = int(R.n_boards);
+    a.root_weights = root_weights[1 - trav].p;
+    a.out_buf = k > 0 ? R.sbuf[trav].p : R.cbuf.p;
+    a.out_scatter = k > 0 ? 1 : 0;
+    a.n_tmpl = int(D.n_tmpl);
+    a.units = D.units.p;
+    a.segs = D.segs.p;
+    a.downs = D.downs.p;
+    a.ups = D.ups.p;
+    a.terms = D.terms.p;
+    a.ev = D.ev.p;
+    a.ev_off = D.ev_off.p;
+    a.seg = D.seg.p;
+    a.sweep_warps = st_sweep_warps;
+    a.pcards = st_pcards[trav].p;
+    a.same_pos = st_same[trav].p;
+    a.scratch = st_scratch.p;
+    a.scratch_stride = st_stride;
+    a.XP = st_XP;
+    a.YP = st_YP;
+    a.max_rows = st_rows;
+    a.max_slots = st_slots;
+    a.trav = trav;
+    a.HpP = int((P.H[trav] + 3) & ~3u);
+    a.HoP = int((P.H[1 - trav] + 3) & ~3u);
+    a.same_order = P.same_order ? 1 : 0;
+    a.n_units = set.street_inst * D.n_tmpl;
+    a.sample_board = (n_paths > 0 && k > 0) ? sample_board[k].p : nullptr;
+    a.prune_threshold = prune_threshold;
+    const int grid = int(std::min<uint64_t>(a.n_units, uint64_t(n_sms) * st_blocks_per_sm));
+    CU(launch_street_kernel(a, mode, grid, st_threads, st_smem, stream));
+    return RS_OK;
+}
+
 int Engine::materialize(int trav, const uint32_t counts[3], TaskSet* out) {
     const TaskList& tl = plan.tl[trav];
     std::vector<NodeTask> t = tl.tasks;
@@ -396,6 +552,23 @@ int Engine::materialize(int trav, const uint32_t counts[3], TaskSet* out) {
     if (!cut_set) out->phase_cut = first;
     out->n_tickets = first;
     out->n_tasks = uint32_t(t.size());
+    out->street_lo = out->street_hi = 0;
+    out->street_inst = counts[plan.n_rounds - 1];
+    if (street_on) {
+        // the node tasks of the final round form one contiguous ticket range: down tasks of the last street are
+        // emitted last, its up tasks first (plan.cpp: TaskGen::run)
+        bool seen = false, closed = false;
+        for (const NodeTask& x : t) {
+            const bool fin = uint32_t(x.round_k) + 1 == plan.n_rounds;
+            if (fin && closed) return set_err(RS_ERR_INVALID, "internal: final-round tasks are not contiguous");
+            if (fin && !seen) {
+                seen = true;
+                out->street_lo = x.first;
+            }
+            if (fin) out->street_hi = x.first + x.count;
+            if (!fin && seen) closed = true;
+        }
+    }
     for (NodeTask& x : t)
         for (int i = 0; i < x.n_dep; ++i)
             if (x.dep[i] >= 0) x.dep[i] = int32_t(t[x.dep[i]].first);
@@ -505,16 +678,24 @@ int Engine::prof_end(uint32_t kind, uint32_t phase, int trav, uint32_t grid, uin
 // algorithmic infoset-table bytes of one traversal launch: traverser cells regret R+W and strategy_sum
 // R+W = 16 B, opponent cells regret read = 4 B.  Phase 1 of a sharded traversal only updates the
 // traverser's tables of the replicated rounds above the shard level.
-uint64_t Engine::table_bytes_of(int trav, int phase) const {
+uint64_t Engine::table_bytes_of(int trav, int phase, bool street) const {
     const Plan& P = plan;
     uint64_t bytes = 0;
-    const bool split = full[trav].phase_cut < full[trav].n_tickets;
+    const bool split = !fused_exchange && full[trav].phase_cut < full[trav].n_tickets;
     for (uint32_t k = 0; k < P.n_rounds; ++k) {
+        if (street && k + 1 == P.n_rounds) continue;  // counted by the street kernel's launch
         const uint64_t own = P.tabs[k][trav].board_off[P.n_boards[k]];
         const uint64_t opp = P.tabs[k][1 - trav].board_off[P.n_boards[k]];
-        const bool above = split && k < P.shard_round;
-        if (phase == 0) bytes += opp * 4 + (above ? 0 : own * 16);
-        else bytes += above ? own * 16 : 0;
+        const bool above = split && k < P.shard_round;  // updated after the all-reduce
+        if (!street) {
+            if (phase == 0) bytes += opp * 4 + (above ? 0 : own * 16);
+            else bytes += above ? own * 16 : 0;
+        } else {
+            // phase 0 = down pass (opponent tables), 1 = up pass before the all-reduce, 2 = after it
+            if (phase == 0) bytes += opp * 4;
+            else if (phase == 1) bytes += above ? 0 : own * 16;
+            else bytes += above ? own * 16 : 0;
+        }
     }
     return bytes;
 }
@@ -533,31 +714,55 @@ int Engine::enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet
         }
     }
     int rc;
-    // with the in-kernel exchange the whole traversal is one launch; else it is cut at the shared chance nodes
-    const uint32_t cuts[3] = {0, fused_exchange ? set->n_tickets : set->phase_cut, set->n_tickets};
-    for (int phase = 0; phase < 2; ++phase) {
-        a.t0 = cuts[phase];
-        a.t1 = cuts[phase + 1];
-        if (a.t1 <= a.t0) continue;
-        const int grid = int(std::min<uint64_t>(uint64_t(a.t1 - a.t0), uint64_t(n_sms) * blocks_per_sm));
+    // Launch schedule.  Without the street kernel a traversal is one launch of the task kernel (with the in-kernel
+    // exchange) or two around the NCCL all-reduce.  With it the final round's tickets [street_lo, street_hi) are
+    // replaced by one launch of the fused street kernel between the down pass of the rounds above and their up pass.
+    struct Step {
+        int kind;  // 0 task kernel [t0, t1), 1 street kernel, 2 all-reduce
+        uint32_t t0, t1, phase;
+    };
+    std::vector<Step> steps;
+    const bool use_street = street_on && set->street_hi > set->street_lo;
+    uint32_t at = 0;
+    if (use_street) {
+        if (set->street_lo > 0) steps.push_back({0, 0, set->street_lo, 0});
+        steps.push_back({1, 0, 0, 0});
+        at = set->street_hi;
+    }
+    const bool split = !fused_exchange && set->phase_cut < set->n_tickets;
+    const uint32_t cut = split ? std::max(set->phase_cut, at) : set->n_tickets;
+    if (cut > at) steps.push_back({0, at, cut, use_street ? 1u : 0u});
+    if (split) {
+        steps.push_back({2, 0, 0, 0});
+        steps.push_back({0, cut, set->n_tickets, 2});
+    }
+    uint64_t vec = 0;
+    for (uint32_t k = 0; k < P.n_rounds; ++k)
+        vec += (uint64_t(tl.n_rbuf[k]) * P.H[1 - trav] + uint64_t(tl.n_cbuf[k]) * P.H[trav]) * rd[k].n_boards * 8;  // written once, read once
+    for (const Step& sp : steps) {
         if ((rc = prof_begin()) != RS_OK) return rc;
-        CU(launch_task_kernel(a, mode, grid, threads, smem_bytes, stream));
-        uint64_t vec = 0;
-        for (uint32_t k = 0; k < P.n_rounds; ++k)
-            vec += (uint64_t(tl.n_rbuf[k]) * P.H[1 - trav] + uint64_t(tl.n_cbuf[k]) * P.H[trav]) * rd[k].n_boards * 8;  // written once, read once
-        if ((rc = prof_end(RS_KERNEL_TRAVERSAL, uint32_t(phase), trav, uint32_t(grid), table_bytes_of(trav, phase), vec)) != RS_OK)
-            return rc;
-        ++*count;
-        if (phase == 0 && !fused_exchange && set->phase_cut < set->n_tickets) {
+        if (sp.kind == 0) {
+            a.t0 = sp.t0;
+            a.t1 = sp.t1;
+            const int grid = int(std::min<uint64_t>(uint64_t(a.t1 - a.t0), uint64_t(n_sms) * blocks_per_sm));
+            CU(launch_task_kernel(a, mode, grid, threads, smem_bytes, stream));
+            if ((rc = prof_end(RS_KERNEL_TRAVERSAL, sp.phase, trav, uint32_t(grid), table_bytes_of(trav, int(sp.phase), use_street), vec)) != RS_OK)
+                return rc;
+        } else if (sp.kind == 1) {
+            if ((rc = enqueue_street(trav, mode, *set, n_paths)) != RS_OK) return rc;
+            const uint32_t k = P.n_rounds - 1;
+            const uint64_t own = P.tabs[k][trav].board_off[P.n_boards[k]], opp = P.tabs[k][1 - trav].board_off[P.n_boards[k]];
+            const uint32_t grid = uint32_t(std::min<uint64_t>(uint64_t(set->street_inst) * street[trav].n_tmpl, uint64_t(n_sms) * st_blocks_per_sm));
+            if ((rc = prof_end(RS_KERNEL_STREET, 0, trav, grid, own * 16 + opp * 4, 0)) != RS_OK) return rc;
+        } else {
             // the one exchange step of the path: counterfactual values at the shared chance nodes
             RoundDev& Par = rd[P.shard_round - 1];
-            if ((rc = prof_begin()) != RS_OK) return rc;
             const size_t n = size_t(Par.n_leaves) * Par.n_boards * ((P.H[trav] + 3) & ~3u);
             int nrc = nccl::g_api.AllReduce(Par.gathered.p, Par.gathered.p, n, nccl::kFloat32, nccl::kSum, comm, stream);
             if (nrc != 0) return set_err(RS_ERR_NCCL, "ncclAllReduce failed");
             if ((rc = prof_end(RS_KERNEL_ALLREDUCE, 0, trav, 0, 0, n * 4)) != RS_OK) return rc;
-            ++*count;
         }
+        ++*count;
     }
     return RS_OK;
 }
@@ -1197,6 +1402,48 @@ int rs_plan_showdown_order(const rs_plan* p, uint32_t player, uint32_t board_id,
         if (order_out) order_out[i] = S.sorted[size_t(board_id) * H + i];
         if (class_out) class_out[i] = S.cls[size_t(board_id) * H + i];
     }
+    return RS_OK;
+}
+
+int rs_plan_street_info(const rs_plan* p, uint32_t traverser, uint32_t out[8]) {
+    if (!p || !out || traverser > 1) return set_err(RS_ERR_INVALID, "bad argument");
+    const StreetPlan& S = p->p.street[traverser];
+    out[0] = S.eligible ? 1u : 0u;
+    out[1] = uint32_t(S.units.size());
+    out[2] = S.max_batches;
+    out[3] = S.max_rows;
+    out[4] = S.max_slots;
+    out[5] = uint32_t(S.segs.size());
+    out[6] = uint32_t(S.downs.size());
+    out[7] = uint32_t(S.ups.size());
+    if (!S.eligible) g_last_error = S.why;
+    return RS_OK;
+}
+
+int rs_plan_street_events(const rs_plan* p, uint32_t traverser, uint32_t board_id, uint32_t* out, size_t cap, uint32_t* n_out) {
+    if (!p || !n_out || traverser > 1) return set_err(RS_ERR_INVALID, "bad argument");
+    const Plan& P = p->p;
+    const StreetPlan& S = P.street[traverser];
+    if (!S.eligible) return set_err(RS_ERR_INVALID, "the final round does not run on the street kernel: " + S.why);
+    const uint32_t k = P.n_rounds - 1;
+    if (board_id < P.local_lo[k] || board_id >= P.local_hi[k]) return set_err(RS_ERR_INVALID, "board is owned by another rank");
+    const uint32_t n = S.ev_off[board_id + 1] - S.ev_off[board_id];
+    *n_out = n;
+    if (out) {
+        if (cap < n) return set_err(RS_ERR_CAPACITY, "output buffer too small");
+        memcpy(out, S.ev.data() + S.ev_off[board_id], size_t(n) * sizeof(uint32_t));
+    }
+    return RS_OK;
+}
+
+int rs_plan_street_segments(const rs_plan* p, uint32_t traverser, uint32_t board_id, uint32_t out[27]) {
+    if (!p || !out || traverser > 1) return set_err(RS_ERR_INVALID, "bad argument");
+    const Plan& P = p->p;
+    const StreetPlan& S = P.street[traverser];
+    if (!S.eligible) return set_err(RS_ERR_INVALID, "the final round does not run on the street kernel: " + S.why);
+    const uint32_t k = P.n_rounds - 1;
+    if (board_id < P.local_lo[k] || board_id >= P.local_hi[k]) return set_err(RS_ERR_INVALID, "board is owned by another rank");
+    memcpy(out, &S.seg[size_t(board_id) * 3 * (SW_SEGS + 1)], 3 * (SW_SEGS + 1) * sizeof(uint32_t));
     return RS_OK;
 }
 

@@ -156,6 +156,7 @@ struct TaskGen {
     Plan* P;
     int trav;
     TaskList tl;
+    StreetPlan sp;
     std::string err;
 
     struct RSrc {
@@ -517,7 +518,265 @@ struct TaskGen {
             err = "more than 3 terminal children under one action node";
             return false;
         }
+        build_street();
         return true;
+    }
+
+    // ---- the final round as fused street programs (street.h) -------------------------------------
+    struct StreetSeg {  // one segment while it is being compiled; rows and slots are local to the segment
+        std::vector<SwDown> downs;
+        std::vector<SwUp> ups;
+        std::vector<SwTerm> terms;
+        std::vector<uint8_t> row_need_y;
+        uint32_t n_slots = 0;
+        int32_t root_row = 0;
+    };
+
+    int16_t street_row(StreetSeg& g) {
+        g.row_need_y.push_back(0);
+        return int16_t(g.row_need_y.size() - 1);
+    }
+    float fold_coef(const PNode& cn) const { return (trav == cn.last_to_act) ? -float(cn.value) : float(cn.value); }  // cfr.rs:525-531
+
+    // terms that add up to the value of opponent node `id` (sigma is inside the child rows, cfr.rs:583-588)
+    void street_opp(StreetSeg& g, int32_t id, int16_t row, std::vector<SwTerm>& value_terms) {
+        const PNode& n = P->nodes[id];
+        SwDown d;
+        std::memset(&d, 0, sizeof(d));
+        d.n_act = uint8_t(n.children.size());
+        d.in_row = row;
+        d.cum_a = n.cum_a;
+        for (int a = 0; a < SW_MAX_ACT; ++a) d.out_row[a] = -1;
+        for (size_t a = 0; a < n.children.size(); ++a) d.out_row[a] = street_row(g);
+        g.downs.push_back(d);  // pre-order: the rows are written before any op below reads them
+        for (size_t a = 0; a < n.children.size(); ++a) {
+            const int32_t c = n.children[a];
+            const PNode& cn = P->nodes[c];
+            const int16_t rc = d.out_row[a];
+            if (cn.kind == PK_FOLD) {
+                value_terms.push_back(SwTerm{ST_FOLD, 0, rc, fold_coef(cn)});
+            } else if (cn.kind == PK_SHOWDOWN) {
+                g.row_need_y[rc] = 1;
+                value_terms.push_back(SwTerm{ST_SHOWDOWN, 0, rc, float(cn.value)});  // cfr.rs:532-543
+            } else {
+                const int16_t slot = street_trav(g, c, rc, false);
+                value_terms.push_back(SwTerm{ST_VALUE, 0, slot, 0.f});
+            }
+        }
+    }
+
+    // traverser node: returns the value slot it writes (-1 for the segment root)
+    int16_t street_trav(StreetSeg& g, int32_t id, int16_t row, bool is_root) {
+        const PNode& n = P->nodes[id];
+        std::vector<std::vector<SwTerm>> per_action(n.children.size());
+        for (size_t a = 0; a < n.children.size(); ++a) {
+            const int32_t c = n.children[a];
+            const PNode& cn = P->nodes[c];
+            if (cn.kind == PK_FOLD) {
+                per_action[a].push_back(SwTerm{ST_FOLD, 0, row, fold_coef(cn)});
+            } else if (cn.kind == PK_SHOWDOWN) {
+                g.row_need_y[row] = 1;
+                per_action[a].push_back(SwTerm{ST_SHOWDOWN, 0, row, float(cn.value)});
+            } else {
+                street_opp(g, c, row, per_action[a]);  // the opponent node sees the same reach
+            }
+        }
+        SwUp u;
+        std::memset(&u, 0, sizeof(u));
+        u.kind = SU_TRAV;
+        u.n_act = uint8_t(n.children.size());
+        u.own_row = row;
+        u.cum_a = n.cum_a;
+        u.out_slot = is_root ? int16_t(-1) : int16_t(g.n_slots++);
+        for (size_t a = 0; a < n.children.size(); ++a) {
+            u.term_first[a] = uint16_t(g.terms.size());
+            g.terms.insert(g.terms.end(), per_action[a].begin(), per_action[a].end());
+        }
+        for (size_t a = n.children.size(); a <= size_t(SW_MAX_ACT); ++a) u.term_first[a] = uint16_t(g.terms.size());
+        g.ups.push_back(u);  // post-order: every slot it reads was written by an earlier op
+        return u.out_slot;
+    }
+
+    void build_street() {
+        StreetPlan& S = sp;
+        const uint32_t R = P->n_rounds, k = R - 1;
+        S = StreetPlan();
+        S.round_k = k;
+        auto no = [&](const char* w) {
+            S.eligible = false;
+            S.why = w;
+        };
+        if (!(P->flags & RS_FLAG_STREET_KERNEL) && !getenv("RS_STREET")) return no("RS_FLAG_STREET_KERNEL is not set");
+        if (P->sd[0].n_live.empty() || P->sd[1].n_live.empty()) return no("the final round has no showdown order");
+        if (!P->loc[k][0].identity || !P->loc[k][1].identity) return no("the final round's tables are bucketed");
+        for (const Segment& sg : P->segs[k]) {
+            std::vector<int32_t> st{sg.root};
+            while (!st.empty()) {
+                const PNode& n = P->nodes[st.back()];
+                st.pop_back();
+                if (n.kind == PK_CHANCE) return no("chance node inside the final round");
+                if (n.kind == PK_ACTION && n.children.size() > size_t(SW_MAX_ACT)) return no("a final-round node has more than 5 actions");
+                for (int32_t c : n.children) st.push_back(c);
+            }
+        }
+        // compile every segment on its own
+        std::vector<StreetSeg> comp(P->segs[k].size());
+        for (uint32_t s = 0; s < P->segs[k].size(); ++s) {
+            StreetSeg& g = comp[s];
+            const int32_t rootid = P->segs[k][s].root;
+            const PNode& rn = P->nodes[rootid];
+            g.root_row = street_row(g);
+            if (rn.kind == PK_ACTION && rn.player == trav) {
+                street_trav(g, rootid, int16_t(g.root_row), true);
+            } else {
+                std::vector<SwTerm> vt;
+                if (rn.kind == PK_ACTION) {
+                    street_opp(g, rootid, int16_t(g.root_row), vt);
+                } else if (rn.kind == PK_SHOWDOWN) {  // bare showdown behind an all-in run-out
+                    g.row_need_y[g.root_row] = 1;
+                    vt.push_back(SwTerm{ST_SHOWDOWN, 0, int16_t(g.root_row), float(rn.value)});
+                } else {
+                    return no("unexpected segment root in the final round");
+                }
+                SwUp u;
+                std::memset(&u, 0, sizeof(u));
+                u.kind = SU_SUM;
+                u.n_act = 1;
+                u.own_row = -1;
+                u.out_slot = -1;
+                u.term_first[0] = uint16_t(g.terms.size());
+                g.terms.insert(g.terms.end(), vt.begin(), vt.end());
+                for (int a = 1; a <= SW_MAX_ACT; ++a) u.term_first[a] = uint16_t(g.terms.size());
+                g.ups.push_back(u);
+            }
+            if (g.row_need_y.size() > size_t(SW_LANES * SW_MAX_BATCH)) return no("a final-round segment needs more than 256 reach rows");
+            if (g.terms.size() > 60000) return no("too many value terms in one segment");
+        }
+        // pack consecutive segments into unit templates of at most `lanes` rows
+        uint32_t lanes = SW_LANES;
+        if (const char* e = getenv("RS_STREET_LANES")) lanes = std::max<uint32_t>(SW_LANES, std::min<uint32_t>(uint32_t(atoi(e)), SW_LANES * SW_MAX_BATCH));
+        auto open_unit = [&]() {
+            SwUnit u;
+            std::memset(&u, 0, sizeof(u));
+            u.seg_first = uint32_t(S.segs.size());
+            return u;
+        };
+        auto close_unit = [&](SwUnit& u) {
+            if (u.seg_count == 0) return;
+            u.n_batches = (u.n_rows + SW_LANES - 1) / SW_LANES;
+            S.max_batches = std::max(S.max_batches, u.n_batches);
+            S.max_rows = std::max(S.max_rows, u.n_rows);
+            S.max_slots = std::max(S.max_slots, u.n_slots);
+            S.units.push_back(u);
+        };
+        SwUnit cur = open_unit();
+        for (uint32_t s = 0; s < comp.size(); ++s) {
+            const StreetSeg& g = comp[s];
+            const uint32_t rows = uint32_t(g.row_need_y.size());
+            if (cur.seg_count > 0 && cur.n_rows + rows > lanes) {
+                close_unit(cur);
+                cur = open_unit();
+            }
+            const int16_t row0 = int16_t(cur.n_rows), slot0 = int16_t(cur.n_slots);
+            const uint16_t term0 = uint16_t(S.terms.size());
+            SwSeg seg;
+            std::memset(&seg, 0, sizeof(seg));
+            seg.down_first = uint32_t(S.downs.size());
+            seg.down_count = uint32_t(g.downs.size());
+            seg.up_first = uint32_t(S.ups.size());
+            seg.up_count = uint32_t(g.ups.size());
+            seg.root_row = g.root_row + row0;
+            seg.root_in = k > 0 ? leaf_rbuf[k - 1][s] : RIN_INITIAL;
+            seg.root_out = segroot_cbuf[k][s];
+            for (SwDown d : g.downs) {
+                d.in_row = int16_t(d.in_row + row0);
+                for (int a = 0; a < d.n_act; ++a) d.out_row[a] = int16_t(d.out_row[a] + row0);
+                S.downs.push_back(d);
+            }
+            if (S.terms.size() + g.terms.size() > 65000) return no("too many value terms");
+            for (SwUp u : g.ups) {
+                if (u.own_row >= 0) u.own_row = int16_t(u.own_row + row0);
+                if (u.out_slot >= 0) u.out_slot = int16_t(u.out_slot + slot0);
+                for (int a = 0; a <= SW_MAX_ACT; ++a) u.term_first[a] = uint16_t(u.term_first[a] + term0);
+                S.ups.push_back(u);
+            }
+            for (SwTerm t : g.terms) {
+                t.id = int16_t(t.id + (t.kind == ST_VALUE ? slot0 : row0));
+                S.terms.push_back(t);
+            }
+            for (uint32_t r = 0; r < rows; ++r)
+                if (g.row_need_y[r]) cur.need_y[(cur.n_rows + r) / SW_LANES] |= 1u << ((cur.n_rows + r) % SW_LANES);
+            cur.n_rows += rows;
+            cur.n_slots += g.n_slots;
+            cur.seg_count++;
+            S.segs.push_back(seg);
+        }
+        close_unit(cur);
+        if (S.max_batches > uint32_t(SW_MAX_BATCH)) return no("a unit needs more than 8 sweep warps");
+        // event streams of the sorted sweep, one per local board: strength classes in ascending order, the
+        // traverser's hands of the class (reads), then the opponent's (adds)
+        const int o = 1 - trav;
+        const uint32_t nB = P->n_boards[k];
+        const LocalTables& Lp = P->loc[k][trav];
+        const LocalTables& Lo = P->loc[k][o];
+        const uint32_t Hp = P->H[trav], Ho = P->H[o];
+        S.ev_off.assign(size_t(nB) + 1, 0);
+        S.seg.assign(size_t(nB) * 3 * (SW_SEGS + 1), 0);
+        std::vector<uint32_t> cls_ev, cls_x, cls_r, cls_cum;  // per class: header index (board-relative), first add / read position, entries before it
+        for (uint32_t b = 0; b < nB; ++b) {
+            S.ev_off[b] = uint32_t(S.ev.size());
+            if (b < P->local_lo[k] || b >= P->local_hi[k]) continue;
+            const uint32_t np = Lp.n_live[b], no_ = Lo.n_live[b];
+            const uint16_t* sp_ = &Lp.slot_of_pos[size_t(b) * Lp.Hpad];
+            const uint16_t* so_ = &Lo.slot_of_pos[size_t(b) * Lo.Hpad];
+            const uint32_t* strp = &P->sd[trav].strength[size_t(b) * Hp];
+            const uint32_t* stro = &P->sd[o].strength[size_t(b) * Ho];
+            uint32_t i = 0, j = 0;
+            cls_ev.clear();
+            cls_x.clear();
+            cls_r.clear();
+            cls_cum.clear();
+            while (i < np || j < no_) {
+                uint32_t st = 0xffffffffu;
+                if (i < np) st = std::min(st, strp[sp_[i]]);
+                if (j < no_) st = std::min(st, stro[so_[j]]);
+                uint32_t i1 = i, j1 = j;
+                while (i1 < np && strp[sp_[i1]] == st) ++i1;
+                while (j1 < no_ && stro[so_[j1]] == st) ++j1;
+                cls_ev.push_back(uint32_t(S.ev.size()) - S.ev_off[b]);
+                cls_x.push_back(j);
+                cls_r.push_back(i);
+                cls_cum.push_back(i + j);
+                S.ev.push_back((i1 - i) | ((j1 - j) << 11));
+                for (uint32_t t = i; t < i1; ++t)
+                    S.ev.push_back(t | (uint32_t(P->hand_cards[trav][2 * sp_[t]]) << 11) | (uint32_t(P->hand_cards[trav][2 * sp_[t] + 1]) << 17));
+                for (uint32_t t = j; t < j1; ++t) {
+                    const uint8_t a = P->hand_cards[o][2 * so_[t]], c = P->hand_cards[o][2 * so_[t] + 1];
+                    uint32_t w = t | (uint32_t(a) << 11) | (uint32_t(c) << 17);
+                    if (t > j) {
+                        const uint8_t pa = P->hand_cards[o][2 * so_[t - 1]], pc = P->hand_cards[o][2 * so_[t - 1] + 1];
+                        if (a == pa || a == pc || c == pa || c == pc) w |= SW_EV_COLLIDES;
+                    }
+                    S.ev.push_back(w);
+                }
+                i = i1;
+                j = j1;
+            }
+            // segment boundaries: the first class at or past every eighth of the entries
+            uint32_t* sg = &S.seg[size_t(b) * 3 * (SW_SEGS + 1)];
+            const uint32_t total = np + no_, n_ev = uint32_t(S.ev.size()) - S.ev_off[b];
+            size_t c = 0;
+            for (int q = 0; q <= SW_SEGS; ++q) {
+                const uint64_t want = uint64_t(total) * q / SW_SEGS;
+                while (c < cls_cum.size() && cls_cum[c] < want) ++c;
+                const bool end = (q == SW_SEGS) || c >= cls_cum.size();
+                sg[q] = end ? n_ev : cls_ev[c];
+                sg[(SW_SEGS + 1) + q] = end ? no_ : cls_x[c];
+                sg[2 * (SW_SEGS + 1) + q] = end ? np : cls_r[c];
+            }
+        }
+        S.ev_off[nB] = uint32_t(S.ev.size());
+        S.eligible = true;
     }
 };
 
@@ -1029,11 +1288,32 @@ bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstrac
         }
     }
 
+    // final round: the hand's cards by board-local position, and whether both players' hands share positions
+    if (any_showdown) {
+        const uint32_t k = P->n_rounds - 1;
+        const uint32_t nB = P->n_boards[k];
+        bool same = P->H[0] == P->H[1];
+        for (int q = 0; q < 2; ++q) {
+            LocalTables& L = P->loc[k][q];
+            L.pcards.assign(size_t(nB) * L.Hpad, 0);
+            for (uint32_t b = P->local_lo[k]; b < P->local_hi[k]; ++b) {
+                const uint16_t* sop = &L.slot_of_pos[size_t(b) * L.Hpad];
+                for (uint32_t i = 0; i < L.n_live[b]; ++i) {
+                    L.pcards[size_t(b) * L.Hpad + i] = uint16_t(P->hand_cards[q][2 * sop[i]] | (P->hand_cards[q][2 * sop[i] + 1] << 8));
+                    if (L.hrec[size_t(b) * L.Hpad + i].same != i) same = false;
+                }
+                if (L.n_live[b] != P->loc[k][1 - q].n_live[b]) same = false;
+            }
+        }
+        P->same_order = same;
+    }
+
     // ---- task graphs, one per traverser ----
     for (int p = 0; p < 2; ++p) {
         TaskGen g{P, p};
         if (!g.run()) return fail(g.err);
         P->tl[p] = std::move(g.tl);
+        P->street[p] = std::move(g.sp);
     }
 
     // ---- update counts (one update = one (node, board, row, action) cell) ----

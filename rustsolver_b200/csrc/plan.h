@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/b200cfr.h"
+#include "street.h"
 #include "tasks.h"
 
 namespace rs {
@@ -80,6 +81,7 @@ struct LocalTables {
     std::vector<uint16_t> cl_pos;         // [nB][2*Hpad] q as opponent: positions of q's live hands, grouped by card
     std::vector<uint16_t> parent_pos;     // [nB][Hpad] (k >= 1) position of the same hand on the parent board
     std::vector<uint16_t> child_pos;      // [nB][Hpad] (k >= 1) indexed by PARENT position: position on this board / 0xFFFF
+    std::vector<uint16_t> pcards;         // [nB][Hpad] final round: the hand's two cards by position, c0 | c1 << 8 (street.h)
 };
 
 struct ShowdownTables {  // final round only, per player q, per GLOBAL board
@@ -119,6 +121,8 @@ struct Plan {
     LocalTables loc[3][2];
     std::vector<int32_t> an_to_pnode;  // ActionNode.index -> PNode id
     TaskList tl[2];                    // per traverser
+    StreetPlan street[2];              // per traverser: the final round as fused street programs (street.h)
+    bool same_order = false;           // final round: both players' live hands sit at the same positions on every local board
 
     uint64_t updates_per_iter_local = 0, updates_per_iter_global = 0;
     uint32_t flags = 0;

@@ -25,6 +25,7 @@ from ._lib import (EngineError, check, f32p, f64p, i32p, rs_abstraction, rs_conf
 RS_ABS_NONE, RS_ABS_ISOMORPHIC, RS_ABS_CLUSTER_ARR, RS_ABS_BUCKET_TABLE = 0, 1, 2, 3
 RS_FLAG_NO_GRAPH = 1
 RS_FLAG_NO_CHAIN_SPLIT = 2
+RS_FLAG_STREET_KERNEL = 4
 NODE_ACTION, NODE_TERMINAL, NODE_PUBLIC_CHANCE, NODE_PRIVATE_CHANCE = 0, 1, 2, 3
 TERM_ALLIN, TERM_SHOWDOWN, TERM_UNCONTESTED = 0, 1, 2
 ACTION_NAMES = {0: "Bet", 1: "Raise", 2: "Check", 3: "Call", 4: "Fold"}
@@ -395,7 +396,7 @@ class Plan(_PlanOrEngine):
 
     def __init__(self, tree: GameTree, ranges: Sequence[np.ndarray], board_mask: int,
                  card_abs: Sequence[CardAbstraction] = (), board_masks: Optional[Sequence[int]] = None,
-                 rank: int = 0, world_size: int = 1):
+                 rank: int = 0, world_size: int = 1, flags: int = 0):
         self._lib = _lib.load()
         self._keep = []
         tv = tree.view()
@@ -408,6 +409,7 @@ class Plan(_PlanOrEngine):
         cfg = rs_config()
         cfg.board_mask = board_mask
         cfg.rank, cfg.world_size = rank, world_size
+        cfg.flags = flags
         h = C.c_void_p()
         if board_masks is not None:
             bm = np.asarray(board_masks, dtype=np.uint64)
@@ -438,6 +440,33 @@ class Plan(_PlanOrEngine):
         nl = C.c_uint32()
         check(self._lib.rs_plan_showdown_order(self._h, player, board_id, _ptr(order, u16p), _ptr(cls, u32p), len(order), C.byref(nl)))
         return order[:nl.value].copy(), cls[:nl.value].copy()
+
+    def street_info(self, traverser: int) -> dict:
+        """The final round as fused street programs (csrc/street.h); `why` is set when the round is not eligible."""
+        out = (C.c_uint32 * 8)()
+        check(self._lib.rs_plan_street_info(self._h, traverser, out))
+        keys = ("eligible", "templates", "max_batches", "max_rows", "max_slots", "segments", "down_ops", "up_ops")
+        d = dict(zip(keys, [int(x) for x in out]))
+        d["why"] = "" if d["eligible"] else self._lib.rs_last_error().decode()
+        return d
+
+    def street_events(self, traverser: int, board_id: int) -> np.ndarray:
+        """Event stream of the sorted sweep on one final-round board (header/read/add words, street.h)."""
+        n = C.c_uint32()
+        check(self._lib.rs_plan_street_events(self._h, traverser, board_id, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint32)
+        check(self._lib.rs_plan_street_events(self._h, traverser, board_id, _ptr(out, u32p), len(out), C.byref(n)))
+        return out
+
+
+def _street_segments(self, traverser: int, board_id: int) -> np.ndarray:
+    """The eight pieces the sweep of one final-round board is cut into: rows = first event word / add position / read position."""
+    out = np.zeros(27, dtype=np.uint32)
+    check(self._lib.rs_plan_street_segments(self._h, traverser, board_id, _ptr(out, u32p)))
+    return out.reshape(3, 9)
+
+
+Plan.street_segments = _street_segments
 
 
 class Engine(_PlanOrEngine):
@@ -544,7 +573,7 @@ class Engine(_PlanOrEngine):
         buf = (_lib.rs_kernel_time * cap)()
         n = C.c_uint32()
         check(self._lib.rs_profile_iteration(self._h, buf, cap, C.byref(n)))
-        kinds = {0: "traversal", 3: "allreduce"}
+        kinds = {0: "traversal", 1: "street", 3: "allreduce"}
         return [dict(kind=kinds[buf[i].kind], phase=buf[i].phase, traverser=buf[i].traverser, grid=buf[i].grid,
                      ms=buf[i].ms, table_bytes=buf[i].table_bytes, vector_bytes=buf[i].vector_bytes) for i in range(n.value)]
 
