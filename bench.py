@@ -191,7 +191,7 @@ def run_ours(args):
     w, tree, ranges = build_workload(args.workload)
     t0 = time.perf_counter()
     eng = rb.Engine(tree, ranges, w.options.board_mask, w.card_abs, board_masks=w.board_masks, device=local_rank,
-                    rank=rank, world_size=world, nccl_id=nccl_id)
+                    rank=rank, world_size=world, nccl_id=nccl_id, flags=int(os.environ.get("RS_ENGINE_FLAGS", "0")))
     fused = False
     if world > 1 and os.environ.get("RS_NO_FUSED", "0") != "1" and eng.stats().n_rounds > 1:
         # the kernel exchanges the chance-node sums itself over NVLink peer memory (False: some rank could not map

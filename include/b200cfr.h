@@ -115,7 +115,12 @@ typedef struct rs_config {
                                     values up to fp32 rounding; measured slower than the task kernel,
                                     so it is off by default.  Lossy (bucketed) final rounds and nodes wider than 5 actions
                                     always take the task path */
-#define RS_FLAG_ALL (RS_FLAG_NO_GRAPH | RS_FLAG_NO_CHAIN_SPLIT | RS_FLAG_STREET_KERNEL) /* rs_create rejects other bits */
+#define RS_FLAG_SHARD_ISOLATED 8u /* world_size > 1 without peers: the rank walks only its own slice of the first dealt-card
+                                     level (rank r of world_size) and never exchanges; the other ranks' boards contribute zero
+                                     to the chance-node sums.  No NCCL communicator is created.  This is public-chance
+                                     sub-sampling without an importance weight: used to solve / check a slice of a subgame
+                                     that is too large to hold (config 4 on 2 of its 49 turn cards) */
+#define RS_FLAG_ALL (RS_FLAG_NO_GRAPH | RS_FLAG_NO_CHAIN_SPLIT | RS_FLAG_STREET_KERNEL | RS_FLAG_SHARD_ISOLATED) /* rs_create rejects other bits */
 
 typedef struct rs_engine rs_engine;
 

@@ -73,6 +73,7 @@ def load():
     lib.orc_literal_to_double.argtypes = [VP, C.c_double]
     lib.orc_num_threads.restype = C.c_int
     lib.orc_iterate_sampled.argtypes = [VP, C.c_int, i32p, i32p]
+    lib.orc_set_shard.argtypes = [VP, C.c_int, C.c_int]
     lib.orc_chance_partials.restype = C.c_int
     lib.orc_chance_partials.argtypes = [VP, C.c_int, C.c_int, C.c_int, f64p, C.c_int]
     _lib = lib
@@ -253,6 +254,10 @@ class OracleGame:
         out = np.zeros((cap_nodes, self.n_hands[p]), dtype=np.float64)
         n = self.lib.orc_chance_partials(self.h, p, lo, hi, out.ctypes.data_as(f64p), cap_nodes)
         return out[:n].copy()
+
+    def set_shard(self, lo: int, hi: int):
+        """Every later traversal deals only the first-level boards [lo, hi) at the round-0 chance nodes (hi <= 0: all)."""
+        self.lib.orc_set_shard(self.h, int(lo), int(hi))
 
     def discount(self, d: float):
         self.lib.orc_discount(self.h, d)

@@ -782,10 +782,19 @@ void orc_average_value(orc_game* g, double out[2]) {
     }
 }
 
+/* Board-shard window for EVERY later traversal (CFR, best response, average value): the chance nodes of round 0 only
+ * deal boards in [lo, hi); hi <= 0 switches the window off.  Mirrors a rank of the board-sharded engine that never
+ * exchanges (RS_FLAG_SHARD_ISOLATED). */
+void orc_set_shard(orc_game* g, int lo, int hi) {
+    g->shard_lo = lo;
+    g->shard_hi = hi > 0 ? hi : 0;
+}
+
 /* Values of the round-0 chance nodes for traverser p under the AVERAGE strategies (no table update), summed
  * over the dealt boards in [lo, hi) only: the partial sums a board-sharded rank contributes before the
  * all-reduce.  Returns the number of chance nodes written (DFS order), each H[p] doubles. */
 int orc_chance_partials(orc_game* g, int p, int lo, int hi, double* out, int cap_nodes) {
+    const int slo = g->shard_lo, shi = g->shard_hi;
     g->shard_lo = lo;
     g->shard_hi = hi;
     g->rec = out;
@@ -794,7 +803,8 @@ int orc_chance_partials(orc_game* g, int p, int lo, int hi, double* out, int cap
     traverse(g, p, MODE_EVAL);
     int n = g->rec_n;
     g->rec = NULL;
-    g->shard_lo = g->shard_hi = 0;
+    g->shard_lo = slo;
+    g->shard_hi = shi;
     return n;
 }
 

@@ -163,6 +163,7 @@ struct Engine {
     cudaGraphExec_t graph_exec = nullptr;
     bool use_graph = true;
     nccl::Comm comm = nullptr;
+    bool isolated = false;  // RS_FLAG_SHARD_ISOLATED: a shard without peers, no exchange of any kind
 
     RoundDev rd[3];
     DevBuf<float> scratch;  // strategy read-outs
@@ -258,6 +259,7 @@ int Engine::init(const rs_config* cfg) {
         return set_err(RS_ERR_INVALID, "threads_per_block is derived from the range size (4 hands per thread) and cannot be set");
     if (cfg->flags & ~uint32_t(RS_FLAG_ALL)) return set_err(RS_ERR_INVALID, "unknown bits in rs_config.flags");
     use_graph = !(cfg->flags & RS_FLAG_NO_GRAPH);
+    isolated = (cfg->flags & RS_FLAG_SHARD_ISOLATED) != 0;
     discount_interval = cfg->discount_interval;
     discount_cap = cfg->discount_cap;
     CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -373,7 +375,7 @@ int Engine::init(const rs_config* cfg) {
     CU(scratch.alloc(size_t(1326) * MAX_ACTIONS));
 
     updates_global = P.updates_per_iter_local;
-    if (P.world > 1) {
+    if (P.world > 1 && !isolated) {
         std::string err;
         if (!nccl::load(&err)) return set_err(RS_ERR_NCCL, err);
         nccl::UniqueId id;
@@ -399,7 +401,7 @@ int Engine::init(const rs_config* cfg) {
         CU(cudaMemcpy(parts, tmp.p, sizeof(parts), cudaMemcpyDeviceToHost));
         updates_global = uint64_t(parts[0]) + (uint64_t(parts[1]) << 20) + (uint64_t(parts[2]) << 40);
     }
-    if (P.world > 1 && P.shard_round >= 1) {
+    if (P.world > 1 && P.shard_round >= 1 && !isolated) {
         const RoundDev& Par = rd[P.shard_round - 1];
         xch_vectors = size_t(Par.n_leaves) * Par.n_boards * size_t(P.world);
         xch_flag_bytes = (2 * xch_vectors * sizeof(uint32_t) + 255) & ~size_t(255);
@@ -681,7 +683,7 @@ int Engine::prof_end(uint32_t kind, uint32_t phase, int trav, uint32_t grid, uin
 uint64_t Engine::table_bytes_of(int trav, int phase, bool street) const {
     const Plan& P = plan;
     uint64_t bytes = 0;
-    const bool split = !fused_exchange && full[trav].phase_cut < full[trav].n_tickets;
+    const bool split = !fused_exchange && !isolated && full[trav].phase_cut < full[trav].n_tickets;
     for (uint32_t k = 0; k < P.n_rounds; ++k) {
         if (street && k + 1 == P.n_rounds) continue;  // counted by the street kernel's launch
         const uint64_t own = P.tabs[k][trav].board_off[P.n_boards[k]];
@@ -729,7 +731,7 @@ int Engine::enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet
         steps.push_back({1, 0, 0, 0});
         at = set->street_hi;
     }
-    const bool split = !fused_exchange && set->phase_cut < set->n_tickets;
+    const bool split = !fused_exchange && !isolated && set->phase_cut < set->n_tickets;
     const uint32_t cut = split ? std::max(set->phase_cut, at) : set->n_tickets;
     if (cut > at) steps.push_back({0, at, cut, use_street ? 1u : 0u});
     if (split) {

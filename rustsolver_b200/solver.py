@@ -26,6 +26,7 @@ RS_ABS_NONE, RS_ABS_ISOMORPHIC, RS_ABS_CLUSTER_ARR, RS_ABS_BUCKET_TABLE = 0, 1, 
 RS_FLAG_NO_GRAPH = 1
 RS_FLAG_NO_CHAIN_SPLIT = 2
 RS_FLAG_STREET_KERNEL = 4
+RS_FLAG_SHARD_ISOLATED = 8
 NODE_ACTION, NODE_TERMINAL, NODE_PUBLIC_CHANCE, NODE_PRIVATE_CHANCE = 0, 1, 2, 3
 TERM_ALLIN, TERM_SHOWDOWN, TERM_UNCONTESTED = 0, 1, 2
 ACTION_NAMES = {0: "Bet", 1: "Raise", 2: "Check", 3: "Call", 4: "Fold"}

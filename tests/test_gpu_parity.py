@@ -367,3 +367,132 @@ def test_sampled_iterations_converge():
         eng.iterate_sampled(_sample_paths(rng, o.board_mask, 4, 1))
     e1 = sum(eng.best_response()) / 2
     assert e1 < 0.25 * e0, (e0, e1)
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size workloads (BASELINE.json configs): what bench.py times is what is checked here
+# ------------------------------------------------------------------------------------------------
+def _workload_pair(w, **kw):
+    n, tree = rb.build_game_tree(w.options)
+    ranges = configs.workload_ranges(w)
+    eng = rb.Engine(tree, ranges, w.options.board_mask, w.card_abs, **kw)
+    return tree, ranges, eng
+
+
+def _root_round_keys(w, ranges):
+    """Bucket keys of the root round for the oracle, computed here from the workload's cluster_arr with the host hand
+    indexer (card_abstraction.rs:204-209: canonical index of hole cards + board -> cluster id), independently of the
+    engine's plan: [1 board, H] per player.  Blocked hands get a key too; the oracle never reads it."""
+    board = [c for c in range(52) if w.options.board_mask >> c & 1]
+    ix = rb.HandIndexer([2, len(board)])
+    arr = w.card_abs[0].cluster_arr
+    per = []
+    for q in range(2):
+        cards = np.zeros((len(ranges[q]), 2 + len(board)), dtype=np.uint8)
+        cards[:, :2] = np.sort(np.asarray(ranges[q], dtype=np.uint8), axis=1)
+        cards[:, 2:] = board
+        per.append(arr[ix.index_many(cards)].astype(np.uint32)[None, :])
+    return per
+
+
+@pytest.mark.parametrize("flags", [0, rb.RS_FLAG_STREET_KERNEL])
+def test_config2_full_size_lockstep(flags):
+    """BASELINE config 2 exactly as bench.py runs it: 1128-hand ranges (several compute warps per CTA), 48 river boards,
+    K = 500 turn buckets, two streets.  Covers the cross-warp scan totals, the parent_pos scatter of the street roots,
+    TK_GATHER over 48 boards and the chain-round split at full size (cfr.rs:502-522)."""
+    w = configs.config2()
+    tree, ranges, eng = _workload_pair(w, flags=flags)
+    keys = [_root_round_keys(w, ranges), None]
+    orc = OracleGame(tree, ranges, w.options.board_mask, keys=keys)
+    assert eng.stats().updates_per_iteration == orc.updates_per_iter
+    util.lockstep(eng, orc, tree, n_free=1, n_locked=2, tol=TOL)
+    br_g, br_o = eng.best_response(), orc.best_response()
+    assert np.allclose(br_g, br_o, rtol=1e-4, atol=1e-4), (br_g, br_o)
+    ev_g, ev_o = eng.average_value(), orc.average_value()
+    assert np.allclose(ev_g, ev_o, rtol=1e-4, atol=1e-4), (ev_g, ev_o)
+
+
+def test_config3_full_size_lockstep():
+    """BASELINE config 3: 1326-slot ranges (352-thread CTAs), 76 action nodes, five-action nodes."""
+    w = configs.config3()
+    tree, ranges, eng = _workload_pair(w)
+    orc = OracleGame(tree, ranges, w.options.board_mask)
+    util.lockstep(eng, orc, tree, n_free=1, n_locked=2, tol=TOL)
+    assert np.allclose(eng.best_response(), orc.best_response(), rtol=1e-4, atol=1e-4)
+
+
+def _shard_compare(eng, orc, tree, lo1, hi1, per2, n_locked):
+    st = eng.stats()
+    nb = [st.n_boards[k] for k in range(st.n_rounds)]
+
+    def mine(k, b):
+        return k == 0 or (lo1 <= b < hi1 if k == 1 else lo1 * per2 <= b < hi1 * per2)
+
+    rk = {int(tree.an_index[i]): int(tree.round_idx[i]) for i in range(tree.n_nodes) if tree.type[i] == 0}
+    slabs = [(an, b) for an, b in util.all_slabs(tree, nb) if mine(rk[an], b)]
+    al = util.RowAligner(eng, orc, tree)
+    for it in range(1 + n_locked):
+        if it > 0:
+            for an, b in slabs:
+                r, s = orc.get_slab(an, b)
+                al.write(an, b, r, s)
+        eng.iterate(1)
+        orc.iterate(1)
+        scales, table, diffs = {}, {"R": 0.0, "S": 0.0}, {}
+        for an, b in slabs:
+            gr, gs = al.read(an, b)
+            orr, os_ = orc.get_slab(an, b)
+            for g, o_, nm in ((gr, orr, "R"), (gs, os_, "S")):
+                if o_.size:
+                    m = float(np.abs(o_).max())
+                    scales[(an, nm)] = max(scales.get((an, nm), 0.0), m)
+                    table[nm] = max(table[nm], m)
+                    diffs[(an, b, nm)] = float(np.abs(g - o_).max())
+        for (an, b, nm), d in diffs.items():
+            bound = TOL * scales[(an, nm)] + util.ABS_FLOOR * table[nm]
+            assert d <= bound, (it, an, b, nm, d, bound)
+
+
+@pytest.mark.parametrize("flags", [0, rb.RS_FLAG_STREET_KERNEL])
+def test_config4_sub_sampled_turn_cards(flags):
+    """BASELINE config 4 (flop-rooted, K = 500 flop buckets, 1176-hand ranges, 2352 river boards) on 2 of its 49 turn cards
+    with all their river children: the slice a rank of a 25-way board-sharded run owns, walked without peers
+    (RS_FLAG_SHARD_ISOLATED) against the oracle restricted to the same window."""
+    w = configs.config4()
+    n, tree = rb.build_game_tree(w.options)
+    ranges = configs.workload_ranges(w)
+    world, rank = 25, 3
+    eng = rb.Engine(tree, ranges, w.options.board_mask, w.card_abs, rank=rank, world_size=world,
+                    flags=flags | rb.RS_FLAG_SHARD_ISOLATED)
+    st = eng.stats()
+    lo1, hi1 = rank * st.n_boards[1] // world, (rank + 1) * st.n_boards[1] // world
+    assert hi1 - lo1 == 2 and st.n_boards_local[2] == 2 * 48
+    keys = [_root_round_keys(w, ranges), None, None]
+    orc = OracleGame(tree, ranges, w.options.board_mask, keys=keys)
+    orc.set_shard(lo1, hi1)
+    _shard_compare(eng, orc, tree, lo1, hi1, st.n_boards[2] // st.n_boards[1], n_locked=1)
+    assert np.allclose(eng.best_response(), orc.best_response(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", ["turn", "flop"])
+def test_every_shard_of_a_sharded_run_alone(case):
+    """Board sharding without a second GPU: each rank of a 2-way (turn-rooted) or 3-way (flop-rooted) split is created in
+    turn as an isolated shard and checked against the oracle restricted to the same boards -- local board numbering,
+    per-rank task lists, partial chance sums and the replicated root street, everything but the exchange itself."""
+    if case == "turn":
+        o = util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]] * 2, [[3.0]] * 2)
+        world = 2
+    else:
+        o = util.small_options("4d5dAs", ["AA,KK,AKs,76s,54s", "QQ,JJ,AQs,65s,32s"], [[1.0]] * 3, [[3.0]] * 3, pot=40, stacks=(60, 60))
+        world = 3
+    n, tree = rb.build_game_tree(o)
+    ranges = o.ranges()
+    for rank in range(world):
+        eng = rb.Engine(tree, ranges, o.board_mask, [], rank=rank, world_size=world, flags=rb.RS_FLAG_SHARD_ISOLATED)
+        st = eng.stats()
+        lo1, hi1 = rank * st.n_boards[1] // world, (rank + 1) * st.n_boards[1] // world
+        orc = OracleGame(tree, ranges, o.board_mask)
+        orc.set_shard(lo1, hi1)
+        per2 = st.n_boards[2] // st.n_boards[1] if st.n_rounds > 2 else 0
+        _shard_compare(eng, orc, tree, lo1, hi1, per2, n_locked=1)
+        eng.close()
