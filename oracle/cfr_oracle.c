@@ -587,6 +587,7 @@ static void runout_showdown(walk_ctx* c, int k, int b, const double* reach, doub
     int per = g->deal_count[k + 1];
     for (int i = 0; i < per; ++i) {
         int cb = b * per + i;
+        if (k == 0 && g->shard_hi > 0 && (cb < g->shard_lo || cb >= g->shard_hi)) continue; /* another rank's board */
         if (!samp_allowed(g, k + 1, cb)) continue;
         for (int j = 0; j < Ho; ++j) r2[j] = (g->hmask[o][j] & g->bmask[k + 1][cb]) ? 0.0 : reach[j];
         runout_showdown(c, k + 1, cb, r2, pi / len, value, tmp);

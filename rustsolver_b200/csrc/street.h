@@ -5,28 +5,33 @@
 // of every multi-street workload.  Its street segments (the subtree below one chance leaf of the previous
 // round, or the whole tree of a river-only game) are independent of each other given the segment's incoming
 // opponent reach, and a segment has no chance node inside.  Instead of one dataflow task per (node, board)
-// (tasks.h) a segment is walked by ONE CTA per board in three phases:
+// (tasks.h) a UNIT = (board, segment) is walked by ONE CTA in three phases:
 //
 //   D  (hand-parallel, no barrier)   opponent nodes in pre-order: regret matching, child reach (cfr.rs:582-586).
 //                                    Every reach vector that a terminal or a traverser node needs becomes one
 //                                    ROW of the unit's scratch matrix X[row][opponent position].
-//   T  (one warp per 32 rows)        terminal evaluation of all rows at once (cfr.rs:523-558): ONE sorted sweep
-//                                    over the board's hands, weakest first, lane = row, with running per-card sums
-//                                    of the opponent reach in shared memory ([card][lane]: conflict-free).  For a
-//                                    traverser hand h of strength class g, cards (a, b):
-//                                        A(h) = S - s[a] - s[b]  before class g is added  (strictly weaker, compatible)
-//                                        B(h) = S - s[a] - s[b]  after class g was added
-//                                    the sweep leaves Y(h) = A(h) + B(h) and the totals S, s[.]; with
-//                                    C(h) = S - s[a] - s[b] at the end:
-//                                        showdown value  = Y(h) - C(h)               (weaker minus stronger reach)
-//                                        fold / mass     = C(h) + x[identical combo]
+//   T  (list-parallel)               terminal evaluation of all rows (cfr.rs:523-558), four rows at a time
+//                                    (a QUAD, interleaved as float4 per position in shared memory).  For a
+//                                    traverser hand h = (a, b) of strength s and an opponent reach row x:
+//                                        A_L(h) = sum of x over the hands of list L strictly weaker than s
+//                                        B_L(h) = the same, weaker or equal
+//                                    where L is the list of ALL live opponent hands (G) or of those holding one
+//                                    card (a, b).  With T_c = sum of x over the opponent hands holding c:
+//                                        C'(h)         = T_G - T_a - T_b
+//                                        showdown term = (A_G + B_G) - (A_a + B_a) - (A_b + B_b) - C'(h)
+//                                        fold / mass   = C'(h) + x[identical combo]
+//                                    One thread walks one (quad, list): it keeps the running sum of its list in
+//                                    registers, loads x by a precomputed PROGRAM of the board (one word per step:
+//                                    which opponent position to add, which traverser hand to emit to, where a
+//                                    strength class starts and ends) and stores A + B for the traverser hands of
+//                                    the list.  The 52 card lists and the global order, cut into SW_CHUNKS pieces
+//                                    at class boundaries, are walked in parallel; no per-hand random gathers, no
+//                                    prefix-sum barriers per terminal.
 //   U  (hand-parallel, no barrier)   traverser nodes in post-order: child values, node value, regret and
-//                                    strategy-sum update (cfr.rs:588, 612-621), values of inner nodes in
-//                                    thread-private scratch; the segment root's value goes where the chance gather
-//                                    (or the root read-out) expects it.
+//                                    strategy-sum update (cfr.rs:588, 612-621); every term is one vector the T
+//                                    phase left (VY showdown, VM mass) or the value slot of a node further down.
 //
-// A UNIT is (board, template): a template is a run of consecutive segments whose rows fit the sweep warps of one
-// CTA.  Everything in here is board-independent except the event streams (SwBoard) that drive the sweep.
+// Everything in here is board-independent except the programs.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -34,23 +39,37 @@
 
 namespace rs {
 
-constexpr int SW_MAX_ACT = 5;    // widest action node the fused street kernel keeps in registers
-constexpr int SW_LANES = 32;     // rows per sweep warp
-constexpr int SW_MAX_BATCH = 8;  // sweep warps per unit
+constexpr int SW_MAX_ACT = 5;   // widest action node the fused street kernel keeps in registers
 constexpr int SW_CARDS = 52;
-constexpr int SW_SEGS = 8;       // pieces the sweep of one board is cut into (sweep warps per batch: 1, 2, 4 or 8)
-constexpr int SW_CT_PITCH = 53;  // totals table: 52 per-card sums + the total, odd pitch
+constexpr int SW_CHUNKS = 64;   // pieces the strength order of a board is cut into (global list)
+constexpr int SW_TT = 53;       // totals table of a quad: 52 per-card sums + the total
+constexpr int SW_MAX_SD_ROWS = 32;  // showdown rows of one segment (sd_need_m is a 32-bit mask)
+
+// program word: one step of a list walk
+//   bits  0..10  opponent position added in this step (HoP = the zero cell: nothing to add)
+//   bits 11..22  emit index: target * (HpP + 1) + traverser position; target 0 / 1 = the list is the hand's lower /
+//                higher card (two arrays, so that two lists never write the same cell); HpP = the dump cell
+//   bit  23      a strength class with traverser hands starts: latch the running sum (A)
+//   bit  24      the class ends with this step's add: m = A + running sum (B); the step's emit already sees it
+constexpr uint32_t SW_ADD_MASK = 0x7ffu;
+constexpr int SW_EMIT_SHIFT = 11;
+constexpr uint32_t SW_EMIT_MASK = 0xfffu;
+constexpr uint32_t SW_CLASS_START = 1u << 23;
+constexpr uint32_t SW_CLASS_END = 1u << 24;
+
+// per traverser position: c0 | c1 << 6 | chunk << 12 | identical-combo opponent position << 18 (HoP: none)
+constexpr int SW_HI_C1_SHIFT = 6, SW_HI_CHUNK_SHIFT = 12, SW_HI_SAME_SHIFT = 18;
 
 enum SwTermKind : uint8_t {
-    ST_FOLD = 0,      // coef * (C + x[identical combo]) of row id        (cfr.rs:525-531)
-    ST_SHOWDOWN = 1,  // coef * (Y - C) of row id                         (cfr.rs:532-556)
+    ST_FOLD = 0,      // coef * VM[row id]   (cfr.rs:525-531)
+    ST_SHOWDOWN = 1,  // coef * VY[row id]   (cfr.rs:532-556)
     ST_VALUE = 2      // value slot id of a traverser node further down
 };
 
 struct SwTerm {
     uint8_t kind;  // SwTermKind
     uint8_t pad;
-    int16_t id;    // row (local to the unit) or value slot
+    int16_t id;    // row (local to the segment) or value slot
     float coef;    // +-pot of a terminal (before the chance weight)
 };
 
@@ -74,21 +93,18 @@ struct SwUp {  // one traverser node (post-order), or the plain sum that values 
     uint16_t term_first[SW_MAX_ACT + 1];  // terms of action a = [term_first[a], term_first[a + 1])
 };
 
+// Rows of a segment are numbered: showdown rows first (quads [0, nq_sd)), then the rows that only need their mass
+// (quads [nq_sd, nq_sd + nq_mo)), then rows that are only read by the D phase.  Quads are padded with unused rows.
 struct SwSeg {
     uint32_t down_first, down_count;
     uint32_t up_first, up_count;
     int32_t root_row;   // row receiving the segment's incoming reach
     int32_t root_in;    // reach buffer id of the PARENT round (chance leaf), or -1 = the opponent's range weights
     int32_t root_out;   // street-root value buffer id (parent-board order pool when the round has a parent, else cbuf id)
-    int32_t pad;
-};
-
-struct SwUnit {  // template: segments [seg_first, seg_first + seg_count) walked by one CTA per board
-    uint32_t seg_first, seg_count;
-    uint32_t n_batches;  // sweep warps = ceil(rows / 32)
-    uint32_t n_rows;
+    uint32_t n_rows;    // all rows, including the padding of the quads
+    uint32_t nq_sd, nq_mo;
     uint32_t n_slots;
-    uint32_t need_y[SW_MAX_BATCH];  // rows whose Y the U phase reads (a showdown is valued from them)
+    uint32_t sd_need_m;  // showdown rows whose mass is read too (bit = row)
 };
 
 // One traverser's final-street programs.
@@ -96,27 +112,17 @@ struct StreetPlan {
     bool eligible = false;
     std::string why;  // why not, for diagnostics
     uint32_t round_k = 0;
-    std::vector<SwUnit> units;
     std::vector<SwSeg> segs;
     std::vector<SwDown> downs;
     std::vector<SwUp> ups;
     std::vector<SwTerm> terms;
-    uint32_t max_batches = 0, max_rows = 0, max_slots = 0;
-    uint32_t ticket_lo = 0, ticket_hi = 0;  // node-task TICKET range (tasks.h numbering of the plan) this replaces
-    // per board of the round (GLOBAL board ids; only local boards are filled)
-    std::vector<uint32_t> ev;      // event streams: [class header][reads...][adds...] ...
-    std::vector<uint32_t> ev_off;  // [n_boards + 1]
-    // the sweep of one board is cut at class boundaries into SW_SEGS pieces of about equal length, so that several warps
-    // can sweep one unit: per board [3][SW_SEGS + 1] = first event word / first add position / first read position
-    std::vector<uint32_t> seg;     // [n_boards][3 * (SW_SEGS + 1)]
+    uint32_t max_rows = 0, max_slots = 0, max_q_sd = 0, max_q_mo = 0;
+    // per LOCAL board of the round (index = board - local_lo): the list programs [l_steps][52] followed by the chunk
+    // programs [c_steps][SW_CHUNKS], one word per (step, list)
+    std::vector<uint32_t> prog;
+    std::vector<uint32_t> prog_off;  // [n_local + 1] word offsets
+    std::vector<uint32_t> l_steps, c_steps;  // [n_local]
+    std::vector<uint32_t> hinfo;     // [n_local][HpP] per traverser position (SW_HI_*)
 };
-
-// event words
-//   header: n_read | n_add << 11
-//   entry : position | card_a << 11 | card_b << 17 | collides << 23
-//           position in the reader's / adder's board-local order; collides: an ADD entry that shares a card with the
-//           ADD entry before it (the two running-sum updates must not be overlapped)
-constexpr uint32_t SW_EV_POS_MASK = 0x7ffu;
-constexpr uint32_t SW_EV_COLLIDES = 1u << 23;
 
 }  // namespace rs
