@@ -109,12 +109,11 @@ typedef struct rs_config {
 #define RS_FLAG_NO_CHAIN_SPLIT 2u /* keep one task per node on rounds with one or two boards (default: such rounds are
                                      chains of dependent tasks and their node tasks are split so that each level of
                                      the chain only waits for what it needs; results are identical either way) */
-#define RS_FLAG_STREET_KERNEL 4u /* EXPERIMENTAL: walk the final betting round with the fused street kernel (one CTA per board
-                                    and run of street segments, terminals valued by one sorted sweep with running per-card
-                                    sums, csrc/street_kernel.cu) instead of the per-(node, board) dataflow tasks.  Same
-                                    values up to fp32 rounding; measured slower than the task kernel,
-                                    so it is off by default.  Lossy (bucketed) final rounds and nodes wider than 5 actions
-                                    always take the task path */
+#define RS_FLAG_STREET_KERNEL 4u /* walk the final betting round with the fused street kernel (one CTA per (board, street
+                                    segment); terminals valued four reach rows at a time by list walks with running sums,
+                                    csrc/street_kernel.cu) instead of the per-(node, board) dataflow tasks.  Same values up
+                                    to fp32 rounding.  Lossy (bucketed) final rounds and nodes wider than 5 actions always
+                                    take the task path */
 #define RS_FLAG_SHARD_ISOLATED 8u /* world_size > 1 without peers: the rank walks only its own slice of the first dealt-card
                                      level (rank r of world_size) and never exchanges; the other ranks' boards contribute zero
                                      to the chance-node sums.  No NCCL communicator is created.  This is public-chance
@@ -307,19 +306,16 @@ int rs_plan_showdown_order(const rs_plan* p, uint32_t player, uint32_t board_id,
                            uint16_t* order_out, uint32_t* class_out, size_t cap,
                            uint32_t* n_live_out);
 
-/* The final betting round as the fused street kernel sees it (csrc/street.h): out = {eligible, unit templates, max sweep
- * warps per unit, max reach rows per unit, max value slots, segments, opponent-node ops, traverser-node ops}.  When the
- * round is not eligible rs_last_error() says why (bucketed tables, a node wider than 5 actions, the flag). */
+/* The final betting round as the fused street kernel sees it (csrc/street.h): out = {eligible, segments, max reach rows
+ * per segment, max value slots, max showdown quads, max mass-only quads, opponent-node ops, traverser-node ops}.  When
+ * the round is not eligible rs_last_error() says why (bucketed tables, a node wider than 5 actions, the flag). */
 int rs_plan_street_info(const rs_plan* p, uint32_t traverser, uint32_t out[8]);
-/* The event stream that drives the sorted sweep of `traverser` on a final-round board: per strength class, weakest
- * first, a header word (n_read | n_add << 11), the traverser's hands of the class (reads), the opponent's (adds); an
- * entry is position | card_a << 11 | card_b << 17 in the owner's board-local (strength-sorted) order.
- * out == NULL: only the count. */
-int rs_plan_street_events(const rs_plan* p, uint32_t traverser, uint32_t board_id, uint32_t* out, size_t cap, uint32_t* n_out);
-/* The eight pieces the sweep of that board is cut into (several warps sweep one board): out[0..8] = first event word of
- * piece q (out[8] = the word count), out[9..17] = first opponent position added, out[18..26] = first traverser position
- * read.  Cuts fall on class boundaries. */
-int rs_plan_street_segments(const rs_plan* p, uint32_t traverser, uint32_t board_id, uint32_t out[27]);
+/* The list programs that drive the terminal evaluation of `traverser` on a final-round board (csrc/street.h): words
+ * [l_steps][52] of the card lists followed by [c_steps][64] of the pieces of the global strength order, and the
+ * per-position word (cards, piece, identical combo) of the traverser's hands, hinfo[Hpad].  dims_out = {l_steps,
+ * c_steps, Hpad of the traverser, Hpad of the opponent}.  words_out == NULL: only the sizes. */
+int rs_plan_street_program(const rs_plan* p, uint32_t traverser, uint32_t board_id, uint32_t* words_out, size_t cap,
+                           uint32_t* n_words_out, uint32_t* hinfo_out, size_t hinfo_cap, uint32_t dims_out[4]);
 
 #ifdef __cplusplus
 }

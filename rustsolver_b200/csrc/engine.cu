@@ -144,13 +144,12 @@ struct TaskSet {
 
 // device copy of one traverser's final-street programs (street.h)
 struct StreetDev {
-    DevBuf<SwUnit> units;
     DevBuf<SwSeg> segs;
     DevBuf<SwDown> downs;
     DevBuf<SwUp> ups;
     DevBuf<SwTerm> terms;
-    DevBuf<uint32_t> ev, ev_off, seg;
-    uint32_t n_tmpl = 0;
+    DevBuf<uint32_t> prog, prog_off, l_steps, c_steps, hinfo;
+    uint32_t n_segs = 0;
 };
 
 struct Engine {
@@ -185,10 +184,9 @@ struct Engine {
     // fused final-street kernel (street_kernel.cu); off: the final round runs as node tasks like the others
     bool street_on = false;
     StreetDev street[2];
-    DevBuf<uint16_t> st_pcards[2], st_same[2];
     DevBuf<float> st_scratch;
     size_t st_stride = 0, st_smem = 0;
-    int st_XP = 0, st_YP = 0, st_rows = 0, st_slots = 0, st_threads = 0, st_blocks_per_sm = 1, st_sweep_warps = 1;
+    int st_XP = 0, st_rows = 0, st_vy_rows = 0, st_vm_rows = 0, st_slots = 0, st_threads = 0, st_blocks_per_sm = 1, st_qs = 1, st_qm = 1;
     int slots = 1;
     size_t smem_bytes = 0;
     int blocks_per_sm = 1, n_sms = 148;
@@ -416,53 +414,46 @@ int Engine::init(const rs_config* cfg) {
 // Upload the final-street programs and size the per-CTA scratch of the fused street kernel.
 int Engine::init_street() {
     const Plan& P = plan;
-    const uint32_t k = P.n_rounds - 1;
-    const uint32_t lo = P.local_lo[k], hi = P.local_hi[k];
-    uint32_t max_batches = 1, max_rows = 1, max_slots = 1;
+    uint32_t max_rows = 1, max_slots = 1, max_q_sd = 1, max_q_mo = 1;
     for (int p = 0; p < 2; ++p) {
         const StreetPlan& S = P.street[p];
         StreetDev& D = street[p];
-        CU(D.units.upload(S.units));
         CU(D.segs.upload(S.segs));
         CU(D.downs.upload(S.downs));
         CU(D.ups.upload(S.ups));
         CU(D.terms.upload(S.terms));
-        {
-            std::vector<uint32_t> ev = S.ev;
-            ev.resize(ev.size() + 64, 0u);  // the sweep's event window prefetches up to 64 words past a board's last event
-            CU(D.ev.upload(ev));
-        }
-        CU(D.seg.upload(slice(S.seg, lo, hi, 3 * (SW_SEGS + 1))));
-        CU(D.ev_off.upload(std::vector<uint32_t>(S.ev_off.begin() + lo, S.ev_off.begin() + hi + 1)));
-        D.n_tmpl = uint32_t(S.units.size());
-        max_batches = std::max(max_batches, S.max_batches);
+        CU(D.prog.upload(S.prog));
+        CU(D.prog_off.upload(S.prog_off));
+        CU(D.l_steps.upload(S.l_steps));
+        CU(D.c_steps.upload(S.c_steps));
+        CU(D.hinfo.upload(S.hinfo));
+        D.n_segs = uint32_t(S.segs.size());
         max_rows = std::max(max_rows, S.max_rows);
         max_slots = std::max(max_slots, S.max_slots);
-        const LocalTables& L = P.loc[k][p];
-        CU(st_pcards[p].upload(slice(L.pcards, lo, hi, L.Hpad)));
-        std::vector<uint16_t> same(size_t(hi - lo) * L.Hpad, 0xFFFF);
-        for (size_t i = 0; i < same.size(); ++i) same[i] = L.hrec[size_t(lo) * L.Hpad + i].same;
-        CU(st_same[p].upload(same));
+        max_q_sd = std::max(max_q_sd, S.max_q_sd);
+        max_q_mo = std::max(max_q_mo, S.max_q_mo);
     }
-    const int HPmax = int(std::max((P.H[0] + 3) & ~3u, (P.H[1] + 3) & ~3u));
+    const int HP[2] = {int((P.H[0] + 3) & ~3u), int((P.H[1] + 3) & ~3u)};
+    const int HPmax = std::max(HP[0], HP[1]);
     st_XP = (HPmax + 31) & ~31;
-    st_YP = st_XP;
-    st_rows = int(max_batches) * SW_LANES;
+    st_rows = int(max_rows);
+    st_vy_rows = 4 * int(max_q_sd);
+    st_vm_rows = 4 * int(max_q_sd + max_q_mo);
     st_slots = int(max_slots);
-    st_stride = size_t(st_rows) * st_XP + size_t(st_rows) * st_YP + size_t(st_slots) * HPmax;
-    st_threads = threads;  // 4 hands per thread in one pass
-    if (const char* e = getenv("RS_STREET_THREADS")) st_threads = std::max(32, std::min(352, atoi(e) / 32 * 32));
-    st_threads = std::max(st_threads, int(max_batches) * 32);
-    // sweep warps per batch of 32 rows: the sweep of a board is cut into that many segments (street.h)
-    int want_sw = 4;
-    if (const char* e = getenv("RS_SWEEP_WARPS")) want_sw = atoi(e);
-    st_sweep_warps = 1;
-    while (st_sweep_warps * 2 <= want_sw && st_sweep_warps * 2 <= SW_SEGS && int(max_batches) * st_sweep_warps * 2 * 32 <= st_threads)
-        st_sweep_warps *= 2;
-    st_smem = street_smem_bytes(int(max_batches), st_sweep_warps);
+    st_stride = size_t(st_rows) * st_XP + size_t(st_vy_rows + st_vm_rows + st_slots) * HPmax;
+    st_threads = threads;  // 4 hands per thread in one pass of the D and U phases
+    if (const char* e = getenv("RS_STREET_THREADS")) st_threads = std::max(64, std::min(352, atoi(e) / 32 * 32));
+    // quads staged per round: as many as fit the shared-memory budget of one CTA (3 CTAs per SM by default)
+    size_t budget = 72 * 1024;
+    if (const char* e = getenv("RS_STREET_SMEM_KB")) budget = size_t(std::max(16, atoi(e))) * 1024;
+    st_qs = st_qm = 1;
+    const int max_q = st_threads / 32;  // one warp per quad reduces the totals
+    while (st_qs < int(max_q_sd) && st_qs < max_q && street_smem_bytes(st_qs + 1, st_qm, HPmax, HPmax) <= budget) ++st_qs;
+    while (st_qm < int(max_q_mo) && st_qm < max_q && street_smem_bytes(st_qs, st_qm + 1, HPmax, HPmax) <= budget) ++st_qm;
+    st_smem = street_smem_bytes(st_qs, st_qm, HPmax, HPmax);
     int max_optin = 0;
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    if (st_smem > size_t(max_optin)) return RS_OK;  // too many sweep warps for one CTA: stay on the task kernel
+    if (st_smem > size_t(max_optin)) return RS_OK;  // does not fit one CTA: stay on the task kernel
     CU(configure_street_kernels(st_smem, st_threads, &st_blocks_per_sm));
     if (st_blocks_per_sm < 1) return RS_OK;
     if (const char* e = getenv("RS_STREET_BLOCKS")) st_blocks_per_sm = std::max(1, std::min(st_blocks_per_sm, atoi(e)));
@@ -505,29 +496,29 @@ int Engine::enqueue_street(int trav, int mode, const TaskSet& set, int n_paths) 
     a.root_weights = root_weights[1 - trav].p;
     a.out_buf = k > 0 ? R.sbuf[trav].p : R.cbuf.p;
     a.out_scatter = k > 0 ? 1 : 0;
-    a.n_tmpl = int(D.n_tmpl);
-    a.units = D.units.p;
+    a.n_segs = int(D.n_segs);
     a.segs = D.segs.p;
     a.downs = D.downs.p;
     a.ups = D.ups.p;
     a.terms = D.terms.p;
-    a.ev = D.ev.p;
-    a.ev_off = D.ev_off.p;
-    a.seg = D.seg.p;
-    a.sweep_warps = st_sweep_warps;
-    a.pcards = st_pcards[trav].p;
-    a.same_pos = st_same[trav].p;
+    a.prog = D.prog.p;
+    a.prog_off = D.prog_off.p;
+    a.l_steps = D.l_steps.p;
+    a.c_steps = D.c_steps.p;
+    a.hinfo = D.hinfo.p;
     a.scratch = st_scratch.p;
     a.scratch_stride = st_stride;
     a.XP = st_XP;
-    a.YP = st_YP;
     a.max_rows = st_rows;
+    a.vy_rows = st_vy_rows;
+    a.vm_rows = st_vm_rows;
     a.max_slots = st_slots;
+    a.qs = st_qs;
+    a.qm = st_qm;
     a.trav = trav;
     a.HpP = int((P.H[trav] + 3) & ~3u);
     a.HoP = int((P.H[1 - trav] + 3) & ~3u);
-    a.same_order = P.same_order ? 1 : 0;
-    a.n_units = set.street_inst * D.n_tmpl;
+    a.n_units = set.street_inst * D.n_segs;
     a.sample_board = (n_paths > 0 && k > 0) ? sample_board[k].p : nullptr;
     a.prune_threshold = prune_threshold;
     const int grid = int(std::min<uint64_t>(a.n_units, uint64_t(n_sms) * st_blocks_per_sm));
@@ -754,7 +745,7 @@ int Engine::enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet
             if ((rc = enqueue_street(trav, mode, *set, n_paths)) != RS_OK) return rc;
             const uint32_t k = P.n_rounds - 1;
             const uint64_t own = P.tabs[k][trav].board_off[P.n_boards[k]], opp = P.tabs[k][1 - trav].board_off[P.n_boards[k]];
-            const uint32_t grid = uint32_t(std::min<uint64_t>(uint64_t(set->street_inst) * street[trav].n_tmpl, uint64_t(n_sms) * st_blocks_per_sm));
+            const uint32_t grid = uint32_t(std::min<uint64_t>(uint64_t(set->street_inst) * street[trav].n_segs, uint64_t(n_sms) * st_blocks_per_sm));
             if ((rc = prof_end(RS_KERNEL_STREET, 0, trav, grid, own * 16 + opp * 4, 0)) != RS_OK) return rc;
         } else {
             // the one exchange step of the path: counterfactual values at the shared chance nodes
@@ -1411,41 +1402,41 @@ int rs_plan_street_info(const rs_plan* p, uint32_t traverser, uint32_t out[8]) {
     if (!p || !out || traverser > 1) return set_err(RS_ERR_INVALID, "bad argument");
     const StreetPlan& S = p->p.street[traverser];
     out[0] = S.eligible ? 1u : 0u;
-    out[1] = uint32_t(S.units.size());
-    out[2] = S.max_batches;
-    out[3] = S.max_rows;
-    out[4] = S.max_slots;
-    out[5] = uint32_t(S.segs.size());
+    out[1] = uint32_t(S.segs.size());
+    out[2] = S.max_rows;
+    out[3] = S.max_slots;
+    out[4] = S.max_q_sd;
+    out[5] = S.max_q_mo;
     out[6] = uint32_t(S.downs.size());
     out[7] = uint32_t(S.ups.size());
     if (!S.eligible) g_last_error = S.why;
     return RS_OK;
 }
 
-int rs_plan_street_events(const rs_plan* p, uint32_t traverser, uint32_t board_id, uint32_t* out, size_t cap, uint32_t* n_out) {
-    if (!p || !n_out || traverser > 1) return set_err(RS_ERR_INVALID, "bad argument");
+int rs_plan_street_program(const rs_plan* p, uint32_t traverser, uint32_t board_id, uint32_t* words_out, size_t cap,
+                           uint32_t* n_words_out, uint32_t* hinfo_out, size_t hinfo_cap, uint32_t dims_out[4]) {
+    if (!p || !n_words_out || !dims_out || traverser > 1) return set_err(RS_ERR_INVALID, "bad argument");
     const Plan& P = p->p;
     const StreetPlan& S = P.street[traverser];
     if (!S.eligible) return set_err(RS_ERR_INVALID, "the final round does not run on the street kernel: " + S.why);
     const uint32_t k = P.n_rounds - 1;
     if (board_id < P.local_lo[k] || board_id >= P.local_hi[k]) return set_err(RS_ERR_INVALID, "board is owned by another rank");
-    const uint32_t n = S.ev_off[board_id + 1] - S.ev_off[board_id];
-    *n_out = n;
-    if (out) {
+    const uint32_t lb = board_id - P.local_lo[k];
+    const uint32_t n = S.prog_off[lb + 1] - S.prog_off[lb];
+    const uint32_t HpP = P.loc[k][traverser].Hpad;
+    *n_words_out = n;
+    dims_out[0] = S.l_steps[lb];
+    dims_out[1] = S.c_steps[lb];
+    dims_out[2] = HpP;
+    dims_out[3] = P.loc[k][1 - traverser].Hpad;
+    if (words_out) {
         if (cap < n) return set_err(RS_ERR_CAPACITY, "output buffer too small");
-        memcpy(out, S.ev.data() + S.ev_off[board_id], size_t(n) * sizeof(uint32_t));
+        memcpy(words_out, S.prog.data() + S.prog_off[lb], size_t(n) * sizeof(uint32_t));
     }
-    return RS_OK;
-}
-
-int rs_plan_street_segments(const rs_plan* p, uint32_t traverser, uint32_t board_id, uint32_t out[27]) {
-    if (!p || !out || traverser > 1) return set_err(RS_ERR_INVALID, "bad argument");
-    const Plan& P = p->p;
-    const StreetPlan& S = P.street[traverser];
-    if (!S.eligible) return set_err(RS_ERR_INVALID, "the final round does not run on the street kernel: " + S.why);
-    const uint32_t k = P.n_rounds - 1;
-    if (board_id < P.local_lo[k] || board_id >= P.local_hi[k]) return set_err(RS_ERR_INVALID, "board is owned by another rank");
-    memcpy(out, &S.seg[size_t(board_id) * 3 * (SW_SEGS + 1)], 3 * (SW_SEGS + 1) * sizeof(uint32_t));
+    if (hinfo_out) {
+        if (hinfo_cap < HpP) return set_err(RS_ERR_CAPACITY, "hinfo buffer too small");
+        memcpy(hinfo_out, S.hinfo.data() + size_t(lb) * HpP, size_t(HpP) * sizeof(uint32_t));
+    }
     return RS_OK;
 }
 

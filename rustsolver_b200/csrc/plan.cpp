@@ -527,13 +527,14 @@ struct TaskGen {
         std::vector<SwDown> downs;
         std::vector<SwUp> ups;
         std::vector<SwTerm> terms;
-        std::vector<uint8_t> row_need_y;
+        std::vector<uint8_t> row_need_y, row_need_m;
         uint32_t n_slots = 0;
         int32_t root_row = 0;
     };
 
     int16_t street_row(StreetSeg& g) {
         g.row_need_y.push_back(0);
+        g.row_need_m.push_back(0);
         return int16_t(g.row_need_y.size() - 1);
     }
     float fold_coef(const PNode& cn) const { return (trav == cn.last_to_act) ? -float(cn.value) : float(cn.value); }  // cfr.rs:525-531
@@ -548,12 +549,15 @@ struct TaskGen {
         d.cum_a = n.cum_a;
         for (int a = 0; a < SW_MAX_ACT; ++a) d.out_row[a] = -1;
         for (size_t a = 0; a < n.children.size(); ++a) d.out_row[a] = street_row(g);
+        const size_t di = g.downs.size();
         g.downs.push_back(d);  // pre-order: the rows are written before any op below reads them
+        (void)di;
         for (size_t a = 0; a < n.children.size(); ++a) {
             const int32_t c = n.children[a];
             const PNode& cn = P->nodes[c];
             const int16_t rc = d.out_row[a];
             if (cn.kind == PK_FOLD) {
+                g.row_need_m[rc] = 1;
                 value_terms.push_back(SwTerm{ST_FOLD, 0, rc, fold_coef(cn)});
             } else if (cn.kind == PK_SHOWDOWN) {
                 g.row_need_y[rc] = 1;
@@ -568,6 +572,7 @@ struct TaskGen {
     // traverser node: returns the value slot it writes (-1 for the segment root)
     int16_t street_trav(StreetSeg& g, int32_t id, int16_t row, bool is_root) {
         const PNode& n = P->nodes[id];
+        g.row_need_m[row] = 1;  // the strategy-sum weight is the compatible opponent reach (cfr.rs:618-619)
         std::vector<std::vector<SwTerm>> per_action(n.children.size());
         for (size_t a = 0; a < n.children.size(); ++a) {
             const int32_t c = n.children[a];
@@ -597,6 +602,40 @@ struct TaskGen {
         return u.out_slot;
     }
 
+    // One list walk as program words (street.h).  classes: ascending strength; adds = opponent positions of the class
+    // inside this list, emits = emit indices of the traverser hands of the class inside this list.
+    struct ProgClass {
+        std::vector<uint32_t> adds, emits;
+    };
+    static void schedule_program(const std::vector<ProgClass>& classes, uint32_t zero_pos, uint32_t dump_idx, std::vector<uint32_t>& words) {
+        words.clear();
+        std::vector<uint32_t> pending;  // emits of the last emitting class that have not found a step yet
+        size_t pend_at = 0;
+        auto pop = [&]() -> uint32_t {
+            if (pend_at < pending.size()) return pending[pend_at++];
+            return dump_idx;
+        };
+        auto left = [&]() { return pending.size() - pend_at; };
+        auto step = [&](uint32_t add, uint32_t emit, uint32_t fl) { words.push_back(add | (emit << SW_EMIT_SHIFT) | fl); };
+        for (const ProgClass& c : classes) {
+            if (c.emits.empty()) {
+                for (uint32_t a : c.adds) step(a, pop(), 0);
+                continue;
+            }
+            const size_t n = std::max<size_t>(1, c.adds.size());
+            // the step that ends this class overwrites m: emits of the class before must be out by then
+            while (left() > n - 1) step(zero_pos, pop(), 0);
+            for (size_t i = 0; i < n; ++i) {
+                const uint32_t a = i < c.adds.size() ? c.adds[i] : zero_pos;
+                const uint32_t fl = (i == 0 ? SW_CLASS_START : 0u) | (i == n - 1 ? SW_CLASS_END : 0u);
+                step(a, i == n - 1 ? c.emits[0] : pop(), fl);
+            }
+            pending.assign(c.emits.begin() + 1, c.emits.end());
+            pend_at = 0;
+        }
+        while (left() > 0) step(zero_pos, pop(), 0);
+    }
+
     void build_street() {
         StreetPlan& S = sp;
         const uint32_t R = P->n_rounds, k = R - 1;
@@ -620,9 +659,8 @@ struct TaskGen {
             }
         }
         // compile every segment on its own
-        std::vector<StreetSeg> comp(P->segs[k].size());
         for (uint32_t s = 0; s < P->segs[k].size(); ++s) {
-            StreetSeg& g = comp[s];
+            StreetSeg g;
             const int32_t rootid = P->segs[k][s].root;
             const PNode& rn = P->nodes[rootid];
             g.root_row = street_row(g);
@@ -649,133 +687,203 @@ struct TaskGen {
                 for (int a = 1; a <= SW_MAX_ACT; ++a) u.term_first[a] = uint16_t(g.terms.size());
                 g.ups.push_back(u);
             }
-            if (g.row_need_y.size() > size_t(SW_LANES * SW_MAX_BATCH)) return no("a final-round segment needs more than 256 reach rows");
-            if (g.terms.size() > 60000) return no("too many value terms in one segment");
-        }
-        // pack consecutive segments into unit templates of at most `lanes` rows
-        uint32_t lanes = SW_LANES;
-        if (const char* e = getenv("RS_STREET_LANES")) lanes = std::max<uint32_t>(SW_LANES, std::min<uint32_t>(uint32_t(atoi(e)), SW_LANES * SW_MAX_BATCH));
-        auto open_unit = [&]() {
-            SwUnit u;
-            std::memset(&u, 0, sizeof(u));
-            u.seg_first = uint32_t(S.segs.size());
-            return u;
-        };
-        auto close_unit = [&](SwUnit& u) {
-            if (u.seg_count == 0) return;
-            u.n_batches = (u.n_rows + SW_LANES - 1) / SW_LANES;
-            S.max_batches = std::max(S.max_batches, u.n_batches);
-            S.max_rows = std::max(S.max_rows, u.n_rows);
-            S.max_slots = std::max(S.max_slots, u.n_slots);
-            S.units.push_back(u);
-        };
-        SwUnit cur = open_unit();
-        for (uint32_t s = 0; s < comp.size(); ++s) {
-            const StreetSeg& g = comp[s];
-            const uint32_t rows = uint32_t(g.row_need_y.size());
-            if (cur.seg_count > 0 && cur.n_rows + rows > lanes) {
-                close_unit(cur);
-                cur = open_unit();
-            }
-            const int16_t row0 = int16_t(cur.n_rows), slot0 = int16_t(cur.n_slots);
-            const uint16_t term0 = uint16_t(S.terms.size());
+            // renumber the rows: showdown rows, mass-only rows (both padded to quads), then the rest
+            const size_t nr = g.row_need_y.size();
+            std::vector<int16_t> newid(nr, -1);
+            uint32_t n_sd = 0, n_mo = 0, sd_need_m = 0;
+            for (size_t r = 0; r < nr; ++r)
+                if (g.row_need_y[r]) {
+                    if (g.row_need_m[r]) sd_need_m |= 1u << n_sd;
+                    newid[r] = int16_t(n_sd++);
+                }
+            if (n_sd > uint32_t(SW_MAX_SD_ROWS)) return no("a final-round segment has more than 32 showdown rows");
+            const uint32_t nq_sd = (n_sd + 3) / 4;
+            for (size_t r = 0; r < nr; ++r)
+                if (!g.row_need_y[r] && g.row_need_m[r]) newid[r] = int16_t(4 * nq_sd + n_mo++);
+            const uint32_t nq_mo = (n_mo + 3) / 4;
+            uint32_t next = 4 * (nq_sd + nq_mo);
+            for (size_t r = 0; r < nr; ++r)
+                if (newid[r] < 0) newid[r] = int16_t(next++);
+            if (next > 2000) return no("a final-round segment needs too many reach rows");
+            if (S.terms.size() + g.terms.size() > 65000) return no("too many value terms");
             SwSeg seg;
             std::memset(&seg, 0, sizeof(seg));
             seg.down_first = uint32_t(S.downs.size());
             seg.down_count = uint32_t(g.downs.size());
             seg.up_first = uint32_t(S.ups.size());
             seg.up_count = uint32_t(g.ups.size());
-            seg.root_row = g.root_row + row0;
+            seg.root_row = newid[g.root_row];
             seg.root_in = k > 0 ? leaf_rbuf[k - 1][s] : RIN_INITIAL;
             seg.root_out = segroot_cbuf[k][s];
+            seg.n_rows = next;
+            seg.nq_sd = nq_sd;
+            seg.nq_mo = nq_mo;
+            seg.n_slots = g.n_slots;
+            seg.sd_need_m = sd_need_m;
+            const uint16_t term0 = uint16_t(S.terms.size());
             for (SwDown d : g.downs) {
-                d.in_row = int16_t(d.in_row + row0);
-                for (int a = 0; a < d.n_act; ++a) d.out_row[a] = int16_t(d.out_row[a] + row0);
+                d.in_row = newid[d.in_row];
+                for (int a = 0; a < d.n_act; ++a) d.out_row[a] = newid[d.out_row[a]];
                 S.downs.push_back(d);
             }
-            if (S.terms.size() + g.terms.size() > 65000) return no("too many value terms");
             for (SwUp u : g.ups) {
-                if (u.own_row >= 0) u.own_row = int16_t(u.own_row + row0);
-                if (u.out_slot >= 0) u.out_slot = int16_t(u.out_slot + slot0);
+                if (u.own_row >= 0) u.own_row = newid[u.own_row];
                 for (int a = 0; a <= SW_MAX_ACT; ++a) u.term_first[a] = uint16_t(u.term_first[a] + term0);
                 S.ups.push_back(u);
             }
             for (SwTerm t : g.terms) {
-                t.id = int16_t(t.id + (t.kind == ST_VALUE ? slot0 : row0));
+                if (t.kind != ST_VALUE) t.id = newid[t.id];
                 S.terms.push_back(t);
             }
-            for (uint32_t r = 0; r < rows; ++r)
-                if (g.row_need_y[r]) cur.need_y[(cur.n_rows + r) / SW_LANES] |= 1u << ((cur.n_rows + r) % SW_LANES);
-            cur.n_rows += rows;
-            cur.n_slots += g.n_slots;
-            cur.seg_count++;
             S.segs.push_back(seg);
+            S.max_rows = std::max(S.max_rows, seg.n_rows);
+            S.max_slots = std::max(S.max_slots, seg.n_slots);
+            S.max_q_sd = std::max(S.max_q_sd, nq_sd);
+            S.max_q_mo = std::max(S.max_q_mo, nq_mo);
         }
-        close_unit(cur);
-        if (S.max_batches > uint32_t(SW_MAX_BATCH)) return no("a unit needs more than 8 sweep warps");
-        // event streams of the sorted sweep, one per local board: strength classes in ascending order, the
-        // traverser's hands of the class (reads), then the opponent's (adds)
+        // list programs of every local board: the 52 card lists, then the global strength order in SW_CHUNKS pieces
         const int o = 1 - trav;
-        const uint32_t nB = P->n_boards[k];
         const LocalTables& Lp = P->loc[k][trav];
         const LocalTables& Lo = P->loc[k][o];
         const uint32_t Hp = P->H[trav], Ho = P->H[o];
-        S.ev_off.assign(size_t(nB) + 1, 0);
-        S.seg.assign(size_t(nB) * 3 * (SW_SEGS + 1), 0);
-        std::vector<uint32_t> cls_ev, cls_x, cls_r, cls_cum;  // per class: header index (board-relative), first add / read position, entries before it
-        for (uint32_t b = 0; b < nB; ++b) {
-            S.ev_off[b] = uint32_t(S.ev.size());
-            if (b < P->local_lo[k] || b >= P->local_hi[k]) continue;
+        const uint32_t HpP = Lp.Hpad, HoP = Lo.Hpad;
+        if (HoP >= SW_ADD_MASK || 2 * (HpP + 1) > SW_EMIT_MASK) return no("range too large for the program words");
+        const uint32_t lo_b = P->local_lo[k], hi_b = P->local_hi[k];
+        S.prog_off.assign(size_t(hi_b - lo_b) + 1, 0);
+        S.l_steps.assign(hi_b - lo_b, 0);
+        S.c_steps.assign(hi_b - lo_b, 0);
+        S.hinfo.assign(size_t(hi_b - lo_b) * HpP, 0);
+        const uint32_t zero_pos = HoP, dump_idx = HpP;
+        std::vector<ProgClass> cls;
+        std::vector<std::vector<uint32_t>> lw(SW_CARDS), cw(SW_CHUNKS);
+        for (uint32_t b = lo_b; b < hi_b; ++b) {
             const uint32_t np = Lp.n_live[b], no_ = Lo.n_live[b];
             const uint16_t* sp_ = &Lp.slot_of_pos[size_t(b) * Lp.Hpad];
             const uint16_t* so_ = &Lo.slot_of_pos[size_t(b) * Lo.Hpad];
             const uint32_t* strp = &P->sd[trav].strength[size_t(b) * Hp];
             const uint32_t* stro = &P->sd[o].strength[size_t(b) * Ho];
-            uint32_t i = 0, j = 0;
-            cls_ev.clear();
-            cls_x.clear();
-            cls_r.clear();
-            cls_cum.clear();
-            while (i < np || j < no_) {
-                uint32_t st = 0xffffffffu;
-                if (i < np) st = std::min(st, strp[sp_[i]]);
-                if (j < no_) st = std::min(st, stro[so_[j]]);
-                uint32_t i1 = i, j1 = j;
-                while (i1 < np && strp[sp_[i1]] == st) ++i1;
-                while (j1 < no_ && stro[so_[j1]] == st) ++j1;
-                cls_ev.push_back(uint32_t(S.ev.size()) - S.ev_off[b]);
-                cls_x.push_back(j);
-                cls_r.push_back(i);
-                cls_cum.push_back(i + j);
-                S.ev.push_back((i1 - i) | ((j1 - j) << 11));
-                for (uint32_t t = i; t < i1; ++t)
-                    S.ev.push_back(t | (uint32_t(P->hand_cards[trav][2 * sp_[t]]) << 11) | (uint32_t(P->hand_cards[trav][2 * sp_[t] + 1]) << 17));
-                for (uint32_t t = j; t < j1; ++t) {
-                    const uint8_t a = P->hand_cards[o][2 * so_[t]], c = P->hand_cards[o][2 * so_[t] + 1];
-                    uint32_t w = t | (uint32_t(a) << 11) | (uint32_t(c) << 17);
-                    if (t > j) {
-                        const uint8_t pa = P->hand_cards[o][2 * so_[t - 1]], pc = P->hand_cards[o][2 * so_[t - 1] + 1];
-                        if (a == pa || a == pc || c == pa || c == pc) w |= SW_EV_COLLIDES;
+            // positions ascend with strength on the final round (LocalTables): a merge of the two orders gives the classes
+            auto classes_of = [&](int card, std::vector<ProgClass>& out) {
+                out.clear();
+                uint32_t i = 0, j = 0;
+                auto skip_p = [&]() {
+                    while (card >= 0 && i < np && P->hand_cards[trav][2 * sp_[i]] != card && P->hand_cards[trav][2 * sp_[i] + 1] != card) ++i;
+                };
+                auto skip_o = [&]() {
+                    while (card >= 0 && j < no_ && P->hand_cards[o][2 * so_[j]] != card && P->hand_cards[o][2 * so_[j] + 1] != card) ++j;
+                };
+                skip_p();
+                skip_o();
+                while (i < np || j < no_) {
+                    uint32_t st = 0xffffffffu;
+                    if (i < np) st = std::min(st, strp[sp_[i]]);
+                    if (j < no_) st = std::min(st, stro[so_[j]]);
+                    ProgClass c;
+                    while (j < no_ && stro[so_[j]] == st) {
+                        c.adds.push_back(j);
+                        ++j;
+                        skip_o();
                     }
-                    S.ev.push_back(w);
+                    while (i < np && strp[sp_[i]] == st) {
+                        const uint32_t tgt = (card >= 0 && P->hand_cards[trav][2 * sp_[i] + 1] == card) ? 1u : 0u;  // hands are stored c0 < c1
+                        c.emits.push_back(tgt * (HpP + 1) + i);
+                        ++i;
+                        skip_p();
+                    }
+                    out.push_back(std::move(c));
                 }
-                i = i1;
-                j = j1;
+            };
+            uint32_t ls = 0;
+            for (int c = 0; c < SW_CARDS; ++c) {
+                classes_of(c, cls);
+                schedule_program(cls, zero_pos, dump_idx, lw[c]);
+                ls = std::max<uint32_t>(ls, uint32_t(lw[c].size()));
             }
-            // segment boundaries: the first class at or past every eighth of the entries
-            uint32_t* sg = &S.seg[size_t(b) * 3 * (SW_SEGS + 1)];
-            const uint32_t total = np + no_, n_ev = uint32_t(S.ev.size()) - S.ev_off[b];
-            size_t c = 0;
-            for (int q = 0; q <= SW_SEGS; ++q) {
-                const uint64_t want = uint64_t(total) * q / SW_SEGS;
-                while (c < cls_cum.size() && cls_cum[c] < want) ++c;
-                const bool end = (q == SW_SEGS) || c >= cls_cum.size();
-                sg[q] = end ? n_ev : cls_ev[c];
-                sg[(SW_SEGS + 1) + q] = end ? no_ : cls_x[c];
-                sg[2 * (SW_SEGS + 1) + q] = end ? np : cls_r[c];
+            // the global order, cut at class boundaries into pieces of about equal length.  A class far longer than a piece
+            // (a board that plays: hundreds of hands tie) becomes a RUN of pieces of its own that only add and combine
+            // (m stays 0); its hands take A + B = (sum before the run) + (sum through the run) from the piece bases.
+            classes_of(-1, cls);
+            uint64_t est = 0;
+            for (const ProgClass& c : cls) est += std::max<size_t>(1, std::max(c.adds.size(), c.emits.size()));
+            const uint64_t per = std::max<uint64_t>(4, (est + SW_CHUNKS - 9) / (SW_CHUNKS - 8));
+            uint32_t* hi_ = &S.hinfo[size_t(b - lo_b) * HpP];
+            uint32_t cs = 0, ch = 0;
+            uint8_t run_end[SW_CHUNKS];
+            for (int c2 = 0; c2 < SW_CHUNKS; ++c2) run_end[c2] = uint8_t(c2);
+            {
+                std::vector<ProgClass> piece;
+                uint64_t acc = 0;
+                auto flush = [&]() {
+                    if (piece.empty()) return;
+                    schedule_program(piece, zero_pos, dump_idx, cw[ch]);
+                    cs = std::max<uint32_t>(cs, uint32_t(cw[ch].size()));
+                    for (const ProgClass& c : piece)
+                        for (uint32_t e : c.emits) hi_[e] |= ch << SW_HI_CHUNK_SHIFT;
+                    piece.clear();
+                    acc = 0;
+                    ++ch;
+                };
+                for (size_t ci = 0; ci < cls.size(); ++ci) {
+                    ProgClass& c = cls[ci];
+                    const uint64_t len = std::max<size_t>(1, std::max(c.adds.size(), c.emits.size()));
+                    const uint32_t left_after = uint32_t(SW_CHUNKS) - ch - (piece.empty() ? 0u : 1u);
+                    if (len > 2 * per && left_after >= 3) {
+                        flush();
+                        uint32_t r = uint32_t(std::min<uint64_t>((len + per - 1) / per, uint64_t(SW_CHUNKS) - ch - 1));
+                        r = std::max<uint32_t>(r, 1);
+                        const uint32_t c1 = ch;
+                        for (uint32_t t = 0; t < r; ++t) {
+                            const size_t a0 = c.adds.size() * t / r, a1 = c.adds.size() * (t + 1) / r;
+                            const size_t e0 = c.emits.size() * t / r, e1 = c.emits.size() * (t + 1) / r;
+                            std::vector<uint32_t>& wv = cw[ch];
+                            wv.clear();
+                            for (size_t i = 0; i < std::max(a1 - a0, e1 - e0); ++i)
+                                wv.push_back((a0 + i < a1 ? c.adds[a0 + i] : zero_pos) | ((e0 + i < e1 ? c.emits[e0 + i] : dump_idx) << SW_EMIT_SHIFT));
+                            cs = std::max<uint32_t>(cs, uint32_t(wv.size()));
+                            ++ch;
+                        }
+                        run_end[c1] = uint8_t(ch);
+                        for (uint32_t e : c.emits) hi_[e] |= c1 << SW_HI_CHUNK_SHIFT;
+                        continue;
+                    }
+                    acc += len;
+                    piece.push_back(std::move(c));
+                    if (acc >= per && ch + 1 < uint32_t(SW_CHUNKS)) flush();
+                }
+                flush();
+                for (uint32_t c2 = ch; c2 < uint32_t(SW_CHUNKS); ++c2) cw[c2].clear();
             }
+            for (uint32_t i = 0; i < np; ++i) {
+                const uint32_t h = sp_[i];
+                uint32_t same = HoP;
+                const uint16_t sm = P->same[trav][h];
+                if (sm != 0xFFFF) {
+                    const uint16_t op = Lo.pos_of_slot[size_t(b) * Ho + sm];
+                    if (op < no_) same = op;
+                }
+                hi_[i] |= uint32_t(P->hand_cards[trav][2 * h]) | (uint32_t(P->hand_cards[trav][2 * h + 1]) << SW_HI_C1_SHIFT) | (same << SW_HI_SAME_SHIFT);
+            }
+            for (uint32_t i = np; i < HpP; ++i) hi_[i] = HoP << SW_HI_SAME_SHIFT;
+            ls = (ls + 3) & ~3u;  // the walks fetch four words at a time
+            cs = (cs + 3) & ~3u;
+            // pack: [ls][52] then [cs][64]; short programs are padded with steps that add nothing and emit to the dump cell
+            const uint32_t nop = zero_pos | (dump_idx << SW_EMIT_SHIFT);
+            const size_t base = S.prog.size();
+            S.prog.resize(base + size_t(ls) * SW_CARDS + size_t(cs) * SW_CHUNKS + SW_CHUNKS / 4, nop);
+            for (int c = 0; c < SW_CARDS; ++c)
+                for (size_t t = 0; t < lw[c].size(); ++t) S.prog[base + t * SW_CARDS + c] = lw[c][t];
+            const size_t cbase = base + size_t(ls) * SW_CARDS;
+            for (int c = 0; c < SW_CHUNKS; ++c)
+                for (size_t t = 0; t < cw[c].size(); ++t) S.prog[cbase + t * SW_CHUNKS + c] = cw[c][t];
+            for (int c = 0; c < SW_CHUNKS / 4; ++c)  // run_end[64] as bytes behind the chunk programs
+                S.prog[cbase + size_t(cs) * SW_CHUNKS + c] = uint32_t(run_end[4 * c]) | (uint32_t(run_end[4 * c + 1]) << 8) | (uint32_t(run_end[4 * c + 2]) << 16) |
+                                                                (uint32_t(run_end[4 * c + 3]) << 24);
+            if (S.prog.size() > 0xfffffff0ull) return no("list programs exceed 32-bit word offsets");
+            S.prog_off[b - lo_b] = uint32_t(base);
+            S.l_steps[b - lo_b] = ls;
+            S.c_steps[b - lo_b] = cs;
         }
-        S.ev_off[nB] = uint32_t(S.ev.size());
+        S.prog_off[hi_b - lo_b] = uint32_t(S.prog.size());
         S.eligible = true;
     }
 };

@@ -118,7 +118,9 @@ struct StreetPlan {
     std::vector<SwTerm> terms;
     uint32_t max_rows = 0, max_slots = 0, max_q_sd = 0, max_q_mo = 0;
     // per LOCAL board of the round (index = board - local_lo): the list programs [l_steps][52] followed by the chunk
-    // programs [c_steps][SW_CHUNKS], one word per (step, list)
+    // programs [c_steps][SW_CHUNKS], one word per (step, list), and run_end[SW_CHUNKS] as bytes: for the first piece of a
+    // run (a strength class cut into several pieces) the piece after the run, else the piece itself.  The hands of
+    // piece c take  base[c] + base[run_end[c]]  from the exclusive prefix of the piece totals (base[64] = total)
     std::vector<uint32_t> prog;
     std::vector<uint32_t> prog_off;  // [n_local + 1] word offsets
     std::vector<uint32_t> l_steps, c_steps;  // [n_local]

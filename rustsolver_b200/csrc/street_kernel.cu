@@ -9,18 +9,6 @@ namespace rs {
 namespace {
 
 constexpr int ST_MAX_THREADS = 352;
-constexpr int XT_POS = 16;      // x tile: [32 rows][16 positions], odd pitch: lane = row reads are conflict-free
-constexpr int XT_PITCH = 17;
-constexpr int RING_POS = 16;    // y ring: [32 rows][2 blocks of 16 positions]
-constexpr int RING_PITCH = 33;
-// shared memory of one sweep warp (floats)
-constexpr int SM_CS = SW_CARDS * SW_LANES;             // running per-card sums [card][lane]
-constexpr int SM_XT = 2 * SW_LANES * XT_PITCH;         // double-buffered x tile
-constexpr int SM_RING = SW_LANES * RING_PITCH;         // y ring
-constexpr int SM_TOT = SW_LANES;                       // the segment's total (pass 0) / starting total (pass 1)
-constexpr int SM_WARP = SM_CS + SM_XT + SM_RING + SM_TOT;
-// after the sweep warps' areas: the totals table [row][53] of every batch
-constexpr int SM_CT = SW_LANES * SW_CT_PITCH;
 
 extern __shared__ __align__(16) float st_smem[];
 
@@ -32,16 +20,10 @@ __device__ __forceinline__ void f4s(float4& v, int i, float x) {
     else if (i == 2) v.z = x;
     else v.w = x;
 }
+__device__ __forceinline__ float4 f4a(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(uint32_t(__cvta_generic_to_shared(dst_smem))), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 __device__ __forceinline__ void unpack4u16(uint2 u, uint32_t (&o)[4]) {
     o[0] = u.x & 0xffffu;
     o[1] = u.x >> 16;
@@ -89,10 +71,10 @@ __device__ __forceinline__ void rows_out(float* __restrict__ slab, int pos4, con
 struct UnitCtx {
     int b;         // local board
     int tid, nthr;
-    float* X;      // [rows][XP]
-    float* Y;      // [rows][YP]
+    float* X;      // [rows][XP]        reach rows by opponent position
+    float* VY;     // [vy_rows][HpP]    showdown term of a row by traverser position
+    float* VM;     // [vm_rows][HpP]    compatible opponent mass of a row by traverser position
     float* VAL;    // [slots][HpP]
-    const float* ctt;  // totals tables of the unit's batches, [row][53]
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -146,372 +128,232 @@ __device__ __forceinline__ void down_node(const StreetArgs& A, const UnitCtx& c,
 }
 
 // ------------------------------------------------------------------------------------------------
-// T: sorted sweep (cfr.rs:523-558), lane = row.  The sweep of a batch of 32 rows is cut into SW segments of the
-// strength order; sweep warp (batch, s) owns segment s.  Pass 0 adds up every segment's per-card sums, a scan over
-// the segments turns them into each segment's starting sums (and the totals), pass 1 is the sweep proper.
+// T: list walks (cfr.rs:523-558), four reach rows (a quad) per thread, see street.h
 // ------------------------------------------------------------------------------------------------
-struct SweepCtx {
-    const float* Xb;   // rows of the batch
-    float* Yb;
-    const uint32_t* ev;  // event words of the board
-    uint32_t ev_lo, ev_hi;  // the segment's words
-    uint32_t x_lo;          // first opponent position added in the segment
-    uint32_t r_lo, r_hi;    // traverser positions read in the segment
-    int XP, YP, lane;
-    float* cs;    // + lane: running per-card sums [card * 32]
-    float* xt;    // x tile [2][32 rows][17]
-    float* ring;  // y ring [32 rows][33]: two blocks of 16 positions
-};
-
-// x tiles: 16 opponent positions of all 32 rows, double-buffered with cp.async (lane -> row parity, position)
-struct XStream {
-    int base, cur;
-    __device__ __forceinline__ void issue(const SweepCtx& w, int b0, int buf) const {
-        if (b0 < w.XP) {
-            const int sub = w.lane >> 4, p = w.lane & 15;
-            float* dst = w.xt + buf * (SW_LANES * XT_PITCH) + sub * XT_PITCH + p;
-            const float* src = w.Xb + size_t(sub) * w.XP + b0 + p;
-#pragma unroll 4
-            for (int v = 0; v < SW_LANES; v += 2) cp_async4(dst + v * XT_PITCH, src + size_t(v) * w.XP);
-        }
-        cp_async_commit();
-    }
-    __device__ __forceinline__ void start(const SweepCtx& w, uint32_t pos) {
-        base = int(pos & ~15u);
-        cur = 0;
-        issue(w, base, 0);
-        issue(w, base + XT_POS, 1);
-        cp_async_wait<1>();
-        __syncwarp();
-    }
-    __device__ __forceinline__ float at(const SweepCtx& w, int pos) {
-        while (pos >= base + XT_POS) {  // uniform: every lane walks the same events
-            cp_async_wait<0>();
-            __syncwarp();
-            base += XT_POS;
-            issue(w, base + XT_POS, cur);  // the tile just left is free
-            cur ^= 1;
-        }
-        return w.xt[cur * (SW_LANES * XT_PITCH) + w.lane * XT_PITCH + (pos - base)];
-    }
-    __device__ __forceinline__ void finish() const {
-        cp_async_wait<0>();
-        __syncwarp();
-    }
-};
-
-// event window: 64 words in two registers per lane, the second half prefetched; a class of at most 32 words is always inside
-struct EvWindow {
-    uint32_t wb, w0, w1;
-    __device__ __forceinline__ void start(const SweepCtx& w, uint32_t idx) {
-        wb = idx & ~31u;
-        w0 = __ldg(w.ev + wb + w.lane);  // reads past the board's words stay inside the allocation (padded) and are never used
-        w1 = __ldg(w.ev + wb + 32 + w.lane);
-    }
-    __device__ __forceinline__ void advance_to(const SweepCtx& w, uint32_t idx) {
-        while (idx - wb >= 32u) {
-            wb += 32;
-            w0 = w1;
-            w1 = __ldg(w.ev + wb + 32 + w.lane);
-        }
-    }
-    __device__ __forceinline__ uint32_t get(uint32_t idx) const {  // wb <= idx < wb + 64
-        const uint32_t d = idx - wb;
-        const uint32_t a = __shfl_sync(0xffffffffu, w0, int(d & 31u)), b = __shfl_sync(0xffffffffu, w1, int(d & 31u));
-        return d < 32u ? a : b;
-    }
-};
-// slow path for classes longer than the window: one word per call from global memory (L1-resident, uniform address)
-__device__ __forceinline__ uint32_t ev_direct(const SweepCtx& w, uint32_t idx) { return __ldg(w.ev + idx); }
-
-#define CS_A(e) (w.cs[(((e) >> 11) & 63u) * SW_LANES])
-#define CS_B(e) (w.cs[(((e) >> 17) & 63u) * SW_LANES])
-
-// pass 0: per-card sums and the total of the segment's adds
-__device__ __forceinline__ float sweep_pass0(const SweepCtx& w) {
-#pragma unroll 4
-    for (int k = 0; k < SW_CARDS; ++k) w.cs[k * SW_LANES] = 0.f;
-    float S = 0.f;
-    if (w.ev_lo >= w.ev_hi) return S;
-    XStream xs;
-    xs.start(w, w.x_lo);
-    EvWindow win;
-    win.start(w, w.ev_lo);
-    uint32_t i = w.ev_lo;
-    while (i < w.ev_hi) {
-        win.advance_to(w, i);
-        const uint32_t hdr = win.get(i);
-        const uint32_t nr = hdr & 0x7ffu, na = (hdr >> 11) & 0x7ffu;
-        i += 1 + nr;
-        if (nr + na <= 32u) {
-            uint32_t r = 0;
-            for (; r + 2 <= na; r += 2) {
-                const uint32_t e0 = win.get(i + r), e1 = win.get(i + r + 1);
-                const float x0 = xs.at(w, int(e0 & SW_EV_POS_MASK)), x1 = xs.at(w, int(e1 & SW_EV_POS_MASK));
-                if (!(e1 & SW_EV_COLLIDES)) {
-                    const float a0 = CS_A(e0), b0 = CS_B(e0), a1 = CS_A(e1), b1 = CS_B(e1);
-                    CS_A(e0) = a0 + x0;
-                    CS_B(e0) = b0 + x0;
-                    CS_A(e1) = a1 + x1;
-                    CS_B(e1) = b1 + x1;
-                } else {
-                    const float a0 = CS_A(e0), b0 = CS_B(e0);
-                    CS_A(e0) = a0 + x0;
-                    CS_B(e0) = b0 + x0;
-                    const float a1 = CS_A(e1), b1 = CS_B(e1);
-                    CS_A(e1) = a1 + x1;
-                    CS_B(e1) = b1 + x1;
-                }
-                S += x0;
-                S += x1;
-            }
-            if (r < na) {
-                const uint32_t e0 = win.get(i + r);
-                const float x0 = xs.at(w, int(e0 & SW_EV_POS_MASK));
-                const float a0 = CS_A(e0), b0 = CS_B(e0);
-                CS_A(e0) = a0 + x0;
-                CS_B(e0) = b0 + x0;
-                S += x0;
-            }
-        } else {
-            for (uint32_t r = 0; r < na; ++r) {
-                const uint32_t e0 = ev_direct(w, i + r);
-                const float x0 = xs.at(w, int(e0 & SW_EV_POS_MASK));
-                const float a0 = CS_A(e0), b0 = CS_B(e0);
-                CS_A(e0) = a0 + x0;
-                CS_B(e0) = b0 + x0;
-                S += x0;
-            }
-        }
-        i += na;
-    }
-    xs.finish();
-    return S;
-}
-
-// y ring: blocks of 16 positions, block k in slot k & 1.  A block leaves as 32 row segments of 64 bytes; only the
-// positions the segment owns are written (a block can straddle two segments = two warps).
-__device__ __forceinline__ void ring_flush(const SweepCtx& w, uint32_t k, uint32_t need_y) {
-    __syncwarp();
-    const int sub = w.lane >> 4, p = w.lane & 15;
-    const uint32_t pos = k * RING_POS + p;
-    if (pos >= w.r_lo && pos < w.r_hi) {
-        const float* src = w.ring + sub * RING_PITCH + (k & 1u) * RING_POS + p;
-        float* dst = w.Yb + size_t(sub) * w.YP + pos;
-#pragma unroll 4
-        for (int v = 0; v < SW_LANES; v += 2)
-            if (need_y >> (v + sub) & 1u) dst[size_t(v) * w.YP] = src[v * RING_PITCH];
-    }
-    __syncwarp();
-}
-// the reverse (large classes park their A values in Y while the class is added)
-__device__ __forceinline__ void ring_reload(const SweepCtx& w, uint32_t k) {
-    __syncwarp();
-    const int sub = w.lane >> 4, p = w.lane & 15;
-    const uint32_t pos = k * RING_POS + p;
-    if (pos >= w.r_lo && pos < w.r_hi) {
-        float* dst = w.ring + sub * RING_PITCH + (k & 1u) * RING_POS + p;
-        const float* src = w.Yb + size_t(sub) * w.YP + pos;
-#pragma unroll 4
-        for (int v = 0; v < SW_LANES; v += 2) dst[v * RING_PITCH] = __ldcg(src + size_t(v) * w.YP);
-    }
-    __syncwarp();
-}
-
-// pass 1: the sweep proper.  cs holds the per-card sums of everything weaker than the segment, S0 their total.
-__device__ __forceinline__ void sweep_pass1(const SweepCtx& w, float S, uint32_t need_y) {
-    if (w.ev_lo >= w.ev_hi) return;
-    XStream xs;
-    xs.start(w, w.x_lo);
-    EvWindow win;
-    win.start(w, w.ev_lo);
-    float* myring = w.ring + w.lane * RING_PITCH;
-    uint32_t flushed = w.r_lo / RING_POS;  // blocks below are done (or belong to the previous segment)
-    uint32_t i = w.ev_lo;
-    while (i < w.ev_hi) {
-        win.advance_to(w, i);
-        const uint32_t hdr = win.get(i);
-        const uint32_t nr = hdr & 0x7ffu, na = (hdr >> 11) & 0x7ffu;
-        ++i;
-        uint32_t done_pos = 0xffffffffu;
-        if (nr <= uint32_t(RING_POS) && nr + na <= 32u) {
-            // A(h): compatible reach strictly weaker than the class; four hands in flight
-            for (uint32_t r = 0; r < nr; r += 4) {
-                uint32_t e[4];
-                float v[4];
+// One list: running sum g of the quad over the list's opponent hands in strength order; a traverser hand of the list gets
+// m = (sum before its strength class) + (sum after it).  Words of the walk: prog[step * stride].  Returns the list total.
+template <bool EMIT>
+__device__ __forceinline__ float4 walk_list(const float* __restrict__ X4, float* __restrict__ Y4, const uint32_t* __restrict__ prog, int stride,
+                                            int steps) {
+    float4 g = f4z(), g0 = f4z(), m = f4z();
+    for (int s = 0; s < steps; s += 4) {
+        uint32_t w[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) e[u] = win.get(i + min(r + u, nr - 1));
+        for (int u = 0; u < 4; ++u) w[u] = __ldg(prog + size_t(s + u) * stride);
+        float4 x[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = S - CS_A(e[u]) - CS_B(e[u]);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (r + u < nr) myring[e[u] & 31u] = v[u];
-            }
-            // the class is added
-            {
-                const uint32_t j0 = i + nr;
-                uint32_t r = 0;
-                for (; r + 2 <= na; r += 2) {
-                    const uint32_t e0 = win.get(j0 + r), e1 = win.get(j0 + r + 1);
-                    const float x0 = xs.at(w, int(e0 & SW_EV_POS_MASK)), x1 = xs.at(w, int(e1 & SW_EV_POS_MASK));
-                    if (!(e1 & SW_EV_COLLIDES)) {
-                        const float a0 = CS_A(e0), b0 = CS_B(e0), a1 = CS_A(e1), b1 = CS_B(e1);
-                        CS_A(e0) = a0 + x0;
-                        CS_B(e0) = b0 + x0;
-                        CS_A(e1) = a1 + x1;
-                        CS_B(e1) = b1 + x1;
-                    } else {
-                        const float a0 = CS_A(e0), b0 = CS_B(e0);
-                        CS_A(e0) = a0 + x0;
-                        CS_B(e0) = b0 + x0;
-                        const float a1 = CS_A(e1), b1 = CS_B(e1);
-                        CS_A(e1) = a1 + x1;
-                        CS_B(e1) = b1 + x1;
-                    }
-                    S += x0;
-                    S += x1;
-                }
-                if (r < na) {
-                    const uint32_t e0 = win.get(j0 + r);
-                    const float x0 = xs.at(w, int(e0 & SW_EV_POS_MASK));
-                    const float a0 = CS_A(e0), b0 = CS_B(e0);
-                    CS_A(e0) = a0 + x0;
-                    CS_B(e0) = b0 + x0;
-                    S += x0;
-                }
-            }
-            // + B(h): the same after the class was added
-            for (uint32_t r = 0; r < nr; r += 4) {
-                uint32_t e[4];
-                float v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) e[u] = win.get(i + min(r + u, nr - 1));
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = S - CS_A(e[u]) - CS_B(e[u]) + myring[e[u] & 31u];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (r + u < nr) myring[e[u] & 31u] = v[u];
-            }
-            if (nr) done_pos = (win.get(i + nr - 1) & SW_EV_POS_MASK) + 1;
-        } else {
-            // a large class (a board that plays, ...): A values are parked in Y block by block, the class is added, then
-            // every block comes back for its B values.  Rare, so one event word per step straight from memory.
-            const uint32_t t0 = nr ? (ev_direct(w, i) & SW_EV_POS_MASK) : 0u;
-            for (uint32_t r = 0; r < nr; ++r) {
-                const uint32_t e = ev_direct(w, i + r);
-                const uint32_t pos = e & SW_EV_POS_MASK;
-                myring[pos & 31u] = S - CS_A(e) - CS_B(e);
-                if ((pos & 15u) == 15u || r + 1 == nr) ring_flush(w, pos / RING_POS, 0xffffffffu);
-            }
-            for (uint32_t r = 0; r < na; ++r) {
-                const uint32_t e = ev_direct(w, i + nr + r);
-                const float x0 = xs.at(w, int(e & SW_EV_POS_MASK));
-                const float a0 = CS_A(e), b0 = CS_B(e);
-                CS_A(e) = a0 + x0;
-                CS_B(e) = b0 + x0;
-                S += x0;
-            }
-            for (uint32_t r = 0; r < nr; ++r) {
-                const uint32_t e = ev_direct(w, i + r);
-                const uint32_t pos = e & SW_EV_POS_MASK;
-                if (r == 0 || (pos & 15u) == 0u) ring_reload(w, pos / RING_POS);
-                myring[pos & 31u] += S - CS_A(e) - CS_B(e);
-                if ((pos & 15u) == 15u || r + 1 == nr) ring_flush(w, pos / RING_POS, 0xffffffffu);
-            }
-            if (nr) {
-                done_pos = t0 + nr;
-                flushed = max(flushed, (t0 + nr) / RING_POS);  // whole blocks went out already; the last partial one stays live
-            }
-        }
-        i += nr + na;
-        if (done_pos != 0xffffffffu) {
-            const uint32_t done = done_pos / RING_POS;
-            while (flushed < done) ring_flush(w, flushed++, need_y);
-        }
-    }
-    // the last (partial) block of the segment
-    {
-        const uint32_t nblk = (w.r_hi + RING_POS - 1) / RING_POS;
-        while (flushed < nblk) ring_flush(w, flushed++, need_y);
-    }
-    xs.finish();
-}
-#undef CS_A
-#undef CS_B
-
-// ------------------------------------------------------------------------------------------------
-// U: traverser nodes in post-order (cfr.rs:588, 612-621)
-// ------------------------------------------------------------------------------------------------
-struct HandCtx {
-    uint32_t ca[4], cb[4];  // the thread's four hands: card indices
-    uint32_t same[4];       // opponent position of the identical combo / 0xFFFF
-    bool same_vec;          // the identical combos are the thread's own four positions
-};
-
-__device__ __forceinline__ float4 c_of(const UnitCtx& c, const HandCtx& h, int row) {
-    const float* t = c.ctt + (row >> 5) * SM_CT + (row & 31) * SW_CT_PITCH;
-    const float tot = t[SW_CARDS];
-    return make_float4(tot - t[h.ca[0]] - t[h.cb[0]], tot - t[h.ca[1]] - t[h.cb[1]], tot - t[h.ca[2]] - t[h.cb[2]],
-                       tot - t[h.ca[3]] - t[h.cb[3]]);
-}
-__device__ __forceinline__ float4 xsame_of(const StreetArgs& A, const UnitCtx& c, const HandCtx& h, int row, int pos4) {
-    const float* x = c.X + size_t(row) * A.XP;
-    if (h.same_vec) return ld4(x + pos4);
-    return make_float4(h.same[0] != 0xffffu ? x[h.same[0]] : 0.f, h.same[1] != 0xffffu ? x[h.same[1]] : 0.f,
-                       h.same[2] != 0xffffu ? x[h.same[2]] : 0.f, h.same[3] != 0xffffu ? x[h.same[3]] : 0.f);
-}
-
-// value of the terms [t0, t1) for the thread's four hands; own_row's C and mass are passed in.  Four terms at a time: their
-// descriptors, then their vectors (independent loads), then the arithmetic.
-__device__ __forceinline__ float4 terms_value(const StreetArgs& A, const UnitCtx& c, const HandCtx& h, int pos4, uint32_t t0, uint32_t t1,
-                                              float scale, int own_row, const float4& c_own, const float4& m_own) {
-    float4 v = f4z();
-    for (uint32_t t = t0; t < t1; t += 4) {
-        SwTerm tm[4];
-        float4 ld[4];
+        for (int u = 0; u < 4; ++u) x[u] = ld4(X4 + 4 * (w[u] & SW_ADD_MASK));
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            tm[u] = A.terms[min(t + u, t1 - 1)];
-            if (t + u >= t1) tm[u].kind = 255;
+            if (EMIT && (w[u] & SW_CLASS_START)) g0 = g;
+            g = f4a(g, x[u]);
+            if (EMIT) {
+                if (w[u] & SW_CLASS_END) m = f4a(g0, g);
+                st4(Y4 + 4 * ((w[u] >> SW_EMIT_SHIFT) & SW_EMIT_MASK), m);
+            }
+        }
+    }
+    return g;
+}
+
+// One piece of the global strength order: like walk_list, but a traverser hand's cell already holds the results of its
+// two card lists (Y4[e], Y4[HpP + 1 + e]) and is left as  (A + B of the piece) - (card lists).  The piece's running sum
+// starts at 0: the copy-out adds twice the sum of the pieces before it.
+__device__ __forceinline__ float4 walk_chunk(const float* __restrict__ X4, float* __restrict__ Y4, int y2_off, const uint32_t* __restrict__ prog,
+                                             int stride, int steps) {
+    float4 g = f4z(), g0 = f4z(), m = f4z();
+    for (int s = 0; s < steps; s += 4) {
+        uint32_t w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = __ldg(prog + size_t(s + u) * stride);
+        float4 x[4], y1[4], y2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            x[u] = ld4(X4 + 4 * (w[u] & SW_ADD_MASK));
+            const uint32_t e = (w[u] >> SW_EMIT_SHIFT) & SW_EMIT_MASK;  // distinct cells (or the dump cell) within a walk
+            y1[u] = ld4(Y4 + 4 * e);
+            y2[u] = ld4(Y4 + 4 * (e + y2_off));
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            ld[u] = f4z();
-            if (tm[u].kind == ST_VALUE) ld[u] = ld4(c.VAL + size_t(tm[u].id) * A.HpP + pos4);
-            else if (tm[u].kind == ST_SHOWDOWN) ld[u] = ld4(c.Y + size_t(tm[u].id) * A.YP + pos4);
-            else if (tm[u].kind == ST_FOLD && tm[u].id != own_row) ld[u] = xsame_of(A, c, h, tm[u].id, pos4);
+            if (w[u] & SW_CLASS_START) g0 = g;
+            g = f4a(g, x[u]);
+            if (w[u] & SW_CLASS_END) m = f4a(g0, g);
+            st4(Y4 + 4 * ((w[u] >> SW_EMIT_SHIFT) & SW_EMIT_MASK), f4sub(f4sub(m, y1[u]), y2[u]));
         }
+    }
+    return g;
+}
+
+// rows of a quad from the unit's scratch into shared memory, interleaved: X4[pos] = (x_r0[pos], .., x_r0+3[pos])
+__device__ __forceinline__ void stage_quad(const StreetArgs& A, const UnitCtx& c, int row0, float* X4) {
+    const float* x0 = c.X + size_t(row0) * A.XP;
+    for (int pos = c.tid; pos < A.HoP; pos += c.nthr)
+        st4(X4 + 4 * pos, make_float4(x0[pos], x0[A.XP + pos], x0[2 * A.XP + pos], x0[3 * A.XP + pos]));
+    if (c.tid == 0) st4(X4 + 4 * A.HoP, f4z());  // the zero cell
+}
+
+__device__ __forceinline__ float4 warp_sum4(float4 v) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (tm[u].kind == 255) continue;
-            if (tm[u].kind == ST_VALUE) {
-                v.x += ld[u].x, v.y += ld[u].y, v.z += ld[u].z, v.w += ld[u].w;
-                continue;
-            }
-            const float cf = tm[u].coef * scale;
-            const bool own = tm[u].id == own_row;
-            const float4 cc = own ? c_own : c_of(c, h, tm[u].id);
-            if (tm[u].kind == ST_FOLD) {
-                const float4 mm = own ? m_own : make_float4(cc.x + ld[u].x, cc.y + ld[u].y, cc.z + ld[u].z, cc.w + ld[u].w);
-                v.x += cf * mm.x, v.y += cf * mm.y, v.z += cf * mm.z, v.w += cf * mm.w;
-            } else {
-                v.x += cf * (ld[u].x - cc.x), v.y += cf * (ld[u].y - cc.y), v.z += cf * (ld[u].z - cc.z), v.w += cf * (ld[u].w - cc.w);
-            }
-        }
+    for (int d = 16; d > 0; d >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, d);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, d);
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, d);
+        v.w += __shfl_xor_sync(0xffffffffu, v.w, d);
     }
     return v;
 }
 
-__device__ __forceinline__ void hand_ctx(const StreetArgs& A, const UnitCtx& c, int pos4, uint32_t nl_p, HandCtx& h) {
-    uint32_t w[4];
-    unpack4u16(__ldg(reinterpret_cast<const uint2*>(A.pcards + size_t(c.b) * A.HpP + pos4)), w);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        h.ca[i] = w[i] & 0xffu;
-        h.cb[i] = w[i] >> 8;
+struct TCtx {
+    float* TT;   // [quad][SW_TT][4]   per-card sums + total of the quads of the current round
+    float* CT;   // [quad][SW_CHUNKS + 1][4] totals, then bases, of the pieces of the global order ([64] = the total)
+    float* RG;   // staged quads
+    const uint32_t* lprog;
+    const uint32_t* cprog;
+    const uint32_t* hinfo;
+    const uint8_t* run_end;  // [SW_CHUNKS] street.h
+    int ls, cs;
+    uint32_t nl_p;
+};
+
+// showdown quads [q0, q0 + nq): everything the U phase reads of their rows goes to VY (and VM where a row's mass is read)
+__device__ __forceinline__ void sd_round(const StreetArgs& A, const UnitCtx& c, const TCtx& t, const SwSeg& sg, int q0, int nq) {
+    const int xq = 4 * (A.HoP + 1), yq = 8 * (A.HpP + 1), per = xq + yq;
+    const int lane = c.tid & 31, warp = c.tid >> 5;
+    for (int q = 0; q < nq; ++q) stage_quad(A, c, 4 * (q0 + q), t.RG + q * per);
+    __syncthreads();
+    for (int it = c.tid; it < nq * SW_CARDS; it += c.nthr) {
+        const int q = it / SW_CARDS, card = it - q * SW_CARDS;
+        float* base = t.RG + q * per;
+        const float4 g = walk_list<true>(base, base + xq, t.lprog + card, SW_CARDS, t.ls);
+        st4(t.TT + (q * SW_TT + card) * 4, g);
     }
-    h.same_vec = A.same_order && uint32_t(pos4 + 3) < nl_p;
-    if (!h.same_vec) unpack4u16(__ldg(reinterpret_cast<const uint2*>(A.same_pos + size_t(c.b) * A.HpP + pos4)), h.same);
+    __syncthreads();
+    for (int it = c.tid; it < nq * SW_CHUNKS; it += c.nthr) {
+        const int q = it / SW_CHUNKS, ch = it - q * SW_CHUNKS;
+        float* base = t.RG + q * per;
+        const float4 g = walk_chunk(base, base + xq, A.HpP + 1, t.cprog + ch, SW_CHUNKS, t.cs);
+        st4(t.CT + (q * (SW_CHUNKS + 1) + ch) * 4, g);
+    }
+    __syncthreads();
+    if (warp < nq) {  // exclusive scan of the 64 piece totals of quad `warp`: two pieces per lane
+        float* ct = t.CT + warp * (SW_CHUNKS + 1) * 4;
+        const float4 a = ld4(ct + 8 * lane), b2 = ld4(ct + 8 * lane + 4);
+        const float4 s = f4a(a, b2);
+        float4 inc = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            float4 o;
+            o.x = __shfl_up_sync(0xffffffffu, inc.x, d);
+            o.y = __shfl_up_sync(0xffffffffu, inc.y, d);
+            o.z = __shfl_up_sync(0xffffffffu, inc.z, d);
+            o.w = __shfl_up_sync(0xffffffffu, inc.w, d);
+            if (lane >= d) inc = f4a(inc, o);
+        }
+        const float4 ex = f4sub(inc, s);
+        st4(ct + 8 * lane, ex);
+        st4(ct + 8 * lane + 4, f4a(ex, a));
+        if (lane == 31) {
+            st4(ct + 4 * SW_CHUNKS, inc);
+            st4(t.TT + (warp * SW_TT + SW_CARDS) * 4, inc);
+        }
+    }
+    __syncthreads();
+    for (int q = 0; q < nq; ++q) {
+        const float* X4 = t.RG + q * per;
+        const float* Y4 = X4 + xq;
+        const float* tt = t.TT + q * SW_TT * 4;
+        const float* ct = t.CT + q * (SW_CHUNKS + 1) * 4;
+        const float4 tot = ld4(tt + SW_CARDS * 4);
+        const int row0 = 4 * (q0 + q);
+        const uint32_t need_m = (sg.sd_need_m >> row0) & 15u;
+        float* vy = c.VY + size_t(row0) * A.HpP;
+        float* vm = c.VM + size_t(row0) * A.HpP;
+        for (int pos = c.tid; pos < A.HpP; pos += c.nthr) {
+            const uint32_t hi = __ldg(t.hinfo + pos);
+            const float4 ta = ld4(tt + 4 * (hi & 63u)), tb = ld4(tt + 4 * ((hi >> SW_HI_C1_SHIFT) & 63u));
+            const uint32_t ch = (hi >> SW_HI_CHUNK_SHIFT) & 63u;
+            const float4 cb = f4a(ld4(ct + 4 * ch), ld4(ct + 4 * uint32_t(__ldg(t.run_end + ch))));  // 2 x base, or base + end of a run
+            const float4 y = ld4(Y4 + 4 * pos);
+            const float4 cp = f4sub(f4sub(tot, ta), tb);
+            const bool live = uint32_t(pos) < t.nl_p;
+            float4 v;
+            v.x = live ? y.x + cb.x - cp.x : 0.f;
+            v.y = live ? y.y + cb.y - cp.y : 0.f;
+            v.z = live ? y.z + cb.z - cp.z : 0.f;
+            v.w = live ? y.w + cb.w - cp.w : 0.f;
+            vy[pos] = v.x;
+            vy[A.HpP + pos] = v.y;
+            vy[2 * A.HpP + pos] = v.z;
+            vy[3 * A.HpP + pos] = v.w;
+            if (need_m) {
+                const float4 xs = ld4(X4 + 4 * (hi >> SW_HI_SAME_SHIFT));
+                vm[pos] = live ? cp.x + xs.x : 0.f;
+                vm[A.HpP + pos] = live ? cp.y + xs.y : 0.f;
+                vm[2 * A.HpP + pos] = live ? cp.z + xs.z : 0.f;
+                vm[3 * A.HpP + pos] = live ? cp.w + xs.w : 0.f;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// mass-only quads [q0, q0 + nq): per-card sums only
+__device__ __forceinline__ void mass_round(const StreetArgs& A, const UnitCtx& c, const TCtx& t, int q0, int nq) {
+    const int xq = 4 * (A.HoP + 1);
+    const int lane = c.tid & 31, warp = c.tid >> 5;
+    for (int q = 0; q < nq; ++q) stage_quad(A, c, 4 * (q0 + q), t.RG + q * xq);
+    __syncthreads();
+    for (int it = c.tid; it < nq * SW_CARDS; it += c.nthr) {
+        const int q = it / SW_CARDS, card = it - q * SW_CARDS;
+        const float4 g = walk_list<false>(t.RG + q * xq, nullptr, t.lprog + card, SW_CARDS, t.ls);
+        st4(t.TT + (q * SW_TT + card) * 4, g);
+    }
+    __syncthreads();
+    if (warp < nq) {  // every hand holds two cards: total = half the sum of the per-card sums
+        const float* tt = t.TT + warp * SW_TT * 4;
+        float4 s = ld4(tt + 4 * lane);
+        if (lane + 32 < SW_CARDS) s = f4a(s, ld4(tt + 4 * (lane + 32)));
+        s = warp_sum4(s);
+        if (lane == 0) st4(t.TT + (warp * SW_TT + SW_CARDS) * 4, make_float4(0.5f * s.x, 0.5f * s.y, 0.5f * s.z, 0.5f * s.w));
+    }
+    __syncthreads();
+    for (int q = 0; q < nq; ++q) {
+        const float* X4 = t.RG + q * xq;
+        const float* tt = t.TT + q * SW_TT * 4;
+        const float4 tot = ld4(tt + SW_CARDS * 4);
+        float* vm = c.VM + size_t(4 * (q0 + q)) * A.HpP;
+        for (int pos = c.tid; pos < A.HpP; pos += c.nthr) {
+            const uint32_t hi = __ldg(t.hinfo + pos);
+            const float4 ta = ld4(tt + 4 * (hi & 63u)), tb = ld4(tt + 4 * ((hi >> SW_HI_C1_SHIFT) & 63u));
+            const float4 xs = ld4(X4 + 4 * (hi >> SW_HI_SAME_SHIFT));
+            const bool live = uint32_t(pos) < t.nl_p;
+            vm[pos] = live ? tot.x - ta.x - tb.x + xs.x : 0.f;
+            vm[A.HpP + pos] = live ? tot.y - ta.y - tb.y + xs.y : 0.f;
+            vm[2 * A.HpP + pos] = live ? tot.z - ta.z - tb.z + xs.z : 0.f;
+            vm[3 * A.HpP + pos] = live ? tot.w - ta.w - tb.w + xs.w : 0.f;
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// U: traverser nodes in post-order (cfr.rs:588, 612-621)
+// ------------------------------------------------------------------------------------------------
+// value of the terms [t0, t1) for the thread's four hands: every term is one vector
+__device__ __forceinline__ float4 terms_value(const StreetArgs& A, const UnitCtx& c, int pos4, uint32_t t0, uint32_t t1, float scale) {
+    float4 v = f4z();
+    for (uint32_t t = t0; t < t1; ++t) {
+        const SwTerm tm = A.terms[t];
+        if (tm.kind == ST_VALUE) {
+            v = f4a(v, ld4(c.VAL + size_t(tm.id) * A.HpP + pos4));
+        } else {
+            const float cf = tm.coef * scale;
+            const float4 x = ld4((tm.kind == ST_FOLD ? c.VM : c.VY) + size_t(tm.id) * A.HpP + pos4);
+            v.x += cf * x.x, v.y += cf * x.y, v.z += cf * x.z, v.w += cf * x.w;
+        }
+    }
+    return v;
 }
 
 __device__ __forceinline__ void store_root(const StreetArgs& A, const UnitCtx& c, const SwSeg& sg, int pos4, float4 v) {
@@ -542,14 +384,10 @@ __device__ __forceinline__ void up_trav(const StreetArgs& A, const UnitCtx& c, c
             else if (!A.out_scatter) st4(A.out_buf + (size_t(sg.root_out) * A.n_boards + c.b) * A.HpP + pos4, f4z());
             continue;
         }
-        HandCtx h;
-        hand_ctx(A, c, pos4, nl_p, h);
-        const float4 c_own = c_of(c, h, u.own_row);
-        const float4 xs = xsame_of(A, c, h, u.own_row, pos4);
-        const float4 mass = make_float4(c_own.x + xs.x, c_own.y + xs.y, c_own.z + xs.z, c_own.w + xs.w);
+        const float4 mass = ld4(c.VM + size_t(u.own_row) * A.HpP + pos4);
         float4 v[NA];
 #pragma unroll
-        for (int a = 0; a < NA; ++a) v[a] = terms_value(A, c, h, pos4, u.term_first[a], u.term_first[a + 1], scale, u.own_row, c_own, mass);
+        for (int a = 0; a < NA; ++a) v[a] = terms_value(A, c, pos4, u.term_first[a], u.term_first[a + 1], scale);
         float g[4 * NA], ss[4 * NA];
         if (MODE == KM_CFR) rows_in<NA>(tabR, pos4, nrp, g);
         if (MODE != KM_BR) rows_in<NA>(tabS, pos4, nrp, ss);
@@ -597,9 +435,7 @@ __device__ __forceinline__ void up_sum(const StreetArgs& A, const UnitCtx& c, co
     for (int pos4 = 4 * c.tid; pos4 < A.HpP; pos4 += 4 * c.nthr) {
         float4 v = f4z();
         if (uint32_t(pos4) < nl_p) {
-            HandCtx h;
-            hand_ctx(A, c, pos4, nl_p, h);
-            v = terms_value(A, c, h, pos4, u.term_first[0], u.term_first[1], scale, -1, v, v);
+            v = terms_value(A, c, pos4, u.term_first[0], u.term_first[1], scale);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (uint32_t(pos4 + i) >= nl_p) f4s(v, i, 0.f);
@@ -611,107 +447,74 @@ __device__ __forceinline__ void up_sum(const StreetArgs& A, const UnitCtx& c, co
 
 template <int MODE, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) street_kernel(const __grid_constant__ StreetArgs A) {
-    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     UnitCtx c;
     c.tid = tid;
     c.nthr = nthr;
     float* scr = A.scratch + size_t(blockIdx.x) * A.scratch_stride;
     c.X = scr;
-    c.Y = scr + size_t(A.max_rows) * A.XP;
-    c.VAL = c.Y + size_t(A.max_rows) * A.YP;
-    const int SW = A.sweep_warps, lane = tid & 31;
-    c.ctt = st_smem + size_t(A.max_rows / SW_LANES) * SW * SM_WARP;
-    float* my_sm = st_smem + size_t(warp) * SM_WARP;
+    c.VY = scr + size_t(A.max_rows) * A.XP;
+    c.VM = c.VY + size_t(A.vy_rows) * A.HpP;
+    c.VAL = c.VM + size_t(A.vm_rows) * A.HpP;
+    TCtx t;
+    const int qt = A.qs > A.qm ? A.qs : A.qm;
+    t.TT = st_smem;
+    t.CT = t.TT + qt * SW_TT * 4;
+    t.RG = t.CT + A.qs * (SW_CHUNKS + 1) * 4;
     for (uint32_t unit = blockIdx.x; unit < A.n_units; unit += gridDim.x) {
-        const uint32_t inst = unit / uint32_t(A.n_tmpl), tm = unit - inst * uint32_t(A.n_tmpl);
+        const uint32_t inst = unit / uint32_t(A.n_segs), si = unit - inst * uint32_t(A.n_segs);
         c.b = A.sample_board ? A.sample_board[inst] : int(inst);
-        const SwUnit& U = A.units[tm];
+        const SwSeg sg = A.segs[si];
         // ---- D ----
-        for (uint32_t s = 0; s < U.seg_count; ++s) {
-            const SwSeg sg = A.segs[U.seg_first + s];
-            root_reach(A, c, sg);
-            for (uint32_t j = 0; j < sg.down_count; ++j) {
-                const SwDown d = A.downs[sg.down_first + j];
-                switch (d.n_act) {
-                    case 1: down_node<MODE, 1>(A, c, d); break;
-                    case 2: down_node<MODE, 2>(A, c, d); break;
-                    case 3: down_node<MODE, 3>(A, c, d); break;
-                    case 4: down_node<MODE, 4>(A, c, d); break;
-                    default: down_node<MODE, 5>(A, c, d); break;
-                }
+        root_reach(A, c, sg);
+        for (uint32_t j = 0; j < sg.down_count; ++j) {
+            const SwDown d = A.downs[sg.down_first + j];
+            switch (d.n_act) {
+                case 1: down_node<MODE, 1>(A, c, d); break;
+                case 2: down_node<MODE, 2>(A, c, d); break;
+                case 3: down_node<MODE, 3>(A, c, d); break;
+                case 4: down_node<MODE, 4>(A, c, d); break;
+                default: down_node<MODE, 5>(A, c, d); break;
             }
         }
         __syncthreads();
         // ---- T ----
-        const uint32_t nsw = U.n_batches * uint32_t(SW);
-        SweepCtx w;
-        uint32_t need_y = 0;
-        if (uint32_t(warp) < nsw) {
-            const int batch = warp / SW, sgi = warp - batch * SW, stride = SW_SEGS / SW;
-            const uint32_t* tab = A.seg + size_t(c.b) * 3 * (SW_SEGS + 1);
-            w.Xb = c.X + size_t(batch) * SW_LANES * A.XP;
-            w.Yb = c.Y + size_t(batch) * SW_LANES * A.YP;
-            w.ev = A.ev + A.ev_off[c.b];
-            w.ev_lo = tab[sgi * stride];
-            w.ev_hi = tab[(sgi + 1) * stride];
-            w.x_lo = tab[(SW_SEGS + 1) + sgi * stride];
-            w.r_lo = tab[2 * (SW_SEGS + 1) + sgi * stride];
-            w.r_hi = tab[2 * (SW_SEGS + 1) + (sgi + 1) * stride];
-            w.XP = A.XP;
-            w.YP = A.YP;
-            w.lane = lane;
-            w.cs = my_sm + lane;
-            w.xt = my_sm + SM_CS;
-            w.ring = my_sm + SM_CS + SM_XT;
-            need_y = U.need_y[batch];
-            my_sm[SM_CS + SM_XT + SM_RING + lane] = sweep_pass0(w);
-        }
-        __syncthreads();
-        // scan over the segments: every sweep warp's sums become the sums of everything weaker than its segment, the
-        // grand totals go to the table the U phase reads ([row][53], cfr.rs:525-531 needs the whole compatible mass)
-        for (uint32_t col = tid; col < U.n_batches * uint32_t(SM_CS + SW_LANES); col += nthr) {
-            const uint32_t batch = col / uint32_t(SM_CS + SW_LANES), j = col - batch * uint32_t(SM_CS + SW_LANES);
-            const uint32_t off = j < uint32_t(SM_CS) ? j : uint32_t(SM_CS + SM_XT + SM_RING) + (j - SM_CS);
-            float run = 0.f;
-            for (int sgi = 0; sgi < SW; ++sgi) {
-                float* p = st_smem + size_t(batch * SW + sgi) * SM_WARP + off;
-                const float t = *p;
-                *p = run;
-                run += t;
+        t.lprog = A.prog + A.prog_off[c.b];
+        t.ls = int(A.l_steps[c.b]);
+        t.cs = int(A.c_steps[c.b]);
+        t.cprog = t.lprog + size_t(t.ls) * SW_CARDS;
+        t.run_end = reinterpret_cast<const uint8_t*>(t.cprog + size_t(t.cs) * SW_CHUNKS);
+        t.hinfo = A.hinfo + size_t(c.b) * A.HpP;
+        t.nl_p = A.rp[A.trav].n_live[c.b];
+        for (int q0 = 0; q0 < int(sg.nq_sd); q0 += A.qs) sd_round(A, c, t, sg, q0, min(A.qs, int(sg.nq_sd) - q0));
+        for (int q0 = int(sg.nq_sd); q0 < int(sg.nq_sd + sg.nq_mo); q0 += A.qm) mass_round(A, c, t, q0, min(A.qm, int(sg.nq_sd + sg.nq_mo) - q0));
+        // ---- U ----  (the rounds end with a barrier: VY / VM are complete)
+        for (uint32_t j = 0; j < sg.up_count; ++j) {
+            const SwUp u = A.ups[sg.up_first + j];
+            if (u.kind == SU_SUM) {
+                up_sum(A, c, sg, u);
+                continue;
             }
-            float* ct = st_smem + size_t(A.max_rows / SW_LANES) * SW * SM_WARP + batch * SM_CT;
-            if (j < uint32_t(SM_CS)) ct[(j & 31u) * SW_CT_PITCH + (j >> 5)] = run;
-            else ct[(j - SM_CS) * SW_CT_PITCH + SW_CARDS] = run;
-        }
-        __syncthreads();
-        if (uint32_t(warp) < nsw) sweep_pass1(w, my_sm[SM_CS + SM_XT + SM_RING + lane], need_y);
-        __syncthreads();
-        // ---- U ----
-        for (uint32_t s = 0; s < U.seg_count; ++s) {
-            const SwSeg sg = A.segs[U.seg_first + s];
-            for (uint32_t j = 0; j < sg.up_count; ++j) {
-                const SwUp u = A.ups[sg.up_first + j];
-                if (u.kind == SU_SUM) {
-                    up_sum(A, c, sg, u);
-                    continue;
-                }
-                switch (u.n_act) {
-                    case 1: up_trav<MODE, 1>(A, c, sg, u); break;
-                    case 2: up_trav<MODE, 2>(A, c, sg, u); break;
-                    case 3: up_trav<MODE, 3>(A, c, sg, u); break;
-                    case 4: up_trav<MODE, 4>(A, c, sg, u); break;
-                    default: up_trav<MODE, 5>(A, c, sg, u); break;
-                }
+            switch (u.n_act) {
+                case 1: up_trav<MODE, 1>(A, c, sg, u); break;
+                case 2: up_trav<MODE, 2>(A, c, sg, u); break;
+                case 3: up_trav<MODE, 3>(A, c, sg, u); break;
+                case 4: up_trav<MODE, 4>(A, c, sg, u); break;
+                default: up_trav<MODE, 5>(A, c, sg, u); break;
             }
         }
-        __syncthreads();  // the next unit's D phase overwrites X rows and the sweep the totals this U phase reads
+        __syncthreads();  // the next unit's D phase overwrites X rows, its T phase the vectors this U phase reads
     }
 }
 
 }  // namespace
 
-size_t street_smem_bytes(int max_batches, int sweep_warps) {
-    return (size_t(max_batches) * sweep_warps * SM_WARP + size_t(max_batches) * SM_CT) * sizeof(float);
+size_t street_smem_bytes(int qs, int qm, int HpP, int HoP) {
+    const int qt = qs > qm ? qs : qm;
+    const size_t fixed = size_t(qt) * SW_TT * 4 + size_t(qs) * (SW_CHUNKS + 1) * 4;
+    const size_t sd = size_t(qs) * (4 * size_t(HoP + 1) + 8 * size_t(HpP + 1));
+    const size_t mo = size_t(qm) * 4 * size_t(HoP + 1);
+    return (fixed + (sd > mo ? sd : mo)) * sizeof(float);
 }
 
 template <int MAXT, int MINB>

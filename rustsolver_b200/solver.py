@@ -446,28 +446,25 @@ class Plan(_PlanOrEngine):
         """The final round as fused street programs (csrc/street.h); `why` is set when the round is not eligible."""
         out = (C.c_uint32 * 8)()
         check(self._lib.rs_plan_street_info(self._h, traverser, out))
-        keys = ("eligible", "templates", "max_batches", "max_rows", "max_slots", "segments", "down_ops", "up_ops")
+        keys = ("eligible", "segments", "max_rows", "max_slots", "max_q_sd", "max_q_mo", "down_ops", "up_ops")
         d = dict(zip(keys, [int(x) for x in out]))
         d["why"] = "" if d["eligible"] else self._lib.rs_last_error().decode()
         return d
 
-    def street_events(self, traverser: int, board_id: int) -> np.ndarray:
-        """Event stream of the sorted sweep on one final-round board (header/read/add words, street.h)."""
+    def street_program(self, traverser: int, board_id: int) -> dict:
+        """List programs of one final-round board (street.h): `lists` [l_steps, 52] and `chunks` [c_steps, 64] program
+        words, `hinfo` [Hpad] per traverser position, `HpP` / `HoP` the padded range sizes."""
         n = C.c_uint32()
-        check(self._lib.rs_plan_street_events(self._h, traverser, board_id, None, 0, C.byref(n)))
-        out = np.zeros(n.value, dtype=np.uint32)
-        check(self._lib.rs_plan_street_events(self._h, traverser, board_id, _ptr(out, u32p), len(out), C.byref(n)))
-        return out
-
-
-def _street_segments(self, traverser: int, board_id: int) -> np.ndarray:
-    """The eight pieces the sweep of one final-round board is cut into: rows = first event word / add position / read position."""
-    out = np.zeros(27, dtype=np.uint32)
-    check(self._lib.rs_plan_street_segments(self._h, traverser, board_id, _ptr(out, u32p)))
-    return out.reshape(3, 9)
-
-
-Plan.street_segments = _street_segments
+        dims = (C.c_uint32 * 4)()
+        check(self._lib.rs_plan_street_program(self._h, traverser, board_id, None, 0, C.byref(n), None, 0, dims))
+        words = np.zeros(max(n.value, 1), dtype=np.uint32)
+        hinfo = np.zeros(dims[2], dtype=np.uint32)
+        check(self._lib.rs_plan_street_program(self._h, traverser, board_id, _ptr(words, u32p), len(words), C.byref(n),
+                                               _ptr(hinfo, u32p), len(hinfo), dims))
+        ls, cs = int(dims[0]), int(dims[1])
+        return {"lists": words[:ls * 52].reshape(ls, 52), "chunks": words[ls * 52:ls * 52 + cs * 64].reshape(cs, 64),
+                "run_end": words[ls * 52 + cs * 64:ls * 52 + cs * 64 + 16].view(np.uint8).copy(),
+                "hinfo": hinfo, "HpP": int(dims[2]), "HoP": int(dims[3])}
 
 
 class Engine(_PlanOrEngine):

@@ -80,9 +80,12 @@ def test_chain_split_is_bit_identical():
 
 
 def test_street_kernel_matches_the_task_kernel():
-    """RS_FLAG_STREET_KERNEL (experimental) walks the final round with the fused street kernel (csrc/street_kernel.cu: per-board
-    subtree walk, terminals by one sorted sweep) instead of the per-(node, board) dataflow tasks.  Different summation orders,
-    same values to fp32 rounding -- on full ranges (several warps per board) and two streets."""
+    """RS_FLAG_STREET_KERNEL walks the final round with the fused street kernel (csrc/street_kernel.cu: one CTA per (board,
+    street segment), terminals by list walks) instead of the per-(node, board) dataflow tasks.  Different summation orders,
+    same values to fp32 rounding -- on full ranges (several warps per board) and two streets.  Both engines run in
+    lock-step with the fp64 oracle at a fifth of the usual tolerance; comparing the two fp32 engines with each other
+    directly is ill-posed on boards where most hands tie (regret matching is discontinuous on rows whose regrets are
+    rounding noise, util.lockstep)."""
     o = util.small_options("4d5dAs3c", ["random", "random"], [[0.5, 1.0]] * 2, [[3.0]] * 2)
     n, tree = rb.build_game_tree(o)
     r = o.ranges()
@@ -91,22 +94,11 @@ def test_street_kernel_matches_the_task_kernel():
     kinds1 = {k["kind"] for k in e1.profile_iteration()}
     kinds2 = {k["kind"] for k in e2.profile_iteration()}
     assert "street" in kinds1 and "street" not in kinds2, (kinds1, kinds2)
-    e1.iterate(2)
-    e2.iterate(2)
-    st = e1.stats()
-    nb = [st.n_boards[k] for k in range(st.n_rounds)]
-    # norm-wise per action node like util.compare_tables: slabs whose exact value is a pure cancellation hold rounding noise
-    diffs, scales, table = {}, {}, [0.0, 0.0]
-    for an, b in util.all_slabs(tree, nb):
-        x, y = e1.read_infoset(an, b), e2.read_infoset(an, b)
-        for w, (u, v) in enumerate(zip(x, y)):
-            assert np.isfinite(u).all()
-            m = float(np.abs(v).max())
-            scales[(an, w)] = max(scales.get((an, w), 0.0), m)
-            table[w] = max(table[w], m)
-            diffs[(an, b, w)] = float(np.abs(u - v).max())
-    worst = max(d / (2e-5 * scales[(an, w)] + 1e-6 * table[w]) for (an, b, w), d in diffs.items())
-    assert worst <= 1.0, (worst, max(diffs.items(), key=lambda kv: kv[1] / (2e-5 * scales[(kv[0][0], kv[0][2])] + 1e-6 * table[kv[0][2]])))
+    for eng in (e1, e2):
+        orc = OracleGame(tree, r, o.board_mask)
+        al = util.RowAligner(eng, orc, tree)
+        util.copy_oracle_to_engine(eng, orc, tree, aligner=al)  # profile_iteration above ran one iteration: back to zero tables
+        util.lockstep(eng, orc, tree, n_free=1, n_locked=2, tol=2e-5)
     assert np.allclose(e1.best_response(), e2.best_response(), rtol=1e-5, atol=1e-5)
     assert np.allclose(e1.average_value(), e2.average_value(), rtol=1e-5, atol=1e-5)
 

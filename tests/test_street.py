@@ -1,9 +1,11 @@
 """Host side of the fused street kernel (csrc/street.h, plan.cpp: TaskGen::build_street), no GPU.
 
-The sorted sweep values every terminal of the final round (cfr.rs:523-558) from one pass over the board's hands in
-strength order with running per-card sums.  Here the event stream the plan compiler emits is replayed in numpy
-(same arithmetic as street_kernel.cu: sweep_batch, in fp64) for random opponent reach vectors and compared with the
-O(H^2) definition: showdown = compatible weaker reach - compatible stronger reach, fold mass = compatible reach.
+The street kernel values every terminal of the final round (cfr.rs:523-558) by list walks: one thread per (four reach
+rows, list) keeps the running sum of its list -- the opponent hands holding one card, or a piece of the global strength
+order -- and follows a precomputed program of the board.  Here the programs the plan compiler emits are replayed in
+numpy (same steps as street_kernel.cu: walk_list / walk_chunk / copy-out, in fp64) for random opponent reach vectors
+and compared with the O(H^2) definition: showdown = compatible weaker reach - compatible stronger reach, fold mass =
+compatible reach.
 """
 import numpy as np
 import pytest
@@ -12,50 +14,53 @@ import rustsolver_b200 as rb
 from rustsolver_b200 import configs
 from tests import util
 
+START, END = 1 << 23, 1 << 24
 
-def replay_sweep(ev, x, n_read_positions):
-    """ev: event words of one board; x: [rows, H_opp] reach by opponent position.  Returns Y [rows, n_read], the
-    totals S [rows] and the per-card sums s [rows, 52] exactly as the kernel's sweep leaves them."""
-    rows = x.shape[0]
-    s = np.zeros((rows, 52))
-    S = np.zeros(rows)
-    Y = np.zeros((rows, n_read_positions))
-    i = 0
-    classes = 0
-    while i < len(ev):
-        nr, na = int(ev[i]) & 0x7FF, (int(ev[i]) >> 11) & 0x7FF
-        i += 1
-        reads = [int(e) for e in ev[i:i + nr]]
-        adds = [int(e) for e in ev[i + nr:i + nr + na]]
-        i += nr + na
-        classes += 1
-        dec = lambda e: (e & 0x7FF, (e >> 11) & 63, (e >> 17) & 63)
-        if nr <= 32:
-            for e in reads:
-                pos, a, b = dec(e)
-                Y[:, pos] = S - s[:, a] - s[:, b]
-            for e in adds:
-                pos, a, b = dec(e)
-                s[:, a] += x[:, pos]
-                s[:, b] += x[:, pos]
-                S += x[:, pos]
-            for e in reads:
-                pos, a, b = dec(e)
-                Y[:, pos] += S - s[:, a] - s[:, b]
-        else:  # large class: class-local sums first
-            g = np.zeros((rows, 52))
-            G = np.zeros(rows)
-            for e in adds:
-                pos, a, b = dec(e)
-                g[:, a] += x[:, pos]
-                g[:, b] += x[:, pos]
-                G += x[:, pos]
-            for e in reads:
-                pos, a, b = dec(e)
-                Y[:, pos] = 2.0 * (S - s[:, a] - s[:, b]) + (G - g[:, a] - g[:, b])
-            s += g
-            S += G
-    return Y, S, s, classes
+
+def replay_programs(prog, x):
+    """prog: Plan.street_program(...); x: [rows, n_live_opp] reach by opponent position.  Returns (VY, VM) [rows, HpP]:
+    the showdown and mass vectors exactly as the kernel's copy-out leaves them."""
+    rows, n_o = x.shape
+    HpP, HoP = prog["HpP"], prog["HoP"]
+    X = np.zeros((rows, HoP + 1))
+    X[:, :n_o] = x
+    Y = np.full((rows, 2 * (HpP + 1)), np.nan)  # every live cell must be written before it is read
+    Y[:, HpP] = 0.0
+    Y[:, 2 * HpP + 1] = 0.0
+    T = np.zeros((rows, 52))
+    for c in range(52):
+        g, g0, m = np.zeros(rows), np.zeros(rows), np.zeros(rows)
+        for w in prog["lists"][:, c]:
+            w = int(w)
+            if w & START:
+                g0 = g.copy()
+            g = g + X[:, w & 0x7FF]
+            if w & END:
+                m = g0 + g
+            Y[:, (w >> 11) & 0xFFF] = m
+        T[:, c] = g
+    ctot = np.zeros((rows, 64))
+    for ch in range(64):
+        g, g0, m = np.zeros(rows), np.zeros(rows), np.zeros(rows)
+        for w in prog["chunks"][:, ch]:
+            w = int(w)
+            if w & START:
+                g0 = g.copy()
+            g = g + X[:, w & 0x7FF]
+            if w & END:
+                m = g0 + g
+            e = (w >> 11) & 0xFFF
+            assert e <= HpP
+            Y[:, e] = m - Y[:, e] - Y[:, HpP + 1 + e]
+        ctot[:, ch] = g
+    cbase = np.concatenate([np.zeros((rows, 1)), np.cumsum(ctot, axis=1)], axis=1)  # [rows, 65]: base of piece c, total at 64
+    tot = cbase[:, 64]
+    hi = prog["hinfo"].astype(np.int64)
+    c0, c1, chunk, same = hi & 63, (hi >> 6) & 63, (hi >> 12) & 63, (hi >> 18) & 0x7FF
+    Cp = tot[:, None] - T[:, c0] - T[:, c1]
+    VY = Y[:, :HpP] + cbase[:, chunk] + cbase[:, prog["run_end"].astype(np.int64)[chunk]] - Cp
+    VM = Cp + X[:, same]
+    return VY, VM, tot, T
 
 
 def naive_terminal_values(cards_p, str_p, cards_o, str_o, x):
@@ -92,34 +97,25 @@ def check_board(plan, ranges, board_cards, board_id, trav, rng, rows=5):
     str_p = np.asarray([rb.evaluate(list(c) + board_cards) for c in cards_p], dtype=np.uint32)
     str_o = np.asarray([rb.evaluate(list(c) + board_cards) for c in cards_o], dtype=np.uint32)
     assert (np.diff(str_p.astype(np.int64)) >= 0).all() and (np.diff(str_o.astype(np.int64)) >= 0).all()
-    ev = plan.street_events(trav, board_id)
+    prog = plan.street_program(trav, board_id)
     x = rng.random((rows, len(cards_o)))
-    Y, S, s, classes = replay_sweep(ev, x, len(cards_p))
+    VY, VM, tot, T = replay_programs(prog, x)
+    n_p = len(cards_p)
     sd_ref, mass_ref = naive_terminal_values(cards_p, str_p, cards_o, str_o, x)
-    ca = np.asarray([c[0] for c in cards_p])
-    cb = np.asarray([c[1] for c in cards_p])
-    Cm = S[:, None] - s[:, ca] - s[:, cb]
-    # identical combo in the opponent's range (it is counted once in S and once in each of its two card sums)
-    pos_o = {tuple(sorted(c)): j for j, c in enumerate(cards_o)}
-    xs = np.zeros_like(Cm)
-    for t, c in enumerate(cards_p):
-        j = pos_o.get(tuple(sorted(c)))
-        if j is not None:
-            xs[:, t] = x[:, j]
-    assert np.allclose(Y - Cm, sd_ref, rtol=0, atol=1e-9 * max(1.0, np.abs(sd_ref).max())), "showdown"
-    assert np.allclose(Cm + xs, mass_ref, rtol=0, atol=1e-9 * max(1.0, np.abs(mass_ref).max())), "fold mass"
-    # every live hand is read once and added once; classes ascend
-    n_read = sum(int(e) & 0x7FF for e in _headers(ev))
-    n_add = sum((int(e) >> 11) & 0x7FF for e in _headers(ev))
-    assert n_read == len(cards_p) and n_add == len(cards_o)
-    return classes
-
-
-def _headers(ev):
-    i = 0
-    while i < len(ev):
-        yield ev[i]
-        i += 1 + (int(ev[i]) & 0x7FF) + ((int(ev[i]) >> 11) & 0x7FF)
+    assert np.isfinite(VY[:, :n_p]).all(), "a live traverser hand was never emitted to"
+    assert np.allclose(VY[:, :n_p], sd_ref, rtol=0, atol=1e-9 * max(1.0, np.abs(sd_ref).max())), "showdown"
+    assert np.allclose(VM[:, :n_p], mass_ref, rtol=0, atol=1e-9 * max(1.0, np.abs(mass_ref).max())), "fold mass"
+    assert np.allclose(tot, x.sum(axis=1))
+    # every opponent hand is added once by the pieces of the global order and once by each of its two card lists; every
+    # traverser hand is emitted to once by each of the three
+    for words, per_hand in ((prog["lists"], 2), (prog["chunks"], 1)):
+        adds = (words.astype(np.int64) & 0x7FF).ravel()
+        assert np.array_equal(np.bincount(adds[adds < prog["HoP"]], minlength=len(cards_o))[:len(cards_o)], np.full(len(cards_o), per_hand))
+        em = ((words.astype(np.int64) >> 11) & 0xFFF).ravel()
+        em = em[em != prog["HpP"]]
+        pos = np.where(em > prog["HpP"], em - prog["HpP"] - 1, em)
+        assert np.array_equal(np.bincount(pos, minlength=n_p)[:n_p], np.full(n_p, per_hand))
+    return prog
 
 
 def _cards_of_mask(mask):
@@ -131,18 +127,17 @@ def test_sweep_equals_the_definition_on_asymmetric_ranges(trav):
     o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]], [[3.0]])
     tree, ranges, plan, k = board_setup(o)
     info = plan.street_info(trav)
-    assert info["eligible"] == 1 and info["templates"] >= 1, info
+    assert info["eligible"] == 1 and info["segments"] >= 1, info
     check_board(plan, ranges, _cards_of_mask(o.board_mask), 0, trav, np.random.default_rng(trav))
 
 
 def test_sweep_full_ranges_with_ties_and_a_board_that_plays():
-    # a broadway straight on board: most hands tie (one class far larger than 32 hands -> the class-local path)
+    # a broadway straight on board: most hands tie (one class holds most of the range: its piece of the global order is long)
     o = util.small_options("AsKdQcJhTs", ["random", "random"], [[1.0]], [[3.0]])
     tree, ranges, plan, k = board_setup(o)
-    classes = check_board(plan, ranges, _cards_of_mask(o.board_mask), 0, 0, np.random.default_rng(7), rows=3)
-    ev = plan.street_events(0, 0)
-    assert max(int(h) & 0x7FF for h in _headers(ev)) > 32
-    assert classes < 200
+    prog = check_board(plan, ranges, _cards_of_mask(o.board_mask), 0, 0, np.random.default_rng(7), rows=3)
+    assert prog["chunks"].shape[0] < 64 and prog["lists"].shape[0] < 120  # the big class is a run of pieces, not one long walk
+    assert (prog["run_end"] != np.arange(64)).any()
 
 
 def test_sweep_on_river_boards_below_a_turn_root():
@@ -164,14 +159,21 @@ def test_street_plan_shapes_of_the_baseline_configs():
     plan = rb.Plan(tree, configs.workload_ranges(w), w.options.board_mask, w.card_abs, flags=rb.RS_FLAG_STREET_KERNEL)
     for p in range(2):
         info = plan.street_info(p)
-        # 11 river subtrees + the 2 all-in run-out showdowns, packed into units of at most 32 reach rows
-        assert info["eligible"] == 1 and info["segments"] == 13 and info["max_rows"] <= 32 and info["max_batches"] == 1, info
+        # 11 river subtrees + the 2 all-in run-out showdowns
+        assert info["eligible"] == 1 and info["segments"] == 13 and info["max_rows"] <= 40 and info["max_q_sd"] <= 4, info
         assert info["down_ops"] + info["up_ops"] >= 118
+        prog = plan.street_program(p, 5)
+        assert 40 <= prog["lists"].shape[0] <= 96 and prog["chunks"].shape[0] <= 64, (prog["lists"].shape, prog["chunks"].shape)
+    w = configs.config5(n_subgames=4)
+    n, tree = rb.build_game_tree(w.options)
+    plan = rb.Plan(tree, configs.workload_ranges(w), 0, w.card_abs, board_masks=w.board_masks, flags=rb.RS_FLAG_STREET_KERNEL)
+    info = plan.street_info(0)
+    assert info["eligible"] == 1 and info["segments"] == 1 and info["max_q_sd"] == 2, info
     w = configs.config3()
     n, tree = rb.build_game_tree(w.options)
     plan = rb.Plan(tree, configs.workload_ranges(w), w.options.board_mask, w.card_abs, flags=rb.RS_FLAG_STREET_KERNEL)
     info = plan.street_info(0)
-    assert info["eligible"] == 1 and info["segments"] == 1 and info["max_batches"] == 4, info  # 5-action nodes, 113 rows
+    assert info["eligible"] == 0 and "32 showdown rows" in info["why"], info  # one board, 75 showdowns: the task kernel's job
     w = configs.config1(lossless=False)
     n, tree = rb.build_game_tree(w.options)
     plan = rb.Plan(tree, configs.workload_ranges(w), w.options.board_mask, w.card_abs, flags=rb.RS_FLAG_STREET_KERNEL)
