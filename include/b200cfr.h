@@ -311,9 +311,9 @@ int rs_plan_showdown_order(const rs_plan* p, uint32_t player, uint32_t board_id,
  * the round is not eligible rs_last_error() says why (bucketed tables, a node wider than 5 actions, the flag). */
 int rs_plan_street_info(const rs_plan* p, uint32_t traverser, uint32_t out[8]);
 /* The list programs that drive the terminal evaluation of `traverser` on a final-round board (csrc/street.h): words
- * [l_steps][52] of the card lists followed by [c_steps][64] of the pieces of the global strength order, and the
- * per-position word (cards, piece, identical combo) of the traverser's hands, hinfo[Hpad].  dims_out = {l_steps,
- * c_steps, Hpad of the traverser, Hpad of the opponent}.  words_out == NULL: only the sizes. */
+ * [l_steps][52 * 4] of the pieces of the card lists followed by [c_steps][128] of the pieces of the global strength
+ * order, and the two per-position words (cards, pieces, identical combo) of the traverser's hands, hinfo[Hpad][2].
+ * dims_out = {l_steps, c_steps, Hpad of the traverser, Hpad of the opponent}.  words_out == NULL: only the sizes. */
 int rs_plan_street_program(const rs_plan* p, uint32_t traverser, uint32_t board_id, uint32_t* words_out, size_t cap,
                            uint32_t* n_words_out, uint32_t* hinfo_out, size_t hinfo_cap, uint32_t dims_out[4]);
 

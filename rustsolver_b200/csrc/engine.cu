@@ -1434,8 +1434,8 @@ int rs_plan_street_program(const rs_plan* p, uint32_t traverser, uint32_t board_
         memcpy(words_out, S.prog.data() + S.prog_off[lb], size_t(n) * sizeof(uint32_t));
     }
     if (hinfo_out) {
-        if (hinfo_cap < HpP) return set_err(RS_ERR_CAPACITY, "hinfo buffer too small");
-        memcpy(hinfo_out, S.hinfo.data() + size_t(lb) * HpP, size_t(HpP) * sizeof(uint32_t));
+        if (hinfo_cap < 2 * size_t(HpP)) return set_err(RS_ERR_CAPACITY, "hinfo buffer too small");
+        memcpy(hinfo_out, S.hinfo.data() + size_t(lb) * HpP * 2, size_t(HpP) * 2 * sizeof(uint32_t));
     }
     return RS_OK;
 }

@@ -741,7 +741,8 @@ struct TaskGen {
             S.max_q_sd = std::max(S.max_q_sd, nq_sd);
             S.max_q_mo = std::max(S.max_q_mo, nq_mo);
         }
-        // list programs of every local board: the 52 card lists, then the global strength order in SW_CHUNKS pieces
+        // list programs of every local board: the 52 card lists in SW_LIST_PIECES pieces each, then the global strength
+        // order in SW_CHUNKS pieces
         const int o = 1 - trav;
         const LocalTables& Lp = P->loc[k][trav];
         const LocalTables& Lo = P->loc[k][o];
@@ -752,10 +753,84 @@ struct TaskGen {
         S.prog_off.assign(size_t(hi_b - lo_b) + 1, 0);
         S.l_steps.assign(hi_b - lo_b, 0);
         S.c_steps.assign(hi_b - lo_b, 0);
-        S.hinfo.assign(size_t(hi_b - lo_b) * HpP, 0);
+        S.hinfo.assign(size_t(hi_b - lo_b) * HpP * 2, 0);
         const uint32_t zero_pos = HoP, dump_idx = HpP;
         std::vector<ProgClass> cls;
-        std::vector<std::vector<uint32_t>> lw(SW_CARDS), cw(SW_CHUNKS);
+        constexpr int NLP = SW_CARDS * SW_LIST_PIECES;
+        std::vector<std::vector<uint32_t>> lw(NLP), cw(SW_CHUNKS);
+        // Cut the classes of one list into at most n_pieces pieces of about equal length and schedule each piece on its own.
+        // A class far longer than a piece (a board that plays: hundreds of hands tie) becomes a RUN of pieces that only
+        // add and combine (m stays 0): its hands take A + B = base[first piece of the run] + base[piece after the run].
+        // on_hand(emit index, lo piece, hi piece): normal classes lo == hi == their piece.
+        auto cut_list = [&](std::vector<ProgClass>& classes, uint32_t n_pieces, std::vector<uint32_t>* words, uint32_t& max_steps,
+                            const std::function<void(uint32_t, uint32_t, uint32_t)>& on_hand) {
+            // steps a class costs: its adds, and its emits but the first trail behind on steps of their own when the classes
+            // after it are short (schedule_program)
+            auto len_of = [](const ProgClass& c) { return uint64_t(std::max<size_t>(1, c.adds.size() + (c.emits.empty() ? 0 : c.emits.size() - 1))); };
+            // pieces used when no piece may be longer than `cap`: classes are packed greedily, a class longer than cap
+            // becomes a run of ceil(len / cap) pieces
+            auto pieces_needed = [&](uint64_t cap) {
+                uint64_t n = 0, acc = 0;
+                for (const ProgClass& c : classes) {
+                    const uint64_t len = len_of(c);
+                    if (len > cap) {
+                        if (acc) ++n, acc = 0;
+                        n += (len + cap - 1) / cap;
+                    } else {
+                        if (acc + len > cap) ++n, acc = 0;
+                        acc += len;
+                    }
+                }
+                return n + (acc ? 1 : 0);
+            };
+            uint64_t lo = 1, hi = 1;
+            for (const ProgClass& c : classes) hi += len_of(c);
+            while (lo < hi) {  // smallest cap that fits n_pieces
+                const uint64_t mid = (lo + hi) / 2;
+                if (pieces_needed(mid) <= n_pieces) hi = mid;
+                else lo = mid + 1;
+            }
+            const uint64_t cap = lo;
+            uint32_t ch = 0;
+            std::vector<ProgClass> piece;
+            uint64_t acc = 0;
+            auto flush = [&]() {
+                if (piece.empty()) return;
+                schedule_program(piece, zero_pos, dump_idx, words[ch]);
+                max_steps = std::max<uint32_t>(max_steps, uint32_t(words[ch].size()));
+                for (const ProgClass& c : piece)
+                    for (uint32_t e : c.emits) on_hand(e, ch, ch);
+                piece.clear();
+                acc = 0;
+                ++ch;
+            };
+            for (size_t ci = 0; ci < classes.size(); ++ci) {
+                ProgClass& c = classes[ci];
+                const uint64_t len = len_of(c);
+                if (len > cap) {
+                    flush();
+                    const uint32_t r = uint32_t((len + cap - 1) / cap);
+                    const uint32_t c1 = ch;
+                    for (uint32_t t = 0; t < r; ++t) {
+                        const size_t a0 = c.adds.size() * t / r, a1 = c.adds.size() * (t + 1) / r;
+                        const size_t e0 = c.emits.size() * t / r, e1 = c.emits.size() * (t + 1) / r;
+                        std::vector<uint32_t>& wv = words[ch];
+                        wv.clear();
+                        for (size_t i = 0; i < std::max(a1 - a0, e1 - e0); ++i)
+                            wv.push_back((a0 + i < a1 ? c.adds[a0 + i] : zero_pos) | ((e0 + i < e1 ? c.emits[e0 + i] : dump_idx) << SW_EMIT_SHIFT));
+                        max_steps = std::max<uint32_t>(max_steps, uint32_t(wv.size()));
+                        ++ch;
+                    }
+                    for (uint32_t e : c.emits) on_hand(e, c1, ch);
+                    continue;
+                }
+                if (acc + len > cap) flush();
+                acc += len;
+                piece.push_back(std::move(c));
+            }
+            flush();
+            for (uint32_t c2 = ch; c2 < n_pieces; ++c2) words[c2].clear();
+        };
         for (uint32_t b = lo_b; b < hi_b; ++b) {
             const uint32_t np = Lp.n_live[b], no_ = Lo.n_live[b];
             const uint16_t* sp_ = &Lp.slot_of_pos[size_t(b) * Lp.Hpad];
@@ -785,7 +860,7 @@ struct TaskGen {
                         skip_o();
                     }
                     while (i < np && strp[sp_[i]] == st) {
-                        const uint32_t tgt = (card >= 0 && P->hand_cards[trav][2 * sp_[i] + 1] == card) ? 1u : 0u;  // hands are stored c0 < c1
+                        const uint32_t tgt = (card >= 0 && P->hand_cards[trav][2 * sp_[i] + 1] == card) ? 1u : 0u;
                         c.emits.push_back(tgt * (HpP + 1) + i);
                         ++i;
                         skip_p();
@@ -793,66 +868,18 @@ struct TaskGen {
                     out.push_back(std::move(c));
                 }
             };
-            uint32_t ls = 0;
+            uint32_t* hi_ = &S.hinfo[size_t(b - lo_b) * HpP * 2];
+            uint32_t ls = 0, cs = 0;
             for (int c = 0; c < SW_CARDS; ++c) {
                 classes_of(c, cls);
-                schedule_program(cls, zero_pos, dump_idx, lw[c]);
-                ls = std::max<uint32_t>(ls, uint32_t(lw[c].size()));
+                cut_list(cls, SW_LIST_PIECES, &lw[size_t(c) * SW_LIST_PIECES], ls, [&](uint32_t e, uint32_t lo, uint32_t hi) {
+                    const bool second = e > HpP;  // emit index of target 1: the list is the hand's second card
+                    const uint32_t pos = second ? e - (HpP + 1) : e;
+                    hi_[2 * pos] |= second ? (lo << SW_HI_P1LO_SHIFT) | (hi << SW_HI_P1HI_SHIFT) : (lo << SW_HI_P0LO_SHIFT) | (hi << SW_HI_P0HI_SHIFT);
+                });
             }
-            // the global order, cut at class boundaries into pieces of about equal length.  A class far longer than a piece
-            // (a board that plays: hundreds of hands tie) becomes a RUN of pieces of its own that only add and combine
-            // (m stays 0); its hands take A + B = (sum before the run) + (sum through the run) from the piece bases.
             classes_of(-1, cls);
-            uint64_t est = 0;
-            for (const ProgClass& c : cls) est += std::max<size_t>(1, std::max(c.adds.size(), c.emits.size()));
-            const uint64_t per = std::max<uint64_t>(4, (est + SW_CHUNKS - 9) / (SW_CHUNKS - 8));
-            uint32_t* hi_ = &S.hinfo[size_t(b - lo_b) * HpP];
-            uint32_t cs = 0, ch = 0;
-            uint8_t run_end[SW_CHUNKS];
-            for (int c2 = 0; c2 < SW_CHUNKS; ++c2) run_end[c2] = uint8_t(c2);
-            {
-                std::vector<ProgClass> piece;
-                uint64_t acc = 0;
-                auto flush = [&]() {
-                    if (piece.empty()) return;
-                    schedule_program(piece, zero_pos, dump_idx, cw[ch]);
-                    cs = std::max<uint32_t>(cs, uint32_t(cw[ch].size()));
-                    for (const ProgClass& c : piece)
-                        for (uint32_t e : c.emits) hi_[e] |= ch << SW_HI_CHUNK_SHIFT;
-                    piece.clear();
-                    acc = 0;
-                    ++ch;
-                };
-                for (size_t ci = 0; ci < cls.size(); ++ci) {
-                    ProgClass& c = cls[ci];
-                    const uint64_t len = std::max<size_t>(1, std::max(c.adds.size(), c.emits.size()));
-                    const uint32_t left_after = uint32_t(SW_CHUNKS) - ch - (piece.empty() ? 0u : 1u);
-                    if (len > 2 * per && left_after >= 3) {
-                        flush();
-                        uint32_t r = uint32_t(std::min<uint64_t>((len + per - 1) / per, uint64_t(SW_CHUNKS) - ch - 1));
-                        r = std::max<uint32_t>(r, 1);
-                        const uint32_t c1 = ch;
-                        for (uint32_t t = 0; t < r; ++t) {
-                            const size_t a0 = c.adds.size() * t / r, a1 = c.adds.size() * (t + 1) / r;
-                            const size_t e0 = c.emits.size() * t / r, e1 = c.emits.size() * (t + 1) / r;
-                            std::vector<uint32_t>& wv = cw[ch];
-                            wv.clear();
-                            for (size_t i = 0; i < std::max(a1 - a0, e1 - e0); ++i)
-                                wv.push_back((a0 + i < a1 ? c.adds[a0 + i] : zero_pos) | ((e0 + i < e1 ? c.emits[e0 + i] : dump_idx) << SW_EMIT_SHIFT));
-                            cs = std::max<uint32_t>(cs, uint32_t(wv.size()));
-                            ++ch;
-                        }
-                        run_end[c1] = uint8_t(ch);
-                        for (uint32_t e : c.emits) hi_[e] |= c1 << SW_HI_CHUNK_SHIFT;
-                        continue;
-                    }
-                    acc += len;
-                    piece.push_back(std::move(c));
-                    if (acc >= per && ch + 1 < uint32_t(SW_CHUNKS)) flush();
-                }
-                flush();
-                for (uint32_t c2 = ch; c2 < uint32_t(SW_CHUNKS); ++c2) cw[c2].clear();
-            }
+            cut_list(cls, SW_CHUNKS, cw.data(), cs, [&](uint32_t e, uint32_t lo, uint32_t hi) { hi_[2 * e + 1] |= lo | (hi << SW_HI_CHHI_SHIFT); });
             for (uint32_t i = 0; i < np; ++i) {
                 const uint32_t h = sp_[i];
                 uint32_t same = HoP;
@@ -861,23 +888,21 @@ struct TaskGen {
                     const uint16_t op = Lo.pos_of_slot[size_t(b) * Ho + sm];
                     if (op < no_) same = op;
                 }
-                hi_[i] |= uint32_t(P->hand_cards[trav][2 * h]) | (uint32_t(P->hand_cards[trav][2 * h + 1]) << SW_HI_C1_SHIFT) | (same << SW_HI_SAME_SHIFT);
+                hi_[2 * i] |= uint32_t(P->hand_cards[trav][2 * h]) | (uint32_t(P->hand_cards[trav][2 * h + 1]) << SW_HI_C1_SHIFT);
+                hi_[2 * i + 1] |= same << SW_HI_SAME_SHIFT;
             }
-            for (uint32_t i = np; i < HpP; ++i) hi_[i] = HoP << SW_HI_SAME_SHIFT;
+            for (uint32_t i = np; i < HpP; ++i) hi_[2 * i + 1] = HoP << SW_HI_SAME_SHIFT;
             ls = (ls + 3) & ~3u;  // the walks fetch four words at a time
             cs = (cs + 3) & ~3u;
-            // pack: [ls][52] then [cs][64]; short programs are padded with steps that add nothing and emit to the dump cell
+            // pack: [ls][208] then [cs][128]; short programs are padded with steps that add nothing and emit to the dump cell
             const uint32_t nop = zero_pos | (dump_idx << SW_EMIT_SHIFT);
             const size_t base = S.prog.size();
-            S.prog.resize(base + size_t(ls) * SW_CARDS + size_t(cs) * SW_CHUNKS + SW_CHUNKS / 4, nop);
-            for (int c = 0; c < SW_CARDS; ++c)
-                for (size_t t = 0; t < lw[c].size(); ++t) S.prog[base + t * SW_CARDS + c] = lw[c][t];
-            const size_t cbase = base + size_t(ls) * SW_CARDS;
+            S.prog.resize(base + size_t(ls) * NLP + size_t(cs) * SW_CHUNKS, nop);
+            for (int c = 0; c < NLP; ++c)
+                for (size_t t = 0; t < lw[c].size(); ++t) S.prog[base + t * NLP + c] = lw[c][t];
+            const size_t cbase = base + size_t(ls) * NLP;
             for (int c = 0; c < SW_CHUNKS; ++c)
                 for (size_t t = 0; t < cw[c].size(); ++t) S.prog[cbase + t * SW_CHUNKS + c] = cw[c][t];
-            for (int c = 0; c < SW_CHUNKS / 4; ++c)  // run_end[64] as bytes behind the chunk programs
-                S.prog[cbase + size_t(cs) * SW_CHUNKS + c] = uint32_t(run_end[4 * c]) | (uint32_t(run_end[4 * c + 1]) << 8) | (uint32_t(run_end[4 * c + 2]) << 16) |
-                                                                (uint32_t(run_end[4 * c + 3]) << 24);
             if (S.prog.size() > 0xfffffff0ull) return no("list programs exceed 32-bit word offsets");
             S.prog_off[b - lo_b] = uint32_t(base);
             S.l_steps[b - lo_b] = ls;

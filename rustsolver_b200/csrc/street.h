@@ -20,13 +20,13 @@
 //                                        C'(h)         = T_G - T_a - T_b
 //                                        showdown term = (A_G + B_G) - (A_a + B_a) - (A_b + B_b) - C'(h)
 //                                        fold / mass   = C'(h) + x[identical combo]
-//                                    One thread walks one (quad, list): it keeps the running sum of its list in
+//                                    One thread walks one (quad, piece of a list): it keeps the running sum in
 //                                    registers, loads x by a precomputed PROGRAM of the board (one word per step:
 //                                    which opponent position to add, which traverser hand to emit to, where a
 //                                    strength class starts and ends) and stores A + B for the traverser hands of
-//                                    the list.  The 52 card lists and the global order, cut into SW_CHUNKS pieces
-//                                    at class boundaries, are walked in parallel; no per-hand random gathers, no
-//                                    prefix-sum barriers per terminal.
+//                                    the piece.  The 52 card lists (4 pieces each) and the global order (128
+//                                    pieces), cut at class boundaries, are walked in parallel; no per-hand random
+//                                    gathers, no prefix-sum barriers per terminal.
 //   U  (hand-parallel, no barrier)   traverser nodes in post-order: child values, node value, regret and
 //                                    strategy-sum update (cfr.rs:588, 612-621); every term is one vector the T
 //                                    phase left (VY showdown, VM mass) or the value slot of a node further down.
@@ -41,8 +41,9 @@ namespace rs {
 
 constexpr int SW_MAX_ACT = 5;   // widest action node the fused street kernel keeps in registers
 constexpr int SW_CARDS = 52;
-constexpr int SW_CHUNKS = 64;   // pieces the strength order of a board is cut into (global list)
-constexpr int SW_TT = 53;       // totals table of a quad: 52 per-card sums + the total
+constexpr int SW_CHUNKS = 128;      // pieces the strength order of a board is cut into (global list)
+constexpr int SW_LIST_PIECES = 4;   // pieces of one card list
+constexpr int SW_LB = SW_LIST_PIECES + 1;  // bases of a card list's pieces + the list total
 constexpr int SW_MAX_SD_ROWS = 32;  // showdown rows of one segment (sd_need_m is a 32-bit mask)
 
 // program word: one step of a list walk
@@ -57,8 +58,14 @@ constexpr uint32_t SW_EMIT_MASK = 0xfffu;
 constexpr uint32_t SW_CLASS_START = 1u << 23;
 constexpr uint32_t SW_CLASS_END = 1u << 24;
 
-// per traverser position: c0 | c1 << 6 | chunk << 12 | identical-combo opponent position << 18 (HoP: none)
-constexpr int SW_HI_C1_SHIFT = 6, SW_HI_CHUNK_SHIFT = 12, SW_HI_SAME_SHIFT = 18;
+// Every list is cut into pieces at class boundaries; a walk starts at 0 and the copy-out adds the sums of the pieces
+// before it: a hand of piece c takes base[lo] + base[hi] with lo = hi = c, or, when its strength class is a RUN of
+// pieces of its own (hundreds of hands tie), lo = first piece of the run, hi = piece after the run.
+// per traverser position, two words:
+//   word 0: c0 | c1 << 6 | lo, hi inside list c0 << 12, 14 | lo, hi inside list c1 << 17, 19
+//   word 1: lo | hi << 7 of the global order | identical-combo opponent position << 15 (HoP: none)
+constexpr int SW_HI_C1_SHIFT = 6, SW_HI_P0LO_SHIFT = 12, SW_HI_P0HI_SHIFT = 14, SW_HI_P1LO_SHIFT = 17, SW_HI_P1HI_SHIFT = 19;
+constexpr int SW_HI_CHHI_SHIFT = 7, SW_HI_SAME_SHIFT = 15;
 
 enum SwTermKind : uint8_t {
     ST_FOLD = 0,      // coef * VM[row id]   (cfr.rs:525-531)
@@ -117,14 +124,12 @@ struct StreetPlan {
     std::vector<SwUp> ups;
     std::vector<SwTerm> terms;
     uint32_t max_rows = 0, max_slots = 0, max_q_sd = 0, max_q_mo = 0;
-    // per LOCAL board of the round (index = board - local_lo): the list programs [l_steps][52] followed by the chunk
-    // programs [c_steps][SW_CHUNKS], one word per (step, list), and run_end[SW_CHUNKS] as bytes: for the first piece of a
-    // run (a strength class cut into several pieces) the piece after the run, else the piece itself.  The hands of
-    // piece c take  base[c] + base[run_end[c]]  from the exclusive prefix of the piece totals (base[64] = total)
+    // per LOCAL board of the round (index = board - local_lo): the programs of the card-list pieces [l_steps][52 * 4]
+    // followed by those of the pieces of the global order [c_steps][SW_CHUNKS], one word per (step, piece)
     std::vector<uint32_t> prog;
     std::vector<uint32_t> prog_off;  // [n_local + 1] word offsets
     std::vector<uint32_t> l_steps, c_steps;  // [n_local]
-    std::vector<uint32_t> hinfo;     // [n_local][HpP] per traverser position (SW_HI_*)
+    std::vector<uint32_t> hinfo;     // [n_local][HpP][2] per traverser position (SW_HI_*)
 };
 
 }  // namespace rs

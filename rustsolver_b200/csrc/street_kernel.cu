@@ -68,6 +68,11 @@ __device__ __forceinline__ void rows_out(float* __restrict__ slab, int pos4, con
     for (int q = 0; q < NA; ++q) st4(slab + size_t(pos4) * NA + 4 * q, make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]));
 }
 
+// bulk L2 prefetch (TMA unit, no destination): bytes a multiple of 16, p 16-byte aligned
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 struct UnitCtx {
     int b;         // local board
     int tid, nthr;
@@ -136,10 +141,17 @@ template <bool EMIT>
 __device__ __forceinline__ float4 walk_list(const float* __restrict__ X4, float* __restrict__ Y4, const uint32_t* __restrict__ prog, int stride,
                                             int steps) {
     float4 g = f4z(), g0 = f4z(), m = f4z();
+    uint32_t wn[4];  // the next four words are in flight while the current four are walked
+#pragma unroll
+    for (int u = 0; u < 4; ++u) wn[u] = steps > 0 ? __ldg(prog + size_t(u) * stride) : 0u;
     for (int s = 0; s < steps; s += 4) {
         uint32_t w[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = __ldg(prog + size_t(s + u) * stride);
+        for (int u = 0; u < 4; ++u) w[u] = wn[u];
+        if (s + 4 < steps) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wn[u] = __ldg(prog + size_t(s + 4 + u) * stride);
+        }
         float4 x[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) x[u] = ld4(X4 + 4 * (w[u] & SW_ADD_MASK));
@@ -162,10 +174,17 @@ __device__ __forceinline__ float4 walk_list(const float* __restrict__ X4, float*
 __device__ __forceinline__ float4 walk_chunk(const float* __restrict__ X4, float* __restrict__ Y4, int y2_off, const uint32_t* __restrict__ prog,
                                              int stride, int steps) {
     float4 g = f4z(), g0 = f4z(), m = f4z();
+    uint32_t wn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) wn[u] = steps > 0 ? __ldg(prog + size_t(u) * stride) : 0u;
     for (int s = 0; s < steps; s += 4) {
         uint32_t w[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = __ldg(prog + size_t(s + u) * stride);
+        for (int u = 0; u < 4; ++u) w[u] = wn[u];
+        if (s + 4 < steps) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wn[u] = __ldg(prog + size_t(s + 4 + u) * stride);
+        }
         float4 x[4], y1[4], y2[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -188,8 +207,15 @@ __device__ __forceinline__ float4 walk_chunk(const float* __restrict__ X4, float
 // rows of a quad from the unit's scratch into shared memory, interleaved: X4[pos] = (x_r0[pos], .., x_r0+3[pos])
 __device__ __forceinline__ void stage_quad(const StreetArgs& A, const UnitCtx& c, int row0, float* X4) {
     const float* x0 = c.X + size_t(row0) * A.XP;
-    for (int pos = c.tid; pos < A.HoP; pos += c.nthr)
-        st4(X4 + 4 * pos, make_float4(x0[pos], x0[A.XP + pos], x0[2 * A.XP + pos], x0[3 * A.XP + pos]));
+    for (int pos = c.tid; pos < A.HoP; pos += 2 * c.nthr) {  // two positions per trip: eight loads in flight
+        const int p2 = pos + c.nthr;
+        const bool two = p2 < A.HoP;
+        const float4 a = make_float4(x0[pos], x0[A.XP + pos], x0[2 * A.XP + pos], x0[3 * A.XP + pos]);
+        float4 b = f4z();
+        if (two) b = make_float4(x0[p2], x0[A.XP + p2], x0[2 * A.XP + p2], x0[3 * A.XP + p2]);
+        st4(X4 + 4 * pos, a);
+        if (two) st4(X4 + 4 * p2, b);
+    }
     if (c.tid == 0) st4(X4 + 4 * A.HoP, f4z());  // the zero cell
 }
 
@@ -203,18 +229,58 @@ __device__ __forceinline__ float4 warp_sum4(float4 v) {
     }
     return v;
 }
+// inclusive scan over groups of WIDTH consecutive lanes
+template <int WIDTH>
+__device__ __forceinline__ float4 group_scan4(float4 v, int lane) {
+#pragma unroll
+    for (int d = 1; d < WIDTH; d <<= 1) {
+        float4 o;
+        o.x = __shfl_up_sync(0xffffffffu, v.x, d, WIDTH);
+        o.y = __shfl_up_sync(0xffffffffu, v.y, d, WIDTH);
+        o.z = __shfl_up_sync(0xffffffffu, v.z, d, WIDTH);
+        o.w = __shfl_up_sync(0xffffffffu, v.w, d, WIDTH);
+        if ((lane & (WIDTH - 1)) >= d) v = f4a(v, o);
+    }
+    return v;
+}
 
 struct TCtx {
-    float* TT;   // [quad][SW_TT][4]   per-card sums + total of the quads of the current round
-    float* CT;   // [quad][SW_CHUNKS + 1][4] totals, then bases, of the pieces of the global order ([64] = the total)
+    float* LB;   // [quad][52][SW_LB][4]     bases of the pieces of every card list, [SW_LIST_PIECES] = the list total
+    float* CB;   // [quad][SW_CHUNKS + 1][4] totals, then bases, of the pieces of the global order ([SW_CHUNKS] = the total)
+    float* TOT;  // [quad][4]                total of a mass-only quad
     float* RG;   // staged quads
     const uint32_t* lprog;
     const uint32_t* cprog;
-    const uint32_t* hinfo;
-    const uint8_t* run_end;  // [SW_CHUNKS] street.h
+    const uint2* hinfo;
     int ls, cs;
     uint32_t nl_p;
 };
+constexpr int NLP = SW_CARDS * SW_LIST_PIECES;  // card-list pieces of a quad
+constexpr int LBQ = SW_CARDS * SW_LB * 4;       // floats of LB per quad
+constexpr int CBQ = (SW_CHUNKS + 1) * 4;
+
+// pieces of the card lists of quads [0, nq): walks, then the bases of every list's pieces by a scan inside the four lanes
+// that walked them
+template <bool EMIT>
+__device__ __forceinline__ void list_pass(const UnitCtx& c, const TCtx& t, int nq, int x_stride, int y_off) {
+    const int lane = c.tid & 31;
+    static_assert(SW_LIST_PIECES == 4, "the lanes of a list are one shuffle group of four");
+    for (int it0 = c.tid - lane; it0 < nq * NLP; it0 += c.nthr) {  // warp-uniform trip count: the shuffles need every lane
+        const int it = it0 + lane;
+        float4 g = f4z();
+        const int q = it / NLP, pid = it - q * NLP;
+        if (it < nq * NLP) {
+            float* base = t.RG + q * x_stride;
+            g = walk_list<EMIT>(base, base + y_off, t.lprog + pid, NLP, t.ls);
+        }
+        const float4 inc = group_scan4<SW_LIST_PIECES>(g, lane);
+        if (it < nq * NLP) {
+            float* lb = t.LB + q * LBQ + (pid >> 2) * (SW_LB * 4);
+            st4(lb + 4 * (pid & 3), f4sub(inc, g));
+            if ((pid & 3) == 3) st4(lb + 4 * SW_LIST_PIECES, inc);
+        }
+    }
+}
 
 // showdown quads [q0, q0 + nq): everything the U phase reads of their rows goes to VY (and VM where a row's mass is read)
 __device__ __forceinline__ void sd_round(const StreetArgs& A, const UnitCtx& c, const TCtx& t, const SwSeg& sg, int q0, int nq) {
@@ -222,72 +288,55 @@ __device__ __forceinline__ void sd_round(const StreetArgs& A, const UnitCtx& c, 
     const int lane = c.tid & 31, warp = c.tid >> 5;
     for (int q = 0; q < nq; ++q) stage_quad(A, c, 4 * (q0 + q), t.RG + q * per);
     __syncthreads();
-    for (int it = c.tid; it < nq * SW_CARDS; it += c.nthr) {
-        const int q = it / SW_CARDS, card = it - q * SW_CARDS;
-        float* base = t.RG + q * per;
-        const float4 g = walk_list<true>(base, base + xq, t.lprog + card, SW_CARDS, t.ls);
-        st4(t.TT + (q * SW_TT + card) * 4, g);
-    }
+    list_pass<true>(c, t, nq, per, xq);
     __syncthreads();
     for (int it = c.tid; it < nq * SW_CHUNKS; it += c.nthr) {
         const int q = it / SW_CHUNKS, ch = it - q * SW_CHUNKS;
         float* base = t.RG + q * per;
         const float4 g = walk_chunk(base, base + xq, A.HpP + 1, t.cprog + ch, SW_CHUNKS, t.cs);
-        st4(t.CT + (q * (SW_CHUNKS + 1) + ch) * 4, g);
+        st4(t.CB + q * CBQ + ch * 4, g);
     }
     __syncthreads();
-    if (warp < nq) {  // exclusive scan of the 64 piece totals of quad `warp`: two pieces per lane
-        float* ct = t.CT + warp * (SW_CHUNKS + 1) * 4;
-        const float4 a = ld4(ct + 8 * lane), b2 = ld4(ct + 8 * lane + 4);
-        const float4 s = f4a(a, b2);
-        float4 inc = s;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            float4 o;
-            o.x = __shfl_up_sync(0xffffffffu, inc.x, d);
-            o.y = __shfl_up_sync(0xffffffffu, inc.y, d);
-            o.z = __shfl_up_sync(0xffffffffu, inc.z, d);
-            o.w = __shfl_up_sync(0xffffffffu, inc.w, d);
-            if (lane >= d) inc = f4a(inc, o);
-        }
+    if (warp < nq) {  // exclusive scan of the piece totals of quad `warp`: four pieces per lane
+        static_assert(SW_CHUNKS == 128, "four pieces per lane");
+        float* cb = t.CB + warp * CBQ + 16 * lane;
+        const float4 a = ld4(cb), b2 = ld4(cb + 4), c2 = ld4(cb + 8), d2 = ld4(cb + 12);
+        const float4 s = f4a(f4a(a, b2), f4a(c2, d2));
+        const float4 inc = group_scan4<32>(s, lane);
         const float4 ex = f4sub(inc, s);
-        st4(ct + 8 * lane, ex);
-        st4(ct + 8 * lane + 4, f4a(ex, a));
-        if (lane == 31) {
-            st4(ct + 4 * SW_CHUNKS, inc);
-            st4(t.TT + (warp * SW_TT + SW_CARDS) * 4, inc);
-        }
+        st4(cb, ex);
+        st4(cb + 4, f4a(ex, a));
+        st4(cb + 8, f4a(f4a(ex, a), b2));
+        st4(cb + 12, f4a(f4a(f4a(ex, a), b2), c2));
+        if (lane == 31) st4(t.CB + warp * CBQ + 4 * SW_CHUNKS, inc);
     }
     __syncthreads();
     for (int q = 0; q < nq; ++q) {
         const float* X4 = t.RG + q * per;
         const float* Y4 = X4 + xq;
-        const float* tt = t.TT + q * SW_TT * 4;
-        const float* ct = t.CT + q * (SW_CHUNKS + 1) * 4;
-        const float4 tot = ld4(tt + SW_CARDS * 4);
+        const float* lbq = t.LB + q * LBQ;
+        const float* cb = t.CB + q * CBQ;
+        const float4 tot = ld4(cb + 4 * SW_CHUNKS);
         const int row0 = 4 * (q0 + q);
         const uint32_t need_m = (sg.sd_need_m >> row0) & 15u;
         float* vy = c.VY + size_t(row0) * A.HpP;
         float* vm = c.VM + size_t(row0) * A.HpP;
         for (int pos = c.tid; pos < A.HpP; pos += c.nthr) {
-            const uint32_t hi = __ldg(t.hinfo + pos);
-            const float4 ta = ld4(tt + 4 * (hi & 63u)), tb = ld4(tt + 4 * ((hi >> SW_HI_C1_SHIFT) & 63u));
-            const uint32_t ch = (hi >> SW_HI_CHUNK_SHIFT) & 63u;
-            const float4 cb = f4a(ld4(ct + 4 * ch), ld4(ct + 4 * uint32_t(__ldg(t.run_end + ch))));  // 2 x base, or base + end of a run
-            const float4 y = ld4(Y4 + 4 * pos);
-            const float4 cp = f4sub(f4sub(tot, ta), tb);
+            const uint2 hi = __ldg(t.hinfo + pos);
+            const float* l0 = lbq + (hi.x & 63u) * (SW_LB * 4);
+            const float* l1 = lbq + ((hi.x >> SW_HI_C1_SHIFT) & 63u) * (SW_LB * 4);
+            const float4 b0 = f4a(ld4(l0 + 4 * ((hi.x >> SW_HI_P0LO_SHIFT) & 3u)), ld4(l0 + 4 * ((hi.x >> SW_HI_P0HI_SHIFT) & 7u)));
+            const float4 b1 = f4a(ld4(l1 + 4 * ((hi.x >> SW_HI_P1LO_SHIFT) & 3u)), ld4(l1 + 4 * ((hi.x >> SW_HI_P1HI_SHIFT) & 7u)));
+            const float4 bg = f4a(ld4(cb + 4 * (hi.y & 127u)), ld4(cb + 4 * ((hi.y >> SW_HI_CHHI_SHIFT) & 255u)));
+            const float4 cp = f4sub(f4sub(tot, ld4(l0 + 4 * SW_LIST_PIECES)), ld4(l1 + 4 * SW_LIST_PIECES));
+            const float4 y = f4sub(f4sub(f4a(ld4(Y4 + 4 * pos), bg), b0), b1);
             const bool live = uint32_t(pos) < t.nl_p;
-            float4 v;
-            v.x = live ? y.x + cb.x - cp.x : 0.f;
-            v.y = live ? y.y + cb.y - cp.y : 0.f;
-            v.z = live ? y.z + cb.z - cp.z : 0.f;
-            v.w = live ? y.w + cb.w - cp.w : 0.f;
-            vy[pos] = v.x;
-            vy[A.HpP + pos] = v.y;
-            vy[2 * A.HpP + pos] = v.z;
-            vy[3 * A.HpP + pos] = v.w;
+            vy[pos] = live ? y.x - cp.x : 0.f;
+            vy[A.HpP + pos] = live ? y.y - cp.y : 0.f;
+            vy[2 * A.HpP + pos] = live ? y.z - cp.z : 0.f;
+            vy[3 * A.HpP + pos] = live ? y.w - cp.w : 0.f;
             if (need_m) {
-                const float4 xs = ld4(X4 + 4 * (hi >> SW_HI_SAME_SHIFT));
+                const float4 xs = ld4(X4 + 4 * (hi.y >> SW_HI_SAME_SHIFT));
                 vm[pos] = live ? cp.x + xs.x : 0.f;
                 vm[A.HpP + pos] = live ? cp.y + xs.y : 0.f;
                 vm[2 * A.HpP + pos] = live ? cp.z + xs.z : 0.f;
@@ -304,29 +353,25 @@ __device__ __forceinline__ void mass_round(const StreetArgs& A, const UnitCtx& c
     const int lane = c.tid & 31, warp = c.tid >> 5;
     for (int q = 0; q < nq; ++q) stage_quad(A, c, 4 * (q0 + q), t.RG + q * xq);
     __syncthreads();
-    for (int it = c.tid; it < nq * SW_CARDS; it += c.nthr) {
-        const int q = it / SW_CARDS, card = it - q * SW_CARDS;
-        const float4 g = walk_list<false>(t.RG + q * xq, nullptr, t.lprog + card, SW_CARDS, t.ls);
-        st4(t.TT + (q * SW_TT + card) * 4, g);
-    }
+    list_pass<false>(c, t, nq, xq, 0);
     __syncthreads();
     if (warp < nq) {  // every hand holds two cards: total = half the sum of the per-card sums
-        const float* tt = t.TT + warp * SW_TT * 4;
-        float4 s = ld4(tt + 4 * lane);
-        if (lane + 32 < SW_CARDS) s = f4a(s, ld4(tt + 4 * (lane + 32)));
+        const float* lbq = t.LB + warp * LBQ + 4 * SW_LIST_PIECES;
+        float4 s = ld4(lbq + lane * (SW_LB * 4));
+        if (lane + 32 < SW_CARDS) s = f4a(s, ld4(lbq + (lane + 32) * (SW_LB * 4)));
         s = warp_sum4(s);
-        if (lane == 0) st4(t.TT + (warp * SW_TT + SW_CARDS) * 4, make_float4(0.5f * s.x, 0.5f * s.y, 0.5f * s.z, 0.5f * s.w));
+        if (lane == 0) st4(t.TOT + 4 * warp, make_float4(0.5f * s.x, 0.5f * s.y, 0.5f * s.z, 0.5f * s.w));
     }
     __syncthreads();
     for (int q = 0; q < nq; ++q) {
         const float* X4 = t.RG + q * xq;
-        const float* tt = t.TT + q * SW_TT * 4;
-        const float4 tot = ld4(tt + SW_CARDS * 4);
+        const float* lbq = t.LB + q * LBQ + 4 * SW_LIST_PIECES;
+        const float4 tot = ld4(t.TOT + 4 * q);
         float* vm = c.VM + size_t(4 * (q0 + q)) * A.HpP;
         for (int pos = c.tid; pos < A.HpP; pos += c.nthr) {
-            const uint32_t hi = __ldg(t.hinfo + pos);
-            const float4 ta = ld4(tt + 4 * (hi & 63u)), tb = ld4(tt + 4 * ((hi >> SW_HI_C1_SHIFT) & 63u));
-            const float4 xs = ld4(X4 + 4 * (hi >> SW_HI_SAME_SHIFT));
+            const uint2 hi = __ldg(t.hinfo + pos);
+            const float4 ta = ld4(lbq + (hi.x & 63u) * (SW_LB * 4)), tb = ld4(lbq + ((hi.x >> SW_HI_C1_SHIFT) & 63u) * (SW_LB * 4));
+            const float4 xs = ld4(X4 + 4 * (hi.y >> SW_HI_SAME_SHIFT));
             const bool live = uint32_t(pos) < t.nl_p;
             vm[pos] = live ? tot.x - ta.x - tb.x + xs.x : 0.f;
             vm[A.HpP + pos] = live ? tot.y - ta.y - tb.y + xs.y : 0.f;
@@ -340,17 +385,24 @@ __device__ __forceinline__ void mass_round(const StreetArgs& A, const UnitCtx& c
 // ------------------------------------------------------------------------------------------------
 // U: traverser nodes in post-order (cfr.rs:588, 612-621)
 // ------------------------------------------------------------------------------------------------
-// value of the terms [t0, t1) for the thread's four hands: every term is one vector
+// value of the terms [t0, t1) for the thread's four hands: every term is one vector.  Four terms at a time: their
+// descriptors, then their vectors (independent loads), then the arithmetic.
 __device__ __forceinline__ float4 terms_value(const StreetArgs& A, const UnitCtx& c, int pos4, uint32_t t0, uint32_t t1, float scale) {
     float4 v = f4z();
-    for (uint32_t t = t0; t < t1; ++t) {
-        const SwTerm tm = A.terms[t];
-        if (tm.kind == ST_VALUE) {
-            v = f4a(v, ld4(c.VAL + size_t(tm.id) * A.HpP + pos4));
-        } else {
-            const float cf = tm.coef * scale;
-            const float4 x = ld4((tm.kind == ST_FOLD ? c.VM : c.VY) + size_t(tm.id) * A.HpP + pos4);
-            v.x += cf * x.x, v.y += cf * x.y, v.z += cf * x.z, v.w += cf * x.w;
+    for (uint32_t t = t0; t < t1; t += 4) {
+        SwTerm tm[4];
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) tm[u] = A.terms[min(t + u, t1 - 1)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float* src = tm[u].kind == ST_VALUE ? c.VAL : (tm[u].kind == ST_FOLD ? c.VM : c.VY);
+            x[u] = ld4(src + size_t(tm[u].id) * A.HpP + pos4);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float cf = t + u < t1 ? (tm[u].kind == ST_VALUE ? 1.0f : tm[u].coef * scale) : 0.f;
+            v.x += cf * x[u].x, v.y += cf * x[u].y, v.z += cf * x[u].z, v.w += cf * x[u].w;
         }
     }
     return v;
@@ -458,13 +510,28 @@ __global__ void __launch_bounds__(MAXT, MINB) street_kernel(const __grid_constan
     c.VAL = c.VM + size_t(A.vm_rows) * A.HpP;
     TCtx t;
     const int qt = A.qs > A.qm ? A.qs : A.qm;
-    t.TT = st_smem;
-    t.CT = t.TT + qt * SW_TT * 4;
-    t.RG = t.CT + A.qs * (SW_CHUNKS + 1) * 4;
+    t.LB = st_smem;
+    t.CB = t.LB + qt * LBQ;
+    t.TOT = t.CB + A.qs * CBQ;
+    t.RG = t.TOT + 4 * qt;
     for (uint32_t unit = blockIdx.x; unit < A.n_units; unit += gridDim.x) {
         const uint32_t inst = unit / uint32_t(A.n_segs), si = unit - inst * uint32_t(A.n_segs);
         c.b = A.sample_board ? A.sample_board[inst] : int(inst);
         const SwSeg sg = A.segs[si];
+        // the slabs this unit reads are pulled into L2 while the phases before their use run: the traverser's own tables
+        // (read in the U phase) now, the opponent's tables of the CTA's NEXT unit when this unit's T phase starts
+        {
+            const DevRoundPlayer& Pp = A.rp[A.trav];
+            const uint32_t nrp = Pp.n_rows_pad[c.b];
+            for (uint32_t j = tid; j < sg.up_count; j += nthr) {
+                const SwUp u = A.ups[sg.up_first + j];
+                if (u.kind != SU_TRAV) continue;
+                const size_t off = Pp.board_off[c.b] + size_t(nrp) * u.cum_a;
+                const uint32_t bytes = nrp * uint32_t(u.n_act) * 4u;
+                if (MODE == KM_CFR) prefetch_l2_bulk(Pp.regrets + off, bytes);
+                if (MODE != KM_BR) prefetch_l2_bulk(Pp.ssum + off, bytes);
+            }
+        }
         // ---- D ----
         root_reach(A, c, sg);
         for (uint32_t j = 0; j < sg.down_count; ++j) {
@@ -479,12 +546,23 @@ __global__ void __launch_bounds__(MAXT, MINB) street_kernel(const __grid_constan
         }
         __syncthreads();
         // ---- T ----
+        if (unit + gridDim.x < A.n_units) {
+            const uint32_t un = unit + gridDim.x;
+            const uint32_t in2 = un / uint32_t(A.n_segs), si2 = un - in2 * uint32_t(A.n_segs);
+            const int b2 = A.sample_board ? A.sample_board[in2] : int(in2);
+            const DevRoundPlayer& O = A.rp[1 - A.trav];
+            const uint32_t nrp = O.n_rows_pad[b2];
+            const uint32_t d0 = A.segs[si2].down_first, dn = A.segs[si2].down_count;
+            for (uint32_t j = tid; j < dn; j += nthr) {
+                const SwDown d = A.downs[d0 + j];
+                prefetch_l2_bulk((MODE == KM_CFR ? O.regrets : O.ssum) + O.board_off[b2] + size_t(nrp) * d.cum_a, nrp * uint32_t(d.n_act) * 4u);
+            }
+        }
         t.lprog = A.prog + A.prog_off[c.b];
         t.ls = int(A.l_steps[c.b]);
         t.cs = int(A.c_steps[c.b]);
-        t.cprog = t.lprog + size_t(t.ls) * SW_CARDS;
-        t.run_end = reinterpret_cast<const uint8_t*>(t.cprog + size_t(t.cs) * SW_CHUNKS);
-        t.hinfo = A.hinfo + size_t(c.b) * A.HpP;
+        t.cprog = t.lprog + size_t(t.ls) * NLP;
+        t.hinfo = reinterpret_cast<const uint2*>(A.hinfo) + size_t(c.b) * A.HpP;
         t.nl_p = A.rp[A.trav].n_live[c.b];
         for (int q0 = 0; q0 < int(sg.nq_sd); q0 += A.qs) sd_round(A, c, t, sg, q0, min(A.qs, int(sg.nq_sd) - q0));
         for (int q0 = int(sg.nq_sd); q0 < int(sg.nq_sd + sg.nq_mo); q0 += A.qm) mass_round(A, c, t, q0, min(A.qm, int(sg.nq_sd + sg.nq_mo) - q0));
@@ -511,7 +589,7 @@ __global__ void __launch_bounds__(MAXT, MINB) street_kernel(const __grid_constan
 
 size_t street_smem_bytes(int qs, int qm, int HpP, int HoP) {
     const int qt = qs > qm ? qs : qm;
-    const size_t fixed = size_t(qt) * SW_TT * 4 + size_t(qs) * (SW_CHUNKS + 1) * 4;
+    const size_t fixed = size_t(qt) * (SW_CARDS * SW_LB * 4 + 4) + size_t(qs) * (SW_CHUNKS + 1) * 4;
     const size_t sd = size_t(qs) * (4 * size_t(HoP + 1) + 8 * size_t(HpP + 1));
     const size_t mo = size_t(qm) * 4 * size_t(HoP + 1);
     return (fixed + (sd > mo ? sd : mo)) * sizeof(float);

@@ -30,7 +30,7 @@ struct StreetArgs {
     const uint32_t* prog_off;      // [nb + 1]
     const uint32_t* l_steps;       // [nb] multiples of 4
     const uint32_t* c_steps;       // [nb] multiples of 4
-    const uint32_t* hinfo;         // [nb][HpP]
+    const uint32_t* hinfo;         // [nb][HpP][2]
     float* scratch;                // per CTA: X[max_rows][XP], VY[vy_rows][HpP], VM[vm_rows][HpP], VAL[max_slots][HpP]
     unsigned long long scratch_stride;
     int XP;

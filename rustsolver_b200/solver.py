@@ -452,19 +452,18 @@ class Plan(_PlanOrEngine):
         return d
 
     def street_program(self, traverser: int, board_id: int) -> dict:
-        """List programs of one final-round board (street.h): `lists` [l_steps, 52] and `chunks` [c_steps, 64] program
-        words, `hinfo` [Hpad] per traverser position, `HpP` / `HoP` the padded range sizes."""
+        """List programs of one final-round board (street.h): `lists` [l_steps, 52 * 4] and `chunks` [c_steps, 128] program
+        words (one column per piece), `hinfo` [Hpad, 2] per traverser position, `HpP` / `HoP` the padded range sizes."""
         n = C.c_uint32()
         dims = (C.c_uint32 * 4)()
         check(self._lib.rs_plan_street_program(self._h, traverser, board_id, None, 0, C.byref(n), None, 0, dims))
         words = np.zeros(max(n.value, 1), dtype=np.uint32)
-        hinfo = np.zeros(dims[2], dtype=np.uint32)
+        hinfo = np.zeros(2 * dims[2], dtype=np.uint32)
         check(self._lib.rs_plan_street_program(self._h, traverser, board_id, _ptr(words, u32p), len(words), C.byref(n),
                                                _ptr(hinfo, u32p), len(hinfo), dims))
         ls, cs = int(dims[0]), int(dims[1])
-        return {"lists": words[:ls * 52].reshape(ls, 52), "chunks": words[ls * 52:ls * 52 + cs * 64].reshape(cs, 64),
-                "run_end": words[ls * 52 + cs * 64:ls * 52 + cs * 64 + 16].view(np.uint8).copy(),
-                "hinfo": hinfo, "HpP": int(dims[2]), "HoP": int(dims[3])}
+        return {"lists": words[:ls * 208].reshape(ls, 208), "chunks": words[ls * 208:ls * 208 + cs * 128].reshape(cs, 128),
+                "hinfo": hinfo.reshape(-1, 2), "HpP": int(dims[2]), "HoP": int(dims[3])}
 
 
 class Engine(_PlanOrEngine):

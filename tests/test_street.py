@@ -17,6 +17,26 @@ from tests import util
 START, END = 1 << 23, 1 << 24
 
 
+def _walk(words, X, Y, rmw_off=None):
+    """one piece: returns its total; emits to Y (plain store, or the chunk pass's combine when rmw_off is given)"""
+    rows = X.shape[0]
+    g, g0, m = np.zeros(rows), np.zeros(rows), np.zeros(rows)
+    for w in words:
+        w = int(w)
+        if w & START:
+            g0 = g.copy()
+        g = g + X[:, w & 0x7FF]
+        if w & END:
+            m = g0 + g
+        e = (w >> 11) & 0xFFF
+        if rmw_off is None:
+            Y[:, e] = m
+        else:
+            assert e < rmw_off
+            Y[:, e] = m - Y[:, e] - Y[:, rmw_off + e]
+    return g
+
+
 def replay_programs(prog, x):
     """prog: Plan.street_program(...); x: [rows, n_live_opp] reach by opponent position.  Returns (VY, VM) [rows, HpP]:
     the showdown and mass vectors exactly as the kernel's copy-out leaves them."""
@@ -27,38 +47,21 @@ def replay_programs(prog, x):
     Y = np.full((rows, 2 * (HpP + 1)), np.nan)  # every live cell must be written before it is read
     Y[:, HpP] = 0.0
     Y[:, 2 * HpP + 1] = 0.0
-    T = np.zeros((rows, 52))
+    LB = np.zeros((rows, 52, 5))  # exclusive prefix of the piece totals of every card list; [4] = the list total
     for c in range(52):
-        g, g0, m = np.zeros(rows), np.zeros(rows), np.zeros(rows)
-        for w in prog["lists"][:, c]:
-            w = int(w)
-            if w & START:
-                g0 = g.copy()
-            g = g + X[:, w & 0x7FF]
-            if w & END:
-                m = g0 + g
-            Y[:, (w >> 11) & 0xFFF] = m
-        T[:, c] = g
-    ctot = np.zeros((rows, 64))
-    for ch in range(64):
-        g, g0, m = np.zeros(rows), np.zeros(rows), np.zeros(rows)
-        for w in prog["chunks"][:, ch]:
-            w = int(w)
-            if w & START:
-                g0 = g.copy()
-            g = g + X[:, w & 0x7FF]
-            if w & END:
-                m = g0 + g
-            e = (w >> 11) & 0xFFF
-            assert e <= HpP
-            Y[:, e] = m - Y[:, e] - Y[:, HpP + 1 + e]
-        ctot[:, ch] = g
-    cbase = np.concatenate([np.zeros((rows, 1)), np.cumsum(ctot, axis=1)], axis=1)  # [rows, 65]: base of piece c, total at 64
-    tot = cbase[:, 64]
-    hi = prog["hinfo"].astype(np.int64)
-    c0, c1, chunk, same = hi & 63, (hi >> 6) & 63, (hi >> 12) & 63, (hi >> 18) & 0x7FF
+        for j in range(4):
+            LB[:, c, j + 1] = LB[:, c, j] + _walk(prog["lists"][:, 4 * c + j], X, Y)
+    CB = np.zeros((rows, 129))
+    for ch in range(128):
+        CB[:, ch + 1] = CB[:, ch] + _walk(prog["chunks"][:, ch], X, Y, rmw_off=HpP + 1)
+    tot = CB[:, 128]
+    w0, w1 = prog["hinfo"][:, 0].astype(np.int64), prog["hinfo"][:, 1].astype(np.int64)
+    c0, c1 = w0 & 63, (w0 >> 6) & 63
+    p0lo, p0hi, p1lo, p1hi = (w0 >> 12) & 3, (w0 >> 14) & 7, (w0 >> 17) & 3, (w0 >> 19) & 7
+    chlo, chhi, same = w1 & 127, (w1 >> 7) & 255, (w1 >> 15) & 0x7FF
+    T = LB[:, :, 4]
     Cp = tot[:, None] - T[:, c0] - T[:, c1]
-    VY = Y[:, :HpP] + cbase[:, chunk] + cbase[:, prog["run_end"].astype(np.int64)[chunk]] - Cp
+    VY = (Y[:, :HpP] + CB[:, chlo] + CB[:, chhi] - LB[:, c0, p0lo] - LB[:, c0, p0hi] - LB[:, c1, p1lo] - LB[:, c1, p1hi]) - Cp
     VM = Cp + X[:, same]
     return VY, VM, tot, T
 
@@ -136,8 +139,9 @@ def test_sweep_full_ranges_with_ties_and_a_board_that_plays():
     o = util.small_options("AsKdQcJhTs", ["random", "random"], [[1.0]], [[3.0]])
     tree, ranges, plan, k = board_setup(o)
     prog = check_board(plan, ranges, _cards_of_mask(o.board_mask), 0, 0, np.random.default_rng(7), rows=3)
-    assert prog["chunks"].shape[0] < 64 and prog["lists"].shape[0] < 120  # the big class is a run of pieces, not one long walk
-    assert (prog["run_end"] != np.arange(64)).any()
+    assert prog["chunks"].shape[0] <= 32 and prog["lists"].shape[0] <= 64  # the big class is a run of pieces, not one long walk
+    w1 = prog["hinfo"][:, 1].astype(np.int64)
+    assert ((w1 & 127) != ((w1 >> 7) & 255)).any()
 
 
 def test_sweep_on_river_boards_below_a_turn_root():
@@ -163,7 +167,7 @@ def test_street_plan_shapes_of_the_baseline_configs():
         assert info["eligible"] == 1 and info["segments"] == 13 and info["max_rows"] <= 40 and info["max_q_sd"] <= 4, info
         assert info["down_ops"] + info["up_ops"] >= 118
         prog = plan.street_program(p, 5)
-        assert 40 <= prog["lists"].shape[0] <= 96 and prog["chunks"].shape[0] <= 64, (prog["lists"].shape, prog["chunks"].shape)
+        assert 8 <= prog["lists"].shape[0] <= 48 and prog["chunks"].shape[0] <= 32, (prog["lists"].shape, prog["chunks"].shape)
     w = configs.config5(n_subgames=4)
     n, tree = rb.build_game_tree(w.options)
     plan = rb.Plan(tree, configs.workload_ranges(w), 0, w.card_abs, board_masks=w.board_masks, flags=rb.RS_FLAG_STREET_KERNEL)
