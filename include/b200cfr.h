@@ -210,6 +210,16 @@ int rs_iterate(rs_engine* e, uint64_t n_iters);
 int rs_iterate_sampled(rs_engine* e, const uint8_t* dealt, uint32_t n_paths);
 /* discount sweep of train()'s monitor thread (cfr.rs:248-261): every table *= d */
 int rs_discount(rs_engine* e, float d);
+/* Bounded waits.  The traversal kernel waits on flags: of its own producer tasks and, with the in-kernel exchange, of
+ * the PEER GPUs (rs_exchange_import).  A peer that never launches the same traversal -- a rank that failed, or a
+ * rank-asymmetric call: rs_iterate, rs_iterate_sampled, rs_best_response, rs_average_value and rs_profile_iteration
+ * are COLLECTIVE on a sharded engine, every rank must make the same calls in the same order -- would leave the others
+ * spinning for ever.  Every wait therefore gives up after `ms` milliseconds (default 30 000; 0 = unbounded) or as
+ * soon as rs_abort() was called (from any host thread, while the kernel runs): the launching call returns
+ * RS_ERR_CUDA, the tables are partly updated and the engine refuses further work (destroy it and create a new one).
+ * Ranks on the NCCL path (no rs_exchange_import) block inside ncclAllReduce instead, which this library cannot bound. */
+int rs_set_wait_timeout_ms(rs_engine* e, uint64_t ms);
+int rs_abort(rs_engine* e);
 /* Pruning as train() switches it on for an iteration (cfr.rs:219): a traverser action whose regret is <= threshold
  * is not explored, i.e. its regret is left alone by the update (cfr.rs:352,379-386,419-440); the node value is
  * unaffected (regret matching gives it probability 0).  The reference's -10 000 000 is in units of S = 100

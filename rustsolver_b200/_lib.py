@@ -83,6 +83,8 @@ ENGINE_API = {
     "rs_iterate_sampled": (C.c_int, [VP, u8p, C.c_uint32]),
     "rs_discount": (C.c_int, [VP, C.c_float]),
     "rs_set_prune_threshold": (C.c_int, [VP, C.c_float]),
+    "rs_set_wait_timeout_ms": (C.c_int, [VP, C.c_uint64]),
+    "rs_abort": (C.c_int, [VP]),
     "rs_reset": (C.c_int, [VP]),
     "rs_read_infoset": (C.c_int, [VP, C.c_uint32, C.c_uint32, f32p, f32p, C.c_size_t, u32p, u32p]),
     "rs_write_infoset": (C.c_int, [VP, C.c_uint32, C.c_uint32, f32p, f32p, C.c_size_t]),

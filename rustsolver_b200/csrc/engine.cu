@@ -181,6 +181,12 @@ struct Engine {
     void* xch_peer_base[RS_MAX_PEERS] = {nullptr};
     bool fused_exchange = false;
     float prune_threshold = -INFINITY;  // rs_set_prune_threshold
+    // bounded waits (kernels.cuh: host_abort / wait_timeout_ns)
+    uint32_t* abort_host = nullptr;   // mapped pinned word the host raises (rs_abort)
+    uint32_t* abort_dev = nullptr;    // its device alias
+    uint64_t wait_timeout_ms = 30000; // rs_set_wait_timeout_ms
+    bool aborted = false;             // a traversal gave up: the tables are partly updated, the engine refuses further work
+    int check_abort(const char* what);
     // fused final-street kernel (street_kernel.cu); off: the final round runs as node tasks like the others
     bool street_on = false;
     StreetDev street[2];
@@ -214,6 +220,7 @@ struct Engine {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph) cudaGraphDestroy(graph);
         if (comm && nccl::g_api.CommDestroy) nccl::g_api.CommDestroy(comm);
+        if (abort_host) cudaFreeHost(abort_host);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -359,6 +366,9 @@ int Engine::init(const rs_config* cfg) {
         c0.exited = 0;
         c0.epoch = 1;  // flags start at 0 = "never completed"
         CU(ctl.upload(&c0, 1));
+        CU(cudaHostAlloc(reinterpret_cast<void**>(&abort_host), sizeof(uint32_t), cudaHostAllocMapped));
+        *abort_host = 0;
+        CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&abort_dev), abort_host, 0));
     }
     size_t smem_need = std::max(task_kernel_smem_bytes(slots, HP[0], HP[1]), task_kernel_smem_bytes(slots, HP[1], HP[0]));
     int max_optin = 0;
@@ -640,6 +650,8 @@ void Engine::fill_args(TaskArgs* a, int trav, const TaskSet& set) const {
     }
     a->slots = slots;
     a->prune_threshold = prune_threshold;
+    a->host_abort = abort_dev;
+    a->wait_timeout_ns = wait_timeout_ms * 1000000ull;
     a->timing = timing.p;
 }
 
@@ -791,6 +803,7 @@ int Engine::enqueue_iteration(uint64_t* count) {
 int Engine::iterate(uint64_t n) {
     CU(cudaSetDevice(device));
     if (n == 0) return RS_OK;
+    if (aborted) return set_err(RS_ERR_CUDA, "an earlier traversal was aborted: the tables are partly updated, create a new engine");
     if (use_graph && !graph_exec) {
         uint64_t cnt = 0;
         CU(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
@@ -831,7 +844,22 @@ int Engine::iterate(uint64_t n) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, ev0, ev1));
     device_ms += ms;
-    return RS_OK;
+    return check_abort("rs_iterate");
+}
+
+// After a synchronised launch sequence: did a waiter inside the kernel give up (rs_abort, or a wait longer than the bound:
+// a peer rank that never launched, a rank-asymmetric call of a collective entry point)?  Only engines that can wait on
+// something outside their own stream pay for the read-back: the in-kernel exchange, or a raised abort word.
+int Engine::check_abort(const char* what) {
+    if (!fused_exchange && !(abort_host && *abort_host)) return RS_OK;
+    TaskCtl c;
+    CU(cudaMemcpy(&c, ctl.p, sizeof(c), cudaMemcpyDeviceToHost));
+    if (!c.abort) return RS_OK;
+    aborted = true;
+    return set_err(RS_ERR_CUDA, std::string(what) + ": the traversal kernel gave up waiting (" +
+                                    ((abort_host && *abort_host) ? "rs_abort was called" : "a wait exceeded the bound of " + std::to_string(wait_timeout_ms) +
+                                                                                               " ms: a peer rank did not launch the same traversal") +
+                                    "); the tables are partly updated, create a new engine");
 }
 
 // root counterfactual values of `player` by hand slot, [root boards][H]
@@ -960,6 +988,30 @@ int rs_gpu_index_hands(uint32_t n_board_cards, const uint8_t* cards, size_t n, u
     if (!ix.init(2, {2, uint8_t(n_board_cards)})) return set_err(RS_ERR_INVALID, "hand indexer init failed");
     std::string err;
     if (!gpu_index_hands(ix, 1, cards, n, out, kernel_ms, &err)) return set_err(RS_ERR_CUDA, err);
+    return RS_OK;
+}
+
+int rs_abort(rs_engine* e) {
+    if (!e) return set_err(RS_ERR_INVALID, "null engine");
+    if (e->e.abort_host) *e->e.abort_host = 1u;  // plain store to mapped pinned memory: safe from any host thread while a kernel runs
+    return RS_OK;
+}
+
+int rs_set_wait_timeout_ms(rs_engine* e, uint64_t ms) {
+    if (!e) return set_err(RS_ERR_INVALID, "null engine");
+    Engine& E = e->e;
+    E.wait_timeout_ms = ms;
+    // the bound is a kernel argument baked into the captured iteration graph: capture again on the next call
+    CU(cudaSetDevice(E.device));
+    CU(cudaStreamSynchronize(E.stream));
+    if (E.graph_exec) {
+        cudaGraphExecDestroy(E.graph_exec);
+        E.graph_exec = nullptr;
+    }
+    if (E.graph) {
+        cudaGraphDestroy(E.graph);
+        E.graph = nullptr;
+    }
     return RS_OK;
 }
 
@@ -1443,12 +1495,14 @@ int rs_plan_street_program(const rs_plan* p, uint32_t traverser, uint32_t board_
 static int score_impl(rs_engine* e, int mode, double out[2]) {
     if (!e || !out) return set_err(RS_ERR_INVALID, "null argument");
     Engine& E = e->e;
+    if (E.aborted) return set_err(RS_ERR_CUDA, "an earlier traversal was aborted: create a new engine");
     CU(cudaSetDevice(E.device));
     for (int p = 0; p < 2; ++p) {
         uint64_t cnt = 0;
         int rc = E.enqueue_traversal(p, mode, &cnt);
         if (rc != RS_OK) return rc;
         CU(cudaStreamSynchronize(E.stream));
+        if ((rc = E.check_abort(mode == KM_BR ? "rs_best_response" : "rs_average_value")) != RS_OK) return rc;
         double s = 0;
         rc = E.root_sum(p, &s);
         if (rc != RS_OK) return rc;

@@ -80,6 +80,27 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
+// Called once per round of a spin loop.  Cheap on most rounds; every 256th looks at the device abort word and the
+// clock, every 4096th at the host's abort word (a read over PCIe).  Returns true when the kernel has to give up.
+__device__ __forceinline__ bool wait_gives_up(const TaskArgs& A, unsigned long long t_start, uint32_t& spins) {
+    if ((++spins & 255u) != 0) return false;
+    if (*reinterpret_cast<const volatile unsigned int*>(&A.ctl->abort)) return true;
+    bool trip = false;
+    if ((spins & 4095u) == 0 && A.host_abort && *A.host_abort) trip = true;
+    if (A.wait_timeout_ns) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (now - t_start > A.wait_timeout_ns) trip = true;
+    }
+    if (trip) atomicExch(&A.ctl->abort, 1u);
+    return trip;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    return now;
+}
+
 struct Ctx {
     int nc;  // compute threads
     int tid, lane, warp, nwarps;
@@ -824,7 +845,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                     published = true;
                 }
             };
-            const uint32_t tk = tk_next;
+            uint32_t tk = tk_next;
             if (tk < A.t1) {
                 unsigned long long pend = 0;
                 if (lane == 0) pend = atomicAdd(&A.ctl->ticket, 1ull);  // consumed at the end of this iteration
@@ -875,6 +896,9 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                 if (lane == 0) prefetch_task_tables<MODE>(A, tk, j);
                 try_publish();
                 (void)b;
+                const unsigned long long t_wait = global_ns();
+                uint32_t spins = 0;
+                bool gave_up = false;
                 for (;;) {  // one flag test per lane per round
                     if (i < total) {
                         if (!has || idx < A.t0 || ld_acquire_u32(A.flags + idx) == epoch) {
@@ -885,8 +909,13 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                     try_publish();
                     if (__all_sync(0xffffffffu, i >= total)) break;
                     __nanosleep(RS_POLL_SLEEP_NS);
+                    if (__any_sync(0xffffffffu, lane == 0 && wait_gives_up(A, t_wait, spins))) {
+                        gave_up = true;
+                        break;
+                    }
                 }
                 tk_next = A.t0 + uint32_t(__shfl_sync(0xffffffffu, pend, 0));
+                if (gave_up) tk = tk_next = A.t1;  // hand the compute warps the end marker: the producers will never finish
             }
             if (lane == 0) {
                 s_slot[buf].ticket = tk;
@@ -1029,7 +1058,13 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                     if (tid < A.xch_world) {
                         st_release_sys_u32(A.xflag_peer[tid] + vec + A.xch_rank, ep);
                         const uint32_t* mine = A.xflag_peer[A.xch_rank] + vec + tid;
-                        while (ld_acquire_sys_u32(mine) != ep) __nanosleep(100);
+                        const unsigned long long t_wait = global_ns();
+                        uint32_t spins = 0;
+                        while (ld_acquire_sys_u32(mine) != ep) {  // a peer that never launches: bounded, see wait_gives_up
+                            __nanosleep(100);
+                            spins += 31;  // this loop sleeps longer than the dispatcher's: look at the clock every 8th round
+                            if (wait_gives_up(A, t_wait, spins)) break;
+                        }
                     }
                     csync(c.nc);
                     if (c.pos4 < c.HpP) {

@@ -91,6 +91,11 @@ struct TaskArgs {
     int xch_world, xch_rank;
     int xch_round;    // the sharded round: the gathers of round xch_round - 1 exchange their sums
     int xch_leaves;   // chance leaves of round xch_round - 1
+    // Waits inside the kernel (producer flags, peer flags of the exchange) are bounded: a waiter gives up when the host
+    // raised *host_abort (mapped pinned memory, rs_abort) or when one wait lasted longer than wait_timeout_ns (0: no
+    // bound); it sets ctl->abort and every CTA leaves.  The host then reports RS_ERR_CUDA instead of hanging.
+    const volatile uint32_t* host_abort;
+    unsigned long long wait_timeout_ns;
     unsigned long long* timing;  // RS_TASK_TIMING builds: [8 kinds][count, wait cycles, body cycles, total cycles]
 };
 

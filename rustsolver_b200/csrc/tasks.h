@@ -112,6 +112,8 @@ struct TaskCtl {  // device-resident dispatcher state, reset by the last CTA to 
     unsigned long long ticket;
     unsigned int exited;
     unsigned int epoch;
+    unsigned int abort;  // set by the first waiter that gives up (host abort word or bounded wait): every CTA leaves
+    unsigned int pad;
 };
 
 }  // namespace rs

@@ -584,6 +584,14 @@ class Engine(_PlanOrEngine):
         """Traverser actions with regret <= threshold keep their regret (cfr.rs:352,379-386); -inf = off."""
         check(self._lib.rs_set_prune_threshold(self._h, float(threshold)))
 
+    def set_wait_timeout_ms(self, ms: int):
+        """Bound of every wait inside the traversal kernel (default 30 s, 0 = unbounded): see rs_set_wait_timeout_ms."""
+        check(self._lib.rs_set_wait_timeout_ms(self._h, int(ms)))
+
+    def abort(self):
+        """Make a running traversal give up (rs_abort); callable from another thread."""
+        check(self._lib.rs_abort(self._h))
+
     def exchange_export(self) -> bytes:
         """Handle of this rank's exchange buffer (board-sharded engines): gather one per rank, then exchange_import."""
         buf = (C.c_uint8 * _lib.RS_EXCHANGE_HANDLE_BYTES)()

@@ -26,37 +26,39 @@ from tests import util  # noqa: E402
 TOL = 1e-4
 
 
-def main():
-    case = sys.argv[1] if len(sys.argv) > 1 else "turn"
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+def new_nccl_id(rank, dev):
+    """A fresh NCCL unique id, made on rank 0 and broadcast through the live torch process group."""
     idt = torch.zeros(128, dtype=torch.uint8, device=dev)
     if rank == 0:
         idt = torch.tensor(list(rb.nccl_unique_id()), dtype=torch.uint8, device=dev)
     dist.broadcast(idt, 0)
-    nccl_id = bytes(idt.cpu().tolist())
+    return bytes(idt.cpu().tolist())
 
+
+def check_case(case, rank, world, local, dev, fused):
+    """One sharded-engine parity case on the live ranks.  Returns (ok on ALL ranks, worst diff / bound on this rank, message,
+    local boards).  Collective: every rank of the process group must call it with the same arguments."""
+    nccl_id = new_nccl_id(rank, dev)
     board_masks = None
     if case == "turn":
         o = util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]] * 2, [[3.0]] * 2)
     elif case == "flop":
         o = util.small_options("4d5dAs", ["AA,KK,AKs,76s,54s", "QQ,JJ,AQs,65s,32s"], [[1.0]] * 3, [[3.0]] * 3, pot=40, stacks=(60, 60))
     else:
-        w = configs.config5(n_subgames=8)
+        w = configs.config5(n_subgames=max(8, world))
         o = w.options
         board_masks = w.board_masks
     n, tree = rb.build_game_tree(o)
     ranges = configs.workload_ranges(w) if case == "batch" else o.ranges()
     eng = rb.Engine(tree, ranges, o.board_mask, [], board_masks=board_masks, device=local, rank=rank, world_size=world,
                     nccl_id=nccl_id)
-    if os.environ.get("RS_FUSED", "0") == "1" and case != "batch":
+    if fused and case != "batch":
         eng.enable_fused_exchange(dist, dev)  # in-kernel exchange over peer memory instead of the NCCL all-reduce
     st = eng.stats()
     n_iters = 3
     ok = True
     msg = ""
+    worst = 0.0
     try:
         if case == "batch":
             n_iters = 2  # free run from zero tables; see tests/util.py:lockstep for why not more
@@ -73,8 +75,10 @@ def main():
                     idx = row_alignment(eng.card_table(0, q, s), og.rows(0, q, 0), og.n_rows(0, q, 0))
                     gr, gs = gr[idx], gs[idx]
                     orr, os_ = og.get_slab(an, 0)
-                    assert np.abs(gr - orr).max() <= TOL * max(np.abs(orr).max(), 1e-12), (s, an)
-                    assert np.abs(gs - os_).max() <= TOL * max(np.abs(os_).max(), 1e-12), (s, an)
+                    for g, oarr in ((gr, orr), (gs, os_)):
+                        r_ = float(np.abs(g - oarr).max() / (TOL * max(np.abs(oarr).max(), 1e-12)))
+                        worst = max(worst, r_)
+                        assert r_ <= 1.0, (s, an, r_)
         else:
             og = OracleGame(tree, ranges, o.board_mask)
             nb = [st.n_boards[k] for k in range(st.n_rounds)]
@@ -89,12 +93,12 @@ def main():
                     return lo1 <= b < hi1
                 return lo1 * per2 <= b < hi1 * per2
 
+            rk = {int(tree.an_index[i]): int(tree.round_idx[i]) for i in range(tree.n_nodes) if tree.type[i] == 0}
             al = util.RowAligner(eng, og, tree)
             for it in range(n_iters):
                 if it > 0:  # lock-step: restart from the oracle's state (see tests/util.py)
                     for an, b in util.all_slabs(tree, nb):
-                        k = int(tree.round_idx[np.nonzero((tree.type == 0) & (tree.an_index == an))[0][0]])
-                        if mine(k, b):
+                        if mine(rk[an], b):
                             r, s = og.get_slab(an, b)
                             al.write(an, b, r, s)
                 eng.iterate(1)
@@ -107,8 +111,7 @@ def main():
                             m = float(np.abs(oarr).max())
                             scales[(an, nm)] = max(scales.get((an, nm), 0.0), m)
                             table[nm] = max(table[nm], m)
-                    k = int(tree.round_idx[np.nonzero((tree.type == 0) & (tree.an_index == an))[0][0]])
-                    if not mine(k, b):
+                    if not mine(rk[an], b):
                         continue
                     gr, gs = al.read(an, b)
                     for g, oarr, nm in ((gr, orr, "R"), (gs, os_, "S")):
@@ -116,8 +119,9 @@ def main():
                             diffs[(an, b, nm)] = float(np.abs(g - oarr).max())
                 for (an, b, nm), d in diffs.items():
                     bound = TOL * scales[(an, nm)] + util.ABS_FLOOR * table[nm]
+                    worst = max(worst, d / bound)
                     assert d <= bound, (it, an, b, nm, d, bound)
-            # best response goes through the same all-reduce
+            # best response goes through the same exchange
             br, obr = eng.best_response(), og.best_response()
             assert np.allclose(br, obr, rtol=1e-4, atol=1e-4), (br, obr)
     except AssertionError as e:
@@ -125,15 +129,68 @@ def main():
         msg = repr(e)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    if not ok:
+    local_boards = [st.n_boards_local[k] for k in range(st.n_rounds)]
+    eng.close()
+    return flag.item() == 1, worst, msg, local_boards
+
+
+def check_timeout(rank, world, local, dev):
+    """A rank that never launches: the others must come back with an error instead of spinning for ever (bounded waits of
+    the in-kernel exchange, rs_set_wait_timeout_ms).  Rank `world - 1` skips its rs_iterate."""
+    nccl_id = new_nccl_id(rank, dev)
+    o = util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]] * 2, [[3.0]] * 2)
+    n, tree = rb.build_game_tree(o)
+    eng = rb.Engine(tree, o.ranges(), o.board_mask, [], device=local, rank=rank, world_size=world, nccl_id=nccl_id)
+    assert eng.enable_fused_exchange(dist, dev)
+    eng.iterate(1)  # everybody: fine
+    eng.set_wait_timeout_ms(400)
+    ok = True
+    msg = ""
+    if rank != world - 1:
+        import time
+        t0 = time.perf_counter()
+        try:
+            eng.iterate(1)
+            ok, msg = False, "rs_iterate returned although a peer never launched"
+        except rb.EngineError as e:
+            dt = time.perf_counter() - t0
+            ok = "gave up waiting" in str(e) and dt < 20.0
+            msg = "" if ok else f"unexpected error / duration: {e} after {dt:.1f} s"
+        try:
+            eng.iterate(1)
+            ok, msg = False, "an aborted engine accepted more work"
+        except rb.EngineError:
+            pass
+    dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    eng.close()
+    return flag.item() == 1, 0.0, msg, []
+
+
+def main():
+    case = sys.argv[1] if len(sys.argv) > 1 else "turn"
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    if case == "timeout":
+        all_ok, worst, msg, boards = check_timeout(rank, world, local, dev)
+        if msg:
+            print(f"[rank {rank}] FAILED {msg}", flush=True)
+        if rank == 0:
+            print(f"mgpu_worker timeout world={world}: {'OK' if all_ok else 'FAILED'}", flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0 if all_ok else 1)
+    all_ok, worst, msg, boards = check_case(case, rank, world, local, dev, os.environ.get("RS_FUSED", "0") == "1")
+    if msg:
         print(f"[rank {rank}] FAILED {msg}", flush=True)
     if rank == 0:
-        print(f"mgpu_worker {case} world={world}: {'OK' if flag.item() == 1 else 'FAILED'} "
-              f"(boards local {[st.n_boards_local[k] for k in range(st.n_rounds)]})", flush=True)
-    eng.close()
+        print(f"mgpu_worker {case} world={world}: {'OK' if all_ok else 'FAILED'} (boards local {boards}, worst diff/bound {worst:.3f})", flush=True)
     dist.barrier()
     dist.destroy_process_group()
-    sys.exit(0 if flag.item() == 1 else 1)
+    sys.exit(0 if all_ok else 1)
 
 
 if __name__ == "__main__":

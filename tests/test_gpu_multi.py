@@ -31,3 +31,16 @@ def test_sharded_engine_matches_oracle(case, fused):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT), env=dict(os.environ, RS_FUSED=str(fused)))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert f"mgpu_worker {case} world={world}: OK" in r.stdout
+
+
+def test_a_rank_that_never_launches_is_an_error_not_a_hang():
+    """Bounded waits of the in-kernel exchange (rs_set_wait_timeout_ms): the last rank skips an rs_iterate, the others get
+    RS_ERR_CUDA within the bound and the aborted engine refuses further work."""
+    import os
+    if _n_gpus() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29642", str(ROOT / "tests" / "mgpu_worker.py"), "timeout"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=str(ROOT), env=dict(os.environ))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "mgpu_worker timeout world=2: OK" in r.stdout
