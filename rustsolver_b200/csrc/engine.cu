@@ -361,7 +361,7 @@ int Engine::init(const rs_config* cfg) {
     CU(flags.alloc(max_tickets));
     CU(flags.zero());
     {
-        TaskCtl c0;
+        TaskCtl c0{};
         c0.ticket = 0;
         c0.exited = 0;
         c0.epoch = 1;  // flags start at 0 = "never completed"
