@@ -180,6 +180,17 @@ int rs_kmeans_fit_regular(const float* points, size_t n, uint32_t dim, float* ce
                           uint32_t rounds, uint32_t* cluster, float* inertia);
 int rs_kmeans_update_min_dists(const float* points, size_t n, uint32_t dim, const float* new_center, uint32_t dist_kind,
                                float* min_dists);
+/* Seeding of the centres.  The reference draws from an unspecified `R: Rng`; here the stream is splitmix64(seed),
+ * gen_range(0, n) = z % n, a uniform f32 = (z >> 40) * 2^-24, WeightedIndex = the first index whose running f32 sum of
+ * the weights exceeds u * total, choose_multiple = a partial Fisher-Yates shuffle.  chosen_out[k] = indices of the
+ * points taken as centres, centers_out [k][dim] (may be NULL) = those points.
+ * rs_kmeans_init_pp     = Kmeans::init_pp (kmeans.rs:60-90): k-means++, one distance sweep on the device per centre
+ * rs_kmeans_init_random = Kmeans::init_random (kmeans.rs:103-166): of n_restarts random sets the most spread out one
+ *                         (largest mean pairwise centre distance, the last one on ties) */
+int rs_kmeans_init_pp(const float* points, size_t n, uint32_t dim, uint32_t k, uint32_t dist_kind, uint64_t seed, uint32_t* chosen_out,
+                      float* centers_out);
+int rs_kmeans_init_random(const float* points, size_t n, uint32_t dim, uint32_t k, uint32_t n_restarts, uint32_t dist_kind, uint64_t seed,
+                          uint32_t* chosen_out, float* centers_out);
 
 #define RS_EXCHANGE_HANDLE_BYTES 64
 int rs_exchange_export(rs_engine* e, uint8_t* out /* RS_EXCHANGE_HANDLE_BYTES */);
@@ -206,8 +217,16 @@ int rs_iterate(rs_engine* e, uint64_t n_iters);
  * run-outs, `dealt[n_paths][n_rounds-1]` cards in deal order; paths must start with distinct cards.  One call =
  * one iteration (player 0 then player 1) over the root street and the sampled boards, for ALL hands at once
  * (public chance sampling); values are importance-weighted by (#possible deals)/(#sampled) so the update is an
- * unbiased estimate of the full iteration's. */
+ * unbiased estimate of the full iteration's.  On a board-sharded engine the call is collective: every rank passes the
+ * SAME paths and walks those whose first card lies in its own slice (the chance-node sums are exchanged as usual).
+ * The discount schedule of rs_config applies to these iterations too. */
 int rs_iterate_sampled(rs_engine* e, const uint8_t* dealt, uint32_t n_paths);
+/* generate_hand's board part (cfr.rs:100-122): n_paths run-outs of n_cards cards each into dealt_out[n_paths][n_cards].
+ * Every card is uniform over 0..51 and drawn again while it is on the board or earlier in the same path, as the
+ * reference does; distinct_first != 0 also draws again while an earlier path starts with the same card
+ * (rs_iterate_sampled needs distinct first cards).  The reference's SmallRng is unspecified; here the stream is
+ * splitmix64(seed) and a card is z % 52 with the top of the 64-bit range rejected (exactly uniform).  Host only. */
+int rs_sample_runouts(uint64_t seed, uint64_t board_mask, uint32_t n_cards, uint32_t n_paths, int distinct_first, uint8_t* dealt_out);
 /* discount sweep of train()'s monitor thread (cfr.rs:248-261): every table *= d */
 int rs_discount(rs_engine* e, float d);
 /* Bounded waits.  The traversal kernel waits on flags: of its own producer tasks and, with the in-kernel exchange, of

@@ -92,6 +92,8 @@ def _abs_lib():
         lib.orc_update_min_dists.argtypes = [f32p, C.c_int64, C.c_int, f32p, C.c_int, f32p]
         lib.orc_kmeans_fit_regular.restype = C.c_float
         lib.orc_kmeans_fit_regular.argtypes = [f32p, C.c_int64, C.c_int, f32p, C.c_int, C.c_int, C.c_int, u32p]
+        lib.orc_kmeans_init_pp.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64, u32p]
+        lib.orc_kmeans_init_random.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, u32p]
         lib._abs_ready = True
     return lib
 
@@ -129,6 +131,22 @@ def kmeans_fit_regular(points, centers, kind: int = 0, rounds: int = 10):
     inertia = _abs_lib().orc_kmeans_fit_regular(x.ctypes.data_as(f32p), len(x), x.shape[1], c.ctypes.data_as(f32p), len(c), kind, rounds,
                                                cl.ctypes.data_as(u32p))
     return cl, c, float(inertia)
+
+
+def kmeans_init_pp(points, k: int, kind: int = 0, seed: int = 1) -> np.ndarray:
+    """Kmeans::init_pp (kmeans.rs:60-90) with the stated splitmix64 stream: indices of the k points taken as centres."""
+    x = np.ascontiguousarray(points, dtype=np.float32)
+    out = np.zeros(k, dtype=np.uint32)
+    _abs_lib().orc_kmeans_init_pp(x.ctypes.data_as(f32p), len(x), x.shape[1], k, kind, seed, out.ctypes.data_as(u32p))
+    return out
+
+
+def kmeans_init_random(points, k: int, n_restarts: int, kind: int = 0, seed: int = 1) -> np.ndarray:
+    """Kmeans::init_random (kmeans.rs:103-166): indices of the centres of the most spread out of n_restarts random sets."""
+    x = np.ascontiguousarray(points, dtype=np.float32)
+    out = np.zeros(k, dtype=np.uint32)
+    _abs_lib().orc_kmeans_init_random(x.ctypes.data_as(f32p), len(x), x.shape[1], k, n_restarts, kind, seed, out.ctypes.data_as(u32p))
+    return out
 
 
 def update_min_dists(points, new_center, min_dists, kind: int = 0):

@@ -219,3 +219,84 @@ float orc_kmeans_fit_regular(const float* points, int64_t n, int dim, float* cen
     free(move);
     return total / (float)n;
 }
+
+
+/* ---- seeding (kmeans.rs:60-166).  The reference draws from an unspecified `R: Rng`; here the stream is splitmix64(seed),
+ * gen_range(0, n) = z % n, a uniform f32 in [0, 1) = (z >> 40) * 2^-24, WeightedIndex = the first index whose running
+ * f32 sum of the weights exceeds u * total (rand 0.7: cumulative weights + partition point), and choose_multiple = a
+ * partial Fisher-Yates shuffle of the indices.  The device drivers (rs_kmeans_init_pp / _init_random) use the same. ---- */
+static uint64_t sm64(uint64_t* st) {
+    *st += 0x9E3779B97F4A7C15ull;
+    uint64_t z = *st;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+/* Kmeans::init_pp (kmeans.rs:60-90): chosen[k] = indices of the points taken as centres */
+void orc_kmeans_init_pp(const float* points, int64_t n, int dim, int k, int kind, uint64_t seed, uint32_t* chosen) {
+    uint64_t st = seed;
+    float* md = (float*)malloc(sizeof(float) * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) md[i] = 3.40282347e+38f;
+    chosen[0] = (uint32_t)(sm64(&st) % (uint64_t)n);
+    for (int c = 1; c < k; ++c) {
+        orc_update_min_dists(points, n, dim, points + (size_t)chosen[c - 1] * dim, kind, md);
+        float total = 0.f;
+        for (int64_t i = 0; i < n; ++i) total += md[i];
+        const float u = (float)(sm64(&st) >> 40) * (1.0f / 16777216.0f);
+        const float x = u * total;
+        float run = 0.f;
+        int64_t idx = n - 1;
+        for (int64_t i = 0; i + 1 < n; ++i) {
+            run += md[i];
+            if (run > x) {
+                idx = i;
+                break;
+            }
+        }
+        chosen[c] = (uint32_t)idx;
+    }
+    free(md);
+}
+
+/* Kmeans::init_random (kmeans.rs:103-166): n_restarts random sets of k distinct points, the most spread out one wins
+ * (largest mean pairwise centre distance; ties: the last, like Iterator::max_by) */
+void orc_kmeans_init_random(const float* points, int64_t n, int dim, int k, int n_restarts, int kind, uint64_t seed, uint32_t* chosen) {
+    uint64_t st = seed;
+    uint32_t* perm = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n);
+    uint32_t* sets = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n_restarts * (size_t)k);
+    for (int r = 0; r < n_restarts; ++r) {
+        for (int64_t i = 0; i < n; ++i) perm[i] = (uint32_t)i;
+        for (int j = 0; j < k; ++j) {
+            const int64_t t = j + (int64_t)(sm64(&st) % (uint64_t)(n - j));
+            const uint32_t tmp = perm[j];
+            perm[j] = perm[t];
+            perm[t] = tmp;
+            sets[(size_t)r * k + j] = perm[j];
+        }
+    }
+    int best = 0;
+    float best_cd = 0.f;
+    for (int r = 0; r < n_restarts; ++r) {
+        const uint32_t* cs = sets + (size_t)r * k;
+        float sum = 0.f;
+        size_t count = 0;
+        for (int i = 0; i < k; ++i) {
+            float di = 0.f;
+            for (int j = 0; j < k; ++j) {
+                if (j == i) continue;
+                di += dist(points + (size_t)cs[i] * dim, points + (size_t)cs[j] * dim, dim, kind);
+                count++;
+            }
+            sum += di;
+        }
+        const float cd = sum / (float)count;
+        if (r == 0 || cd >= best_cd) {
+            best = r;
+            best_cd = cd;
+        }
+    }
+    memcpy(chosen, sets + (size_t)best * k, sizeof(uint32_t) * (size_t)k);
+    free(perm);
+    free(sets);
+}

@@ -70,6 +70,8 @@ ENGINE_API = {
     "rs_kmeans_fit_regular": (C.c_int, [f32p, C.c_size_t, C.c_uint32, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f32p]),
     "rs_histogram_distances": (C.c_int, [f32p, f32p, C.c_size_t, C.c_uint32, C.c_uint32, f32p]),
     "rs_kmeans_update_min_dists": (C.c_int, [f32p, C.c_size_t, C.c_uint32, f32p, C.c_uint32, f32p]),
+    "rs_kmeans_init_pp": (C.c_int, [f32p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, u32p, f32p]),
+    "rs_kmeans_init_random": (C.c_int, [f32p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, u32p, f32p]),
     "rs_gpu_index_hands": (C.c_int, [C.c_uint32, u8p, C.c_size_t, u64p, f32p]),
     "rs_exchange_export": (C.c_int, [VP, u8p]),
     "rs_exchange_import": (C.c_int, [VP, u8p, C.c_uint32]),
@@ -85,6 +87,7 @@ ENGINE_API = {
     "rs_set_prune_threshold": (C.c_int, [VP, C.c_float]),
     "rs_set_wait_timeout_ms": (C.c_int, [VP, C.c_uint64]),
     "rs_abort": (C.c_int, [VP]),
+    "rs_sample_runouts": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, u8p]),
     "rs_reset": (C.c_int, [VP]),
     "rs_read_infoset": (C.c_int, [VP, C.c_uint32, C.c_uint32, f32p, f32p, C.c_size_t, u32p, u32p]),
     "rs_write_infoset": (C.c_int, [VP, C.c_uint32, C.c_uint32, f32p, f32p, C.c_size_t]),

@@ -407,4 +407,99 @@ bool gpu_kmeans_fit_regular(const float* points, size_t n, uint32_t dim, float* 
     return true;
 }
 
+// splitmix64: the stated stream of the seeding drivers (the reference's `R: Rng` is unspecified)
+static inline uint64_t sm64(uint64_t& st) {
+    st += 0x9E3779B97F4A7C15ull;
+    uint64_t z = st;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// Kmeans::init_pp (kmeans.rs:60-90).  The data set stays on the device; every round is one distance sweep against the
+// centre chosen last (update_min_dists, kmeans.rs:603-619) and one weighted draw on the host (WeightedIndex: running f32
+// sum of the weights, first index whose sum exceeds u * total).
+bool gpu_kmeans_init_pp(const float* points, size_t n, uint32_t dim, uint32_t k, uint32_t kind, uint64_t seed, uint32_t* chosen, std::string* err) {
+    Dev<float> d_pts, d_out, d_md;
+    ABS_CU(d_pts.alloc(n * dim));
+    ABS_CU(d_out.alloc(n));
+    ABS_CU(d_md.alloc(n));
+    ABS_CU(cudaMemcpy(d_pts.p, points, n * dim * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> md(n, 3.40282347e+38f);
+    ABS_CU(cudaMemcpy(d_md.p, md.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    const size_t smem = smem_bytes(int(dim));
+    ABS_CU(cudaFuncSetAttribute(pair_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const unsigned blocks = unsigned((n + ABS_THREADS - 1) / ABS_THREADS);
+    uint64_t st = seed;
+    chosen[0] = uint32_t(sm64(st) % uint64_t(n));
+    for (uint32_t c = 1; c < k; ++c) {
+        pair_dist_kernel<<<blocks, ABS_THREADS, smem>>>(d_pts.p, d_pts.p + size_t(chosen[c - 1]) * dim, 0, n, int(dim), int(kind), d_out.p);
+        ABS_CU(cudaGetLastError());
+        square_min_kernel<<<unsigned((n + 255) / 256), 256>>>(d_out.p, n, d_md.p);
+        ABS_CU(cudaGetLastError());
+        ABS_CU(cudaMemcpy(md.data(), d_md.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+        float total = 0.f;
+        for (size_t i = 0; i < n; ++i) total += md[i];
+        const float u = float(sm64(st) >> 40) * (1.0f / 16777216.0f);
+        const float x = u * total;
+        float run = 0.f;
+        size_t idx = n - 1;
+        for (size_t i = 0; i + 1 < n; ++i) {
+            run += md[i];
+            if (run > x) {
+                idx = i;
+                break;
+            }
+        }
+        chosen[c] = uint32_t(idx);
+    }
+    return true;
+}
+
+// Kmeans::init_random (kmeans.rs:103-166): n_restarts random sets of k distinct points (partial Fisher-Yates), all
+// k * (k - 1) centre distances of every set on the device, the sums on the host in the reference's order.
+bool gpu_kmeans_init_random(const float* points, size_t n, uint32_t dim, uint32_t k, uint32_t n_restarts, uint32_t kind, uint64_t seed,
+                            uint32_t* chosen, std::string* err) {
+    uint64_t st = seed;
+    std::vector<uint32_t> perm(n), sets(size_t(n_restarts) * k);
+    for (uint32_t r = 0; r < n_restarts; ++r) {
+        for (size_t i = 0; i < n; ++i) perm[i] = uint32_t(i);
+        for (uint32_t j = 0; j < k; ++j) {
+            const size_t t = j + size_t(sm64(st) % uint64_t(n - j));
+            std::swap(perm[j], perm[t]);
+            sets[size_t(r) * k + j] = perm[j];
+        }
+    }
+    const size_t pairs = size_t(k) * (k - 1);
+    std::vector<float> hp(pairs * dim), hq(pairs * dim), d(pairs);
+    int best = 0;
+    float best_cd = 0.f;
+    for (uint32_t r = 0; r < n_restarts; ++r) {
+        const uint32_t* cs = &sets[size_t(r) * k];
+        size_t e = 0;
+        for (uint32_t i = 0; i < k; ++i)
+            for (uint32_t j = 0; j < k; ++j) {
+                if (j == i) continue;
+                memcpy(&hp[e * dim], points + size_t(cs[i]) * dim, dim * sizeof(float));
+                memcpy(&hq[e * dim], points + size_t(cs[j]) * dim, dim * sizeof(float));
+                ++e;
+            }
+        if (!gpu_pair_dist(hp.data(), hq.data(), false, pairs, dim, kind, d.data(), nullptr, err)) return false;
+        float sum = 0.f;
+        e = 0;
+        for (uint32_t i = 0; i < k; ++i) {
+            float di = 0.f;
+            for (uint32_t j = 0; j + 1 < k; ++j) di += d[e++];
+            sum += di;
+        }
+        const float cd = sum / float(pairs);
+        if (r == 0 || cd >= best_cd) {
+            best = int(r);
+            best_cd = cd;
+        }
+    }
+    memcpy(chosen, &sets[size_t(best) * k], k * sizeof(uint32_t));
+    return true;
+}
+
 }  // namespace rs

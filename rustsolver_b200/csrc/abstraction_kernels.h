@@ -20,4 +20,10 @@ bool gpu_pair_dist(const float* p, const float* q, bool q_shared, size_t n, uint
 bool gpu_kmeans_fit_regular(const float* points, size_t n, uint32_t dim, float* centers, uint32_t k, uint32_t kind, uint32_t rounds,
                             uint32_t* cluster, float* inertia, std::string* err);
 
+// Kmeans::init_pp (kmeans.rs:60-90) and Kmeans::init_random (kmeans.rs:103-166) with a stated splitmix64 stream:
+// chosen[k] = indices of the points taken as centres
+bool gpu_kmeans_init_pp(const float* points, size_t n, uint32_t dim, uint32_t k, uint32_t kind, uint64_t seed, uint32_t* chosen, std::string* err);
+bool gpu_kmeans_init_random(const float* points, size_t n, uint32_t dim, uint32_t k, uint32_t n_restarts, uint32_t kind, uint64_t seed,
+                            uint32_t* chosen, std::string* err);
+
 }  // namespace rs

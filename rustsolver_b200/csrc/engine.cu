@@ -187,6 +187,8 @@ struct Engine {
     uint64_t wait_timeout_ms = 30000; // rs_set_wait_timeout_ms
     bool aborted = false;             // a traversal gave up: the tables are partly updated, the engine refuses further work
     int check_abort(const char* what);
+    int maybe_discount();
+    uint64_t last_discount_period = 0;
     // fused final-street kernel (street_kernel.cu); off: the final round runs as node tasks like the others
     bool street_on = false;
     StreetDev street[2];
@@ -221,6 +223,7 @@ struct Engine {
         if (graph) cudaGraphDestroy(graph);
         if (comm && nccl::g_api.CommDestroy) nccl::g_api.CommDestroy(comm);
         if (abort_host) cudaFreeHost(abort_host);
+        if (root_stage) cudaFreeHost(root_stage);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -229,14 +232,19 @@ struct Engine {
     int init(const rs_config* cfg);
     void fill_args(TaskArgs* a, int trav, const TaskSet& set) const;
     int materialize(int trav, const uint32_t counts[3], TaskSet* out);
-    int enqueue_sampled(int n_paths, uint64_t* count);
-    int enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet* set = nullptr, int n_paths = 0);
+    int enqueue_sampled(int n_paths, int n_paths_global, uint64_t* count);
+    // n_paths >= 0: sampled iteration on this rank's n_paths run-outs (of n_paths_global over all ranks)
+    int enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet* set = nullptr, int n_paths = -1, int n_paths_global = 0);
     int init_street();
     int enqueue_street(int trav, int mode, const TaskSet& set, int n_paths);
     int enqueue_iteration(uint64_t* count);
     int iterate(uint64_t n);
     int root_sum(int player, double* out);
     int root_values(int player, std::vector<float>* out);
+    int root_values_into(int player, float* dst);
+    DevBuf<float> root_out;
+    float* root_stage = nullptr;
+    size_t root_stage_n = 0;
     int prof_begin();
     int prof_end(uint32_t kind, uint32_t k, int trav, uint32_t grid, uint64_t table_bytes, uint64_t vector_bytes);
     uint64_t table_bytes_of(int trav, int phase, bool street) const;
@@ -529,7 +537,7 @@ int Engine::enqueue_street(int trav, int mode, const TaskSet& set, int n_paths) 
     a.HpP = int((P.H[trav] + 3) & ~3u);
     a.HoP = int((P.H[1 - trav] + 3) & ~3u);
     a.n_units = set.street_inst * D.n_segs;
-    a.sample_board = (n_paths > 0 && k > 0) ? sample_board[k].p : nullptr;
+    a.sample_board = (n_paths >= 0 && k > 0) ? sample_board[k].p : nullptr;
     a.prune_threshold = prune_threshold;
     const int grid = int(std::min<uint64_t>(a.n_units, uint64_t(n_sms) * st_blocks_per_sm));
     CU(launch_street_kernel(a, mode, grid, st_threads, st_smem, stream));
@@ -705,17 +713,17 @@ uint64_t Engine::table_bytes_of(int trav, int phase, bool street) const {
     return bytes;
 }
 
-int Engine::enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet* set, int n_paths) {
+int Engine::enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet* set, int n_paths, int n_paths_global) {
     const Plan& P = plan;
     const TaskList& tl = P.tl[trav];
     if (!set) set = &full[trav];
     TaskArgs a;
     fill_args(&a, trav, *set);
-    if (n_paths > 0) {
+    if (n_paths >= 0) {
         a.n_paths = n_paths;
         for (uint32_t k = 1; k < P.n_rounds; ++k) {
             a.sample_board[k] = sample_board[k].p;
-            a.gather_scale[k - 1] = float(P.deal_count[k]) / float(k == 1 ? n_paths : 1);
+            a.gather_scale[k - 1] = float(P.deal_count[k]) / float(k == 1 ? n_paths_global : 1);
         }
     }
     int rc;
@@ -773,7 +781,7 @@ int Engine::enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet
 }
 
 // one iteration on sampled run-outs: sample_board[] already holds the board ids
-int Engine::enqueue_sampled(int n_paths, uint64_t* count) {
+int Engine::enqueue_sampled(int n_paths, int n_paths_global, uint64_t* count) {
     auto it = sampled_sets.find(n_paths);
     if (it == sampled_sets.end()) {
         std::unique_ptr<TaskSet[]> sets(new TaskSet[2]);
@@ -785,7 +793,7 @@ int Engine::enqueue_sampled(int n_paths, uint64_t* count) {
         it = sampled_sets.emplace(n_paths, std::move(sets)).first;
     }
     for (int p = 0; p < 2; ++p) {
-        int rc = enqueue_traversal(p, KM_CFR, count, &it->second[p], n_paths);
+        int rc = enqueue_traversal(p, KM_CFR, count, &it->second[p], n_paths, n_paths_global);
         if (rc != RS_OK) return rc;
     }
     return RS_OK;
@@ -827,16 +835,9 @@ int Engine::iterate(uint64_t n) {
             launches_per_iter = cnt;
         }
         ++iterations;
-        if (discount_interval && iterations % discount_interval == 0 && (!discount_cap || iterations <= discount_cap)) {
-            // monitor thread of train(): d = p/(p+1), p = t / DISCOUNT_INTERVAL (cfr.rs:248-261)
-            const float pf = float(iterations / discount_interval);
-            const float d = pf / (pf + 1.0f);
-            for (uint32_t k = 0; k < plan.n_rounds; ++k)
-                for (int q = 0; q < 2; ++q) {
-                    CU(launch_scale(rd[k].regrets[q].p, rd[k].regrets[q].n, d, stream));
-                    CU(launch_scale(rd[k].ssum[q].p, rd[k].ssum[q].n, d, stream));
-                    launches += 2;
-                }
+        {
+            int rc = maybe_discount();
+            if (rc != RS_OK) return rc;
         }
     }
     CU(cudaEventRecord(ev1, stream));
@@ -845,6 +846,25 @@ int Engine::iterate(uint64_t n) {
     CU(cudaEventElapsedTime(&ms, ev0, ev1));
     device_ms += ms;
     return check_abort("rs_iterate");
+}
+
+// monitor thread of train() (cfr.rs:243-262): when the iteration count crosses into a new period p = t / DISCOUNT_INTERVAL
+// (and t has not passed the cap) every table is scaled by d = p / (p + 1).  Shared by rs_iterate and rs_iterate_sampled.
+int Engine::maybe_discount() {
+    if (!discount_interval) return RS_OK;
+    const uint64_t period = iterations / discount_interval;
+    if (period == last_discount_period) return RS_OK;
+    last_discount_period = period;
+    if (discount_cap && iterations > discount_cap) return RS_OK;
+    const float pf = float(period);
+    const float d = pf / (pf + 1.0f);
+    for (uint32_t k = 0; k < plan.n_rounds; ++k)
+        for (int q = 0; q < 2; ++q) {
+            CU(launch_scale(rd[k].regrets[q].p, rd[k].regrets[q].n, d, stream));
+            CU(launch_scale(rd[k].ssum[q].p, rd[k].ssum[q].n, d, stream));
+            launches += 2;
+        }
+    return RS_OK;
 }
 
 // After a synchronised launch sequence: did a waiter inside the kernel give up (rs_abort, or a wait longer than the bound:
@@ -863,22 +883,32 @@ int Engine::check_abort(const char* what) {
 }
 
 // root counterfactual values of `player` by hand slot, [root boards][H]
-int Engine::root_values(int player, std::vector<float>* out) {
+// root counterfactual values by hand slot straight into `dst` (n_boards * H floats): the permutation from the board-local
+// order runs on the device, the copy goes through a pinned staging buffer
+int Engine::root_values_into(int player, float* dst) {
     const Plan& P = plan;
     const RoundDev& R = rd[0];
-    const size_t hp = (P.H[player] + 3) & ~3u;
-    std::vector<float> v(size_t(R.n_boards) * hp);
-    CU(cudaStreamSynchronize(stream));
-    CU(cudaMemcpy(v.data(), R.cbuf.p + size_t(P.tl[player].root_cbuf) * R.n_boards * hp, v.size() * sizeof(float),
-                  cudaMemcpyDeviceToHost));
-    out->assign(size_t(R.n_boards) * P.H[player], 0.f);
-    const LocalTables& L = P.loc[0][player];
-    for (uint32_t b = 0; b < R.n_boards; ++b) {
-        const uint32_t gb = P.local_lo[0] + b;
-        for (uint32_t i = 0; i < L.n_live[gb]; ++i)
-            (*out)[size_t(b) * P.H[player] + L.slot_of_pos[size_t(gb) * L.Hpad + i]] = v[size_t(b) * hp + i];
+    const uint32_t hp = (P.H[player] + 3) & ~3u, H = P.H[player];
+    const size_t n = size_t(R.n_boards) * H;
+    if (root_out.n < n) CU(root_out.alloc(n));
+    if (root_stage_n < n) {
+        if (root_stage) cudaFreeHost(root_stage);
+        root_stage = nullptr;
+        CU(cudaHostAlloc(reinterpret_cast<void**>(&root_stage), n * sizeof(float), cudaHostAllocDefault));
+        root_stage_n = n;
     }
+    CU(cudaMemsetAsync(root_out.p, 0, n * sizeof(float), stream));
+    CU(launch_unpermute(R.cbuf.p + size_t(P.tl[player].root_cbuf) * R.n_boards * hp, R.slot_of_pos[player].p, R.n_live[player].p, root_out.p,
+                        R.n_boards, hp, H, stream));
+    CU(cudaMemcpyAsync(root_stage, root_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    memcpy(dst, root_stage, n * sizeof(float));
     return RS_OK;
+}
+
+int Engine::root_values(int player, std::vector<float>* out) {
+    out->assign(size_t(rd[0].n_boards) * plan.H[player], 0.f);
+    return root_values_into(player, out->data());
 }
 
 int Engine::root_sum(int player, double* out) {
@@ -976,6 +1006,30 @@ int rs_kmeans_update_min_dists(const float* points, size_t n, uint32_t dim, cons
     if (!min_dists) return set_err(RS_ERR_INVALID, "null argument");
     std::string err;
     if (!gpu_pair_dist(points, new_center, true, n, dim, dist_kind, nullptr, min_dists, &err)) return set_err(RS_ERR_CUDA, err);
+    return RS_OK;
+}
+
+int rs_kmeans_init_pp(const float* points, size_t n, uint32_t dim, uint32_t k, uint32_t dist_kind, uint64_t seed, uint32_t* chosen_out,
+                      float* centers_out) {
+    int rc = abstraction_args_ok(points, points, dim, dist_kind);
+    if (rc != RS_OK) return rc;
+    if (!chosen_out || k == 0 || n == 0 || k > n) return set_err(RS_ERR_INVALID, "need 1 <= k <= n and an output buffer");
+    std::string err;
+    if (!gpu_kmeans_init_pp(points, n, dim, k, dist_kind, seed, chosen_out, &err)) return set_err(RS_ERR_CUDA, err);
+    if (centers_out)
+        for (uint32_t c = 0; c < k; ++c) memcpy(centers_out + size_t(c) * dim, points + size_t(chosen_out[c]) * dim, dim * sizeof(float));
+    return RS_OK;
+}
+
+int rs_kmeans_init_random(const float* points, size_t n, uint32_t dim, uint32_t k, uint32_t n_restarts, uint32_t dist_kind, uint64_t seed,
+                          uint32_t* chosen_out, float* centers_out) {
+    int rc = abstraction_args_ok(points, points, dim, dist_kind);
+    if (rc != RS_OK) return rc;
+    if (!chosen_out || k < 2 || n == 0 || k > n || n_restarts == 0) return set_err(RS_ERR_INVALID, "need 2 <= k <= n, n_restarts >= 1 and an output buffer");
+    std::string err;
+    if (!gpu_kmeans_init_random(points, n, dim, k, n_restarts, dist_kind, seed, chosen_out, &err)) return set_err(RS_ERR_CUDA, err);
+    if (centers_out)
+        for (uint32_t c = 0; c < k; ++c) memcpy(centers_out + size_t(c) * dim, points + size_t(chosen_out[c]) * dim, dim * sizeof(float));
     return RS_OK;
 }
 
@@ -1176,15 +1230,19 @@ int rs_iterate_sampled(rs_engine* e, const uint8_t* dealt, uint32_t n_paths) {
     if (!e || !dealt) return set_err(RS_ERR_INVALID, "null argument");
     Engine& E = e->e;
     const Plan& P = E.plan;
+    if (E.aborted) return set_err(RS_ERR_CUDA, "an earlier traversal was aborted: create a new engine");
     if (P.n_rounds < 2) return set_err(RS_ERR_INVALID, "a single-street tree has no chance node to sample");
-    if (P.n_sub != 1 || P.world != 1) return set_err(RS_ERR_UNSUPPORTED, "sampled iterations need one root board on one GPU");
+    if (P.n_sub != 1) return set_err(RS_ERR_UNSUPPORTED, "sampled iterations need one root board");
     if (n_paths == 0 || n_paths > P.n_boards[1]) return set_err(RS_ERR_INVALID, "n_paths must be in 1..#first-street deals");
     const uint32_t L = P.n_rounds - 1;  // cards per path
+    // Board-sharded engines: every rank is handed the SAME paths (the call is collective) and keeps those whose first
+    // dealt card falls into its own slice of the first dealt-card level; the importance weight uses the global count.
     std::vector<int32_t> ids[3];
     std::vector<uint8_t> seen(52, 0);
     for (uint32_t s = 0; s < n_paths; ++s) {
         uint32_t id = 0;
         uint64_t mask = P.board_mask[0][0];
+        int32_t path_ids[3] = {0, 0, 0};
         for (uint32_t k = 1; k <= L; ++k) {
             const int c = dealt[s * L + (k - 1)];
             if (c >= 52 || (mask & (1ull << c))) return set_err(RS_ERR_INVALID, "sampled card already on the board");
@@ -1194,19 +1252,23 @@ int rs_iterate_sampled(rs_engine* e, const uint8_t* dealt, uint32_t n_paths) {
             }
             id = id * P.deal_count[k] + uint32_t(__builtin_popcountll(~mask & ((1ull << c) - 1)));
             mask |= 1ull << c;
-            ids[k].push_back(int32_t(id));
+            path_ids[k] = int32_t(id);
         }
+        if (uint32_t(path_ids[1]) < P.local_lo[1] || uint32_t(path_ids[1]) >= P.local_hi[1]) continue;  // another rank's
+        for (uint32_t k = 1; k <= L; ++k) ids[k].push_back(path_ids[k] - int32_t(P.local_lo[k]));
     }
+    const uint32_t n_local = uint32_t(ids[1].size());
     CU(cudaSetDevice(E.device));
-    if (int(n_paths) > E.sample_cap) {
-        for (uint32_t k = 1; k <= L; ++k) CU(E.sample_board[k].alloc(n_paths));
-        E.sample_cap = int(n_paths);
+    if (int(n_local) > E.sample_cap || E.sample_cap == 0) {
+        for (uint32_t k = 1; k <= L; ++k) CU(E.sample_board[k].alloc(std::max<uint32_t>(n_local, 1)));
+        E.sample_cap = int(std::max<uint32_t>(n_local, 1));
     }
-    for (uint32_t k = 1; k <= L; ++k)
-        CU(cudaMemcpyAsync(E.sample_board[k].p, ids[k].data(), n_paths * sizeof(int32_t), cudaMemcpyHostToDevice, E.stream));
+    if (n_local)
+        for (uint32_t k = 1; k <= L; ++k)
+            CU(cudaMemcpyAsync(E.sample_board[k].p, ids[k].data(), n_local * sizeof(int32_t), cudaMemcpyHostToDevice, E.stream));
     CU(cudaEventRecord(E.ev0, E.stream));
     uint64_t cnt = 0;
-    int rc = E.enqueue_sampled(int(n_paths), &cnt);
+    int rc = E.enqueue_sampled(int(n_local), int(n_paths), &cnt);
     if (rc != RS_OK) return rc;
     CU(cudaEventRecord(E.ev1, E.stream));
     CU(cudaStreamSynchronize(E.stream));  // ids[] are host temporaries
@@ -1215,6 +1277,44 @@ int rs_iterate_sampled(rs_engine* e, const uint8_t* dealt, uint32_t n_paths) {
     E.device_ms += ms;
     E.launches += cnt;
     E.iterations += 1;
+    if ((rc = E.maybe_discount()) != RS_OK) return rc;
+    return E.check_abort("rs_iterate_sampled");
+}
+
+/* generate_hand's board part (cfr.rs:100-122), see b200cfr.h */
+int rs_sample_runouts(uint64_t seed, uint64_t board_mask, uint32_t n_cards, uint32_t n_paths, int distinct_first, uint8_t* dealt_out) {
+    if (!dealt_out) return set_err(RS_ERR_INVALID, "null argument");
+    const int n_board = __builtin_popcountll(board_mask);
+    if (n_cards == 0 || n_board + int(n_cards) > 52) return set_err(RS_ERR_INVALID, "n_cards out of range");
+    if (distinct_first && n_paths > uint32_t(52 - n_board)) return set_err(RS_ERR_INVALID, "more paths than distinct first cards");
+    uint64_t state = seed;
+    auto next = [&]() {  // splitmix64
+        state += 0x9E3779B97F4A7C15ull;
+        uint64_t z = state;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    const uint64_t zone = (~0ull / 52ull) * 52ull;  // Uniform::from(0..52): reject the top of the range, exactly uniform
+    auto card = [&]() {
+        for (;;) {
+            const uint64_t z = next();
+            if (z < zone) return int(z % 52ull);
+        }
+    };
+    uint64_t firsts = 0;
+    for (uint32_t s = 0; s < n_paths; ++s) {
+        uint64_t used = board_mask;
+        for (uint32_t i = 0; i < n_cards;) {
+            const int c = card();
+            if (used & (1ull << c)) continue;                           // cfr.rs:115-121: draw again
+            if (i == 0 && distinct_first && (firsts & (1ull << c))) continue;
+            if (i == 0) firsts |= 1ull << c;
+            used |= 1ull << c;
+            dealt_out[size_t(s) * n_cards + i] = uint8_t(c);
+            ++i;
+        }
+    }
     return RS_OK;
 }
 
@@ -1521,11 +1621,7 @@ int rs_root_values(rs_engine* e, uint32_t player, float* out, size_t cap) {
     const size_t n = size_t(E.rd[0].n_boards) * E.plan.H[player];
     if (cap < n) return set_err(RS_ERR_CAPACITY, "output buffer too small");
     CU(cudaSetDevice(E.device));
-    std::vector<float> v;
-    int rc = E.root_values(int(player), &v);
-    if (rc != RS_OK) return rc;
-    memcpy(out, v.data(), n * sizeof(float));
-    return RS_OK;
+    return E.root_values_into(int(player), out);
 }
 
 int rs_set_range_weights(rs_engine* e, uint32_t player, const float* weights, size_t n) {

@@ -989,6 +989,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                     case 2: task_down<MODE, 2>(A, c, nt, Rk, k, b); break;
                     case 3: task_down<MODE, 3>(A, c, nt, Rk, k, b); break;
                     case 4: task_down<MODE, 4>(A, c, nt, Rk, k, b); break;
+                    case 5: task_down<MODE, 5>(A, c, nt, Rk, k, b); break;
                     default: task_down_generic<MODE>(A, c, nt, Rk, k, b); break;
                 }
                 break;
@@ -998,6 +999,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                     case 2: task_trav<MODE, 2>(A, c, nt, Rk, k, b); break;
                     case 3: task_trav<MODE, 3>(A, c, nt, Rk, k, b); break;
                     case 4: task_trav<MODE, 4>(A, c, nt, Rk, k, b); break;
+                    case 5: task_trav<MODE, 5>(A, c, nt, Rk, k, b); break;
                     default: task_trav_generic<MODE>(A, c, nt, Rk, k, b); break;
                 }
                 break;
@@ -1149,6 +1151,13 @@ __global__ void normalize_kernel(const float* __restrict__ in, float* __restrict
         out[size_t(row) * A + a] = norm > 0.f ? fmaxf(in[size_t(row) * A + a], 0.f) / norm : 1.0f / float(A);
 }
 
+__global__ void unpermute_kernel(const float* __restrict__ in, const uint16_t* __restrict__ slot_of_pos, const uint32_t* __restrict__ n_live,
+                                 float* __restrict__ out, uint32_t hp, uint32_t H) {
+    const uint32_t b = blockIdx.y;
+    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos < n_live[b]) out[size_t(b) * H + slot_of_pos[size_t(b) * hp + pos]] = in[size_t(b) * hp + pos];
+}
+
 }  // namespace
 
 size_t task_kernel_smem_bytes(int slots, int Hp_pad, int Ho_pad) {
@@ -1204,6 +1213,13 @@ cudaError_t launch_scale(float* data, size_t n, float d, cudaStream_t st) {
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 16) blocks = 148 * 16;
     scale_kernel<<<unsigned(blocks), threads, 0, st>>>(data, n, d);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpermute(const float* in, const uint16_t* slot_of_pos, const uint32_t* n_live, float* out, uint32_t n_boards, uint32_t hp,
+                             uint32_t H, cudaStream_t st) {
+    if (n_boards == 0) return cudaSuccess;
+    unpermute_kernel<<<dim3((hp + 255) / 256, n_boards), 256, 0, st>>>(in, slot_of_pos, n_live, out, hp, H);
     return cudaGetLastError();
 }
 

@@ -106,5 +106,9 @@ cudaError_t launch_task_kernel(const TaskArgs& a, int mode, int grid, int thread
 cudaError_t launch_scale(float* data, size_t n, float d, cudaStream_t st);
 // out[row][a] = regret-matched strategy of in[row][0..A)
 cudaError_t launch_normalize(const float* in, float* out, uint32_t n_rows, uint32_t A, cudaStream_t st);
+// out[board][hand slot] = in[board][position] for the live positions of every board (out must be zeroed): root values
+// from the board-local hand order back to the caller's hand order
+cudaError_t launch_unpermute(const float* in, const uint16_t* slot_of_pos, const uint32_t* n_live, float* out, uint32_t n_boards, uint32_t hp,
+                             uint32_t H, cudaStream_t st);
 
 }  // namespace rs

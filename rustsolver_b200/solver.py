@@ -272,6 +272,26 @@ def kmeans_update_min_dists(points: np.ndarray, new_center: np.ndarray, min_dist
     return md
 
 
+def kmeans_init_pp(points: np.ndarray, k: int, dist: int = RS_DIST_EMD_1D, seed: int = 1):
+    """Kmeans::init_pp (kmeans.rs:60-90) on the GPU with the stated splitmix64 stream: (chosen indices [k], centres [k][dim])."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(points, dtype=np.float32)
+    chosen = np.zeros(k, dtype=np.uint32)
+    centers = np.zeros((k, x.shape[1]), dtype=np.float32)
+    check(lib.rs_kmeans_init_pp(_ptr(x, f32p), len(x), x.shape[1], k, dist, seed, _ptr(chosen, u32p), _ptr(centers, f32p)))
+    return chosen, centers
+
+
+def kmeans_init_random(points: np.ndarray, k: int, n_restarts: int, dist: int = RS_DIST_EMD_1D, seed: int = 1):
+    """Kmeans::init_random (kmeans.rs:103-166) on the GPU: (chosen indices [k], centres [k][dim]) of the most spread out set."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(points, dtype=np.float32)
+    chosen = np.zeros(k, dtype=np.uint32)
+    centers = np.zeros((k, x.shape[1]), dtype=np.float32)
+    check(lib.rs_kmeans_init_random(_ptr(x, f32p), len(x), x.shape[1], k, n_restarts, dist, seed, _ptr(chosen, u32p), _ptr(centers, f32p)))
+    return chosen, centers
+
+
 class HandIndexer:
     """rust_poker::hand_indexer_s (card_abstraction.rs:88-90)."""
 
@@ -464,6 +484,13 @@ class Plan(_PlanOrEngine):
         ls, cs = int(dims[0]), int(dims[1])
         return {"lists": words[:ls * 208].reshape(ls, 208), "chunks": words[ls * 208:ls * 208 + cs * 128].reshape(cs, 128),
                 "hinfo": hinfo.reshape(-1, 2), "HpP": int(dims[2]), "HoP": int(dims[3])}
+
+
+def sample_runouts(seed: int, board_mask: int, n_cards: int, n_paths: int, distinct_first: bool = True) -> np.ndarray:
+    """generate_hand's board part (cfr.rs:100-122) behind the ABI (rs_sample_runouts): uint8 [n_paths, n_cards]."""
+    out = np.zeros((n_paths, n_cards), dtype=np.uint8)
+    check(_lib.load().rs_sample_runouts(seed, board_mask, n_cards, n_paths, int(distinct_first), _ptr(out, u8p)))
+    return out
 
 
 class Engine(_PlanOrEngine):

@@ -134,6 +134,60 @@ def check_case(case, rank, world, local, dev, fused):
     return flag.item() == 1, worst, msg, local_boards
 
 
+def check_sampled(rank, world, local, dev, fused):
+    """Sampled-board iterations (rs_iterate_sampled, run-outs from rs_sample_runouts) on a board-sharded engine: every rank
+    passes the same paths and walks those of its own slice; lock-step against the oracle's sampled iteration."""
+    nccl_id = new_nccl_id(rank, dev)
+    o = util.small_options("4d5dAs", ["AA,KK,AKs,76s,54s", "QQ,JJ,AQs,65s,32s"], [[1.0]] * 3, [[3.0]] * 3, pot=40, stacks=(60, 60))
+    n, tree = rb.build_game_tree(o)
+    ranges = o.ranges()
+    eng = rb.Engine(tree, ranges, o.board_mask, [], device=local, rank=rank, world_size=world, nccl_id=nccl_id)
+    if fused:
+        eng.enable_fused_exchange(dist, dev)
+    og = OracleGame(tree, ranges, o.board_mask)
+    og.iterate(2)
+    st = eng.stats()
+    nb = [st.n_boards[k] for k in range(st.n_rounds)]
+    lo1, hi1 = rank * nb[1] // world, (rank + 1) * nb[1] // world
+    per2 = nb[2] // nb[1]
+    rk = {int(tree.an_index[i]): int(tree.round_idx[i]) for i in range(tree.n_nodes) if tree.type[i] == 0}
+    mine = lambda k, b: k == 0 or (lo1 <= b < hi1 if k == 1 else lo1 * per2 <= b < hi1 * per2)
+    slabs = [(an, b) for an, b in util.all_slabs(tree, nb) if mine(rk[an], b)]
+    al = util.RowAligner(eng, og, tree)
+    ok, msg, worst = True, "", 0.0
+    try:
+        for draw in range(3):
+            paths = rb.sample_runouts(100 + draw, o.board_mask, 2, 5 + draw)  # the same on every rank
+            for an, b in slabs:
+                r, s = og.get_slab(an, b)
+                al.write(an, b, r, s)
+            eng.iterate_sampled(paths)
+            og.iterate_sampled(paths)
+            scales, table, diffs = {}, {"R": 0.0, "S": 0.0}, {}
+            for an, b in util.all_slabs(tree, nb):
+                orr, os_ = og.get_slab(an, b)
+                for oarr, nm in ((orr, "R"), (os_, "S")):
+                    if oarr.size:
+                        m = float(np.abs(oarr).max())
+                        scales[(an, nm)] = max(scales.get((an, nm), 0.0), m)
+                        table[nm] = max(table[nm], m)
+                if mine(rk[an], b):
+                    gr, gs = al.read(an, b)
+                    for g, oarr, nm in ((gr, orr, "R"), (gs, os_, "S")):
+                        if oarr.size:
+                            diffs[(an, b, nm)] = float(np.abs(g - oarr).max())
+            for (an, b, nm), d in diffs.items():
+                bound = TOL * scales[(an, nm)] + util.ABS_FLOOR * table[nm]
+                worst = max(worst, d / bound)
+                assert d <= bound, (draw, an, b, nm, d, bound)
+    except AssertionError as e:
+        ok, msg = False, repr(e)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    eng.close()
+    return flag.item() == 1, worst, msg, [st.n_boards_local[k] for k in range(st.n_rounds)]
+
+
 def check_timeout(rank, world, local, dev):
     """A rank that never launches: the others must come back with an error instead of spinning for ever (bounded waits of
     the in-kernel exchange, rs_set_wait_timeout_ms).  Rank `world - 1` skips its rs_iterate."""
@@ -174,12 +228,15 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    if case == "timeout":
-        all_ok, worst, msg, boards = check_timeout(rank, world, local, dev)
+    if case in ("timeout", "sampled"):
+        if case == "timeout":
+            all_ok, worst, msg, boards = check_timeout(rank, world, local, dev)
+        else:
+            all_ok, worst, msg, boards = check_sampled(rank, world, local, dev, os.environ.get("RS_FUSED", "0") == "1")
         if msg:
             print(f"[rank {rank}] FAILED {msg}", flush=True)
         if rank == 0:
-            print(f"mgpu_worker timeout world={world}: {'OK' if all_ok else 'FAILED'}", flush=True)
+            print(f"mgpu_worker {case} world={world}: {'OK' if all_ok else 'FAILED'}", flush=True)
         dist.barrier()
         dist.destroy_process_group()
         sys.exit(0 if all_ok else 1)

@@ -111,3 +111,23 @@ def test_fit_regular_with_a_metric_equals_plain_lloyd():
     assert np.array_equal(cl, want_cl)
     assert np.allclose(c, want_c, rtol=0, atol=0)
     assert inertia >= 0
+
+
+def test_kmeans_seeding_restatements():
+    """Kmeans::init_pp / init_random (kmeans.rs:60-166) with the stated splitmix64 stream: reproducible, distinct centres,
+    and k-means++ really prefers far points (three tight, far apart blobs: one centre lands in each)."""
+    import oracle
+    rng = np.random.default_rng(3)
+    blobs = np.concatenate([np.abs(rng.normal(c, 0.01, size=(200, 8))) for c in (0.1, 1.0, 3.0)]).astype(np.float32)
+    for seed in range(1, 6):
+        ch = oracle.kmeans_init_pp(blobs, 3, 1, seed)
+        assert np.array_equal(ch, oracle.kmeans_init_pp(blobs, 3, 1, seed))
+        assert sorted(int(c) // 200 for c in ch) == [0, 1, 2], ch
+    x = rng.random((500, 10)).astype(np.float32)
+    ch = oracle.kmeans_init_random(x, 6, 9, 0, 4)
+    assert len(set(ch.tolist())) == 6 and np.array_equal(ch, oracle.kmeans_init_random(x, 6, 9, 0, 4))
+    # the winner is the most spread out of the restarts: its mean pairwise distance is the maximum over single-restart runs
+    def spread(idx):
+        c = x[idx]
+        return np.mean([oracle.emd_1d(c[i], c[j]) for i in range(6) for j in range(6) if i != j])
+    assert spread(ch) >= spread(oracle.kmeans_init_random(x, 6, 1, 0, 4)) - 1e-6

@@ -62,3 +62,24 @@ def test_product_never_imports_the_oracle():
         if p.suffix in (".py", ".cpp", ".cu", ".h", ".cuh"):
             t = p.read_text()
             assert "import oracle" not in t and "from oracle" not in t and "liborc" not in t.replace("oracle/liborc.so with gcc", "").replace('ORACLE_SO = ROOT / "oracle" / "liborc.so"', ""), p
+
+
+def test_sample_runouts_restates_generate_hands_board_part():
+    """rs_sample_runouts (cfr.rs:100-122): cards off the board, distinct inside a path, distinct first cards on request,
+    reproducible for a seed and uniform over the live cards."""
+    import numpy as np
+    import rustsolver_b200 as rb
+    bm = rb.get_card_mask("4d5dAs")
+    a = rb.sample_runouts(7, bm, 2, 20)
+    b = rb.sample_runouts(7, bm, 2, 20)
+    assert np.array_equal(a, b) and a.shape == (20, 2)
+    assert not np.array_equal(a, rb.sample_runouts(8, bm, 2, 20))
+    assert all(not (bm >> int(c)) & 1 for c in a.ravel()) and all(x != y for x, y in a)
+    assert len(set(a[:, 0].tolist())) == 20
+    full = rb.sample_runouts(3, bm, 1, 49)
+    assert sorted(full.ravel().tolist()) == [c for c in range(52) if not (bm >> c) & 1]
+    with pytest.raises(rb.EngineError):
+        rb.sample_runouts(3, bm, 1, 50)
+    many = rb.sample_runouts(11, bm, 2, 20000, distinct_first=False)
+    counts = np.bincount(many[:, 1], minlength=52)[[c for c in range(52) if not (bm >> c) & 1]]
+    assert counts.min() > 0.8 * counts.mean() and counts.max() < 1.2 * counts.mean()

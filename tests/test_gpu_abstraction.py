@@ -67,3 +67,20 @@ def test_fit_regular_matches_the_cpu_restatement(kind):
     assert np.array_equal(c, oc)
     assert inertia == oin
     assert len(np.unique(cl)) > 5
+
+
+@pytest.mark.parametrize("kind", [rb.RS_DIST_EMD_1D, rb.RS_DIST_L2])
+def test_kmeans_seeding_matches_the_cpu_restatement(kind):
+    """Kmeans::init_pp / init_random (kmeans.rs:60-166) on the device against the CPU restatement with the same stated
+    random stream: the same points are chosen (the distances under the draws are bit-identical)."""
+    import oracle
+    rng = np.random.default_rng(5)
+    x = rng.random((3000, 20)).astype(np.float32)
+    x /= x.sum(axis=1, keepdims=True)
+    for seed in (1, 2):
+        chosen, centers = rb.kmeans_init_pp(x, 25, kind, seed)
+        assert np.array_equal(chosen, oracle.kmeans_init_pp(x, 25, kind, seed))
+        assert np.array_equal(centers, x[chosen]) and len(set(chosen.tolist())) > 20
+        chosen, centers = rb.kmeans_init_random(x, 12, 7, kind, seed)
+        assert np.array_equal(chosen, oracle.kmeans_init_random(x, 12, 7, kind, seed))
+        assert np.array_equal(centers, x[chosen]) and len(set(chosen.tolist())) == 12

@@ -17,7 +17,7 @@ def _n_gpus():
         return 0
 
 
-@pytest.mark.parametrize("case,fused", [("turn", 0), ("flop", 0), ("batch", 0), ("turn", 1), ("flop", 1)])
+@pytest.mark.parametrize("case,fused", [("turn", 0), ("flop", 0), ("batch", 0), ("turn", 1), ("flop", 1), ("sampled", 0), ("sampled", 1)])
 def test_sharded_engine_matches_oracle(case, fused):
     """fused = 1: the traversal kernel exchanges the chance-node sums itself over peer memory (rs_exchange_import);
     fused = 0: two launches with an ncclAllReduce between them."""

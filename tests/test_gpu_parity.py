@@ -131,14 +131,17 @@ def test_bucketed_rows_many_to_one():
     util.lockstep(eng, orc, tree, n_free=1, n_locked=4, tol=TOL)
 
 
-@pytest.mark.parametrize("bucketed", [False, True])
-def test_wide_nodes_take_the_generic_path(bucketed):
-    """Three bet sizes and three raise sizes (config 3's action abstraction): nodes with five actions, more than the
-    four the register-resident task bodies are specialised for (task_down_generic / task_trav_generic)."""
-    o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.33, 0.66, 1.0]], [[2.0, 3.0, 4.0]])
+@pytest.mark.parametrize("bucketed,n_sizes", [(False, 3), (True, 3), (False, 4), (True, 4)])
+def test_wide_nodes(bucketed, n_sizes):
+    """Three bet sizes and three raise sizes (config 3's action abstraction): nodes with five actions, the widest the
+    register-resident task bodies are specialised for; four sizes: six actions, the generic bodies (task_down_generic /
+    task_trav_generic)."""
+    bets = [[0.33, 0.66, 1.0]] if n_sizes == 3 else [[0.25, 0.5, 0.75, 1.0]]
+    raises = [[2.0, 3.0, 4.0]] if n_sizes == 3 else [[1.5, 2.0, 3.0, 4.0]]
+    o = util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], bets, raises)
     n, tree = rb.build_game_tree(o)
     widths = np.diff(tree.child_offset)[tree.type == 0]
-    assert widths.max() >= 5, widths.max()
+    assert widths.max() == n_sizes + 2, widths.max()
     r = o.ranges()
     if bucketed:
         k0 = util.bucket_keys_for(None, r, 1, 9, seed=8)
