@@ -140,6 +140,22 @@ struct TaskSet {
     uint32_t n_tickets = 0, phase_cut = 0, n_tasks = 0;
     uint32_t street_lo = 0, street_hi = 0;  // tickets of the final round's node tasks (replaced by the street kernel)
     uint32_t street_inst = 0;               // instances (boards or sampled run-outs) of the final round
+    // Tickets are emitted street by street (plan.cpp: TaskGen::run): [down r0][down r1][down r2][up r2][gather][up r1]...
+    // A run is a maximal ticket range whose tasks need the same block size (Engine::round_threads); a traversal is
+    // launched run by run, so the rounds with fewer live hands (the river: 1081 of 1176 / 1326) run at the smaller
+    // block with one more resident CTA per SM.
+    struct Run {
+        uint32_t t0, t1;
+        int threads;
+    };
+    std::vector<Run> runs;
+    uint32_t xch_lo = 0, xch_hi = 0;  // tickets of the gathers that exchange their sums between the ranks (none: lo == hi)
+    struct Section {  // the down or up tasks of one round: where its algorithmic table bytes are accounted
+        uint32_t first;
+        uint32_t round_k;
+        bool up;
+    };
+    std::vector<Section> sections;
 };
 
 // device copy of one traverser's final-street programs (street.h)
@@ -198,6 +214,12 @@ struct Engine {
     int slots = 1;
     size_t smem_bytes = 0;
     int blocks_per_sm = 1, n_sms = 148;
+    int round_threads[3] = {0, 0, 0};  // compute threads the tasks of round k need: live hands / 4, a warp multiple
+    int bps_small = 0;                 // resident CTAs per SM of the 288-thread specialisation (0: no round fits it)
+    // a piece of `tickets` instances at `thr` compute threads: the wide specialisation unless a third CTA per SM gets work
+    bool wide_for(int thr, uint64_t tickets) const {
+        return thr > 288 || bps_small == 0 || getenv("RS_WIDE_ONLY") || (tickets <= uint64_t(n_sms) * blocks_per_sm && !getenv("RS_SMALL_ONLY"));
+    }
     // profiling: when non-null, enqueue_traversal brackets every launch with an event pair
     std::vector<rs_kernel_time>* prof = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -247,7 +269,6 @@ struct Engine {
     size_t root_stage_n = 0;
     int prof_begin();
     int prof_end(uint32_t kind, uint32_t k, int trav, uint32_t grid, uint64_t table_bytes, uint64_t vector_bytes);
-    uint64_t table_bytes_of(int trav, int phase, bool street) const;
 };
 
 template <class T>
@@ -289,6 +310,17 @@ int Engine::init(const rs_config* cfg) {
     const bool street_wanted = P.street[0].eligible && P.street[1].eligible;
     threads = int(((maxHP / 4) + 31) / 32 * 32);
     if (threads > MAX_TASK_THREADS) return set_err(RS_ERR_UNSUPPORTED, "range larger than 1326 hands");
+    // Per-round block size.  Live hands come first in the board-local order, so a round whose boards hold c public cards
+    // never touches a position past min(H, C(52 - c, 2)): its tasks run with that many quads of threads.  The bound only
+    // depends on the number of public cards, so every rank of a sharded engine cuts its launches at the same places.
+    for (uint32_t k = 0; k < P.n_rounds; ++k) {
+        round_threads[k] = threads;
+        if (!P.board_mask[k].empty() && !getenv("RS_UNIFORM_BLOCK")) {
+            const int left = 52 - __builtin_popcountll(P.board_mask[k][0]);
+            const size_t live_max = std::min<size_t>(maxHP, size_t(left) * size_t(left - 1) / 2);
+            round_threads[k] = std::min(threads, int((((live_max + 3) / 4) + 31) / 32 * 32));
+        }
+    }
     n_sms = prop.multiProcessorCount;
     if (street_wanted) {  // sets street_on when the fused street kernel fits
         int rc = init_street();
@@ -372,6 +404,7 @@ int Engine::init(const rs_config* cfg) {
         TaskCtl c0{};
         c0.ticket = 0;
         c0.exited = 0;
+        c0.xch_seq = 1;
         c0.epoch = 1;  // flags start at 0 = "never completed"
         CU(ctl.upload(&c0, 1));
         CU(cudaHostAlloc(reinterpret_cast<void**>(&abort_host), sizeof(uint32_t), cudaHostAllocMapped));
@@ -385,8 +418,13 @@ int Engine::init(const rs_config* cfg) {
         return set_err(RS_ERR_UNSUPPORTED, "node too wide for one CTA's shared memory: need " +
                                                std::to_string(smem_need) + " B, device allows " + std::to_string(max_optin));
     smem_bytes = smem_need;
-    CU(configure_task_kernels(smem_need, threads, &blocks_per_sm));
+    CU(configure_task_kernels(smem_need, threads, true, &blocks_per_sm));  // the wide specialisation, used by every engine
     if (blocks_per_sm < 1) return set_err(RS_ERR_UNSUPPORTED, "task kernel does not fit on an SM");
+    for (uint32_t k = 0; k < P.n_rounds; ++k)
+        if (round_threads[k] <= 288 && bps_small == 0) {
+            CU(configure_task_kernels(smem_need, 288, false, &bps_small));
+            if (bps_small < 1) return set_err(RS_ERR_UNSUPPORTED, "task kernel does not fit on an SM");
+        }
     n_sms = prop.multiProcessorCount;
     CU(scratch.alloc(size_t(1326) * MAX_ACTIONS));
 
@@ -580,6 +618,25 @@ int Engine::materialize(int trav, const uint32_t counts[3], TaskSet* out) {
             if (!fin && seen) closed = true;
         }
     }
+    out->runs.clear();
+    out->sections.clear();
+    out->xch_lo = out->xch_hi = 0;
+    for (const NodeTask& x : t) {
+        if (x.count == 0) continue;
+        if (x.kind == TK_GATHER && plan.world > 1 && plan.shard_round >= 1 && uint32_t(x.round_k) + 1 == plan.shard_round) {
+            if (out->xch_hi == out->xch_lo) out->xch_lo = x.first;
+            out->xch_hi = x.first + x.count;
+        }
+        const int thr = round_threads[x.round_k];
+        if (out->runs.empty() || out->runs.back().threads != thr) out->runs.push_back({x.first, x.first + x.count, thr});
+        else out->runs.back().t1 = x.first + x.count;
+        const bool up = x.kind == TK_UP_TRAV, down = x.kind == TK_DOWN;
+        if (up || down) {
+            bool seen = false;
+            for (const TaskSet::Section& sc : out->sections) seen |= (sc.round_k == x.round_k && sc.up == up);
+            if (!seen) out->sections.push_back({x.first, uint32_t(x.round_k), up});
+        }
+    }
     for (NodeTask& x : t)
         for (int i = 0; i < x.n_dep; ++i)
             if (x.dep[i] >= 0) x.dep[i] = int32_t(t[x.dep[i]].first);
@@ -688,31 +745,6 @@ int Engine::prof_end(uint32_t kind, uint32_t phase, int trav, uint32_t grid, uin
     return RS_OK;
 }
 
-// algorithmic infoset-table bytes of one traversal launch: traverser cells regret R+W and strategy_sum
-// R+W = 16 B, opponent cells regret read = 4 B.  Phase 1 of a sharded traversal only updates the
-// traverser's tables of the replicated rounds above the shard level.
-uint64_t Engine::table_bytes_of(int trav, int phase, bool street) const {
-    const Plan& P = plan;
-    uint64_t bytes = 0;
-    const bool split = !fused_exchange && !isolated && full[trav].phase_cut < full[trav].n_tickets;
-    for (uint32_t k = 0; k < P.n_rounds; ++k) {
-        if (street && k + 1 == P.n_rounds) continue;  // counted by the street kernel's launch
-        const uint64_t own = P.tabs[k][trav].board_off[P.n_boards[k]];
-        const uint64_t opp = P.tabs[k][1 - trav].board_off[P.n_boards[k]];
-        const bool above = split && k < P.shard_round;  // updated after the all-reduce
-        if (!street) {
-            if (phase == 0) bytes += opp * 4 + (above ? 0 : own * 16);
-            else bytes += above ? own * 16 : 0;
-        } else {
-            // phase 0 = down pass (opponent tables), 1 = up pass before the all-reduce, 2 = after it
-            if (phase == 0) bytes += opp * 4;
-            else if (phase == 1) bytes += above ? 0 : own * 16;
-            else bytes += above ? own * 16 : 0;
-        }
-    }
-    return bytes;
-}
-
 int Engine::enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet* set, int n_paths, int n_paths_global) {
     const Plan& P = plan;
     const TaskList& tl = P.tl[trav];
@@ -755,12 +787,41 @@ int Engine::enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet
     for (const Step& sp : steps) {
         if ((rc = prof_begin()) != RS_OK) return rc;
         if (sp.kind == 0) {
-            a.t0 = sp.t0;
-            a.t1 = sp.t1;
-            const int grid = int(std::min<uint64_t>(uint64_t(a.t1 - a.t0), uint64_t(n_sms) * blocks_per_sm));
-            CU(launch_task_kernel(a, mode, grid, threads, smem_bytes, stream));
-            if ((rc = prof_end(RS_KERNEL_TRAVERSAL, sp.phase, trav, uint32_t(grid), table_bytes_of(trav, int(sp.phase), use_street), vec)) != RS_OK)
-                return rc;
+            // one launch per run of equal block size inside [t0, t1); the longest piece keeps the step's phase label and
+            // the others report as phase + 8 (bench.py's roofline reads phase 0).  Table bytes go to the piece that holds
+            // the first ticket of a round's down (opponent regrets read) or up (own tables read + written) tasks.
+            struct Piece {
+                uint32_t t0, t1;
+                int threads;
+            };
+            std::vector<Piece> pieces;
+            for (const TaskSet::Run& r : set->runs) {
+                const uint32_t lo = std::max(sp.t0, r.t0), hi = std::min(sp.t1, r.t1);
+                if (lo < hi) pieces.push_back({lo, hi, r.threads});
+            }
+            size_t longest = 0;
+            for (size_t i = 1; i < pieces.size(); ++i)
+                if (pieces[i].t1 - pieces[i].t0 > pieces[longest].t1 - pieces[longest].t0) longest = i;
+            for (size_t i = 0; i < pieces.size(); ++i) {
+                if (i > 0 && (rc = prof_begin()) != RS_OK) return rc;
+                a.t0 = pieces[i].t0;
+                a.t1 = pieces[i].t1;
+                a.xch_bump = (fused_exchange && set->xch_lo < set->xch_hi && a.t0 <= set->xch_lo && set->xch_lo < a.t1) ? 1 : 0;
+                const int thr = pieces[i].threads;
+                const bool wide = wide_for(thr, a.t1 - a.t0);
+                const int grid = int(std::min<uint64_t>(uint64_t(a.t1 - a.t0), uint64_t(n_sms) * (wide ? blocks_per_sm : bps_small)));
+                CU(launch_task_kernel(a, mode, grid, thr, wide, smem_bytes, stream));
+                uint64_t bytes = 0;
+                for (const TaskSet::Section& sc : set->sections)
+                    if (sc.first >= a.t0 && sc.first < a.t1) {
+                        const uint64_t own = P.tabs[sc.round_k][trav].board_off[P.n_boards[sc.round_k]];
+                        const uint64_t opp = P.tabs[sc.round_k][1 - trav].board_off[P.n_boards[sc.round_k]];
+                        bytes += sc.up ? own * 16 : opp * 4;
+                    }
+                if ((rc = prof_end(RS_KERNEL_TRAVERSAL, sp.phase + (i == longest ? 0u : 8u), trav, uint32_t(grid), bytes, i == longest ? vec : 0)) != RS_OK)
+                    return rc;
+                if (i + 1 < pieces.size()) ++*count;
+            }
         } else if (sp.kind == 1) {
             if ((rc = enqueue_street(trav, mode, *set, n_paths)) != RS_OK) return rc;
             const uint32_t k = P.n_rounds - 1;

@@ -803,7 +803,8 @@ __device__ __forceinline__ void prefetch_task_tables(const TaskArgs& A, uint32_t
 struct TaskSlot {
     uint32_t ticket;  // >= t1: no more work
     uint32_t epoch;   // launch number: the value that marks flags "done" in this launch
-    uint32_t pad[2];
+    uint32_t xseq;    // ctl->xch_seq at launch: flag value and buffer parity of the in-kernel exchange
+    uint32_t pad;
     NodeTask nt;
 };
 
@@ -825,8 +826,11 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
         // testing the mbarrier and publishes the flag of the task the compute warps just finished the moment they
         // are done: a finished task is never held back by the look-ahead (that would deadlock across CTAs).
         const int lane = tid - NC;
-        uint32_t epoch = 0;
-        if (lane == 0) epoch = ld_acquire_u32(&A.ctl->epoch);
+        uint32_t epoch = 0, xseq = 0;
+        if (lane == 0) {
+            epoch = ld_acquire_u32(&A.ctl->epoch);
+            xseq = *reinterpret_cast<const volatile unsigned int*>(&A.ctl->xch_seq);  // only written by the last CTA of a launch
+        }
         epoch = __shfl_sync(0xffffffffu, epoch, 0);
         uint32_t prev_tk = 0xffffffffu, parity = 0;
         int buf = 0;
@@ -920,6 +924,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
             if (lane == 0) {
                 s_slot[buf].ticket = tk;
                 s_slot[buf].epoch = epoch;
+                s_slot[buf].xseq = xseq;
             }
             __syncwarp();
             hsync(NC + 32);  // slot[buf] handed over; the compute warps are done with the previous task
@@ -941,6 +946,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
             if (e == gridDim.x - 1) {
                 A.ctl->ticket = 0ull;
                 A.ctl->exited = 0u;
+                if (A.xch_bump) A.ctl->xch_seq = xseq + 1;
                 __threadfence();
                 st_release_u32(&A.ctl->epoch, epoch + 1);
             }
@@ -1046,9 +1052,10 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                     // partial vector straight into the peers' exchange buffers (NVLink stores), raises one flag per
                     // peer, waits for the partials of all ranks to land in its own buffer and adds them up in rank
                     // order (bit-identical on every GPU).  This is the one exchange step of the path, inside the
-                    // traversal kernel: no second launch, no NCCL call.  Buffers alternate with the launch parity: a
-                    // rank can be at most one traversal ahead of a peer that still reads.
-                    const uint32_t ep = s_slot[buf].epoch;
+                    // traversal kernel: no second launch, no NCCL call.  Buffers alternate with the parity of the exchange
+                    // sequence number (TaskCtl::xch_seq, the same on every rank): a rank can be at most one traversal ahead
+                    // of a peer that still reads.
+                    const uint32_t ep = s_slot[buf].xseq;
                     const size_t vec = ((size_t(ep & 1u) * A.xch_leaves + nt.out) * Rk.n_boards + b) * A.xch_world;
                     if (c.pos4 < c.HpP) {
                         const float4 part = ldcg4(Rk.gathered + (size_t(nt.out) * Rk.n_boards + b) * c.HpP + c.pos4);
@@ -1184,8 +1191,8 @@ static cudaError_t configure_for(size_t smem, int threads, int* blocks_per_sm) {
     return cudaSuccess;
 }
 
-cudaError_t configure_task_kernels(size_t smem, int threads, int* blocks_per_sm) {
-    if (threads <= 288) return configure_for<288, RS_MIN_BLOCKS_288>(smem, threads, blocks_per_sm);
+cudaError_t configure_task_kernels(size_t smem, int threads, bool wide, int* blocks_per_sm) {
+    if (threads <= 288 && !wide) return configure_for<288, RS_MIN_BLOCKS_288>(smem, threads, blocks_per_sm);
     return configure_for<352, RS_MIN_BLOCKS_352>(smem, threads, blocks_per_sm);
 }
 
@@ -1199,9 +1206,9 @@ static void launch_for(const TaskArgs& a, int mode, int grid, int threads, size_
     }
 }
 
-cudaError_t launch_task_kernel(const TaskArgs& a, int mode, int grid, int threads, size_t smem, cudaStream_t st) {
+cudaError_t launch_task_kernel(const TaskArgs& a, int mode, int grid, int threads, bool wide, size_t smem, cudaStream_t st) {
     if (grid <= 0 || a.t1 <= a.t0) return cudaSuccess;
-    if (threads <= 288) launch_for<288, RS_MIN_BLOCKS_288>(a, mode, grid, threads, smem, st);
+    if (threads <= 288 && !wide) launch_for<288, RS_MIN_BLOCKS_288>(a, mode, grid, threads, smem, st);
     else launch_for<352, RS_MIN_BLOCKS_352>(a, mode, grid, threads, smem, st);
     return cudaGetLastError();
 }

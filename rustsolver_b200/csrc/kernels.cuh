@@ -91,6 +91,7 @@ struct TaskArgs {
     int xch_world, xch_rank;
     int xch_round;    // the sharded round: the gathers of round xch_round - 1 exchange their sums
     int xch_leaves;   // chance leaves of round xch_round - 1
+    int xch_bump;     // this launch holds the exchanging gathers: the last CTA to leave advances ctl->xch_seq
     // Waits inside the kernel (producer flags, peer flags of the exchange) are bounded: a waiter gives up when the host
     // raised *host_abort (mapped pinned memory, rs_abort) or when one wait lasted longer than wait_timeout_ns (0: no
     // bound); it sets ctl->abort and every CTA leaves.  The host then reports RS_ERR_CUDA instead of hanging.
@@ -100,8 +101,12 @@ struct TaskArgs {
 };
 
 size_t task_kernel_smem_bytes(int slots, int Hp_pad, int Ho_pad);
-cudaError_t configure_task_kernels(size_t smem, int threads, int* blocks_per_sm);
-cudaError_t launch_task_kernel(const TaskArgs& a, int mode, int grid, int threads, size_t smem, cudaStream_t st);
+// Two register specialisations of the kernel: blocks of up to 288 compute threads built for three resident CTAs per SM
+// (64 registers), and a wide one (up to 352 threads, two CTAs per SM, 80 registers).  `wide` selects the second one for a
+// block that would fit the first: a launch with too few tickets to populate a third CTA per SM is latency-bound and runs
+// faster with the registers.
+cudaError_t configure_task_kernels(size_t smem, int threads, bool wide, int* blocks_per_sm);
+cudaError_t launch_task_kernel(const TaskArgs& a, int mode, int grid, int threads, bool wide, size_t smem, cudaStream_t st);
 
 cudaError_t launch_scale(float* data, size_t n, float d, cudaStream_t st);
 // out[row][a] = regret-matched strategy of in[row][0..A)

@@ -113,7 +113,8 @@ struct TaskCtl {  // device-resident dispatcher state, reset by the last CTA to 
     unsigned int exited;
     unsigned int epoch;
     unsigned int abort;  // set by the first waiter that gives up (host abort word or bounded wait): every CTA leaves
-    unsigned int pad;
+    unsigned int xch_seq;  // number of the next EXCHANGING launch (board-sharded traversals): the value the exchange flags carry and
+                           // the parity of the exchange buffer.  Counts the same on every rank however a traversal is cut into launches
 };
 
 }  // namespace rs
