@@ -245,6 +245,24 @@ int rs_abort(rs_engine* e);
  * (cfr.rs:424): pass -1e5 for the same cut on this engine's unscaled fp32 regrets.  -INFINITY (the default)
  * switches pruning off.  Applies to rs_iterate and rs_iterate_sampled from the next call on. */
 int rs_set_prune_threshold(rs_engine* e, float threshold);
+/* External sampling for every hand at once -- the opponent arm of mccfr() (cfr.rs:466-475): at an opponent action node
+ * each opponent hand draws ONE action from its current strategy (WeightedIndex over get_strategy()) and continues on
+ * that child only; the traverser still explores every action (cfr.rs:378-400).  The draw of hand slot h at action node
+ * n on (global) board b in traversal number t (counted from this call, both players' traversals) is
+ *     key = splitmix64_finalize(seed + 0x9E3779B97F4A7C15 * t)
+ *     z   = splitmix64_finalize'(key ^ n << 44 ^ b << 20 ^ h),  u = (z >> 40) / 2^24
+ * (the two 64-bit mixers of splitmix64; see xs_uniform in csrc/kernels.cuh), and the action is the first a with
+ * u < sigma_0 + ... + sigma_a.  It does not depend on the GPU count, the sharding or the launch schedule.
+ *   RS_OPP_FULL               every action with reach * sigma (the vector form of cfr(), the default)
+ *   RS_OPP_SAMPLE             the drawn action keeps the hand's whole reach: unbiased external sampling
+ *   RS_OPP_SAMPLE_TIMES_SIGMA the drawn action keeps reach * sigma(drawn action): what the reference's code does
+ *                             (cfr.rs:474 multiplies cfr_reach by strategy[a_idx] after sampling a_idx)
+ * Applies to rs_iterate and rs_iterate_sampled from the next call on (those launches are not graph replays); best
+ * response and average-strategy walks are never sampled.  Not available with RS_FLAG_STREET_KERNEL. */
+#define RS_OPP_FULL 0u
+#define RS_OPP_SAMPLE 1u
+#define RS_OPP_SAMPLE_TIMES_SIGMA 2u
+int rs_set_opponent_sampling(rs_engine* e, uint32_t mode, uint64_t seed);
 int rs_reset(rs_engine* e);
 
 /* infoset_table[round,player][board][action node] -> [row][n_actions] (README.md:45-47).

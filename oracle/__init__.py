@@ -40,6 +40,9 @@ def load():
     lib.orc_destroy.argtypes = [VP]
     lib.orc_set_options.argtypes = [VP, C.c_int, C.c_int, C.c_int]
     lib.orc_set_prune_threshold.argtypes = [VP, C.c_double]
+    lib.orc_set_opponent_sampling.argtypes = [VP, C.c_int, C.c_uint64]
+    lib.orc_xs_min_margin.argtypes = [VP]
+    lib.orc_xs_min_margin.restype = C.c_double
     lib.orc_iterate.argtypes = [VP, C.c_int]
     lib.orc_traverse_player.argtypes = [VP, C.c_int]
     lib.orc_best_response.argtypes = [VP, f64p]
@@ -227,6 +230,14 @@ class OracleGame:
         self.lib.orc_set_prune_threshold(self.h, float(thr))
 
     # --- vector-form fp64 CFR ---
+    def set_opponent_sampling(self, mode: int, seed: int = 0):
+        """mccfr()'s opponent arm for every hand at once (cfr.rs:466-475); the draw is the hash rs_set_opponent_sampling states."""
+        self.lib.orc_set_opponent_sampling(self.h, int(mode), int(seed))
+
+    def xs_min_margin(self) -> float:
+        """smallest |u - cumulative sigma| of any draw with non-zero reach since set_opponent_sampling"""
+        return float(self.lib.orc_xs_min_margin(self.h))
+
     def iterate(self, n: int = 1):
         self.lib.orc_iterate(self.h, n)
 

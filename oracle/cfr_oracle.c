@@ -168,6 +168,12 @@ typedef struct orc_game {
      * deal the boards listed in samp[k+1] and weight them by (#possible deals)/(#sampled children) */
     int samp_n;
     int* samp[3];
+    /* sampled opponent actions, the opponent arm of mccfr() (cfr.rs:466-475) for every hand at once: xs_mode 1 = the drawn
+     * action keeps the hand's reach, 2 = reach * sigma(drawn action) as the code does; the draw is a counter-based hash
+     * (include/b200cfr.h: rs_set_opponent_sampling states it) */
+    int xs_mode;
+    uint64_t xs_seed, xs_count, xs_key;
+    double xs_min_margin; /* smallest |u - cumulative sigma| seen at a draw since the mode was set (tests: fp32 vs fp64 flips) */
 } orc_game;
 
 static void* xcalloc(size_t n, size_t sz) {
@@ -452,6 +458,24 @@ void orc_destroy(orc_game* g) {
 }
 
 /* Infoset::get_strategy (infoset.rs:83-102) on doubles */
+static uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+/* uniform number of one draw: 24 bits, exact in fp32 and fp64 (rs_set_opponent_sampling) */
+static double xs_uniform(uint64_t key, uint32_t an, uint32_t board, uint32_t slot) {
+    uint64_t z = mix64(key ^ ((uint64_t)an << 44) ^ ((uint64_t)board << 20) ^ (uint64_t)slot);
+    return (double)(uint32_t)(z >> 40) / 16777216.0;
+}
+void orc_set_opponent_sampling(orc_game* g, int mode, uint64_t seed) {
+    g->xs_mode = mode;
+    g->xs_seed = seed;
+    g->xs_count = 0;
+    g->xs_min_margin = 1.0;
+}
+double orc_xs_min_margin(const orc_game* g) { return g->xs_min_margin; }
+
 static void regret_match(const double* r, int A, double* s) {
     double norm = 0;
     for (int i = 0; i < A; ++i)
@@ -674,14 +698,38 @@ static void walk(walk_ctx* c, int node, int k, int b, const double* reach, doubl
         double* r2 = (double*)xcalloc(Ho, 8);
         double* tmp = (double*)xcalloc(Hp, 8);
         for (int h = 0; h < Hp; ++h) out[h] = 0;
+        int* pick = NULL;
+        if (c->mode == MODE_CFR && g->xs_mode) {
+            /* cfr.rs:466-475 per opponent hand: draw one action from sigma (WeightedIndex), first a with u < cumulative */
+            pick = (int*)xcalloc(Ho, sizeof(int));
+            for (int j = 0; j < Ho; ++j) {
+                pick[j] = -1;
+                if (rows[j] < 0) continue;
+                const double* sg = &sigma[(size_t)rows[j] * A];
+                double u = xs_uniform(g->xs_key, (uint32_t)an, (uint32_t)b, (uint32_t)j), cum = 0;
+                pick[j] = A - 1;
+                for (int a = 0; a + 1 < A; ++a) {
+                    cum += sg[a];
+                    if (reach[j] != 0 && fabs(u - cum) < g->xs_min_margin) g->xs_min_margin = fabs(u - cum);
+                    if (pick[j] == A - 1 && u < cum) {
+                        pick[j] = a;
+                        if (reach[j] == 0) break;
+                    }
+                }
+            }
+        }
         for (int a = 0; a < A; ++a) {
             for (int j = 0; j < Ho; ++j) r2[j] = rows[j] < 0 ? 0.0 : reach[j] * sigma[(size_t)rows[j] * A + a]; /* cfr.rs:583-586 */
+            if (pick)
+                for (int j = 0; j < Ho; ++j)
+                    if (rows[j] >= 0) r2[j] = pick[j] != a ? 0.0 : (g->xs_mode == 2 ? r2[j] : reach[j]); /* cfr.rs:474 */
             walk(c, g->children[g->child_off[node] + a], k, b, r2, pi, tmp);
             for (int h = 0; h < Hp; ++h) out[h] += tmp[h];
         }
         free(r2);
         free(tmp);
         free(sigma);
+        free(pick);
         return;
     }
     double* cv = (double*)xcalloc((size_t)A * Hp, 8);
@@ -740,6 +788,7 @@ static void traverse(orc_game* g, int p, int mode) {
     ensure_strength(g);
     walk_ctx c = {g, p, mode};
     int o = 1 - p;
+    if (mode == MODE_CFR && g->xs_mode) g->xs_key = mix64(g->xs_seed + 0x9E3779B97F4A7C15ull * (++g->xs_count));
     double* reach = (double*)xcalloc(g->H[o], 8);
     for (int j = 0; j < g->H[o]; ++j) reach[j] = (g->hmask[o][j] & g->bmask[0][0]) ? 0.0 : 1.0;
     walk(&c, 0, 0, 0, reach, 1.0 / g->n_combos, g->root_cfv[p]); /* cfr.rs:491 */

@@ -85,6 +85,7 @@ ENGINE_API = {
     "rs_iterate_sampled": (C.c_int, [VP, u8p, C.c_uint32]),
     "rs_discount": (C.c_int, [VP, C.c_float]),
     "rs_set_prune_threshold": (C.c_int, [VP, C.c_float]),
+    "rs_set_opponent_sampling": (C.c_int, [VP, C.c_uint32, C.c_uint64]),
     "rs_set_wait_timeout_ms": (C.c_int, [VP, C.c_uint64]),
     "rs_abort": (C.c_int, [VP]),
     "rs_sample_runouts": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, u8p]),

@@ -136,7 +136,8 @@ struct RoundDev {
 struct TaskSet {
     DevBuf<NodeTask> tasks;
     DevBuf<TaskSrc> srcs;
-    DevBuf<uint32_t> tix;  // ticket -> node-task index
+    DevBuf<uint32_t> tix;  // instance slot -> node-task index
+    DevBuf<uint32_t> order;  // ticket -> instance slot (empty: identity), see TaskArgs::order
     uint32_t n_tickets = 0, phase_cut = 0, n_tasks = 0;
     uint32_t street_lo = 0, street_hi = 0;  // tickets of the final round's node tasks (replaced by the street kernel)
     uint32_t street_inst = 0;               // instances (boards or sampled run-outs) of the final round
@@ -197,6 +198,9 @@ struct Engine {
     void* xch_peer_base[RS_MAX_PEERS] = {nullptr};
     bool fused_exchange = false;
     float prune_threshold = -INFINITY;  // rs_set_prune_threshold
+    // rs_set_opponent_sampling: every CFR traversal draws one action per opponent hand and node (kernels.cuh: xs_uniform)
+    int xs_mode = 0;
+    uint64_t xs_seed = 0, xs_count = 0;  // traversals since the mode was set: the key of a traversal is splitmix64(seed + count)
     // bounded waits (kernels.cuh: host_abort / wait_timeout_ns)
     uint32_t* abort_host = nullptr;   // mapped pinned word the host raises (rs_abort)
     uint32_t* abort_dev = nullptr;    // its device alias
@@ -648,6 +652,47 @@ int Engine::materialize(int trav, const uint32_t counts[3], TaskSet* out) {
     CU(out->tasks.upload(t));
     CU(out->srcs.upload(sr));
     CU(out->tix.upload(tix));
+    // Execution order of the final round when it is large (config 4: 2 352 river boards, ~10 GB of reach / value vectors
+    // per traversal).  Task-major slots touch every board once per node task, so a board's index tables (hand records,
+    // card lists, position maps: ~50 KB per player) come back from DRAM for every one of the ~500 tasks that run on it
+    // (measured: DRAM traffic 2.4x the algorithmic bytes).  Instead the round is walked parent board by parent board:
+    // inside one parent's group of child boards the slots stay task-major (every depth level of the group is still a
+    // few thousand independent instances, enough for every CTA), the group's index tables stay in L2 for all its
+    // tasks, and a reach vector is read back one level later instead of 2 352 boards later.  Producers still precede
+    // consumers.  (Walking a group street segment by street segment keeps even more in L2 but starves the in-order
+    // ticket dispenser: measured 3.4x slower.)
+    const uint32_t kf = plan.n_rounds - 1;
+    const bool full_boards = counts[kf] == rd[kf].n_boards;
+    if (plan.n_rounds >= 2 && full_boards && !getenv("RS_TASK_MAJOR")) {
+        const TaskList& tlp = plan.tl[trav];
+        const uint64_t vec_bytes = (uint64_t(tlp.n_rbuf[kf]) + tlp.n_cbuf[kf]) * counts[kf] * std::max(plan.H[0], plan.H[1]) * 4;
+        uint32_t lo = UINT32_MAX, hi = 0;
+        std::vector<uint32_t> fin;  // node tasks of the final round, list order (downs by depth, then ups deepest first)
+        for (size_t j = 0; j < t.size(); ++j)
+            if (t[j].round_k == kf && t[j].count) {
+                fin.push_back(uint32_t(j));
+                lo = std::min(lo, t[j].first);
+                hi = std::max(hi, t[j].first + t[j].count);
+            }
+        uint64_t covered = 0;
+        for (uint32_t j : fin) covered += t[j].count;
+        const bool contiguous = !fin.empty() && covered == uint64_t(hi - lo);
+        if (contiguous && (vec_bytes > (96ull << 20) || getenv("RS_BOARD_MAJOR"))) {
+            std::vector<uint32_t> ord(first);
+            for (uint32_t i = 0; i < first; ++i) ord[i] = i;
+            const int32_t* par = plan.board_parent[kf].data() + plan.local_lo[kf];
+            uint32_t pos = lo;
+            for (uint32_t b0 = 0; b0 < counts[kf];) {
+                uint32_t b1 = b0 + 1;
+                while (b1 < counts[kf] && par[b1] == par[b0]) ++b1;
+                for (uint32_t j : fin)
+                    for (uint32_t b = b0; b < b1; ++b) ord[pos++] = t[j].first + b;
+                b0 = b1;
+            }
+            if (pos != hi) return set_err(RS_ERR_INVALID, "internal: execution order does not cover the final round");
+            CU(out->order.upload(ord));
+        }
+    }
     return RS_OK;
 }
 
@@ -687,6 +732,7 @@ void Engine::fill_args(TaskArgs* a, int trav, const TaskSet& set) const {
         ra.sbuf = R.sbuf[trav].p;
         ra.gathered = R.gathered.p;
         ra.n_boards = int(R.n_boards);
+        ra.board_base = int(P.local_lo[k]);
         if (k + 1 < P.n_rounds) {
             const bool sharded_next = (P.world > 1 && k + 1 == P.shard_round);
             ra.per_parent = sharded_next ? 0 : int(P.deal_count[k + 1]);
@@ -696,6 +742,7 @@ void Engine::fill_args(TaskArgs* a, int trav, const TaskSet& set) const {
     a->tasks = set.tasks.p;
     a->srcs = set.srcs.p;
     a->task_of_ticket = set.tix.p;
+    a->order = set.order.n ? set.order.p : nullptr;
     a->n_tasks = set.n_tasks;
     a->flags = flags.p;
     a->ctl = ctl.p;
@@ -757,6 +804,15 @@ int Engine::enqueue_traversal(int trav, int mode, uint64_t* count, const TaskSet
             a.sample_board[k] = sample_board[k].p;
             a.gather_scale[k - 1] = float(P.deal_count[k]) / float(k == 1 ? n_paths_global : 1);
         }
+    }
+    if (mode == KM_CFR && xs_mode) {
+        // sampled opponent actions: a fresh key per traversal (a kernel argument, so these launches are never graph replays)
+        uint64_t z = xs_seed + 0x9E3779B97F4A7C15ull * (++xs_count);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        a.xs_key = z ^ (z >> 31);
+        a.xs_mode = xs_mode;
+        mode = KM_CFR_XS;
     }
     int rc;
     // Launch schedule.  Without the street kernel a traversal is one launch of the task kernel (with the in-kernel
@@ -873,6 +929,7 @@ int Engine::iterate(uint64_t n) {
     CU(cudaSetDevice(device));
     if (n == 0) return RS_OK;
     if (aborted) return set_err(RS_ERR_CUDA, "an earlier traversal was aborted: the tables are partly updated, create a new engine");
+    const bool use_graph = this->use_graph && !xs_mode;  // the traversal key of the sampling mode changes with every launch
     if (use_graph && !graph_exec) {
         uint64_t cnt = 0;
         CU(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
@@ -1127,6 +1184,19 @@ int rs_set_wait_timeout_ms(rs_engine* e, uint64_t ms) {
         cudaGraphDestroy(E.graph);
         E.graph = nullptr;
     }
+    return RS_OK;
+}
+
+int rs_set_opponent_sampling(rs_engine* e, uint32_t mode, uint64_t seed) {
+    if (!e) return set_err(RS_ERR_INVALID, "null engine");
+    if (mode > 2) return set_err(RS_ERR_INVALID, "mode must be RS_OPP_FULL (0), RS_OPP_SAMPLE (1) or RS_OPP_SAMPLE_TIMES_SIGMA (2)");
+    Engine& E = e->e;
+    if (mode && E.street_on) return set_err(RS_ERR_UNSUPPORTED, "sampled opponent actions are not available with RS_FLAG_STREET_KERNEL");
+    CU(cudaSetDevice(E.device));
+    CU(cudaStreamSynchronize(E.stream));
+    E.xs_mode = int(mode);
+    E.xs_seed = seed;
+    E.xs_count = 0;
     return RS_OK;
 }
 

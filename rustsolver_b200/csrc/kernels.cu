@@ -386,7 +386,25 @@ __device__ __forceinline__ void load_rows(const float* __restrict__ slab, bool i
 // ------------------------------------------------------------------------------------------------
 // TK_DOWN: opponent node (cfr.rs:582-586) + its terminal children (cfr.rs:523-558)
 // ------------------------------------------------------------------------------------------------
-template <int MODE, int NA>
+// one sampled action per opponent hand (cfr.rs:466-475): the first action whose cumulative probability exceeds u
+template <int NA>
+__device__ __forceinline__ void xs_pick(const TaskArgs& A, float u, float (&sg)[NA]) {
+    int pick = NA - 1;
+    bool found = false;
+    float cum = 0.f;
+#pragma unroll
+    for (int a = 0; a + 1 < NA; ++a) {
+        cum += sg[a];
+        if (!found && u < cum) {
+            pick = a;
+            found = true;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) sg[a] = (a == pick) ? (A.xs_mode == 2 ? sg[a] : 1.0f) : 0.f;
+}
+
+template <int MODE, int NA, bool XS>
 __device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b) {
     const DevRoundPlayer& O = Rk.rp[c.o];
     const uint32_t nrp = O.n_rows_pad[b];
@@ -401,10 +419,13 @@ __device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const
     float g[4 * NA];
     load_rows<NA>(slab, O.identity != 0, c.pos4, nrp, rows, g);
     float4 v[NA];
+    uint32_t xs_slot[4] = {0, 0, 0, 0};
+    if (XS && c.pos4 < c.HoP) unpack4(__ldg(reinterpret_cast<const uint2*>(O.slot_of_pos + size_t(b) * c.HoP + c.pos4)), xs_slot);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float sg[NA];
         sigma_row<NA>(g, i, sg);
+        if (XS) xs_pick<NA>(A, xs_uniform(A.xs_key, nt.an_index, uint32_t(Rk.board_base + b), xs_slot[i]), sg);
         const float r = f4get(r4, i);
 #pragma unroll
         for (int a = 0; a < NA; ++a) f4set(v[a], i, r * sg[a]);
@@ -456,7 +477,7 @@ __device__ __forceinline__ void task_down(const TaskArgs& A, const Ctx& c, const
 }
 
 // any number of actions, any row mapping: scalar loads, two passes over the actions
-template <int MODE>
+template <int MODE, bool XS>
 __device__ __forceinline__ void task_down_generic(const TaskArgs& A, const Ctx& c, const NodeTask& nt, const RoundArgs& Rk, int k, int b) {
     const DevRoundPlayer& O = Rk.rp[c.o];
     const uint32_t nrp = O.n_rows_pad[b];
@@ -473,10 +494,24 @@ __device__ __forceinline__ void task_down_generic(const TaskArgs& A, const Ctx& 
             float norm = 0.f;
             if (live)
                 for (int a = 0; a < n_act; ++a) norm += fmaxf(slab[size_t(rows[i]) * n_act + a], 0.f);
+            int pick = -1;  // sampled-opponent-action mode: the one action this hand keeps its reach on
+            if (XS && live) {
+                const float u = xs_uniform(A.xs_key, nt.an_index, uint32_t(Rk.board_base + b), O.slot_of_pos[size_t(b) * c.HoP + c.pos4 + i]);
+                pick = n_act - 1;
+                float cum = 0.f;
+                for (int a = 0; a + 1 < n_act; ++a) {
+                    cum += norm > 0.f ? fmaxf(slab[size_t(rows[i]) * n_act + a], 0.f) / norm : 1.0f / float(n_act);
+                    if (u < cum) {
+                        pick = a;
+                        break;
+                    }
+                }
+            }
             int slot = 0;
             for (int a = 0; a < n_act; ++a) {
                 float v = 0.f;
                 if (live) v = norm > 0.f ? r * fmaxf(slab[size_t(rows[i]) * n_act + a], 0.f) / norm : r / float(n_act);
+                if (XS && live) v = (a == pick) ? (A.xs_mode == 2 ? v : r) : 0.f;
                 const int ck = nt.child[a].kind;
                 if (ck == CK_FOLD || ck == CK_SHOWDOWN) SM_X[(slot++) * c.Hx + c.pos4 + i] = v;
                 else if (nt.child[a].buf >= 0) __stcg(Rk.rbuf + (size_t(nt.child[a].buf) * Rk.n_boards + b) * c.HoP + c.pos4 + i, v);
@@ -801,14 +836,14 @@ __device__ __forceinline__ void prefetch_task_tables(const TaskArgs& A, uint32_t
 }
 
 struct TaskSlot {
-    uint32_t ticket;  // >= t1: no more work
+    uint32_t ticket;  // the instance slot (first slot of its node task + instance); >= t1: no more work
     uint32_t epoch;   // launch number: the value that marks flags "done" in this launch
     uint32_t xseq;    // ctl->xch_seq at launch: flag value and buffer parity of the in-kernel exchange
     uint32_t pad;
     NodeTask nt;
 };
 
-template <int MODE, int MAXT, int MINB>
+template <int MODE, int MAXT, int MINB, bool XS>
 __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_constant__ TaskArgs A) {
     __shared__ __align__(16) TaskSlot s_slot[2];
 
@@ -850,10 +885,12 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                 }
             };
             uint32_t tk = tk_next;
+            uint32_t sl = A.t1;  // the instance slot this ticket stands for (flags, descriptors and instances go by slot)
             if (tk < A.t1) {
                 unsigned long long pend = 0;
                 if (lane == 0) pend = atomicAdd(&A.ctl->ticket, 1ull);  // consumed at the end of this iteration
-                const uint32_t j = __ldg(A.task_of_ticket + tk);
+                sl = A.order ? __ldg(A.order + tk) : tk;
+                const uint32_t j = __ldg(A.task_of_ticket + sl);
                 const NodeTask* gt = A.tasks + j;
                 NodeTask& st = s_slot[buf].nt;
                 for (int i = lane; i < int(sizeof(NodeTask) / 4); i += 32)
@@ -861,7 +898,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                 __syncwarp();
                 const int kind = st.kind;
                 const int k = st.round_k;
-                const int inst = int(tk - st.first);
+                const int inst = int(sl - st.first);
                 const int b = board_of(A, k, inst);
                 const RoundArgs& Rk = A.rounds[k];
                 const int nd = st.n_dep;
@@ -897,7 +934,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                 bool has = false;
                 uint32_t idx = 0;
                 if (i < total) idx = flag_index(i, has);
-                if (lane == 0) prefetch_task_tables<MODE>(A, tk, j);
+                if (lane == 0) prefetch_task_tables<MODE>(A, sl, j);
                 try_publish();
                 (void)b;
                 const unsigned long long t_wait = global_ns();
@@ -919,10 +956,10 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
                     }
                 }
                 tk_next = A.t0 + uint32_t(__shfl_sync(0xffffffffu, pend, 0));
-                if (gave_up) tk = tk_next = A.t1;  // hand the compute warps the end marker: the producers will never finish
+                if (gave_up) tk = tk_next = sl = A.t1;  // hand the compute warps the end marker: the producers will never finish
             }
             if (lane == 0) {
-                s_slot[buf].ticket = tk;
+                s_slot[buf].ticket = sl;
                 s_slot[buf].epoch = epoch;
                 s_slot[buf].xseq = xseq;
             }
@@ -936,7 +973,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
             }
             if (prev_tk != 0xffffffffu) parity ^= 1;
             if (tk >= A.t1) break;
-            prev_tk = tk;
+            prev_tk = sl;
             buf ^= 1;
         }
         // the last CTA to leave re-arms the dispatcher state for the next launch
@@ -992,11 +1029,11 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
         switch (kind) {
             case TK_DOWN: {
                 switch (nt.n_act) {
-                    case 2: task_down<MODE, 2>(A, c, nt, Rk, k, b); break;
-                    case 3: task_down<MODE, 3>(A, c, nt, Rk, k, b); break;
-                    case 4: task_down<MODE, 4>(A, c, nt, Rk, k, b); break;
-                    case 5: task_down<MODE, 5>(A, c, nt, Rk, k, b); break;
-                    default: task_down_generic<MODE>(A, c, nt, Rk, k, b); break;
+                    case 2: task_down<MODE, 2, XS>(A, c, nt, Rk, k, b); break;
+                    case 3: task_down<MODE, 3, XS>(A, c, nt, Rk, k, b); break;
+                    case 4: task_down<MODE, 4, XS>(A, c, nt, Rk, k, b); break;
+                    case 5: task_down<MODE, 5, XS>(A, c, nt, Rk, k, b); break;
+                    default: task_down_generic<MODE, XS>(A, c, nt, Rk, k, b); break;
                 }
                 break;
             }
@@ -1176,17 +1213,22 @@ size_t task_kernel_smem_bytes(int slots, int Hp_pad, int Ho_pad) {
 template <int MAXT, int MINB>
 static cudaError_t configure_for(size_t smem, int threads, int* blocks_per_sm) {
     cudaError_t e;
-    e = cudaFuncSetAttribute(task_kernel<KM_CFR, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    e = cudaFuncSetAttribute(task_kernel<KM_CFR, MAXT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(task_kernel<KM_BR, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    e = cudaFuncSetAttribute(task_kernel<KM_CFR, MAXT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(task_kernel<KM_EVAL, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    e = cudaFuncSetAttribute(task_kernel<KM_BR, MAXT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    int n = 0, m = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, task_kernel<KM_CFR, MAXT, MINB>, threads + 32, smem);
+    e = cudaFuncSetAttribute(task_kernel<KM_EVAL, MAXT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, task_kernel<KM_BR, MAXT, MINB>, threads + 32, smem);
+    int n = 0, m = 0, x = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, task_kernel<KM_CFR, MAXT, MINB, false>, threads + 32, smem);
     if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, task_kernel<KM_BR, MAXT, MINB, false>, threads + 32, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&x, task_kernel<KM_CFR, MAXT, MINB, true>, threads + 32, smem);
+    if (e != cudaSuccess) return e;
+    n = n < x ? n : x;
     *blocks_per_sm = n < m ? n : m;
     return cudaSuccess;
 }
@@ -1200,9 +1242,10 @@ template <int MAXT, int MINB>
 static void launch_for(const TaskArgs& a, int mode, int grid, int threads, size_t smem, cudaStream_t st) {
     switch (mode) {
         // one extra warp per CTA: the dispatcher
-        case KM_CFR: task_kernel<KM_CFR, MAXT, MINB><<<grid, threads + 32, smem, st>>>(a); break;
-        case KM_BR: task_kernel<KM_BR, MAXT, MINB><<<grid, threads + 32, smem, st>>>(a); break;
-        default: task_kernel<KM_EVAL, MAXT, MINB><<<grid, threads + 32, smem, st>>>(a); break;
+        case KM_CFR: task_kernel<KM_CFR, MAXT, MINB, false><<<grid, threads + 32, smem, st>>>(a); break;
+        case KM_CFR_XS: task_kernel<KM_CFR, MAXT, MINB, true><<<grid, threads + 32, smem, st>>>(a); break;
+        case KM_BR: task_kernel<KM_BR, MAXT, MINB, false><<<grid, threads + 32, smem, st>>>(a); break;
+        default: task_kernel<KM_EVAL, MAXT, MINB, false><<<grid, threads + 32, smem, st>>>(a); break;
     }
 }
 

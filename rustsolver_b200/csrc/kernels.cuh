@@ -26,7 +26,18 @@ constexpr int RS_MAX_PEERS = 8;        // GPUs of one NVSwitch box
 constexpr int FAST_ACTIONS = 4;        // nodes up to this many actions keep their table rows in registers
 constexpr int MAX_TASK_THREADS = 352;  // ceil(1326 / 4) rounded up to a warp multiple
 
-enum KernelMode { KM_CFR = 0, KM_BR = 1, KM_EVAL = 2 };
+enum KernelMode { KM_CFR = 0, KM_BR = 1, KM_EVAL = 2, KM_CFR_XS = 3 };  // KM_CFR_XS: CFR with per-hand sampled opponent actions
+
+// Uniform number in [0, 1) of the sampled-opponent-action mode (rs_set_opponent_sampling): a counter-based hash of the
+// traversal key, the action node, the GLOBAL board id and the opponent's hand slot, so that the draw does not depend
+// on the board-local hand order, the sharding or the launch schedule.  24 bits: exact in fp32 and fp64.
+__host__ __device__ inline float xs_uniform(unsigned long long key, uint32_t an_index, uint32_t board, uint32_t slot) {
+    unsigned long long z = key ^ ((unsigned long long)an_index << 44) ^ ((unsigned long long)board << 20) ^ (unsigned long long)slot;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return float(uint32_t(z >> 40)) * (1.0f / 16777216.0f);
+}
 
 struct DevRoundPlayer {  // round k, player q; every array is indexed [board][...] in board-local hand order
     const uint16_t* row_of_pos;   // [nb][Hpad]
@@ -58,14 +69,21 @@ struct RoundArgs {
     int n_boards;
     int per_parent;  // boards of the NEXT round per board of this one (0: every local next-round board hangs off board 0)
     int n_boards_next;
-    int pad;
+    int board_base;  // global id of local board 0 (board-sharded engines): only the sampled-opponent-action hash needs it
 };
 
 struct TaskArgs {
     RoundArgs rounds[3];
     const NodeTask* tasks;
     const TaskSrc* srcs;
-    const uint32_t* task_of_ticket;  // [n_tickets] node-task index of every ticket
+    const uint32_t* task_of_ticket;  // [n_tickets] node-task index of every instance slot
+    // Execution order.  Instances are identified by their SLOT = first slot of the node task + instance (flags, the
+    // dependency fields and task_of_ticket go by slot); the dispatcher hands out TICKETS 0, 1, 2, ... and runs slot
+    // order[ticket].  order is a permutation inside every launch's range [t0, t1) and a topological order of the
+    // dependencies (null = identity: slots in task-major order).  The engine uses it to walk a round with thousands of
+    // boards parent board by parent board and street segment by street segment, so that a board's index tables and
+    // the vectors one task hands to the next are still in L2 when they are read again (engine.cu: materialize).
+    const uint32_t* order;
     uint32_t n_tasks;
     uint32_t* flags;  // [n_tickets] epoch of completion
     TaskCtl* ctl;
@@ -91,6 +109,11 @@ struct TaskArgs {
     int xch_world, xch_rank;
     int xch_round;    // the sharded round: the gathers of round xch_round - 1 exchange their sums
     int xch_leaves;   // chance leaves of round xch_round - 1
+    // Sampled opponent actions (KM_CFR_XS, cfr.rs:466-475 for every hand at once): at an opponent node each opponent hand
+    // draws ONE action from its current strategy and keeps its whole reach on that child (xs_mode 1, unbiased external
+    // sampling) or its reach times the probability of the drawn action (xs_mode 2, what the reference's code does).
+    unsigned long long xs_key;  // key of this traversal
+    int xs_mode;
     int xch_bump;     // this launch holds the exchanging gathers: the last CTA to leave advances ctl->xch_seq
     // Waits inside the kernel (producer flags, peer flags of the exchange) are bounded: a waiter gives up when the host
     // raised *host_abort (mapped pinned memory, rs_abort) or when one wait lasted longer than wait_timeout_ns (0: no

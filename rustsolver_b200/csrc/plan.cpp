@@ -307,6 +307,7 @@ struct TaskGen {
                             t.aux = nb;
                             // dependency is added at emission (producer index known by then for parent rounds)
                             pend.push_back({t, id, n.depth});
+                            pend.back().t.seg = s;
                             rsrc[id].buf = nb;
                             rsrc[id].parent_round = 0;
                             // stash the original source in the task
@@ -346,10 +347,12 @@ struct TaskGen {
                             NodeTask reach = t;
                             reach.out = -1;
                             pend.push_back({reach, id, n.depth});
+                            pend.back().t.seg = s;
                             for (size_t a = 0; a < n.children.size(); ++a)
                                 if (t.child[a].kind == CK_ACTION || t.child[a].kind == CK_CHANCE) t.child[a].buf = -1;  // not written again
                         }
                         pend.push_back({t, id, n.depth});
+                            pend.back().t.seg = s;
                     } else if (n.kind == PK_ACTION && n.player == trav && chain_round(k)) {
                         // chain round: scan + per-hand terms of the traverser node as soon as its reach exists
                         NodeTask t = blank(TK_TRAV_TERMS, k);
@@ -364,6 +367,7 @@ struct TaskGen {
                         }
                         terms_buf[id] = t.out;
                         pend.push_back({t, id, n.depth});
+                            pend.back().t.seg = s;
                     }
                 }
             std::stable_sort(pend.begin(), pend.end(), [](const Pending& a, const Pending& b) { return a.depth < b.depth; });
@@ -406,11 +410,13 @@ struct TaskGen {
                         t.child[0].kind = CK_SHOWDOWN;
                         t.child[0].coef = float(n.value);
                         pend.push_back({t, id, n.depth});
+                            pend.back().t.seg = s;
                     } else if (n.kind == PK_CHANCE && is_root) {
                         NodeTask t = blank(TK_CHANCE_UP, uint32_t(k));
                         t.out = cbuf[id];
                         t.aux = n.leaf_id;
                         pend.push_back({t, id, n.depth});
+                            pend.back().t.seg = s;
                     } else if (n.kind == PK_ACTION) {
                         const bool opp = (n.player != trav);
                         if (opp && !is_root && P->nodes[n.parent].kind == PK_ACTION && P->nodes[n.parent].player == trav) continue;
@@ -421,6 +427,7 @@ struct TaskGen {
                         t.out = cbuf[id];
                         if (!opp) tl.max_children = std::max<uint32_t>(tl.max_children, t.n_act);
                         pend.push_back({t, id, n.depth});
+                            pend.back().t.seg = s;
                     }
                 }
             std::stable_sort(pend.begin(), pend.end(), [](const Pending& a, const Pending& b) { return a.depth > b.depth; });

@@ -87,8 +87,9 @@ struct NodeTask {
     uint8_t dep_kind[MAX_TASK_DEPS]; // DepKind
     TaskChild child[MAX_TASK_CHILDREN];
     uint32_t pre_terms;  // TK_UP_TRAV: 1 = mass and showdown terms come from value buffers aux, aux + 1 (TK_TRAV_TERMS)
+    uint32_t seg;        // street segment of the node inside its round (plan.h: Segment); gathers: the child segment
 };
-static_assert(sizeof(NodeTask) == 8 + 4 * 8 + 4 * MAX_TASK_DEPS + MAX_TASK_DEPS + 12 * MAX_TASK_CHILDREN + 4, "NodeTask layout");
+static_assert(sizeof(NodeTask) == 8 + 4 * 8 + 4 * MAX_TASK_DEPS + MAX_TASK_DEPS + 12 * MAX_TASK_CHILDREN + 8, "NodeTask layout");
 static_assert(sizeof(NodeTask) % 4 == 0, "NodeTask is copied to shared memory as words");
 
 // Per-hand record of the traverser on one board (16 bytes, one 128-bit load), local hand order:

@@ -611,6 +611,11 @@ class Engine(_PlanOrEngine):
         """Traverser actions with regret <= threshold keep their regret (cfr.rs:352,379-386); -inf = off."""
         check(self._lib.rs_set_prune_threshold(self._h, float(threshold)))
 
+    def set_opponent_sampling(self, mode: int, seed: int = 0):
+        """mccfr()'s opponent arm for every hand at once (cfr.rs:466-475): 0 = off, 1 = one sampled action per opponent
+        hand and node keeps the whole reach, 2 = keeps reach * sigma(sampled action) as the reference's code does."""
+        check(self._lib.rs_set_opponent_sampling(self._h, int(mode), int(seed)))
+
     def set_wait_timeout_ms(self, ms: int):
         """Bound of every wait inside the traversal kernel (default 30 s, 0 = unbounded): see rs_set_wait_timeout_ms."""
         check(self._lib.rs_set_wait_timeout_ms(self._h, int(ms)))

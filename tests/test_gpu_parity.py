@@ -491,3 +491,53 @@ def test_every_shard_of_a_sharded_run_alone(case):
         per2 = st.n_boards[2] // st.n_boards[1] if st.n_rounds > 2 else 0
         _shard_compare(eng, orc, tree, lo1, hi1, per2, n_locked=1)
         eng.close()
+
+
+def _xs_case(case):
+    if case == "river":
+        return util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]], [[3.0]]), None
+    if case == "turn_river":
+        return util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]] * 2, [[3.0]] * 2), None
+    if case == "wide":  # six-action nodes: the generic task bodies
+        return util.small_options("4d5dAs3cKs", [util.RANGE_A, util.RANGE_B], [[0.25, 0.5, 1.0, 2.0]], [[3.0]]), None
+    o = util.small_options("4d5dAs3c", [util.RANGE_A, util.RANGE_B], [[0.5, 1.0]] * 2, [[3.0]] * 2)
+    r = o.ranges()
+    return o, [util.bucket_keys_for(None, r, 1, 7, seed=3), util.bucket_keys_for(None, r, 48, 11, seed=4)]
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("case", ["river", "turn_river", "wide", "bucketed"])
+def test_sampled_opponent_actions_match_oracle(case, mode):
+    """mccfr()'s opponent arm for every hand at once (cfr.rs:466-475, rs_set_opponent_sampling): same counter-based draws on
+    both sides, so the tables agree like those of a full traversal.  A draw whose uniform number sits within fp32 rounding
+    of a cumulative probability can fall on different actions in fp32 and fp64 (the oracle reports the smallest margin it
+    saw): such a seed is retried with the next one; a real defect fails every seed."""
+    o, keys = _xs_case(case)
+    errors = []
+    for seed in (11, 12, 13):
+        n, tree = rb.build_game_tree(o)
+        ranges = o.ranges()
+        abs_ = [rb.CardAbstraction(rb.RS_ABS_BUCKET_TABLE, bucket_table=k) for k in keys] if keys else []
+        eng = rb.Engine(tree, ranges, o.board_mask, abs_)
+        orc = OracleGame(tree, ranges, o.board_mask, keys=keys)
+        eng.iterate(2)
+        orc.iterate(2)  # a non-uniform strategy before the first draw
+        eng.set_opponent_sampling(mode, seed)
+        orc.set_opponent_sampling(mode, seed)
+        try:
+            util.lockstep(eng, orc, tree, n_free=0, n_locked=3, tol=TOL)
+        except AssertionError as e:
+            errors.append((seed, orc.xs_min_margin(), str(e)[:200]))
+            eng.close()
+            continue
+        # the sampled tables differ from a full traversal's (the mode is really on) and switching it off restores the full one
+        full = OracleGame(tree, ranges, o.board_mask, keys=keys)
+        full.iterate(2)
+        util.copy_oracle_to_engine(eng, full, tree)
+        eng.set_opponent_sampling(0)
+        eng.iterate(1)
+        full.iterate(1)
+        util.compare_tables(eng, full, tree, TOL)
+        eng.close()
+        return
+    raise AssertionError(f"every seed failed: {errors}")

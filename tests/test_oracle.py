@@ -146,3 +146,51 @@ def test_pruning_freezes_regrets_at_or_below_the_threshold():
         n_frozen += int(m.sum())
         n_moved += int((rb_[m] != before[an][m]).sum())
     assert n_frozen > 10 and n_moved > 0  # without pruning those cells do move
+
+
+def _table_delta(og, tree, before):
+    out = []
+    for an, b in util.all_slabs(tree, [og.n_boards(k) for k in range(og.n_rounds)]):
+        r, _ = og.get_slab(an, b)
+        out.append((r - before[(an, b)][0]).ravel())
+    return np.concatenate(out)
+
+
+def test_sampled_opponent_actions_are_unbiased():
+    """mccfr()'s opponent arm for every hand at once (cfr.rs:466-475, mode 1): the expected regret update of one traversal
+    with one sampled action per opponent hand and node equals the update of the full traversal from the same tables."""
+    o, tree = _small()
+    og = OracleGame(tree, o.ranges(), o.board_mask, fast_terminals=True)
+    og.iterate(3)  # a non-uniform current strategy
+    slabs = list(util.all_slabs(tree, [og.n_boards(k) for k in range(og.n_rounds)]))
+    state = {(an, b): og.get_slab(an, b) for an, b in slabs}
+
+    def restore():
+        for (an, b), (r, s) in state.items():
+            og.set_slab(an, b, r, s)
+
+    og.traverse_player(0)
+    full = _table_delta(og, tree, state)
+    n = 400
+    acc = np.zeros_like(full)
+    one = None
+    for seed in range(n):
+        restore()
+        og.set_opponent_sampling(1, seed + 1)
+        og.traverse_player(0)
+        d = _table_delta(og, tree, state)
+        one = d if one is None else one
+        acc += d
+    og.set_opponent_sampling(0)
+    mean = acc / n
+    rel_mean = np.linalg.norm(mean - full) / np.linalg.norm(full)
+    rel_one = np.linalg.norm(one - full) / np.linalg.norm(full)
+    assert rel_one > 4 * rel_mean, (rel_one, rel_mean)  # a single sample is far off, the mean converges like 1/sqrt(n)
+    assert rel_mean < 0.12, rel_mean
+    # mode 2 multiplies the kept reach by sigma of the drawn action (cfr.rs:474): biased, as the reference's code is
+    restore()
+    og.set_opponent_sampling(2, 1)
+    og.traverse_player(0)
+    two = _table_delta(og, tree, state)
+    og.set_opponent_sampling(0)
+    assert np.linalg.norm(two) < np.linalg.norm(one)
