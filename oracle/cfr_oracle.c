@@ -707,10 +707,12 @@ static void walk(walk_ctx* c, int node, int k, int b, const double* reach, doubl
                 if (rows[j] < 0) continue;
                 const double* sg = &sigma[(size_t)rows[j] * A];
                 double u = xs_uniform(g->xs_key, (uint32_t)an, (uint32_t)b, (uint32_t)j), cum = 0;
+                int shaped = 0; /* a row without positive regret plays 1/A: those cumulative sums never sit between a 24-bit u and its fp32 image */
+                for (int a = 0; a < A; ++a) shaped |= R[(size_t)rows[j] * A + a] > 0;
                 pick[j] = A - 1;
                 for (int a = 0; a + 1 < A; ++a) {
                     cum += sg[a];
-                    if (reach[j] != 0 && fabs(u - cum) < g->xs_min_margin) g->xs_min_margin = fabs(u - cum);
+                    if (shaped && reach[j] != 0 && fabs(u - cum) < g->xs_min_margin) g->xs_min_margin = fabs(u - cum);
                     if (pick[j] == A - 1 && u < cum) {
                         pick[j] = a;
                         if (reach[j] == 0) break;

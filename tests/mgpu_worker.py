@@ -81,6 +81,28 @@ def check_case(case, rank, world, local, dev, fused):
                         assert r_ <= 1.0, (s, an, r_)
         else:
             og = OracleGame(tree, ranges, o.board_mask)
+            xs = int(os.environ.get("RS_XS", "0"))
+            if xs:  # sampled opponent actions: the draws are keyed by GLOBAL board ids, so the sharding must not show
+                n_iters = 2
+                # Lock-step from the first sampled iteration on (the engine starts from the oracle's state after two full
+                # iterations): in a free run a row whose regrets are rounding noise plays an arbitrary strategy in any two
+                # arithmetics, which a full traversal does not notice (the row is indifferent) but a sampled one does.
+                # A draw whose uniform number sits within fp32 rounding of a cumulative probability can also fall on
+                # different actions in fp32 and fp64: the lock-step trajectory is the oracle's, so a dry run of the oracle
+                # alone finds (identically on every rank) a seed whose draws all keep a safe margin.
+                og.iterate(2)
+                seed = None
+                for cand in range(7, 27):
+                    dry = OracleGame(tree, ranges, o.board_mask)
+                    dry.iterate(2)
+                    dry.set_opponent_sampling(xs, cand)
+                    dry.iterate(n_iters)
+                    if dry.xs_min_margin() > 5e-6:
+                        seed = cand
+                        break
+                assert seed is not None, "no seed with a safe margin"
+                eng.set_opponent_sampling(xs, seed)
+                og.set_opponent_sampling(xs, seed)
             nb = [st.n_boards[k] for k in range(st.n_rounds)]
             lo1 = rank * nb[1] // world
             hi1 = (rank + 1) * nb[1] // world
@@ -96,7 +118,7 @@ def check_case(case, rank, world, local, dev, fused):
             rk = {int(tree.an_index[i]): int(tree.round_idx[i]) for i in range(tree.n_nodes) if tree.type[i] == 0}
             al = util.RowAligner(eng, og, tree)
             for it in range(n_iters):
-                if it > 0:  # lock-step: restart from the oracle's state (see tests/util.py)
+                if it > 0 or xs:  # lock-step: restart from the oracle's state (see tests/util.py)
                     for an, b in util.all_slabs(tree, nb):
                         if mine(rk[an], b):
                             r, s = og.get_slab(an, b)
@@ -117,10 +139,18 @@ def check_case(case, rank, world, local, dev, fused):
                     for g, oarr, nm in ((gr, orr, "R"), (gs, os_, "S")):
                         if oarr.size:
                             diffs[(an, b, nm)] = float(np.abs(g - oarr).max())
+                bad = None
                 for (an, b, nm), d in diffs.items():
                     bound = TOL * scales[(an, nm)] + util.ABS_FLOOR * table[nm]
                     worst = max(worst, d / bound)
-                    assert d <= bound, (it, an, b, nm, d, bound)
+                    if d > bound and bad is None:
+                        bad = (it, an, b, nm, d, bound)
+                # every rank learns about a failure before the next collective launch (a rank that stopped iterating would
+                # leave its peers waiting inside the exchange for ever)
+                agree = torch.tensor([0 if bad is None else 1], device=dev)
+                dist.all_reduce(agree, op=dist.ReduceOp.MAX)
+                assert bad is None, bad
+                assert agree.item() == 0, "a peer rank reported a parity failure"
             # best response goes through the same exchange
             br, obr = eng.best_response(), og.best_response()
             assert np.allclose(br, obr, rtol=1e-4, atol=1e-4), (br, obr)
