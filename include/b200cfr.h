@@ -178,6 +178,16 @@ int rs_histogram_distances(const float* p, const float* q, size_t n, uint32_t di
  * are restated as written, including s not being reset between rounds). */
 int rs_kmeans_fit_regular(const float* points, size_t n, uint32_t dim, float* centers, uint32_t k, uint32_t dist_kind,
                           uint32_t rounds, uint32_t* cluster, float* inertia);
+/* Kmeans::fit_growbatch (kmeans.rs:336-494), the fit gen_emd runs (main.rs:368, batch 10 000).  The reference's loop
+ * ends with an unconditional `break` (kmeans.rs:492): ONE pass -- shuffle the data set (SliceRandom::shuffle on the
+ * stated splitmix64(seed) stream: for i in (1..n).rev() swap(i, z % (i + 1))), init_s from f32::MAX, assign the first
+ * initial_batch_size shuffled points with fresh bounds (assignment_with_bounds, kmeans.rs:212-262, on the device),
+ * accumulate them in shuffled order and replace the centres by the means.  centers [k][dim] in/out (k >= 2);
+ * batch_index_out [batch] = data-set index of every batch point, cluster_out [batch] = its centre, stats_out [2] =
+ * {min_change (kmeans.rs:463-467), inertia (kmeans.rs:473)} as the reference prints them; all three may be NULL. */
+int rs_kmeans_fit_growbatch(const float* points, size_t n, uint32_t dim, float* centers, uint32_t k, uint32_t dist_kind,
+                            uint32_t initial_batch_size, uint64_t seed, uint32_t* batch_index_out, uint32_t* cluster_out,
+                            float* stats_out);
 int rs_kmeans_update_min_dists(const float* points, size_t n, uint32_t dim, const float* new_center, uint32_t dist_kind,
                                float* min_dists);
 /* Seeding of the centres.  The reference draws from an unspecified `R: Rng`; here the stream is splitmix64(seed),

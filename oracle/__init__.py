@@ -97,6 +97,7 @@ def _abs_lib():
         lib.orc_kmeans_fit_regular.argtypes = [f32p, C.c_int64, C.c_int, f32p, C.c_int, C.c_int, C.c_int, u32p]
         lib.orc_kmeans_init_pp.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64, u32p]
         lib.orc_kmeans_init_random.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, u32p]
+        lib.orc_kmeans_fit_growbatch.argtypes = [f32p, C.c_int64, C.c_int, f32p, C.c_int, C.c_int, C.c_int, C.c_uint64, u32p, u32p, f32p]
         lib._abs_ready = True
     return lib
 
@@ -134,6 +135,18 @@ def kmeans_fit_regular(points, centers, kind: int = 0, rounds: int = 10):
     inertia = _abs_lib().orc_kmeans_fit_regular(x.ctypes.data_as(f32p), len(x), x.shape[1], c.ctypes.data_as(f32p), len(c), kind, rounds,
                                                cl.ctypes.data_as(u32p))
     return cl, c, float(inertia)
+
+
+def kmeans_fit_growbatch(points, centers, batch: int, kind: int = 0, seed: int = 1):
+    """Kmeans::fit_growbatch (kmeans.rs:336-494, one pass): (batch indices, cluster[batch], new centers, min_change, inertia)."""
+    x = np.ascontiguousarray(points, dtype=np.float32)
+    c = np.array(centers, dtype=np.float32, copy=True, order="C")
+    idx = np.zeros(batch, dtype=np.uint32)
+    cl = np.zeros(batch, dtype=np.uint32)
+    stats = np.zeros(2, dtype=np.float32)
+    _abs_lib().orc_kmeans_fit_growbatch(x.ctypes.data_as(f32p), len(x), x.shape[1], c.ctypes.data_as(f32p), len(c), kind, batch, seed,
+                                        idx.ctypes.data_as(u32p), cl.ctypes.data_as(u32p), stats.ctypes.data_as(f32p))
+    return idx, cl, c, float(stats[0]), float(stats[1])
 
 
 def kmeans_init_pp(points, k: int, kind: int = 0, seed: int = 1) -> np.ndarray:

@@ -300,3 +300,103 @@ void orc_kmeans_init_random(const float* points, int64_t n, int dim, int k, int 
     free(perm);
     free(sets);
 }
+
+
+/* ---- Kmeans::fit_growbatch (kmeans.rs:336-494).  The loop ends with an unconditional `break` (kmeans.rs:492): one pass.
+ *   shuffle             kmeans.rs:350-351   SliceRandom::shuffle (rand 0.7): for i in (1..n).rev() swap(i, gen_range(0, i + 1))
+ *   init_s              kmeans.rs:369       from f32::MAX
+ *   assignment          kmeans.rs:212-262   assignment_with_bounds on the first `batch` shuffled points, bounds (0, MAX), centre 0
+ *   accumulate          kmeans.rs:398-405   shuffled order, f32; square_dist_sum += upper^2
+ *   new centres         kmeans.rs:407-419   bins with positive mass (and a non-empty centre) divided by the count
+ *   movements, bounds   kmeans.rs:421-448   upper += movement of the own centre
+ *   min_change, inertia kmeans.rs:450-473   min over centres of std_dev / (movement + 1e-9); sum of the upper bounds / min(n, 2 * batch)
+ * centers [k][dim] in/out, batch_index [batch], cluster [batch], stats[2] = {min_change, inertia}. */
+void orc_kmeans_fit_growbatch(const float* points, int64_t n, int dim, float* centers, int k, int kind, int batch, uint64_t seed,
+                              uint32_t* batch_index, uint32_t* cluster, float* stats) {
+    uint32_t* perm = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) perm[i] = (uint32_t)i;
+    uint64_t st = seed;
+    for (int64_t i = n - 1; i >= 1; --i) {
+        int64_t j = (int64_t)(sm64(&st) % (uint64_t)(i + 1));
+        uint32_t t = perm[i];
+        perm[i] = perm[j];
+        perm[j] = t;
+    }
+    float* s = (float*)malloc(sizeof(float) * (size_t)k);
+    float* hi = (float*)malloc(sizeof(float) * (size_t)batch);
+    float* mass = (float*)calloc((size_t)k * dim, sizeof(float));
+    float* count = (float*)calloc((size_t)k, sizeof(float));
+    float* sq = (float*)calloc((size_t)k, sizeof(float));
+    float* move = (float*)malloc(sizeof(float) * (size_t)k);
+    for (int i = 0; i < k; ++i) {
+        float v = 3.40282347e+38f;
+        for (int j = 0; j < k; ++j) {
+            if (i == j) continue;
+            float d = dist(centers + (size_t)i * dim, centers + (size_t)j * dim, dim, kind);
+            if (d < v) v = d;
+        }
+        s[i] = v / 2.0f;
+    }
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < batch; ++i) {
+        const float* x = points + (size_t)perm[i] * dim;
+        int min_cluster = 0;
+        float lo = 0.0f, up = 3.40282347e+38f;
+        float ucb = s[0] > lo ? s[0] : lo;
+        cluster[i] = 0;
+        if (!(up <= ucb)) {
+            float u2 = dist(x, centers, dim, kind);
+            up = u2;
+            if (!(up <= ucb)) {
+                float l2 = 3.40282347e+38f;
+                for (int j = 1; j < k; ++j) {
+                    float d2 = dist(x, centers + (size_t)j * dim, dim, kind);
+                    if (d2 < u2) {
+                        l2 = u2;
+                        u2 = d2;
+                        min_cluster = j;
+                    } else if (d2 < l2) {
+                        l2 = d2;
+                    }
+                }
+                if (min_cluster != 0) {
+                    up = u2;
+                    cluster[i] = (uint32_t)min_cluster;
+                }
+            }
+        }
+        hi[i] = up;
+    }
+    for (int i = 0; i < batch; ++i) {
+        uint32_t a = cluster[i];
+        sq[a] += hi[i] * hi[i];
+        count[a] += 1.0f;
+        const float* x = points + (size_t)perm[i] * dim;
+        for (int b = 0; b < dim; ++b) mass[(size_t)a * dim + b] += x[b];
+    }
+    for (int j = 0; j < k; ++j)
+        for (int b = 0; b < dim; ++b)
+            if (mass[(size_t)j * dim + b] > 0.0f && count[j] > 0.0f) mass[(size_t)j * dim + b] /= count[j];
+    float min_change = INFINITY, total = 0.0f;
+    for (int j = 0; j < k; ++j) {
+        move[j] = dist(mass + (size_t)j * dim, centers + (size_t)j * dim, dim, kind);
+        float sd = count[j] <= 1.0f ? INFINITY : sqrtf(fabsf(sq[j] / (count[j] * (count[j] - 1.0f))));
+        float c = sd / (move[j] + 1e-9f);
+        if (c < min_change) min_change = c;
+    }
+    for (int i = 0; i < batch; ++i) total += hi[i] + move[cluster[i]];
+    int64_t next_batch = (int64_t)batch * 2 < n ? (int64_t)batch * 2 : n;
+    memcpy(centers, mass, sizeof(float) * (size_t)k * dim);
+    if (batch_index) memcpy(batch_index, perm, sizeof(uint32_t) * (size_t)batch);
+    if (stats) {
+        stats[0] = min_change;
+        stats[1] = total / (float)next_batch;
+    }
+    free(perm);
+    free(s);
+    free(hi);
+    free(mass);
+    free(count);
+    free(sq);
+    free(move);
+}

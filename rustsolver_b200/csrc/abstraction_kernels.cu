@@ -19,6 +19,8 @@
 #include "../../include/b200cfr.h"
 #include "abstraction_kernels.h"
 
+#include <cmath>
+
 namespace rs {
 
 namespace {
@@ -499,6 +501,101 @@ bool gpu_kmeans_init_random(const float* points, size_t n, uint32_t dim, uint32_
         }
     }
     memcpy(chosen, &sets[size_t(best) * k], k * sizeof(uint32_t));
+    return true;
+}
+
+// Kmeans::fit_growbatch as the reference runs it (kmeans.rs:336-494; gen_emd calls it with a batch of 10 000, main.rs:368).
+// Its loop ends with an unconditional `break` (kmeans.rs:492), so the fit is ONE pass: shuffle the data set, init_s from
+// f32::MAX, assign the first `batch` shuffled points with fresh bounds (0, MAX) -- assignment_with_bounds (kmeans.rs:212-262)
+// is reassign_clusters on the shuffled slice, same kernel --, accumulate them in shuffled order and replace the centres
+// by the means.  The statistics the reference prints (min_change = min std_dev / movement, inertia = sum of the updated
+// upper bounds / min(n, 2 * batch)) are returned for parity.  Shuffle: rand 0.7's SliceRandom::shuffle,
+// `for i in (1..n).rev() { swap(i, gen_range(0, i + 1)) }`, on the stated splitmix64 stream.
+bool gpu_kmeans_fit_growbatch(const float* points, size_t n, uint32_t dim, float* centers, uint32_t k, uint32_t kind, uint32_t batch, uint64_t seed,
+                              uint32_t* batch_index, uint32_t* cluster, float* stats, std::string* err) {
+    std::vector<uint32_t> perm(n);
+    for (size_t i = 0; i < n; ++i) perm[i] = uint32_t(i);
+    uint64_t st = seed;
+    for (size_t i = n - 1; i >= 1; --i) std::swap(perm[i], perm[size_t(sm64(st) % uint64_t(i + 1))]);
+    std::vector<float> bp(size_t(batch) * dim);
+    for (uint32_t i = 0; i < batch; ++i) memcpy(&bp[size_t(i) * dim], points + size_t(perm[i]) * dim, dim * sizeof(float));
+    Dev<float> d_pts, d_ctr, d_new, d_s, d_lo, d_hi, d_move;
+    Dev<uint32_t> d_cl;
+    ABS_CU(d_pts.alloc(size_t(batch) * dim));
+    ABS_CU(d_ctr.alloc(size_t(k) * dim));
+    ABS_CU(d_new.alloc(size_t(k) * dim));
+    ABS_CU(d_s.alloc(k));
+    ABS_CU(d_lo.alloc(batch));
+    ABS_CU(d_hi.alloc(batch));
+    ABS_CU(d_move.alloc(k));
+    ABS_CU(d_cl.alloc(batch));
+    const float fmax = 3.40282347e+38f;
+    std::vector<float> h_s(k, fmax), h_hi(batch, fmax), h_mass(size_t(k) * dim, 0.0f), h_count(k, 0.0f), h_sq(k, 0.0f), h_move(k);
+    std::vector<uint32_t> h_cl(batch, 0);
+    ABS_CU(cudaMemcpy(d_pts.p, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ABS_CU(cudaMemcpy(d_ctr.p, centers, size_t(k) * dim * sizeof(float), cudaMemcpyHostToDevice));
+    ABS_CU(cudaMemcpy(d_s.p, h_s.data(), k * sizeof(float), cudaMemcpyHostToDevice));
+    ABS_CU(cudaMemcpy(d_hi.p, h_hi.data(), batch * sizeof(float), cudaMemcpyHostToDevice));
+    ABS_CU(cudaMemset(d_lo.p, 0, size_t(batch) * sizeof(float)));
+    ABS_CU(cudaMemset(d_cl.p, 0, size_t(batch) * sizeof(uint32_t)));
+    const size_t smem = smem_bytes(int(dim));
+    ABS_CU(cudaFuncSetAttribute(centre_half_min_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    ABS_CU(cudaFuncSetAttribute(kmeans_reassign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    ABS_CU(cudaFuncSetAttribute(pair_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const unsigned pblocks = unsigned((batch + ABS_THREADS - 1) / ABS_THREADS), cblocks = unsigned((k + ABS_THREADS - 1) / ABS_THREADS);
+    centre_half_min_kernel<<<cblocks, ABS_THREADS, smem>>>(d_ctr.p, int(k), int(dim), int(kind), d_s.p);
+    kmeans_reassign_kernel<<<pblocks, ABS_THREADS, smem>>>(d_pts.p, batch, int(dim), d_ctr.p, int(k), int(kind), d_s.p, d_cl.p, d_lo.p, d_hi.p);
+    ABS_CU(cudaGetLastError());
+    ABS_CU(cudaMemcpy(h_cl.data(), d_cl.p, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    ABS_CU(cudaMemcpy(h_hi.data(), d_hi.p, batch * sizeof(float), cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < batch; ++i) {  // kmeans.rs:398-405, shuffled order, f32
+        const uint32_t a = h_cl[i];
+        h_sq[a] += h_hi[i] * h_hi[i];  // powf(2.0)
+        h_count[a] += 1.0f;
+        float* m = &h_mass[size_t(a) * dim];
+        const float* x = &bp[size_t(i) * dim];
+        for (uint32_t b = 0; b < dim; ++b) m[b] += x[b];
+    }
+    for (uint32_t j = 0; j < k; ++j)
+        for (uint32_t b = 0; b < dim; ++b)
+            if (h_mass[size_t(j) * dim + b] > 0.0f && h_count[j] > 0.0f) h_mass[size_t(j) * dim + b] /= h_count[j];
+    ABS_CU(cudaMemcpy(d_new.p, h_mass.data(), size_t(k) * dim * sizeof(float), cudaMemcpyHostToDevice));
+    pair_dist_kernel<<<cblocks, ABS_THREADS, smem>>>(d_new.p, d_ctr.p, dim, k, int(dim), int(kind), d_move.p);
+    ABS_CU(cudaGetLastError());
+    ABS_CU(cudaMemcpy(h_move.data(), d_move.p, k * sizeof(float), cudaMemcpyDeviceToHost));
+    int longest_idx = 0;
+    float longest = h_move[0], second = h_move[1];
+    if (longest < second) {
+        longest = h_move[1];
+        second = h_move[0];
+        longest_idx = 1;
+    }
+    for (uint32_t j = 2; j < k; ++j) {
+        if (longest < h_move[j]) {
+            second = longest;
+            longest = h_move[j];
+            longest_idx = int(j);
+        } else if (second < h_move[j]) {
+            second = h_move[j];
+        }
+    }
+    (void)longest_idx;
+    (void)second;
+    float min_change = INFINITY, total = 0.0f;
+    for (uint32_t j = 0; j < k; ++j) {  // kmeans.rs:450-467
+        const float sd = h_count[j] <= 1.0f ? INFINITY : sqrtf(fabsf(h_sq[j] / (h_count[j] * (h_count[j] - 1.0f))));
+        const float c = sd / (h_move[j] + 1e-9f);
+        if (c < min_change) min_change = c;
+    }
+    for (uint32_t i = 0; i < batch; ++i) total += h_hi[i] + h_move[h_cl[i]];  // the upper bounds after the update (kmeans.rs:441,473)
+    const size_t next_batch = std::min<size_t>(n, size_t(batch) * 2);
+    memcpy(centers, h_mass.data(), size_t(k) * dim * sizeof(float));
+    if (batch_index) memcpy(batch_index, perm.data(), size_t(batch) * sizeof(uint32_t));
+    if (cluster) memcpy(cluster, h_cl.data(), size_t(batch) * sizeof(uint32_t));
+    if (stats) {
+        stats[0] = min_change;
+        stats[1] = total / float(next_batch);
+    }
     return true;
 }
 

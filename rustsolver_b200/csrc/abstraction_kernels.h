@@ -23,6 +23,8 @@ bool gpu_kmeans_fit_regular(const float* points, size_t n, uint32_t dim, float* 
 // Kmeans::init_pp (kmeans.rs:60-90) and Kmeans::init_random (kmeans.rs:103-166) with a stated splitmix64 stream:
 // chosen[k] = indices of the points taken as centres
 bool gpu_kmeans_init_pp(const float* points, size_t n, uint32_t dim, uint32_t k, uint32_t kind, uint64_t seed, uint32_t* chosen, std::string* err);
+bool gpu_kmeans_fit_growbatch(const float* points, size_t n, uint32_t dim, float* centers, uint32_t k, uint32_t kind, uint32_t batch, uint64_t seed,
+                              uint32_t* batch_index, uint32_t* cluster, float* stats, std::string* err);
 bool gpu_kmeans_init_random(const float* points, size_t n, uint32_t dim, uint32_t k, uint32_t n_restarts, uint32_t kind, uint64_t seed,
                             uint32_t* chosen, std::string* err);
 

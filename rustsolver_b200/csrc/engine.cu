@@ -1109,6 +1109,19 @@ int rs_kmeans_fit_regular(const float* points, size_t n, uint32_t dim, float* ce
     return RS_OK;
 }
 
+int rs_kmeans_fit_growbatch(const float* points, size_t n, uint32_t dim, float* centers, uint32_t k, uint32_t dist_kind, uint32_t initial_batch_size,
+                            uint64_t seed, uint32_t* batch_index_out, uint32_t* cluster_out, float* stats_out) {
+    int rc = abstraction_args_ok(points, centers, dim, dist_kind);
+    if (rc != RS_OK) return rc;
+    if (k < 2) return set_err(RS_ERR_INVALID, "fit_growbatch needs at least two centres (kmeans.rs:423-424 reads center_movements[1])");
+    if (initial_batch_size == 0 || size_t(initial_batch_size) > n)
+        return set_err(RS_ERR_INVALID, "need 1 <= initial_batch_size <= n (the reference indexes shuffled_data[0 .. batch))");
+    std::string err;
+    if (!gpu_kmeans_fit_growbatch(points, n, dim, centers, k, dist_kind, initial_batch_size, seed, batch_index_out, cluster_out, stats_out, &err))
+        return set_err(RS_ERR_CUDA, err);
+    return RS_OK;
+}
+
 int rs_histogram_distances(const float* p, const float* q, size_t n, uint32_t dim, uint32_t dist_kind, float* out) {
     int rc = abstraction_args_ok(p, q, dim, dist_kind);
     if (rc != RS_OK) return rc;

@@ -251,6 +251,21 @@ def kmeans_fit_regular(points: np.ndarray, centers: np.ndarray, dist: int = RS_D
     return cl, c, float(inertia.value)
 
 
+def kmeans_fit_growbatch(points: np.ndarray, centers: np.ndarray, initial_batch_size: int, dist: int = RS_DIST_EMD_1D, seed: int = 1):
+    """Kmeans::fit_growbatch (kmeans.rs:336-494; one pass, its loop ends with `break`) on the GPU:
+    (batch indices [batch], cluster [batch], new centers [k][dim], min_change, inertia)."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(points, dtype=np.float32)
+    c = np.array(centers, dtype=np.float32, copy=True, order="C")
+    assert x.ndim == 2 and c.ndim == 2 and x.shape[1] == c.shape[1]
+    idx = np.zeros(initial_batch_size, dtype=np.uint32)
+    cl = np.zeros(initial_batch_size, dtype=np.uint32)
+    stats = np.zeros(2, dtype=np.float32)
+    check(lib.rs_kmeans_fit_growbatch(_ptr(x, f32p), len(x), x.shape[1], _ptr(c, f32p), len(c), dist, initial_batch_size, seed,
+                                      _ptr(idx, u32p), _ptr(cl, u32p), _ptr(stats, f32p)))
+    return idx, cl, c, float(stats[0]), float(stats[1])
+
+
 def histogram_distances(p: np.ndarray, q: np.ndarray, dist: int = RS_DIST_EMD_1D) -> np.ndarray:
     """out[i] = emd_1d(p[i], q[i]) (emd.rs:54-113) or l2_dist (kmeans.rs:622-630) on the GPU."""
     lib = _lib.load()

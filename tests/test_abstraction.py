@@ -131,3 +131,24 @@ def test_kmeans_seeding_restatements():
         c = x[idx]
         return np.mean([oracle.emd_1d(c[i], c[j]) for i in range(6) for j in range(6) if i != j])
     assert spread(ch) >= spread(oracle.kmeans_init_random(x, 6, 1, 0, 4)) - 1e-6
+
+
+def test_fit_growbatch_is_one_mini_batch_step():
+    """Kmeans::fit_growbatch (kmeans.rs:336-494) ends its loop with `break`: one pass over the first `batch` shuffled points.
+    The restatement's assignment equals the nearest centre (first on ties) and the new centres are the batch means."""
+    rng = np.random.default_rng(5)
+    x = K.random_histograms(rng, 800, 20)
+    c0 = x[rng.choice(len(x), 9, replace=False)].copy()
+    for kind in (0, 1):
+        idx, cl, c, min_change, inertia = oracle.kmeans_fit_growbatch(x, c0, 300, kind, seed=11)
+        assert len(set(idx.tolist())) == 300 and idx.max() < len(x)  # a prefix of a permutation
+        idx2, *_ = oracle.kmeans_fit_growbatch(x, c0, 800, kind, seed=11)
+        assert sorted(idx2.tolist()) == list(range(len(x))) and np.array_equal(idx2[:300], idx)
+        want, _, _ = oracle.kmeans_predict(x[idx], c0, kind)
+        assert np.array_equal(cl, want)
+        for j in range(len(c0)):
+            members = x[idx][cl == j]
+            if len(members):
+                mean = members.astype(np.float64).mean(axis=0)
+                assert np.allclose(c[j], mean, rtol=1e-5, atol=1e-7)
+        assert np.isfinite(inertia) and inertia > 0 and min_change > 0

@@ -84,3 +84,20 @@ def test_kmeans_seeding_matches_the_cpu_restatement(kind):
         chosen, centers = rb.kmeans_init_random(x, 12, 7, kind, seed)
         assert np.array_equal(chosen, oracle.kmeans_init_random(x, 12, 7, kind, seed))
         assert np.array_equal(centers, x[chosen]) and len(set(chosen.tolist())) == 12
+
+
+@pytest.mark.parametrize("kind", [rb.RS_DIST_EMD_1D, rb.RS_DIST_L2])
+def test_fit_growbatch_matches_the_cpu_restatement(kind):
+    """Kmeans::fit_growbatch (kmeans.rs:336-494; one pass because its loop ends with `break`): shuffle, init_s,
+    assignment_with_bounds of the first batch, mean update -- device vs CPU restatement, bit for bit."""
+    rng = np.random.default_rng(77 + kind)
+    x = K.random_histograms(rng, 5000, 30)
+    c0 = x[rng.choice(len(x), 24, replace=False)].copy()
+    for batch, seed in ((1000, 3), (5000, 4)):
+        idx, cl, c, mc, inertia = rb.kmeans_fit_growbatch(x, c0, batch, kind, seed)
+        oidx, ocl, oc, omc, oin = oracle.kmeans_fit_growbatch(x, c0, batch, kind, seed)
+        assert np.array_equal(idx, oidx)
+        assert np.array_equal(cl, ocl)
+        assert np.array_equal(c, oc)
+        assert mc == omc and inertia == oin
+        assert len(np.unique(cl)) > 5
