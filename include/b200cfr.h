@@ -178,6 +178,16 @@ int rs_histogram_distances(const float* p, const float* q, size_t n, uint32_t di
  * are restated as written, including s not being reset between rounds). */
 int rs_kmeans_fit_regular(const float* points, size_t n, uint32_t dim, float* centers, uint32_t k, uint32_t dist_kind,
                           uint32_t rounds, uint32_t* cluster, float* inertia);
+/* generate_histograms (gen_abstraction/main.rs:79-159): the k-means features.  For the canonical hands
+ * [first_index, first_index + count) of `round` (0 preflop .. 3 river; indexers of ehs.rs:26-31, un-indexed like
+ * main.rs:117-121) draw `samples` random completions of the board (rejection sampling, main.rs:129-140), bin the EHS of
+ * the seven cards (get_bin, main.rs:58-70) and divide by the sample count.  The reference looks the EHS up in ehs.dat,
+ * a Monte-Carlo table this repository does not have (src/bin/gen_ehs.rs, out of scope); here it is computed exactly
+ * on the device: (wins + ties / 2) / 990 against every opponent hole-card combo.  Random stream of hand i: splitmix64
+ * from seed + 0x9E3779B97F4A7C15 * (i + 1), card = z % 52, redrawn while taken.  out [count][bins] (bins <= 128);
+ * cards_out [count][7] (may be NULL) = the un-indexed hands (first 2 + board cards of every row); kernel_ms may be NULL. */
+int rs_generate_histograms(uint32_t round, uint64_t first_index, size_t count, uint32_t samples, uint32_t bins, uint64_t seed,
+                           float* out, uint8_t* cards_out, float* kernel_ms);
 /* Kmeans::fit_growbatch (kmeans.rs:336-494), the fit gen_emd runs (main.rs:368, batch 10 000).  The reference's loop
  * ends with an unconditional `break` (kmeans.rs:492): ONE pass -- shuffle the data set (SliceRandom::shuffle on the
  * stated splitmix64(seed) stream: for i in (1..n).rev() swap(i, z % (i + 1))), init_s from f32::MAX, assign the first

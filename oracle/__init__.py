@@ -97,6 +97,7 @@ def _abs_lib():
         lib.orc_kmeans_fit_regular.argtypes = [f32p, C.c_int64, C.c_int, f32p, C.c_int, C.c_int, C.c_int, u32p]
         lib.orc_kmeans_init_pp.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64, u32p]
         lib.orc_kmeans_init_random.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, u32p]
+        lib.orc_generate_histograms.argtypes = [u8p, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_uint64, f32p]
         lib.orc_kmeans_fit_growbatch.argtypes = [f32p, C.c_int64, C.c_int, f32p, C.c_int, C.c_int, C.c_int, C.c_uint64, u32p, u32p, f32p]
         lib._abs_ready = True
     return lib
@@ -135,6 +136,14 @@ def kmeans_fit_regular(points, centers, kind: int = 0, rounds: int = 10):
     inertia = _abs_lib().orc_kmeans_fit_regular(x.ctypes.data_as(f32p), len(x), x.shape[1], c.ctypes.data_as(f32p), len(c), kind, rounds,
                                                cl.ctypes.data_as(u32p))
     return cl, c, float(inertia)
+
+
+def generate_histograms(cards7, n_known: int, first_index: int, samples: int, bins: int, seed: int = 1) -> np.ndarray:
+    """generate_histograms (gen_abstraction/main.rs:79-159) with the EHS computed exactly; cards7 [count][7] = the un-indexed hands."""
+    c = np.ascontiguousarray(cards7, dtype=np.uint8)
+    out = np.zeros((len(c), bins), dtype=np.float32)
+    _abs_lib().orc_generate_histograms(c.ctypes.data_as(u8p), n_known, first_index, len(c), samples, bins, seed, out.ctypes.data_as(f32p))
+    return out
 
 
 def kmeans_fit_growbatch(points, centers, batch: int, kind: int = 0, seed: int = 1):

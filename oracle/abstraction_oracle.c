@@ -400,3 +400,67 @@ void orc_kmeans_fit_growbatch(const float* points, int64_t n, int dim, float* ce
     free(sq);
     free(move);
 }
+
+
+/* ---- generate_histograms (gen_abstraction/main.rs:79-159) with the EHS computed exactly (the reference reads ehs.dat, a
+ * Monte-Carlo table of the same quantity written by src/bin/gen_ehs.rs).
+ *   hands               main.rs:117-121   un-indexed by the caller: cards7 [count][7], the first n_known of every row
+ *   board completion    main.rs:129-140   rejection sampling; stream of hand i = splitmix64 from seed + GOLDEN * (i + 1), card = z % 52
+ *   EHS                 ehs.rs get_ehs    here: (wins + ties / 2) / 990 over the C(45, 2) opponent hole-card combos, one f32 division
+ *   get_bin             main.rs:58-70     thresholds by repeated f32 subtraction
+ *   normalisation       main.rs:146-148   every bin divided by the sample count (f32)
+ * out [count][bins]. */
+uint32_t orc_evaluate(const uint8_t* cards, int n);
+static int hist_get_bin(float value, int bins) {
+    float interval = 1.0f / (float)bins;
+    int bin = bins - 1;
+    float threshold = 1.0f - interval;
+    while (bin > 0) {
+        if (value > threshold) return bin;
+        bin -= 1;
+        threshold -= interval;
+    }
+    return 0;
+}
+void orc_generate_histograms(const uint8_t* cards7, int n_known, uint64_t first_index, int64_t count, int samples, int bins, uint64_t seed, float* out) {
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t h = 0; h < count; ++h) {
+        uint8_t c[7];
+        uint64_t known = 0;
+        for (int k = 0; k < n_known; ++k) {
+            c[k] = cards7[h * 7 + k];
+            known |= 1ull << c[k];
+        }
+        uint64_t st = seed + 0x9E3779B97F4A7C15ull * (first_index + (uint64_t)h + 1);
+        float* hist = out + h * bins;
+        for (int b = 0; b < bins; ++b) hist[b] = 0.0f;
+        for (int s = 0; s < samples; ++s) {
+            uint64_t m = known;
+            for (int k = n_known; k < 7; ++k) {
+                for (;;) {
+                    int x = (int)(sm64(&st) % 52ull);
+                    if (!((m >> x) & 1ull)) {
+                        m |= 1ull << x;
+                        c[k] = (uint8_t)x;
+                        break;
+                    }
+                }
+            }
+            uint32_t hero = orc_evaluate(c, 7);
+            uint8_t o[7];
+            for (int k = 2; k < 7; ++k) o[k] = c[k];
+            unsigned tot = 0;
+            for (int a = 1; a < 52; ++a)
+                for (int b = 0; b < a; ++b) {
+                    if (((m >> a) & 1ull) || ((m >> b) & 1ull)) continue;
+                    o[0] = (uint8_t)a;
+                    o[1] = (uint8_t)b;
+                    uint32_t sc = orc_evaluate(o, 7);
+                    tot += sc < hero ? 2u : (sc == hero ? 1u : 0u);
+                }
+            float ehs = (float)tot / 1980.0f;
+            hist[hist_get_bin(ehs, bins)] += 1.0f;
+        }
+        for (int b = 0; b < bins; ++b) hist[b] /= (float)samples;
+    }
+}

@@ -71,6 +71,7 @@ ENGINE_API = {
     "rs_histogram_distances": (C.c_int, [f32p, f32p, C.c_size_t, C.c_uint32, C.c_uint32, f32p]),
     "rs_kmeans_update_min_dists": (C.c_int, [f32p, C.c_size_t, C.c_uint32, f32p, C.c_uint32, f32p]),
     "rs_kmeans_init_pp": (C.c_int, [f32p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, u32p, f32p]),
+    "rs_generate_histograms": (C.c_int, [C.c_uint32, C.c_uint64, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint64, f32p, u8p, f32p]),
     "rs_kmeans_fit_growbatch": (C.c_int, [f32p, C.c_size_t, C.c_uint32, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, u32p, u32p, f32p]),
     "rs_kmeans_init_random": (C.c_int, [f32p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, u32p, f32p]),
     "rs_gpu_index_hands": (C.c_int, [C.c_uint32, u8p, C.c_size_t, u64p, f32p]),

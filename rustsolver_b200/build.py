@@ -16,7 +16,7 @@ CSRC = ROOT / "rustsolver_b200" / "csrc"
 ENGINE_SO = ROOT / "rustsolver_b200" / "libb200cfr.so"
 ORACLE_SO = ROOT / "oracle" / "liborc.so"
 
-ENGINE_SOURCES = ["kernels.cu", "street_kernel.cu", "indexer_kernel.cu", "abstraction_kernels.cu", "engine.cu", "plan.cpp", "poker.cpp", "game.cpp", "hand_indexer.cpp",
+ENGINE_SOURCES = ["kernels.cu", "street_kernel.cu", "indexer_kernel.cu", "abstraction_kernels.cu", "histogram_kernel.cu", "engine.cu", "plan.cpp", "poker.cpp", "game.cpp", "hand_indexer.cpp",
                   "trainer.cpp", "host_api.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall,-O3"]

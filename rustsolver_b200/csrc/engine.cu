@@ -18,6 +18,7 @@
 #include <cmath>
 
 #include "abstraction_kernels.h"
+#include "histogram_kernel.h"
 #include "indexer_kernel.h"
 #include "kernels.cuh"
 #include "plan.h"
@@ -1119,6 +1120,31 @@ int rs_kmeans_fit_growbatch(const float* points, size_t n, uint32_t dim, float* 
     std::string err;
     if (!gpu_kmeans_fit_growbatch(points, n, dim, centers, k, dist_kind, initial_batch_size, seed, batch_index_out, cluster_out, stats_out, &err))
         return set_err(RS_ERR_CUDA, err);
+    return RS_OK;
+}
+
+int rs_generate_histograms(uint32_t round, uint64_t first_index, size_t count, uint32_t samples, uint32_t bins, uint64_t seed, float* out,
+                           uint8_t* cards_out, float* kernel_ms) {
+    if (!out) return set_err(RS_ERR_INVALID, "null argument");
+    if (round > 3) return set_err(RS_ERR_INVALID, "round must be 0 (preflop) .. 3 (river)");
+    if (samples == 0 || bins == 0 || bins > HIST_MAX_BINS) return set_err(RS_ERR_INVALID, "need samples >= 1 and 1 <= bins <= 128");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(RS_ERR_CUDA, "no CUDA device available (no CPU fallback)");
+    // EHS::new()'s indexers (ehs.rs:26-31): [2] for the preflop, [2, 3 / 4 / 5] afterwards; hands of the LAST round
+    static const uint8_t board_cards[4] = {0, 3, 4, 5};
+    HandIndexer ix;
+    const bool ok = round == 0 ? ix.init(1, {2}) : ix.init(2, {2, board_cards[round]});
+    if (!ok) return set_err(RS_ERR_INVALID, "hand indexer init failed");
+    const int ir = round == 0 ? 0 : 1;
+    const uint64_t size = ix.size(ir);
+    if (first_index > size || count > size - first_index) return set_err(RS_ERR_INVALID, "index range exceeds the round size " + std::to_string(size));
+    const uint32_t n_known = 2 + board_cards[round];
+    std::vector<uint8_t> cards(count * 7, 0);
+    for (size_t i = 0; i < count; ++i)
+        if (!ix.get_hand(ir, first_index + i, &cards[i * 7])) return set_err(RS_ERR_INVALID, "hand un-index failed");
+    if (cards_out) memcpy(cards_out, cards.data(), cards.size());
+    std::string err;
+    if (!gpu_generate_histograms(cards.data(), n_known, first_index, count, samples, bins, seed, out, kernel_ms, &err)) return set_err(RS_ERR_CUDA, err);
     return RS_OK;
 }
 

@@ -1,102 +1,14 @@
 #include "poker.h"
 
+#include "eval_inline.h"
+
 #include <algorithm>
 #include <cstring>
 
 namespace rs {
 
-namespace {
-
-// Highest rank of a 5-long run in a 13-bit rank mask (wheel counts, top = rank 3); -1 if none.
-inline int straight_high(uint32_t ranks) {
-    uint32_t m = (ranks << 1) | ((ranks >> 12) & 1u);  // bit 0 = ace played low
-    uint32_t run = m & (m >> 1) & (m >> 2) & (m >> 3) & (m >> 4);
-    if (!run) return -1;
-    int i = 31 - __builtin_clz(run);
-    return i + 3;
-}
-
-inline uint32_t pack(int cat, int a, int b = 0, int c = 0, int d = 0, int e = 0) {
-    return (uint32_t(cat) << 20) | (uint32_t(a) << 16) | (uint32_t(b) << 12) | (uint32_t(c) << 8) |
-           (uint32_t(d) << 4) | uint32_t(e);
-}
-
-// top `n` set bits of a rank mask, written high to low into out[]
-inline void top_ranks(uint32_t mask, int n, int* out) {
-    for (int i = 0; i < n; ++i) {
-        if (!mask) { out[i] = 0; continue; }
-        int r = 31 - __builtin_clz(mask);
-        out[i] = r;
-        mask &= ~(1u << r);
-    }
-}
-
-}  // namespace
-
-uint32_t evaluate_mask(uint64_t cards) {
-    uint32_t suit_ranks[4] = {0, 0, 0, 0};
-    int cnt[13];
-    std::memset(cnt, 0, sizeof(cnt));
-    uint64_t m = cards;
-    while (m) {
-        int c = __builtin_ctzll(m);
-        m &= m - 1;
-        suit_ranks[c & 3] |= 1u << (c >> 2);
-        cnt[c >> 2]++;
-    }
-    uint32_t all = suit_ranks[0] | suit_ranks[1] | suit_ranks[2] | suit_ranks[3];
-
-    int flush_suit = -1;
-    for (int s = 0; s < 4; ++s)
-        if (__builtin_popcount(suit_ranks[s]) >= 5) flush_suit = s;
-    if (flush_suit >= 0) {
-        int sf = straight_high(suit_ranks[flush_suit]);
-        if (sf >= 0) return pack(8, sf);
-    }
-    uint32_t quads = 0, trips = 0, pairs = 0;
-    for (int r = 0; r < 13; ++r) {
-        if (cnt[r] == 4) quads |= 1u << r;
-        else if (cnt[r] == 3) trips |= 1u << r;
-        else if (cnt[r] == 2) pairs |= 1u << r;
-    }
-    int k[5];
-    if (quads) {
-        int q = 31 - __builtin_clz(quads);
-        top_ranks(all & ~(1u << q), 1, k);
-        return pack(7, q, k[0]);
-    }
-    if (trips && (pairs || (trips & (trips - 1)))) {
-        int t = 31 - __builtin_clz(trips);
-        uint32_t rest = (trips & ~(1u << t)) | pairs;
-        int p = 31 - __builtin_clz(rest);
-        return pack(6, t, p);
-    }
-    if (flush_suit >= 0) {
-        top_ranks(suit_ranks[flush_suit], 5, k);
-        return pack(5, k[0], k[1], k[2], k[3], k[4]);
-    }
-    int st = straight_high(all);
-    if (st >= 0) return pack(4, st);
-    if (trips) {
-        int t = 31 - __builtin_clz(trips);
-        top_ranks(all & ~(1u << t), 2, k);
-        return pack(3, t, k[0], k[1]);
-    }
-    if (pairs & (pairs - 1)) {
-        int p1 = 31 - __builtin_clz(pairs);
-        uint32_t rest = pairs & ~(1u << p1);
-        int p2 = 31 - __builtin_clz(rest);
-        top_ranks(all & ~(1u << p1) & ~(1u << p2), 1, k);
-        return pack(2, p1, p2, k[0]);
-    }
-    if (pairs) {
-        int p = 31 - __builtin_clz(pairs);
-        top_ranks(all & ~(1u << p), 3, k);
-        return pack(1, p, k[0], k[1], k[2]);
-    }
-    top_ranks(all, 5, k);
-    return pack(0, k[0], k[1], k[2], k[3], k[4]);
-}
+// the evaluator is one inline function shared with the device code (eval_inline.h)
+uint32_t evaluate_mask(uint64_t cards) { return evaluate_mask_inline(cards); }
 
 uint32_t evaluate_cards(const uint8_t* cards, int n) {
     uint64_t m = 0;

@@ -251,6 +251,17 @@ def kmeans_fit_regular(points: np.ndarray, centers: np.ndarray, dist: int = RS_D
     return cl, c, float(inertia.value)
 
 
+def generate_histograms(round_: int, first_index: int, count: int, samples: int, bins: int, seed: int = 1, return_ms: bool = False):
+    """generate_histograms (gen_abstraction/main.rs:79-159) on the GPU with the EHS computed exactly instead of read from
+    ehs.dat: (histograms [count][bins], un-indexed hands [count][7])."""
+    lib = _lib.load()
+    out = np.zeros((count, bins), dtype=np.float32)
+    cards = np.zeros((count, 7), dtype=np.uint8)
+    ms = C.c_float(0.0)
+    check(lib.rs_generate_histograms(round_, first_index, count, samples, bins, seed, _ptr(out, f32p), _ptr(cards, u8p), C.byref(ms)))
+    return (out, cards, float(ms.value)) if return_ms else (out, cards)
+
+
 def kmeans_fit_growbatch(points: np.ndarray, centers: np.ndarray, initial_batch_size: int, dist: int = RS_DIST_EMD_1D, seed: int = 1):
     """Kmeans::fit_growbatch (kmeans.rs:336-494; one pass, its loop ends with `break`) on the GPU:
     (batch indices [batch], cluster [batch], new centers [k][dim], min_change, inertia)."""

@@ -152,3 +152,30 @@ def test_fit_growbatch_is_one_mini_batch_step():
                 mean = members.astype(np.float64).mean(axis=0)
                 assert np.allclose(c[j], mean, rtol=1e-5, atol=1e-7)
         assert np.isfinite(inertia) and inertia > 0 and min_change > 0
+
+
+def test_generate_histograms_restatement():
+    """generate_histograms (gen_abstraction/main.rs:79-159) with the EHS computed exactly: every row is a distribution over
+    the bins; on the river nothing is left to draw, so a row is one spike at the bin of the hand's equity; a royal flush
+    sits in the top bin, and the equities follow the evaluator's order."""
+    import rustsolver_b200 as rb
+    ix = rb.HandIndexer([2, 5])
+    first, count, bins = 1000, 24, 30
+    cards = np.zeros((count, 7), dtype=np.uint8)
+    for i in range(count):
+        cards[i] = ix.get_hand(1, first + i)
+    h = oracle.generate_histograms(cards, 7, first, samples=5, bins=bins, seed=3)
+    assert h.shape == (count, bins) and np.allclose(h.sum(axis=1), 1.0)
+    assert ((h == 1.0).sum(axis=1) == 1).all()
+    royal = np.array([[4 * 12, 4 * 11, 4 * 10, 4 * 9, 4 * 8, 1, 6]], dtype=np.uint8)  # As Ks | Qs Js Ts 2h 3c
+    assert oracle.generate_histograms(royal, 7, 0, 3, bins, 1)[0, bins - 1] == 1.0
+    # flop hands: 2 cards drawn per sample, rows are distributions, the stream depends on the hand index and the seed only
+    ixf = rb.HandIndexer([2, 3])
+    cf = np.zeros((8, 7), dtype=np.uint8)
+    for i in range(8):
+        cf[i, :5] = ixf.get_hand(1, 500 + i)
+    a = oracle.generate_histograms(cf, 5, 500, samples=40, bins=10, seed=9)
+    b = oracle.generate_histograms(cf[3:], 5, 503, samples=40, bins=10, seed=9)
+    assert np.allclose(a.sum(axis=1), 1.0) and (a > 0).sum(axis=1).min() >= 2
+    assert np.array_equal(a[3:], b)
+    assert not np.array_equal(a, oracle.generate_histograms(cf, 5, 500, samples=40, bins=10, seed=10))

@@ -101,3 +101,16 @@ def test_fit_growbatch_matches_the_cpu_restatement(kind):
         assert np.array_equal(c, oc)
         assert mc == omc and inertia == oin
         assert len(np.unique(cl)) > 5
+
+
+@pytest.mark.parametrize("round_,first,count,samples,bins", [(0, 0, 169, 60, 30), (1, 12345, 40, 50, 50), (2, 999999, 32, 40, 30), (3, 5000000, 48, 3, 20)])
+def test_generate_histograms_matches_the_cpu_restatement(round_, first, count, samples, bins):
+    """generate_histograms (gen_abstraction/main.rs:79-159) on the device, EHS computed exactly: bit for bit the CPU
+    restatement's histograms on the hands the product un-indexed (the indexer is pinned separately, tests/test_poker.py)."""
+    h, cards = rb.generate_histograms(round_, first, count, samples, bins, seed=21)
+    n_known = [2, 5, 6, 7][round_]
+    want = oracle.generate_histograms(cards, n_known, first, samples, bins, seed=21)
+    assert np.array_equal(h, want), np.abs(h - want).max()
+    assert np.allclose(h.sum(axis=1), 1.0)
+    ix = rb.HandIndexer([2] if round_ == 0 else [2, [0, 3, 4, 5][round_]])
+    assert list(cards[3, :n_known]) == list(ix.get_hand(0 if round_ == 0 else 1, first + 3))
