@@ -376,6 +376,12 @@ int rs_plan_showdown_order(const rs_plan* p, uint32_t player, uint32_t board_id,
 /* The final betting round as the fused street kernel sees it (csrc/street.h): out = {eligible, segments, max reach rows
  * per segment, max value slots, max showdown quads, max mass-only quads, opponent-node ops, traverser-node ops}.  When
  * the round is not eligible rs_last_error() says why (bucketed tables, a node wider than 5 actions, the flag). */
+/* The board-local index tables the traversal kernel evaluates terminals with (csrc/tasks.h: HandRec and the cl_pos entry
+ * format), for host-side checks: hrec_words_out [Hpad][4] = `player` as traverser, cl_pos_out [2 * Hpad] = `player` as
+ * opponent, slot_of_pos_out [Hpad] = hand slot at every board-local position; dims_out = {Hpad, live hands}.  Any output
+ * pointer may be NULL; call once with all NULL to size the buffers. */
+int rs_plan_local_tables(const rs_plan* p, uint32_t round_idx, uint32_t player, uint32_t board_id, uint32_t* hrec_words_out,
+                         uint16_t* cl_pos_out, uint16_t* slot_of_pos_out, uint32_t dims_out[2]);
 int rs_plan_street_info(const rs_plan* p, uint32_t traverser, uint32_t out[8]);
 /* The list programs that drive the terminal evaluation of `traverser` on a final-round board (csrc/street.h): words
  * [l_steps][52 * 4] of the pieces of the card lists followed by [c_steps][128] of the pieces of the global strength

@@ -1720,6 +1720,21 @@ int rs_plan_showdown_order(const rs_plan* p, uint32_t player, uint32_t board_id,
     return RS_OK;
 }
 
+int rs_plan_local_tables(const rs_plan* p, uint32_t round_idx, uint32_t player, uint32_t board_id, uint32_t* hrec_words_out, uint16_t* cl_pos_out,
+                         uint16_t* slot_of_pos_out, uint32_t dims_out[2]) {
+    if (!p || player > 1 || !dims_out) return set_err(RS_ERR_INVALID, "bad argument");
+    const Plan& P = p->p;
+    if (round_idx >= P.n_rounds || board_id >= P.n_boards[round_idx]) return set_err(RS_ERR_INVALID, "round or board out of range");
+    if (board_id < P.local_lo[round_idx] || board_id >= P.local_hi[round_idx]) return set_err(RS_ERR_INVALID, "board belongs to another rank");
+    const LocalTables& L = P.loc[round_idx][player];
+    dims_out[0] = L.Hpad;
+    dims_out[1] = L.n_live[board_id];
+    if (hrec_words_out) memcpy(hrec_words_out, &L.hrec[size_t(board_id) * L.Hpad], size_t(L.Hpad) * sizeof(HandRec));
+    if (cl_pos_out) memcpy(cl_pos_out, &L.cl_pos[size_t(board_id) * 2 * L.Hpad], size_t(2) * L.Hpad * sizeof(uint16_t));
+    if (slot_of_pos_out) memcpy(slot_of_pos_out, &L.slot_of_pos[size_t(board_id) * L.Hpad], size_t(L.Hpad) * sizeof(uint16_t));
+    return RS_OK;
+}
+
 int rs_plan_street_info(const rs_plan* p, uint32_t traverser, uint32_t out[8]) {
     if (!p || !out || traverser > 1) return set_err(RS_ERR_INVALID, "bad argument");
     const StreetPlan& S = p->p.street[traverser];

@@ -114,6 +114,8 @@ struct Ctx {
 //   SM_P   [HCAP + 4]    exclusive prefix of reach by position (strength order on the river)
 //   SM_GB  [2*HCAP + 8]  exclusive prefix of reach over the opponent's per-card lists
 //   SM_WSA / SM_WSB [32] warp totals of the two scans
+//   SM_B   [64]          boundaries of the opponent's non-empty card lists: B[j] = GB at the start of list j, B[J] = the
+//                        total; B[54] = B[55] = 0 for a card the opponent does not hold (tasks.h: HandRec)
 //   SM_REC [4][HCAP]     the traverser's per-hand records of the board, staged by cp.async at the start of a task
 //   SM_CL  [HCAP] words  the opponent's per-card lists of the board (u16 pairs), staged the same way
 //   SM_X   [slots][Hx]   scratch vectors (terminal-child reach, bucketed rows), Hx known at run time
@@ -124,9 +126,10 @@ extern __shared__ __align__(16) float smem_raw[];
 #define SM_GB (smem_raw + 2 * HCAP + 4)
 #define SM_WSA (smem_raw + 4 * HCAP + 12)
 #define SM_WSB (smem_raw + 4 * HCAP + 44)
-#define SM_REC (reinterpret_cast<uint32_t*>(smem_raw + 4 * HCAP + 76))
-#define SM_CL (reinterpret_cast<uint32_t*>(smem_raw + 8 * HCAP + 76))
-#define SM_X (smem_raw + 9 * HCAP + 76)
+#define SM_B (smem_raw + 4 * HCAP + 76)
+#define SM_REC (reinterpret_cast<uint32_t*>(smem_raw + 4 * HCAP + 140))
+#define SM_CL (reinterpret_cast<uint32_t*>(smem_raw + 8 * HCAP + 140))
+#define SM_X (smem_raw + 9 * HCAP + 140)
 
 // Copy the thread's eight entries of the opponent's per-card lists (cl_pos of the board, u16) into shared memory with
 // cp.async; scan_reach reads them back.  Like the hand records (stage_recs) this is issued when a task starts, so the
@@ -148,17 +151,21 @@ __device__ __forceinline__ float scan_reach(const Ctx& c, const float* r) {
     float4 x = f4zero();
     if (c.pos4 < c.HoP) x = *reinterpret_cast<const float4*>(r + c.pos4);
     float y[8];
+    uint32_t w[4];
     {
         // the thread's eight list entries were staged by stage_lists when the task started
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        uint4 u = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        uint4 u = make_uint4(0x07ff07ffu, 0x07ff07ffu, 0x07ff07ffu, 0x07ff07ffu);
         if (8 * c.tid < 2 * c.HoP) u = *reinterpret_cast<const uint4*>(SM_CL + 4 * c.tid);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        w[0] = u.x;
+        w[1] = u.y;
+        w[2] = u.z;
+        w[3] = u.w;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const uint32_t a = w[i] & 0xffffu, b = w[i] >> 16;
-            y[2 * i] = a != 0xffffu ? r[a] : 0.f;
-            y[2 * i + 1] = b != 0xffffu ? r[b] : 0.f;
+            const uint32_t a = w[i] & CL_POS_MASK, b = (w[i] >> 16) & CL_POS_MASK;
+            y[2 * i] = a != CL_POS_NONE ? r[a] : 0.f;
+            y[2 * i + 1] = b != CL_POS_NONE ? r[b] : 0.f;
         }
     }
     const float la = (x.x + x.y) + (x.z + x.w);
@@ -217,6 +224,17 @@ __device__ __forceinline__ float scan_reach(const Ctx& c, const float* r) {
         o1.w = o1.z + y[6];
         *reinterpret_cast<float4*>(SM_GB + 8 * c.tid) = o0;
         *reinterpret_cast<float4*>(SM_GB + 8 * c.tid + 4) = o1;
+        // boundaries of the card lists: an entry flagged CL_FIRST stores its exclusive prefix as B[ordinal]; the thread's
+        // first ordinal rides in the spare bits of its first two entries (thread 0 carries the number of lists there)
+        const uint32_t ord0 = ((w[0] >> 11) & 7u) | (((w[0] >> 27) & 7u) << 3);
+        float* bp = SM_B + (c.tid == 0 ? 0u : ord0);
+        const float ex[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool first = ((w[i >> 1] >> ((i & 1) * 16)) & CL_FIRST) != 0;
+            if (first) *bp++ = ex[i];
+        }
+        if (c.tid == 0) SM_B[ord0] = total_b;  // ord0 of thread 0 = J, the number of non-empty lists
     }
     if (c.tid == 0) {
         SM_P[c.HoP] = total;
@@ -268,19 +286,19 @@ __device__ __forceinline__ void staged_recs4(const Ctx& c, uint4 (&rec)[4]) {
 // After scan_reach: for the traverser's hand record `rec`
 //   mass = opponent reach compatible with the hand (total - both cards' sums + the identical combo)
 //   sd   = weaker minus stronger compatible opponent reach (showdown, cfr.rs:532-556)
+__device__ __forceinline__ float ldsb(const float* base, uint32_t byte_off) {  // shared-memory load at base + byte offset
+    return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + byte_off);
+}
 __device__ __forceinline__ void hand_terms(const Ctx& c, const float* r, float total, const uint4& rec, float& mass, float& sd) {
-    const uint32_t lo = rec.x & 0xffffu, hi = rec.x >> 16;
-    const uint32_t s0 = rec.y & 0xffffu, dlo0 = (rec.y >> 16) & 0xffu, dhi0 = rec.y >> 24;
-    const uint32_t s1 = rec.z & 0xffffu, dlo1 = (rec.z >> 16) & 0xffu, dhi1 = rec.z >> 24;
-    const uint32_t n0 = rec.w & 0xffu, n1 = (rec.w >> 8) & 0xffu, same = rec.w >> 16;
-    const float g0s = SM_GB[s0], g0e = SM_GB[s0 + n0], g1s = SM_GB[s1], g1e = SM_GB[s1 + n1];
-    mass = total - (g0e - g0s) - (g1e - g1s) + (same != 0xffffu ? r[same] : 0.f);
-    sd = SM_P[lo] + SM_P[hi] - total - SM_GB[s0 + dlo0] - SM_GB[s0 + dhi0] + g0s + g0e - SM_GB[s1 + dlo1] - SM_GB[s1 + dhi1] + g1s + g1e;
+    const uint32_t k0 = rec.w & 0x1ffu, k1 = (rec.w >> 9) & 0x1ffu, same4 = rec.w >> 18;
+    const float g0s = ldsb(SM_B, k0), g0e = ldsb(SM_B + 1, k0), g1s = ldsb(SM_B, k1), g1e = ldsb(SM_B + 1, k1);
+    mass = total - (g0e - g0s) - (g1e - g1s) + (same4 != HREC_SAME_NONE ? ldsb(r, same4) : 0.f);
+    sd = ldsb(SM_P, rec.x & 0xffffu) + ldsb(SM_P, rec.x >> 16) - total - ldsb(SM_GB, rec.y & 0xffffu) - ldsb(SM_GB, rec.y >> 16) + g0s + g0e -
+         ldsb(SM_GB, rec.z & 0xffffu) - ldsb(SM_GB, rec.z >> 16) + g1s + g1e;
 }
 __device__ __forceinline__ float hand_mass(const Ctx& c, const float* r, float total, const uint4& rec) {
-    const uint32_t s0 = rec.y & 0xffffu, s1 = rec.z & 0xffffu;
-    const uint32_t n0 = rec.w & 0xffu, n1 = (rec.w >> 8) & 0xffu, same = rec.w >> 16;
-    return total - (SM_GB[s0 + n0] - SM_GB[s0]) - (SM_GB[s1 + n1] - SM_GB[s1]) + (same != 0xffffu ? r[same] : 0.f);
+    const uint32_t k0 = rec.w & 0x1ffu, k1 = (rec.w >> 9) & 0x1ffu, same4 = rec.w >> 18;
+    return total - (ldsb(SM_B + 1, k0) - ldsb(SM_B, k0)) - (ldsb(SM_B + 1, k1) - ldsb(SM_B, k1)) + (same4 != HREC_SAME_NONE ? ldsb(r, same4) : 0.f);
 }
 
 // Opponent reach of the thread's four positions for this task (masked by what the board removes).
@@ -852,6 +870,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) task_kernel(const __grid_cons
     const int NC = blockDim.x - 32;  // compute threads; the last warp is the dispatcher
     const int tid = threadIdx.x;
     if (tid == 0) mbar_init(&s_done, uint32_t(NC >> 5));
+    if (tid < 2) SM_B[54 + tid] = 0.f;  // boundaries of "a card the opponent does not hold" (HREC_K_NONE), never overwritten
     __syncthreads();
 
     if (tid >= NC) {
@@ -1215,7 +1234,7 @@ __global__ void unpermute_kernel(const float* __restrict__ in, const uint16_t* _
 
 size_t task_kernel_smem_bytes(int slots, int Hp_pad, int Ho_pad) {
     const int hx = Hp_pad > Ho_pad ? Hp_pad : Ho_pad;
-    size_t floats = size_t(9 * HCAP + 76) + size_t(slots) * hx;  // fixed-offset arrays (SM_*), then the scratch vectors
+    size_t floats = size_t(9 * HCAP + 140) + size_t(slots) * hx;  // fixed-offset arrays (SM_*), then the scratch vectors
     return floats * sizeof(float);
 }
 

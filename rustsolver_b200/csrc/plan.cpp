@@ -1342,8 +1342,8 @@ bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstrac
         const bool final_round = any_showdown && k == P->n_rounds - 1;
         for (int q = 0; q < 2; ++q) {
             LocalTables& L = P->loc[k][q];
-            L.cl_pos.assign(size_t(nB) * 2 * L.Hpad, 0xFFFF);
-            L.hrec.assign(size_t(nB) * L.Hpad, HandRec{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0xFFFF});
+            L.cl_pos.assign(size_t(nB) * 2 * L.Hpad, uint16_t(CL_POS_NONE));
+            L.hrec.assign(size_t(nB) * L.Hpad, HandRec{0, 0, 0, HREC_K_NONE | (HREC_K_NONE << 9) | (HREC_SAME_NONE << 18)});
             if (k > 0) {
                 L.parent_pos.assign(size_t(nB) * L.Hpad, 0xFFFF);
                 L.child_pos.assign(size_t(nB) * P->loc[k - 1][q].Hpad, 0xFFFF);
@@ -1351,6 +1351,7 @@ bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstrac
         }
         for (uint32_t b = P->local_lo[k]; b < P->local_hi[k]; ++b) {
             uint32_t seg_start[2][53];
+            int seg_ord[2][52];                    // ordinal of the card among the player's non-empty lists, -1 = empty
             std::vector<uint32_t> seg_str[2][52];  // strengths inside each card segment (final round)
             for (int q = 0; q < 2; ++q) {
                 LocalTables& L = P->loc[k][q];
@@ -1371,6 +1372,26 @@ bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstrac
                         const int c = P->hand_cards[q][2 * sop[i] + w];
                         cl[fill[c]++] = uint16_t(i);
                         if (final_round) seg_str[q][c].push_back(P->sd[q].strength[size_t(b) * H + sop[i]]);
+                    }
+                }
+                // boundary flags and per-thread first ordinals (tasks.h: cl_pos entry format)
+                uint32_t n_lists = 0;
+                for (int c = 0; c < 52; ++c) {
+                    seg_ord[q][c] = -1;
+                    if (seg_start[q][c + 1] > seg_start[q][c]) {
+                        seg_ord[q][c] = int(n_lists++);
+                        cl[seg_start[q][c]] |= uint16_t(CL_FIRST);
+                    }
+                }
+                {
+                    uint32_t started = 0;  // lists that start before the current entry
+                    const uint32_t n_entries = 2 * L.Hpad;
+                    for (uint32_t e = 0; e < n_entries; e += 8) {
+                        const uint32_t ord = e == 0 ? n_lists : started;
+                        cl[e] |= uint16_t((ord & 7u) << 11);
+                        cl[e + 1] |= uint16_t(((ord >> 3) & 7u) << 11);
+                        for (uint32_t x = e; x < e + 8 && x < n_entries; ++x)
+                            if (cl[x] & CL_FIRST) ++started;
                     }
                 }
                 if (k > 0) {
@@ -1400,28 +1421,37 @@ bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstrac
                 for (uint32_t i = 0; i < L.n_live[b]; ++i) {
                     const uint32_t h = sop[i];
                     const int c0 = P->hand_cards[q][2 * h], c1 = P->hand_cards[q][2 * h + 1];
-                    HandRec r{};
-                    r.s0 = uint16_t(seg_start[o][c0]);
-                    r.n0 = uint8_t(seg_start[o][c0 + 1] - seg_start[o][c0]);
-                    r.s1 = uint16_t(seg_start[o][c1]);
-                    r.n1 = uint8_t(seg_start[o][c1 + 1] - seg_start[o][c1]);
+                    uint32_t lo = 0, hi = 0, ab[2][2] = {{0, 0}, {0, 0}}, kk[2] = {HREC_K_NONE, HREC_K_NONE}, same4 = HREC_SAME_NONE;
+                    const int cc[2] = {c0, c1};
                     const uint16_t sm = P->same[q][h];
-                    r.same = 0xFFFF;
                     if (sm != 0xFFFF) {
                         const uint16_t op = Lo.pos_of_slot[size_t(b) * Ho + sm];
-                        if (op < Lo.n_live[b]) r.same = op;
+                        if (op < Lo.n_live[b]) same4 = uint32_t(op) * 4u;
                     }
+                    const uint32_t st = final_round ? P->sd[q].strength[size_t(b) * H + h] : 0;
                     if (final_round) {
-                        const uint32_t st = P->sd[q].strength[size_t(b) * H + h];
-                        r.lo = uint16_t(std::lower_bound(ostr.begin(), ostr.end(), st) - ostr.begin());
-                        r.hi = uint16_t(std::upper_bound(ostr.begin(), ostr.end(), st) - ostr.begin());
-                        const auto& l0 = seg_str[o][c0];
-                        const auto& l1 = seg_str[o][c1];
-                        r.dlo0 = uint8_t(std::lower_bound(l0.begin(), l0.end(), st) - l0.begin());
-                        r.dhi0 = uint8_t(std::upper_bound(l0.begin(), l0.end(), st) - l0.begin());
-                        r.dlo1 = uint8_t(std::lower_bound(l1.begin(), l1.end(), st) - l1.begin());
-                        r.dhi1 = uint8_t(std::upper_bound(l1.begin(), l1.end(), st) - l1.begin());
+                        lo = uint32_t(std::lower_bound(ostr.begin(), ostr.end(), st) - ostr.begin());
+                        hi = uint32_t(std::upper_bound(ostr.begin(), ostr.end(), st) - ostr.begin());
                     }
+                    for (int w = 0; w < 2; ++w) {
+                        const int c = cc[w];
+                        if (seg_ord[o][c] < 0) continue;  // the opponent holds no hand with this card: GB[0] = 0 and B[54..55] = 0
+                        kk[w] = uint32_t(seg_ord[o][c]) * 4u;
+                        const uint32_t s0 = seg_start[o][c];
+                        uint32_t dlo = 0, dhi = 0;
+                        if (final_round) {
+                            const auto& l = seg_str[o][c];
+                            dlo = uint32_t(std::lower_bound(l.begin(), l.end(), st) - l.begin());
+                            dhi = uint32_t(std::upper_bound(l.begin(), l.end(), st) - l.begin());
+                        }
+                        ab[w][0] = (s0 + dlo) * 4u;
+                        ab[w][1] = (s0 + dhi) * 4u;
+                    }
+                    HandRec r;
+                    r.w0 = (lo * 4u) | ((hi * 4u) << 16);
+                    r.w1 = ab[0][0] | (ab[0][1] << 16);
+                    r.w2 = ab[1][0] | (ab[1][1] << 16);
+                    r.w3 = kk[0] | (kk[1] << 9) | (same4 << 18);
                     L.hrec[size_t(b) * L.Hpad + i] = r;
                 }
             }
@@ -1440,7 +1470,7 @@ bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstrac
                 const uint16_t* sop = &L.slot_of_pos[size_t(b) * L.Hpad];
                 for (uint32_t i = 0; i < L.n_live[b]; ++i) {
                     L.pcards[size_t(b) * L.Hpad + i] = uint16_t(P->hand_cards[q][2 * sop[i]] | (P->hand_cards[q][2 * sop[i] + 1] << 8));
-                    if (L.hrec[size_t(b) * L.Hpad + i].same != i) same = false;
+                    if ((L.hrec[size_t(b) * L.Hpad + i].w3 >> 18) != i * 4u) same = false;  // same4: the identical combo sits at the same position
                 }
                 if (L.n_live[b] != P->loc[k][1 - q].n_live[b]) same = false;
             }

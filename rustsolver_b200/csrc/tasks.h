@@ -92,22 +92,29 @@ struct NodeTask {
 static_assert(sizeof(NodeTask) == 8 + 4 * 8 + 4 * MAX_TASK_DEPS + MAX_TASK_DEPS + 12 * MAX_TASK_CHILDREN + 8, "NodeTask layout");
 static_assert(sizeof(NodeTask) % 4 == 0, "NodeTask is copied to shared memory as words");
 
-// Per-hand record of the traverser on one board (16 bytes, one 128-bit load), local hand order:
-//   u16 lo, hi      #opponent live hands strictly weaker / weaker-or-equal (final round only)
-//   u16 s0; u8 dlo0, dhi0   start of card c0's segment in the opponent's per-card list; #weaker / #weaker-or-equal inside it
-//   u16 s1; u8 dlo1, dhi1   same for card c1
-//   u8 n0, n1       lengths of the two segments
-//   u16 same        position of the identical combo in the opponent's order (0xFFFF: none)
+// Per-hand record of the traverser on one board (16 bytes = four words, one 128-bit load), local hand order.  Every field
+// is a ready-made BYTE offset into one of the scan's shared-memory arrays, so that a gather costs one mask or shift:
+//   w0 = lo4 | hi4 << 16      P[lo], P[hi]: #opponent live hands strictly weaker / weaker-or-equal, x 4 (final round only)
+//   w1 = a0  | b0  << 16      GB[s0 + dlo0], GB[s0 + dhi0] x 4: inside the opponent's list of card c0, the entries weaker /
+//                             weaker-or-equal than the hand (final round; 0 = GB[0] = 0 when that list is empty)
+//   w2 = a1  | b1  << 16      the same for card c1
+//   w3 = k0 | k1 << 9 | same4 << 18
+//        k0, k1  (9 bits)     ordinal of card c0 / c1 among the opponent's NON-EMPTY card lists, x 4: B[k] and B[k + 1]
+//                             are the list's start and end prefix sums; HREC_K_NONE when the opponent holds no hand
+//                             with that card (B[54] = B[55] = 0)
+//        same4   (14 bits)    position of the identical combo in the opponent's order x 4, HREC_SAME_NONE if there is none
 struct HandRec {
-    uint16_t lo, hi;
-    uint16_t s0;
-    uint8_t dlo0, dhi0;
-    uint16_t s1;
-    uint8_t dlo1, dhi1;
-    uint8_t n0, n1;
-    uint16_t same;
+    uint32_t w0, w1, w2, w3;
 };
 static_assert(sizeof(HandRec) == 16, "HandRec is one 128-bit load");
+constexpr uint32_t HREC_K_NONE = 54u * 4u;
+constexpr uint32_t HREC_SAME_NONE = 0x3FFFu;
+// The opponent's per-card lists (cl_pos, u16 entries, eight per thread):
+//   bits 0-10   position of the hand in the opponent's order, CL_POS_NONE = padding
+//   bits 11-13  entries 8t and 8t + 1 only: the low / high three bits of the number of lists that START before entry 8t
+//               (thread t's first boundary ordinal); thread 0 stores the number of non-empty lists J there instead
+//   bit 15      first entry of a (non-empty) card list: the scan stores its exclusive prefix as boundary B[ordinal]
+constexpr uint32_t CL_POS_MASK = 0x7FFu, CL_POS_NONE = 0x7FFu, CL_FIRST = 0x8000u;
 
 struct TaskCtl {  // device-resident dispatcher state, reset by the last CTA to leave
     unsigned long long ticket;

@@ -488,6 +488,18 @@ class Plan(_PlanOrEngine):
         check(self._lib.rs_plan_showdown_order(self._h, player, board_id, _ptr(order, u16p), _ptr(cls, u32p), len(order), C.byref(nl)))
         return order[:nl.value].copy(), cls[:nl.value].copy()
 
+    def local_tables(self, round_idx: int, player: int, board_id: int):
+        """(hand records [Hpad][4] u32 of `player` as traverser, card-list entries [2 * Hpad] u16 of `player` as opponent,
+        slot_of_pos [Hpad], live hands) in the board-local hand order (csrc/tasks.h)."""
+        dims = (C.c_uint32 * 2)()
+        check(self._lib.rs_plan_local_tables(self._h, round_idx, player, board_id, None, None, None, dims))
+        hp, nl = int(dims[0]), int(dims[1])
+        rec = np.zeros((hp, 4), dtype=np.uint32)
+        cl = np.zeros(2 * hp, dtype=np.uint16)
+        sop = np.zeros(hp, dtype=np.uint16)
+        check(self._lib.rs_plan_local_tables(self._h, round_idx, player, board_id, _ptr(rec, u32p), _ptr(cl, u16p), _ptr(sop, u16p), dims))
+        return rec, cl, sop, nl
+
     def street_info(self, traverser: int) -> dict:
         """The final round as fused street programs (csrc/street.h); `why` is set when the round is not eligible."""
         out = (C.c_uint32 * 8)()
