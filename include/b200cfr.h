@@ -382,6 +382,14 @@ int rs_plan_showdown_order(const rs_plan* p, uint32_t player, uint32_t board_id,
  * pointer may be NULL; call once with all NULL to size the buffers. */
 int rs_plan_local_tables(const rs_plan* p, uint32_t round_idx, uint32_t player, uint32_t board_id, uint32_t* hrec_words_out,
                          uint16_t* cl_pos_out, uint16_t* slot_of_pos_out, uint32_t dims_out[2]);
+/* Host-side proof obligation of the traversal kernel's scheduler: tickets are handed out in order and an instance waits
+ * for its producers, so the execution order (ticket -> instance slot; a large final round is walked parent board by parent
+ * board, force_board_major != 0 applies that whatever the size) must run every producer before its consumers.  Rebuilds the
+ * order exactly as rs_create does and checks it against a host mirror of the dispatcher's dependency resolution.
+ * RS_OK = deadlock-free; n_moved_out = slots that are not at their task-major ticket.  force_board_major < 0 is the
+ * checker's self-test: the reversed order, which must come back as RS_ERR_INVALID. */
+int rs_plan_check_execution_order(const rs_plan* p, uint32_t traverser, int force_board_major, uint32_t* n_tickets_out,
+                                  uint32_t* n_moved_out);
 int rs_plan_street_info(const rs_plan* p, uint32_t traverser, uint32_t out[8]);
 /* The list programs that drive the terminal evaluation of `traverser` on a final-round board (csrc/street.h): words
  * [l_steps][52 * 4] of the pieces of the card lists followed by [c_steps][128] of the pieces of the global strength

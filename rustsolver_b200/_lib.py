@@ -115,6 +115,7 @@ ENGINE_API = {
     "rs_plan_infoset_offset": (C.c_int, [VP, C.c_uint32, C.c_uint32, u64p, u32p, u32p]),
     "rs_plan_showdown_order": (C.c_int, [VP, C.c_uint32, C.c_uint32, u16p, u32p, C.c_size_t, u32p]),
     "rs_plan_local_tables": (C.c_int, [VP, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u16p, u16p, u32p]),
+    "rs_plan_check_execution_order": (C.c_int, [VP, C.c_uint32, C.c_int, u32p, u32p]),
     "rs_plan_street_info": (C.c_int, [VP, C.c_uint32, u32p]),
     "rs_plan_street_program": (C.c_int, [VP, C.c_uint32, C.c_uint32, u32p, C.c_size_t, u32p, u32p, C.c_size_t, u32p]),
 }

@@ -588,22 +588,12 @@ int Engine::enqueue_street(int trav, int mode, const TaskSet& set, int n_paths) 
 }
 
 int Engine::materialize(int trav, const uint32_t counts[3], TaskSet* out) {
-    const TaskList& tl = plan.tl[trav];
-    std::vector<NodeTask> t = tl.tasks;
-    std::vector<TaskSrc> sr = tl.srcs;
-    uint32_t first = 0;
-    out->phase_cut = 0;
-    bool cut_set = false;
-    for (size_t j = 0; j < t.size(); ++j) {
-        if (!cut_set && tl.tasks[j].first >= tl.phase_cut) {
-            out->phase_cut = first;
-            cut_set = true;
-        }
-        t[j].first = first;
-        t[j].count = counts[t[j].round_k];
-        first += t[j].count;
-    }
-    if (!cut_set) out->phase_cut = first;
+    MaterializedTasks mt;
+    materialize_tasks(plan, trav, counts, &mt);  // slot numbering + dependencies as first slots (plan.cpp, shared with the CPU checks)
+    std::vector<NodeTask>& t = mt.tasks;
+    std::vector<TaskSrc>& sr = mt.srcs;
+    const uint32_t first = mt.n_tickets;
+    out->phase_cut = mt.phase_cut;
     out->n_tickets = first;
     out->n_tasks = uint32_t(t.size());
     out->street_lo = out->street_hi = 0;
@@ -642,11 +632,6 @@ int Engine::materialize(int trav, const uint32_t counts[3], TaskSet* out) {
             if (!seen) out->sections.push_back({x.first, uint32_t(x.round_k), up});
         }
     }
-    for (NodeTask& x : t)
-        for (int i = 0; i < x.n_dep; ++i)
-            if (x.dep[i] >= 0) x.dep[i] = int32_t(t[x.dep[i]].first);
-    for (TaskSrc& x : sr)
-        if (x.dep >= 0) x.dep = int32_t(t[x.dep].first);
     std::vector<uint32_t> tix(first);
     for (size_t j = 0; j < t.size(); ++j)
         for (uint32_t i = 0; i < t[j].count; ++i) tix[t[j].first + i] = uint32_t(j);
@@ -662,37 +647,11 @@ int Engine::materialize(int trav, const uint32_t counts[3], TaskSet* out) {
     // tasks, and a reach vector is read back one level later instead of 2 352 boards later.  Producers still precede
     // consumers.  (Walking a group street segment by street segment keeps even more in L2 but starves the in-order
     // ticket dispenser: measured 3.4x slower.)
-    const uint32_t kf = plan.n_rounds - 1;
-    const bool full_boards = counts[kf] == rd[kf].n_boards;
-    if (plan.n_rounds >= 2 && full_boards && !getenv("RS_TASK_MAJOR")) {
-        const TaskList& tlp = plan.tl[trav];
-        const uint64_t vec_bytes = (uint64_t(tlp.n_rbuf[kf]) + tlp.n_cbuf[kf]) * counts[kf] * std::max(plan.H[0], plan.H[1]) * 4;
-        uint32_t lo = UINT32_MAX, hi = 0;
-        std::vector<uint32_t> fin;  // node tasks of the final round, list order (downs by depth, then ups deepest first)
-        for (size_t j = 0; j < t.size(); ++j)
-            if (t[j].round_k == kf && t[j].count) {
-                fin.push_back(uint32_t(j));
-                lo = std::min(lo, t[j].first);
-                hi = std::max(hi, t[j].first + t[j].count);
-            }
-        uint64_t covered = 0;
-        for (uint32_t j : fin) covered += t[j].count;
-        const bool contiguous = !fin.empty() && covered == uint64_t(hi - lo);
-        if (contiguous && (vec_bytes > (96ull << 20) || getenv("RS_BOARD_MAJOR"))) {
-            std::vector<uint32_t> ord(first);
-            for (uint32_t i = 0; i < first; ++i) ord[i] = i;
-            const int32_t* par = plan.board_parent[kf].data() + plan.local_lo[kf];
-            uint32_t pos = lo;
-            for (uint32_t b0 = 0; b0 < counts[kf];) {
-                uint32_t b1 = b0 + 1;
-                while (b1 < counts[kf] && par[b1] == par[b0]) ++b1;
-                for (uint32_t j : fin)
-                    for (uint32_t b = b0; b < b1; ++b) ord[pos++] = t[j].first + b;
-                b0 = b1;
-            }
-            if (pos != hi) return set_err(RS_ERR_INVALID, "internal: execution order does not cover the final round");
-            CU(out->order.upload(ord));
-        }
+    if (!getenv("RS_TASK_MAJOR")) {
+        std::vector<uint32_t> ord;
+        std::string oerr;
+        if (!build_execution_order(plan, trav, mt, counts, getenv("RS_BOARD_MAJOR") != nullptr, &ord, &oerr)) return set_err(RS_ERR_INVALID, oerr);
+        if (!ord.empty()) CU(out->order.upload(ord));
     }
     return RS_OK;
 }
@@ -1732,6 +1691,31 @@ int rs_plan_local_tables(const rs_plan* p, uint32_t round_idx, uint32_t player, 
     if (hrec_words_out) memcpy(hrec_words_out, &L.hrec[size_t(board_id) * L.Hpad], size_t(L.Hpad) * sizeof(HandRec));
     if (cl_pos_out) memcpy(cl_pos_out, &L.cl_pos[size_t(board_id) * 2 * L.Hpad], size_t(2) * L.Hpad * sizeof(uint16_t));
     if (slot_of_pos_out) memcpy(slot_of_pos_out, &L.slot_of_pos[size_t(board_id) * L.Hpad], size_t(L.Hpad) * sizeof(uint16_t));
+    return RS_OK;
+}
+
+int rs_plan_check_execution_order(const rs_plan* p, uint32_t traverser, int force_board_major, uint32_t* n_tickets_out, uint32_t* n_moved_out) {
+    if (!p || traverser > 1) return set_err(RS_ERR_INVALID, "bad argument");
+    const Plan& P = p->p;
+    uint32_t counts[3] = {0, 0, 0};
+    for (uint32_t k = 0; k < P.n_rounds; ++k) counts[k] = P.boards_local(k);
+    MaterializedTasks mt;
+    materialize_tasks(P, int(traverser), counts, &mt);
+    std::vector<uint32_t> ord;
+    std::string err;
+    if (!build_execution_order(P, int(traverser), mt, counts, force_board_major > 0, &ord, &err)) return set_err(RS_ERR_INVALID, err);
+    if (force_board_major < 0) {  // self-test of the checker: tickets in REVERSE slot order must be rejected
+        ord.resize(mt.n_tickets);
+        for (uint32_t i = 0; i < mt.n_tickets; ++i) ord[i] = mt.n_tickets - 1 - i;
+    }
+    err = check_execution_order(P, int(traverser), mt, counts, ord);
+    if (!err.empty()) return set_err(RS_ERR_INVALID, "execution order: " + err);
+    if (n_tickets_out) *n_tickets_out = mt.n_tickets;
+    if (n_moved_out) {
+        uint32_t moved = 0;
+        for (uint32_t i = 0; i < ord.size(); ++i) moved += ord[i] != i;
+        *n_moved_out = moved;
+    }
     return RS_OK;
 }
 

@@ -1497,4 +1497,125 @@ bool compile_plan(const rs_tree* tree, const rs_ranges* ranges, const rs_abstrac
     return true;
 }
 
+void materialize_tasks(const Plan& P, int trav, const uint32_t counts[3], MaterializedTasks* out) {
+    const TaskList& tl = P.tl[trav];
+    std::vector<NodeTask>& t = out->tasks;
+    std::vector<TaskSrc>& sr = out->srcs;
+    t = tl.tasks;
+    sr = tl.srcs;
+    uint32_t first = 0;
+    out->phase_cut = 0;
+    bool cut_set = false;
+    for (size_t j = 0; j < t.size(); ++j) {
+        if (!cut_set && tl.tasks[j].first >= tl.phase_cut) {
+            out->phase_cut = first;
+            cut_set = true;
+        }
+        t[j].first = first;
+        t[j].count = counts[t[j].round_k];
+        first += t[j].count;
+    }
+    if (!cut_set) out->phase_cut = first;
+    out->n_tickets = first;
+    for (NodeTask& x : t)
+        for (int i = 0; i < x.n_dep; ++i)
+            if (x.dep[i] >= 0) x.dep[i] = int32_t(t[x.dep[i]].first);
+    for (TaskSrc& x : sr)
+        if (x.dep >= 0) x.dep = int32_t(t[x.dep].first);
+}
+
+bool build_execution_order(const Plan& P, int trav, const MaterializedTasks& m, const uint32_t counts[3], bool force, std::vector<uint32_t>* ord,
+                           std::string* err) {
+    ord->clear();
+    const std::vector<NodeTask>& t = m.tasks;
+    const uint32_t kf = P.n_rounds - 1;
+    if (P.n_rounds < 2 || counts[kf] != P.boards_local(kf)) return true;
+    const TaskList& tlp = P.tl[trav];
+    const uint64_t vec_bytes = (uint64_t(tlp.n_rbuf[kf]) + tlp.n_cbuf[kf]) * counts[kf] * std::max(P.H[0], P.H[1]) * 4;
+    uint32_t lo = UINT32_MAX, hi = 0;
+    std::vector<uint32_t> fin;  // node tasks of the final round, list order (downs by depth, then ups deepest first)
+    for (size_t j = 0; j < t.size(); ++j)
+        if (t[j].round_k == kf && t[j].count) {
+            fin.push_back(uint32_t(j));
+            lo = std::min(lo, t[j].first);
+            hi = std::max(hi, t[j].first + t[j].count);
+        }
+    uint64_t covered = 0;
+    for (uint32_t j : fin) covered += t[j].count;
+    const bool contiguous = !fin.empty() && covered == uint64_t(hi - lo);
+    if (!contiguous || !(vec_bytes > (96ull << 20) || force)) return true;
+    ord->resize(m.n_tickets);
+    for (uint32_t i = 0; i < m.n_tickets; ++i) (*ord)[i] = i;
+    const int32_t* par = P.board_parent[kf].data() + P.local_lo[kf];
+    uint32_t pos = lo;
+    for (uint32_t b0 = 0; b0 < counts[kf];) {
+        uint32_t b1 = b0 + 1;
+        while (b1 < counts[kf] && par[b1] == par[b0]) ++b1;
+        for (uint32_t j : fin)
+            for (uint32_t b = b0; b < b1; ++b) (*ord)[pos++] = t[j].first + b;
+        b0 = b1;
+    }
+    if (pos != hi) {
+        if (err) *err = "internal: execution order does not cover the final round";
+        return false;
+    }
+    return true;
+}
+
+std::string check_execution_order(const Plan& P, int trav, const MaterializedTasks& m, const uint32_t counts[3], const std::vector<uint32_t>& ord) {
+    (void)trav;
+    const uint32_t n = m.n_tickets;
+    std::vector<uint32_t> pos(n);
+    if (ord.empty()) {
+        for (uint32_t i = 0; i < n; ++i) pos[i] = i;
+    } else {
+        if (ord.size() != n) return "order has the wrong length";
+        std::vector<uint8_t> seen(n, 0);
+        for (uint32_t tk = 0; tk < n; ++tk) {
+            if (ord[tk] >= n || seen[ord[tk]]) return "order is not a permutation (ticket " + std::to_string(tk) + ")";
+            seen[ord[tk]] = 1;
+            pos[ord[tk]] = tk;
+        }
+    }
+    auto bad = [&](uint32_t producer, uint32_t slot, size_t j) -> std::string {
+        if (producer >= n) return "task " + std::to_string(j) + ": producer slot " + std::to_string(producer) + " out of range";
+        if (pos[producer] >= pos[slot])
+            return "task " + std::to_string(j) + " slot " + std::to_string(slot) + " (ticket " + std::to_string(pos[slot]) + ") runs before its producer slot " +
+                   std::to_string(producer) + " (ticket " + std::to_string(pos[producer]) + ")";
+        return "";
+    };
+    for (size_t j = 0; j < m.tasks.size(); ++j) {
+        const NodeTask& st = m.tasks[j];
+        const uint32_t k = st.round_k;
+        for (uint32_t inst = 0; inst < st.count; ++inst) {
+            const uint32_t slot = st.first + inst, b = inst;
+            if (st.kind == TK_GATHER) {
+                const bool sharded_next = P.world > 1 && k + 1 == P.shard_round;
+                const uint32_t per_parent = sharded_next ? 0u : P.deal_count[k + 1];
+                const uint32_t gfirst = uint32_t(st.dep[0]) + (per_parent > 0 ? b * per_parent : 0u);
+                const uint32_t total = per_parent > 0 ? per_parent : counts[k + 1];
+                for (uint32_t c = 0; c < total; ++c) {
+                    const std::string e = bad(gfirst + c, slot, j);
+                    if (!e.empty()) return e;
+                }
+                continue;
+            }
+            for (int i = 0; i < st.n_dep; ++i) {
+                if (st.dep[i] < 0) continue;
+                uint32_t off = inst;
+                if (st.dep_kind[i] == DK_PARENT_BOARD) off = uint32_t(P.board_parent[k][P.local_lo[k] + b] - int32_t(P.local_lo[k - 1]));
+                const std::string e = bad(uint32_t(st.dep[i]) + off, slot, j);
+                if (!e.empty()) return e;
+            }
+            for (uint32_t s = 0; s < st.n_src_all; ++s) {
+                const int32_t d = m.srcs[st.src_all_first + s].dep;
+                if (d < 0) continue;
+                const std::string e = bad(uint32_t(d) + inst, slot, j);
+                if (!e.empty()) return e;
+            }
+        }
+    }
+    return "";
+}
+
 }  // namespace rs

@@ -130,6 +130,24 @@ struct Plan {
     uint32_t boards_local(uint32_t k) const { return local_hi[k] - local_lo[k]; }
 };
 
+// A traversal's task list with the slot numbering materialised for a given number of instances per round: task j owns the
+// slots [first, first + count); the dependency fields of the tasks and sources hold FIRST SLOTS instead of task indices.
+struct MaterializedTasks {
+    std::vector<NodeTask> tasks;
+    std::vector<TaskSrc> srcs;
+    uint32_t n_tickets = 0, phase_cut = 0;
+};
+void materialize_tasks(const Plan& P, int trav, const uint32_t counts[3], MaterializedTasks* out);
+// Execution order (ticket -> slot) of a traversal: empty = identity (task-major slots).  A large final round is walked
+// parent board by parent board (see engine.cu: Engine::materialize for why); `force` applies it whatever the size.
+// Only defined for full traversals (counts = the local boards of every round).  False + err on an internal inconsistency.
+bool build_execution_order(const Plan& P, int trav, const MaterializedTasks& m, const uint32_t counts[3], bool force, std::vector<uint32_t>* ord,
+                           std::string* err);
+// Host mirror of the dispatcher's dependency resolution (kernels.cu: flag_index) for a full traversal: "" when `ord` is a
+// permutation of the slots in which every producer of every instance runs before it (what rules out a deadlock of the
+// in-order ticket dispenser), else a description of the first violation.
+std::string check_execution_order(const Plan& P, int trav, const MaterializedTasks& m, const uint32_t counts[3], const std::vector<uint32_t>& ord);
+
 // Optional batch indexer: out[i] = ix.get_index(cards + i * n_cards) for i < n.  The engine passes the device
 // implementation (indexer_kernel.cu); without one the host indexer is used.  Both are bit-identical.
 class HandIndexer;

@@ -488,6 +488,12 @@ class Plan(_PlanOrEngine):
         check(self._lib.rs_plan_showdown_order(self._h, player, board_id, _ptr(order, u16p), _ptr(cls, u32p), len(order), C.byref(nl)))
         return order[:nl.value].copy(), cls[:nl.value].copy()
 
+    def check_execution_order(self, traverser: int, force_board_major: bool = False):
+        """(tickets, slots moved off their task-major ticket); raises EngineError if a consumer could run before a producer."""
+        n, moved = C.c_uint32(), C.c_uint32()
+        check(self._lib.rs_plan_check_execution_order(self._h, traverser, int(force_board_major), C.byref(n), C.byref(moved)))
+        return int(n.value), int(moved.value)
+
     def local_tables(self, round_idx: int, player: int, board_id: int):
         """(hand records [Hpad][4] u32 of `player` as traverser, card-list entries [2 * Hpad] u16 of `player` as opponent,
         slot_of_pos [Hpad], live hands) in the board-local hand order (csrc/tasks.h)."""
