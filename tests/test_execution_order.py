@@ -48,3 +48,16 @@ def test_the_checker_rejects_an_order_that_runs_consumers_first():
     plan = _plan("turn")
     with pytest.raises(rb.EngineError, match="runs before its producer"):
         plan.check_execution_order(0, force_board_major=-1)
+
+
+@pytest.mark.parametrize("world,rank", [(1, 0), (8, 0), (8, 7)])
+def test_config4_at_full_size(world, rank):
+    """The bench workload itself: 1.4 - 1.6 M instances per traversal, the river walked parent board by parent board
+    (the order rs_create uploads for config 4), unsharded and on the first / last rank of an 8-GPU run."""
+    from rustsolver_b200 import configs
+    w = configs.config4()
+    n, tree = rb.build_game_tree(w.options)
+    plan = rb.Plan(tree, configs.workload_ranges(w), w.options.board_mask, w.card_abs, rank=rank, world_size=world)
+    for trav in range(2):
+        tickets, moved = plan.check_execution_order(trav)  # not forced: config 4's vectors exceed the L2-sized threshold
+        assert tickets > 150_000 and moved > tickets // 2
